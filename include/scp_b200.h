@@ -1,0 +1,84 @@
+/*
+ * scp_b200.h — C ABI of the B200-native hot path of kywind/self-corr-pose.
+ *
+ * Every entry point takes raw DEVICE pointers (fp32 unless stated), explicit sizes and an
+ * explicit CUDA stream (passed as void* = cudaStream_t).  Nothing allocates; callers own all
+ * buffers.  Return value: 0 on success, otherwise a cudaError_t value (or -1 for an argument
+ * this build does not support) — never a silent fallback.  All functions are re-entrant per
+ * stream.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   scp_softras_forward / scp_softras_backward
+ *       third-party/softras/soft_renderer/cuda/soft_rasterize_cuda.cpp:59-91, :94-132
+ *       (pybind names forward_soft_rasterize / backward_soft_rasterize, :135-138), kernels
+ *       soft_rasterize_cuda_kernel.cu:245-305, :308-483, :486-668.
+ *   scp_corr_match_forward / scp_corr_match_backward
+ *       model/module/correspondence.py:36-73 (Correspondence.match: bmm + mask + two softmaxes
+ *       + two weighted sums), reached through torch ops in the reference.
+ *   scp_colsoftmax_bmm_forward / _backward
+ *       model/module/correspondence.py:105-110 (rotation-cycle similarity, column softmax, grid.bmm).
+ *   scp_vit_*  — see the ViT section below
+ *       third-party/zsp/zsp/method/vision_transformer_flexible.py:85-101,116-132,214-262 and
+ *       model/module/network/dino.py:102-109.
+ */
+#ifndef SCP_B200_H
+#define SCP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------- */
+
+/* ABI version of this header; bumped on any signature change. */
+int scp_abi_version(void);
+/* Last error text recorded by a failing call on this host thread (never NULL). */
+const char *scp_last_error(void);
+
+/* ---- SoftRas soft rasteriser ----------------------------------------------------------- */
+/* enum values are the reference's (functional/soft_rasterize.py:22-25) */
+#define SCP_DIST_HARD 0
+#define SCP_DIST_BARYCENTRIC 1
+#define SCP_DIST_EUCLIDEAN 2
+#define SCP_RGB_HARD 0
+#define SCP_RGB_SOFTMAX 1
+#define SCP_ALPHA_HARD 0
+#define SCP_ALPHA_SUM 1
+#define SCP_ALPHA_PROD 2
+#define SCP_TEX_SURFACE 0
+#define SCP_TEX_VERTEX 1
+
+/* Scratch bytes the two SoftRas calls need for (B, nf) (per-face packed records + bboxes). */
+size_t scp_softras_workspace_bytes(int B, int nf);
+
+/*
+ * forward_soft_rasterize.  faces[B,nf,3,3] screen-space face vertices (x,y in NDC, z depth),
+ * textures[B,nf,T,3]; caller pre-fills soft_colors[B,4,is,is] with the background colour and
+ * zeroes faces_info[B,nf,27] and aggrs_info[B,2,is,is] (functional/soft_rasterize.py:47-53).
+ * dist_eps is the already transformed ln(1/dist_eps-1) (soft_rasterize.py:35).
+ * Writes faces_info, aggrs_info, soft_colors in place.
+ */
+int scp_softras_forward(const float *faces, const float *textures, float *faces_info, float *aggrs_info,
+                        float *soft_colors, int B, int nf, int T, int image_size, float near_, float far_,
+                        float eps, float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
+                        int func_id_rgb, int func_id_alpha, int texture_sample_type, int double_side,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * backward_soft_rasterize.  grad_faces[B,nf,9] and grad_textures[B,nf,T,3] must be zero-filled
+ * by the caller (soft_rasterize.py:88-89) and are accumulated into.
+ */
+int scp_softras_backward(const float *faces, const float *textures, const float *soft_colors,
+                         const float *faces_info, const float *aggrs_info, float *grad_faces,
+                         float *grad_textures, const float *grad_soft_colors, int B, int nf, int T,
+                         int image_size, float near_, float far_, float eps, float sigma_val, int func_id_dist,
+                         float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
+                         int texture_sample_type, int double_side, void *workspace, size_t workspace_bytes,
+                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCP_B200_H */

@@ -1,0 +1,75 @@
+"""ctypes binding of the C-ABI library (include/scp_b200.h -> libscp_b200.so).
+
+This is the only place the product touches native code.  There is NO fallback: if the library
+is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libscp_b200.so')
+ABI_VERSION = 1
+
+_f = ctypes.c_void_p   # device pointers travel as integers
+_i = ctypes.c_int
+_fl = ctypes.c_float
+_sz = ctypes.c_size_t
+
+_SOFTRAS_SCALARS = [_i, _i, _i, _i, _fl, _fl, _fl, _fl, _i, _fl, _fl, _i, _i, _i, _i]
+
+_SIGNATURES = {
+    'scp_abi_version': ([], _i),
+    'scp_last_error': ([], ctypes.c_char_p),
+    'scp_softras_workspace_bytes': ([_i, _i], _sz),
+    'scp_softras_forward': ([_f] * 5 + _SOFTRAS_SCALARS + [_f, _sz, _f], _i),
+    'scp_softras_backward': ([_f] * 8 + _SOFTRAS_SCALARS + [_f, _sz, _f], _i),
+}
+
+_lib = None
+
+
+class ScpNativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libscp_b200.so once; raises if it has not been built (python -m self_corr_pose_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ScpNativeError(
+                'native library %s is missing: run `python -m self_corr_pose_b200.build` '
+                '(there is no CPU / PyTorch fallback for the hot path)' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        if handle.scp_abi_version() != ABI_VERSION:
+            raise ScpNativeError('libscp_b200.so ABI %d != expected %d: rebuild' %
+                                 (handle.scp_abi_version(), ABI_VERSION))
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().scp_last_error().decode('utf-8', 'replace')
+        raise ScpNativeError('%s failed (code %d): %s' % (what, rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a CUDA fp32/int tensor that must already be contiguous."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ScpNativeError('expected a CUDA tensor (the hot path has no CPU implementation)')
+    if not t.is_contiguous():
+        raise ScpNativeError('expected a contiguous tensor')
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
