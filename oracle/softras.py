@@ -51,6 +51,8 @@ def _get(kind):
     if kind not in _cache:
         if kind == 'oracle':
             _cache[kind] = _load(os.path.join(_HERE, 'liboracle_softras.so'), 'scp_oracle_softras_', 1)
+        elif kind == 'oracle_fma':
+            _cache[kind] = _load(os.path.join(_HERE, 'liboracle_softras_fma.so'), 'scp_oracle_softras_', 1)
         else:
             _cache[kind] = _load(os.path.join(_HERE, '_ref', 'libsoftras_ref_cpu.so'), 'scp_ref_softras_', 0)
     return _cache[kind]
@@ -94,7 +96,7 @@ def _forward(kind, face_vertices, textures, image_size=256, background_color=(0,
     args = [_p(faces), _p(tex_pad), _p(faces_info), _p(aggrs_info), _p(soft_colors)] + \
         list(_scalars(B, nf, T, image_size, near, far, eps, sigma_val, dist_func, dist_eps, gamma_val,
                       aggr_func_rgb, aggr_func_alpha, texture_type, fill_back))
-    if kind == 'oracle':
+    if kind.startswith('oracle'):
         args.append(nthreads)
     rc = fwd(*args)
     assert rc == 0
@@ -118,21 +120,22 @@ def _backward(kind, face_vertices, textures, soft_colors, faces_info, aggrs_info
             _p(grad_faces), _p(grad_textures), _p(g)] + \
         list(_scalars(B, nf, T, image_size, near, far, eps, sigma_val, dist_func, dist_eps, gamma_val,
                       aggr_func_rgb, aggr_func_alpha, texture_type, fill_back))
-    if kind == 'oracle':
+    if kind.startswith('oracle'):
         args.append(nthreads)
     rc = bwd(*args)
     assert rc == 0
     return grad_faces.reshape(B, nf, 3, 3), grad_textures
 
 
-def forward(*a, **k):
-    """Our restatement. Returns (soft_colors[B,4,is,is], faces_info[B,nf,27], aggrs_info[B,2,is,is])."""
-    return _forward('oracle', *a, **k)
+def forward(*a, fma=False, **k):
+    """Our restatement. Returns (soft_colors[B,4,is,is], faces_info[B,nf,27], aggrs_info[B,2,is,is]).
+    fma=True runs the build with FMA contraction (same source, nvcc-like rounding)."""
+    return _forward('oracle_fma' if fma else 'oracle', *a, **k)
 
 
-def backward(*a, **k):
+def backward(*a, fma=False, **k):
     """Our restatement. Returns (grad_faces[B,nf,3,3], grad_textures[B,nf,T,3])."""
-    return _backward('oracle', *a, **k)
+    return _backward('oracle_fma' if fma else 'oracle', *a, **k)
 
 
 def ref_forward(*a, **k):

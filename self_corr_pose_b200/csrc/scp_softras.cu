@@ -5,10 +5,13 @@
 // pixel over ALL faces; here one CTA owns a 16x16 pixel tile, culls the face list against the
 // tile (ordered stream compaction, so every pixel still visits its faces in ascending face
 // index -- needed for the hard z-buffer tie-break and for a reproducible online softmax),
-// stages packed 192-byte face records in shared memory and lets each thread (one pixel, warps
-// cover 8x4 pixel blocks) evaluate only the surviving faces.  The backward pass reduces the
-// per-(pixel,face) gradients inside the warp (shuffles), then inside the CTA (shared-memory
-// accumulators) and issues one global atomic per face value per tile instead of one per pixel.
+// then every warp (an 8x4 pixel block, one pixel per lane) culls that list once more against its
+// own footprint and evaluates only the surviving faces, reading packed 192-byte face records
+// through L1 (all lanes read the same record: one transaction).  After the tile list is built the
+// warps run independently -- no CTA barrier in the pair loop.  The backward pass reduces the
+// per-(pixel,face) gradients across the warp with a folded butterfly (20 shuffles for 18 values,
+// each lane ending up with one total) and issues one global reduction per value per
+// (warp, face) instead of one per (pixel, face).
 #include <stdarg.h>
 
 #include "../../include/scp_b200.h"
@@ -21,52 +24,54 @@ constexpr int TILE = 16;        // pixels per tile side
 constexpr int NTHREADS = 256;   // one thread per tile pixel
 constexpr int REC = 48;         // floats per packed face record (12 x float4)
 constexpr int REC4 = REC / 4;
-constexpr int LIST_CAP = 128;   // records staged per round
-constexpr int NGRAD = 18;       // 9 face-coordinate + 9 vertex-texture gradients per face
+constexpr int NWARPS = NTHREADS / 32;
+constexpr int SCAN = 4;         // faces tested per thread per culling round
+constexpr int LIST_CAP = 2048;  // tile face list capacity (indices) per phase
 
 struct Params {
     int B, nf, T, R, is, tiles_x;
     float near_, far_, eps, sigma, gamma, threshold, margin;
+    float inv_sigma, inv_gamma, inv_depth_range;
     int dist_mode, rgb_mode, alpha_mode, tex_mode, double_side;
 };
 
 // Packed per-face record (float4 slots):
 //  0: bbox  (xmin-m, xmax+m, ymin-m, ymax+m)        m = sqrt(dist_eps*sigma)
-//  1: inv[0..3]   2: inv[4..7]   3: inv[8], x0, y0, z0
-//  4: x1, y1, z1, x2            5: y2, z2, front-facing flag, face index (int bits)
-//  6..8: E_k = sym[row k] - sym[row k+1] (3 floats) and den_k = E_k[k] - E_k[k+1]
+//  1: inv[0..3]   2: inv[4..7]   3: inv[8], x0, y0, 1/z0
+//  4: x1, y1, 1/z1, x2          5: y2, 1/z2, front-facing flag, face index (int bits)
+//  6..8: E_k = sym[row k] - sym[row k+1] (3 floats) and 1/den_k, den_k = E_k[k] - E_k[k+1]
 //  9: tex[0..3]  10: tex[4..7]  11: tex[8], obt0, obt1, obt2
 struct Face {
     float bx0, bx1, by0, by1;
     float inv[9];
-    float x[3], y[3], z[3];
+    float x[3], y[3], rz[3];
     float front;
     int idx;
-    float E[3][3], den[3];
+    float E[3][3], rden[3];
     float tex[9];
     float obt[3];
 };
 
 __device__ __forceinline__ void load_bbox(const float *r, float &bx0, float &bx1, float &by0, float &by1)
 {
-    const float4 q = *reinterpret_cast<const float4 *>(r);
+    const float4 q = __ldg(reinterpret_cast<const float4 *>(r));
     bx0 = q.x; bx1 = q.y; by0 = q.z; by1 = q.w;
 }
 
 __device__ __forceinline__ void load_face(const float *r, Face &f)
 {
     const float4 *q = reinterpret_cast<const float4 *>(r);
-    float4 a = q[1], b = q[2], c = q[3], d = q[4], e = q[5];
+    float4 a = __ldg(q + 1), b = __ldg(q + 2), c = __ldg(q + 3), d = __ldg(q + 4), e = __ldg(q + 5);
     f.inv[0] = a.x; f.inv[1] = a.y; f.inv[2] = a.z; f.inv[3] = a.w;
     f.inv[4] = b.x; f.inv[5] = b.y; f.inv[6] = b.z; f.inv[7] = b.w;
-    f.inv[8] = c.x; f.x[0] = c.y; f.y[0] = c.z; f.z[0] = c.w;
-    f.x[1] = d.x; f.y[1] = d.y; f.z[1] = d.z; f.x[2] = d.w;
-    f.y[2] = e.x; f.z[2] = e.y; f.front = e.z; f.idx = __float_as_int(e.w);
-    a = q[6]; b = q[7]; c = q[8];
-    f.E[0][0] = a.x; f.E[0][1] = a.y; f.E[0][2] = a.z; f.den[0] = a.w;
-    f.E[1][0] = b.x; f.E[1][1] = b.y; f.E[1][2] = b.z; f.den[1] = b.w;
-    f.E[2][0] = c.x; f.E[2][1] = c.y; f.E[2][2] = c.z; f.den[2] = c.w;
-    a = q[9]; b = q[10]; c = q[11];
+    f.inv[8] = c.x; f.x[0] = c.y; f.y[0] = c.z; f.rz[0] = c.w;
+    f.x[1] = d.x; f.y[1] = d.y; f.rz[1] = d.z; f.x[2] = d.w;
+    f.y[2] = e.x; f.rz[2] = e.y; f.front = e.z; f.idx = __float_as_int(e.w);
+    a = __ldg(q + 6); b = __ldg(q + 7); c = __ldg(q + 8);
+    f.E[0][0] = a.x; f.E[0][1] = a.y; f.E[0][2] = a.z; f.rden[0] = a.w;
+    f.E[1][0] = b.x; f.E[1][1] = b.y; f.E[1][2] = b.z; f.rden[1] = b.w;
+    f.E[2][0] = c.x; f.E[2][1] = c.y; f.E[2][2] = c.z; f.rden[2] = c.w;
+    a = __ldg(q + 9); b = __ldg(q + 10); c = __ldg(q + 11);
     f.tex[0] = a.x; f.tex[1] = a.y; f.tex[2] = a.z; f.tex[3] = a.w;
     f.tex[4] = b.x; f.tex[5] = b.y; f.tex[6] = b.z; f.tex[7] = b.w;
     f.tex[8] = c.x; f.obt[0] = c.y; f.obt[1] = c.z; f.obt[2] = c.w;
@@ -76,10 +81,11 @@ __device__ __forceinline__ void load_face(const float *r, Face &f)
 __global__ void __launch_bounds__(256) pack_kernel(Params p, const float *__restrict__ faces,
                                                    const float *__restrict__ textures, float *faces_info,
                                                    int compute_info, float4 *__restrict__ bbox,
-                                                   float *__restrict__ rec)
+                                                   float *__restrict__ rec, int *img_bbox)
 {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long)p.B * p.nf) return;
+    const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = i0 < (long)p.B * p.nf;
+    const long i = in_range ? i0 : (long)p.B * p.nf - 1;  // out-of-range lanes shadow the last face (no stores)
     const float *f = faces + i * 9;
     const float x0 = f[0], y0 = f[1], z0 = f[2], x1 = f[3], y1 = f[4], z1 = f[5], x2 = f[6], y2 = f[7], z2 = f[8];
     float inv[9], sym[9], obt[3] = { 0.f, 0.f, 0.f };
@@ -104,10 +110,12 @@ __global__ void __launch_bounds__(256) pack_kernel(Params p, const float *__rest
             const bool o = (px[k1] - px[k]) * (px[k2] - px[k]) + (py[k1] - py[k]) * (py[k2] - py[k]) < 0.f;
             if (o && !found) { obt[k] = 1.f; found = true; }
         }
+        if (in_range) {
 #pragma unroll
-        for (int k = 0; k < 9; k++) { info[k] = inv[k]; info[9 + k] = sym[k]; }
+            for (int k = 0; k < 9; k++) { info[k] = inv[k]; info[9 + k] = sym[k]; }
 #pragma unroll
-        for (int k = 0; k < 3; k++) info[18 + k] = obt[k];
+            for (int k = 0; k < 3; k++) info[18 + k] = obt[k];
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < 9; k++) { inv[k] = info[k]; sym[k] = info[9 + k]; }
@@ -117,6 +125,29 @@ __global__ void __launch_bounds__(256) pack_kernel(Params p, const float *__rest
     const float m = p.margin;
     const float4 bb = make_float4(fminf(fminf(x0, x1), x2) - m, fmaxf(fmaxf(x0, x1), x2) + m,
                                   fminf(fminf(y0, y1), y2) - m, fmaxf(fmaxf(y0, y1), y2) + m);
+    {
+        // whole-mesh screen bbox per image: min over faces of (xmin, -xmax, ymin, -ymax) as ordered ints
+        const int bimg = (int)(i / p.nf);
+        int key[4] = { __float_as_int(bb.x), __float_as_int(-bb.y), __float_as_int(bb.z), __float_as_int(-bb.w) };
+#pragma unroll
+        for (int k = 0; k < 4; k++) key[k] = key[k] >= 0 ? key[k] : key[k] ^ 0x7fffffff;
+        const int b_first = __shfl_sync(0xffffffffu, bimg, 0);
+        if (__all_sync(0xffffffffu, bimg == b_first)) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) key[k] = min(key[k], __shfl_xor_sync(0xffffffffu, key[k], o));
+            }
+            if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) atomicMin(img_bbox + 4 * bimg + k, key[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) atomicMin(img_bbox + 4 * bimg + k, key[k]);
+        }
+    }
+    if (!in_range) return;
     bbox[i] = bb;
     float E[3][3], den[3];
 #pragma unroll
@@ -139,12 +170,12 @@ __global__ void __launch_bounds__(256) pack_kernel(Params p, const float *__rest
     r[0] = bb;
     r[1] = make_float4(inv[0], inv[1], inv[2], inv[3]);
     r[2] = make_float4(inv[4], inv[5], inv[6], inv[7]);
-    r[3] = make_float4(inv[8], x0, y0, z0);
-    r[4] = make_float4(x1, y1, z1, x2);
-    r[5] = make_float4(y2, z2, front, __int_as_float((int)(i % p.nf)));
-    r[6] = make_float4(E[0][0], E[0][1], E[0][2], den[0]);
-    r[7] = make_float4(E[1][0], E[1][1], E[1][2], den[1]);
-    r[8] = make_float4(E[2][0], E[2][1], E[2][2], den[2]);
+    r[3] = make_float4(inv[8], x0, y0, 1.f / z0);
+    r[4] = make_float4(x1, y1, 1.f / z1, x2);
+    r[5] = make_float4(y2, 1.f / z2, front, __int_as_float((int)(i % p.nf)));
+    r[6] = make_float4(E[0][0], E[0][1], E[0][2], 1.f / den[0]);
+    r[7] = make_float4(E[1][0], E[1][1], E[1][2], 1.f / den[1]);
+    r[8] = make_float4(E[2][0], E[2][1], E[2][2], 1.f / den[2]);
     r[9] = make_float4(tex[0], tex[1], tex[2], tex[3]);
     r[10] = make_float4(tex[4], tex[5], tex[6], tex[7]);
     r[11] = make_float4(tex[8], obt[0], obt[1], obt[2]);
@@ -162,7 +193,7 @@ template <int K>
 __device__ __forceinline__ float edge_param(const Face &f, const float *w)
 {
     constexpr int K1 = (K + 1) % 3;
-    return (w[0] * f.E[K][0] + w[1] * f.E[K][1] + w[2] * f.E[K][2] - f.E[K][K1]) / f.den[K];
+    return (w[0] * f.E[K][0] + w[1] * f.E[K][1] + w[2] * f.E[K][2] - f.E[K][K1]) * f.rden[K];
 }
 
 template <int K>
@@ -246,14 +277,14 @@ __device__ __forceinline__ bool eval_frag(const Params &p, const Face &f, float 
         euclid(f, xp, yp, o);
         o.dis = o.dx * o.dx + o.dy * o.dy;
         if (o.sign < 0.f && o.dis >= p.threshold) return false;
-        o.frag = 1.f / (1.f + expf(-o.sign * o.dis / p.sigma));
+        o.frag = __fdividef(1.f, 1.f + __expf(-o.sign * o.dis * p.inv_sigma));
     } else if (dist_mode == SCP_DIST_BARYCENTRIC) {
         const float *w = o.w;
         const float d = w[0] > w[1] ? (w[1] > w[2] ? w[2] : w[1]) : (w[0] > w[2] ? w[2] : w[0]);
         o.dis = d > 0.f ? d * d : -(d * d);
         o.c[0] = w[0]; o.c[1] = w[1]; o.c[2] = w[2];
         if (-o.dis >= p.threshold) return false;
-        o.frag = 1.f / (1.f + expf(-o.dis / p.sigma));
+        o.frag = __fdividef(1.f, 1.f + __expf(-o.dis * p.inv_sigma));
     } else {
         if (!inside_closed(o.w)) return false;
         o.frag = 1.f;
@@ -265,11 +296,11 @@ __device__ __forceinline__ bool eval_frag(const Params &p, const Face &f, float 
 __device__ __forceinline__ float clip_and_depth(const Face &f, const float *w, float *wc)
 {
 #pragma unroll
-    for (int k = 0; k < 3; k++) wc[k] = fmaxf(fminf(w[k], 1.f), 0.f);
-    const float s = fmaxf(wc[0] + wc[1] + wc[2], 1e-5f);
+    for (int k = 0; k < 3; k++) wc[k] = __saturatef(w[k]);
+    const float rs = __fdividef(1.f, fmaxf(wc[0] + wc[1] + wc[2], 1e-5f));
 #pragma unroll
-    for (int k = 0; k < 3; k++) wc[k] /= s;
-    return 1.f / (wc[0] / f.z[0] + wc[1] / f.z[1] + wc[2] / f.z[2]);
+    for (int k = 0; k < 3; k++) wc[k] *= rs;
+    return __fdividef(1.f, wc[0] * f.rz[0] + wc[1] * f.rz[1] + wc[2] * f.rz[2]);
 }
 
 // surface-texture texel index (kernel.cu:181-188), clamped into the table (the reference can read
@@ -300,201 +331,387 @@ __device__ __forceinline__ void sample_color(const Params &p, const Face &f, con
 }
 
 // ---- ordered tile culling -----------------------------------------------------------------
-// Scans faces [base, base+256) of image b against the tile rectangle and writes the surviving
-// face indices to s_list in ascending order.  Returns the count (uniform across the CTA).
-__device__ __forceinline__ int cull_chunk(const Params &p, const float4 *__restrict__ bbox, int b, int base,
-                                          float x_lo, float x_hi, float y_lo, float y_hi, int *s_list,
-                                          int *s_warp_cnt)
+// Scans faces [base, base + SCAN*256) of image b against the tile rectangle and APPENDS the
+// surviving face indices to s_list[n0..] in ascending order.  Returns the new count (uniform).
+__device__ __forceinline__ int cull_round(const Params &p, const float4 *__restrict__ bbox, int b, int base,
+                                          float x_lo, float x_hi, float y_lo, float y_hi, int n0, int *s_list,
+                                          int *s_cnt)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int fidx = base + tid;
-    bool hit = false;
-    if (fidx < p.nf) {
-        const float4 bb = bbox[(size_t)b * p.nf + fidx];
-        hit = !(x_lo > bb.y || x_hi < bb.x || y_lo > bb.w || y_hi < bb.z);
-    }
-    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
-    __syncthreads();
-    int off = 0, total = 0;
+    unsigned ballots[SCAN];
 #pragma unroll
-    for (int k = 0; k < NTHREADS / 32; k++) {
-        const int c = s_warp_cnt[k];
-        if (k < warp) off += c;
-        total += c;
+    for (int k = 0; k < SCAN; k++) {
+        const int fidx = base + k * NTHREADS + tid;
+        bool hit = false;
+        if (fidx < p.nf) {
+            const float4 bb = __ldg(bbox + (size_t)b * p.nf + fidx);
+            hit = !(x_lo > bb.y || x_hi < bb.x || y_lo > bb.w || y_hi < bb.z);
+        }
+        ballots[k] = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_cnt[k * NWARPS + warp] = __popc(ballots[k]);
     }
-    if (hit) s_list[off + __popc(ballot & ((1u << lane) - 1u))] = fidx;
     __syncthreads();
-    return total;
-}
-
-__device__ __forceinline__ void stage_records(const float *__restrict__ rec, int b, int nf, const int *s_list,
-                                              int start, int m, float *s_rec)
-{
-    const float4 *src = reinterpret_cast<const float4 *>(rec);
-    float4 *dst = reinterpret_cast<float4 *>(s_rec);
-    for (int i = threadIdx.x; i < m * REC4; i += NTHREADS) {
-        const int j = i / REC4, q = i - j * REC4;
-        dst[i] = src[((size_t)b * nf + s_list[start + j]) * REC4 + q];
+    // exclusive prefix over the (k, warp) grid in face order
+    int total = 0, my_off[SCAN];
+#pragma unroll
+    for (int k = 0; k < SCAN; k++) {
+#pragma unroll
+        for (int w = 0; w < NWARPS; w++) {
+            if (w == warp) my_off[k] = total;
+            total += s_cnt[k * NWARPS + w];
+        }
     }
+#pragma unroll
+    for (int k = 0; k < SCAN; k++) {
+        if (ballots[k] & (1u << lane))
+            s_list[n0 + my_off[k] + __popc(ballots[k] & ((1u << lane) - 1u))] = base + k * NTHREADS + tid;
+    }
+    __syncthreads();
+    return n0 + total;
 }
 
 struct Pixel {
     int px, py, pn;
     bool valid;
     float xp, yp;
+    // footprint of this lane's warp (pixel centres of its 8x4 block, clipped to the image)
+    float wx_lo, wx_hi, wy_lo, wy_hi;
 };
+
+__device__ __forceinline__ float centre_x(int px, int is) { return (float)(2 * px + 1 - is) / (float)is; }
+// row 0 = top (kernel.cu:343-346); numerators are exact integers
+__device__ __forceinline__ float centre_y(int py, int is) { return (float)(2 * (is - 1 - py) + 1 - is) / (float)is; }
 
 __device__ __forceinline__ void tile_setup(const Params &p, Pixel &px, float &x_lo, float &x_hi, float &y_lo,
                                            float &y_hi)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = (blockIdx.x % p.tiles_x) * TILE, ty0 = (blockIdx.x / p.tiles_x) * TILE;
-    px.px = tx0 + (warp & 1) * 8 + (lane & 7);
-    px.py = ty0 + (warp >> 1) * 4 + (lane >> 3);
+    const int bx = tx0 + (warp & 1) * 8, by = ty0 + (warp >> 1) * 4;
+    px.px = bx + (lane & 7);
+    px.py = by + (lane >> 3);
     px.valid = px.px < p.is && px.py < p.is;
     px.pn = px.py * p.is + px.px;
-    const float fis = (float)p.is;
-    // pixel centres, row 0 = top (kernel.cu:343-346); numerators are exact integers
-    px.xp = (float)(2 * px.px + 1 - p.is) / fis;
-    px.yp = (float)(2 * (p.is - 1 - px.py) + 1 - p.is) / fis;
-    const int tx1 = min(tx0 + TILE - 1, p.is - 1), ty1 = min(ty0 + TILE - 1, p.is - 1);
-    x_lo = (float)(2 * tx0 + 1 - p.is) / fis;
-    x_hi = (float)(2 * tx1 + 1 - p.is) / fis;
-    y_hi = (float)(2 * (p.is - 1 - ty0) + 1 - p.is) / fis;
-    y_lo = (float)(2 * (p.is - 1 - ty1) + 1 - p.is) / fis;
+    px.xp = centre_x(px.px, p.is);
+    px.yp = centre_y(px.py, p.is);
+    px.wx_lo = centre_x(bx, p.is);
+    px.wx_hi = centre_x(min(bx + 7, p.is - 1), p.is);
+    px.wy_hi = centre_y(by, p.is);
+    px.wy_lo = centre_y(min(by + 3, p.is - 1), p.is);
+    x_lo = centre_x(tx0, p.is);
+    x_hi = centre_x(min(tx0 + TILE - 1, p.is - 1), p.is);
+    y_hi = centre_y(ty0, p.is);
+    y_lo = centre_y(min(ty0 + TILE - 1, p.is - 1), p.is);
+}
+
+// whole-mesh screen bbox of image b (written by pack_kernel): tiles outside it have no work
+__device__ __forceinline__ bool tile_outside_mesh(const int *__restrict__ img_bbox, int b, float x_lo, float x_hi,
+                                                  float y_lo, float y_hi)
+{
+    const int4 q = __ldg(reinterpret_cast<const int4 *>(img_bbox) + b);
+    // ordered-int encoding of floats: (xmin, -xmax, ymin, -ymax) minima
+    const float mx0 = __int_as_float(q.x >= 0 ? q.x : q.x ^ 0x7fffffff);
+    const float mx1 = -__int_as_float(q.y >= 0 ? q.y : q.y ^ 0x7fffffff);
+    const float my0 = __int_as_float(q.z >= 0 ? q.z : q.z ^ 0x7fffffff);
+    const float my1 = -__int_as_float(q.w >= 0 ? q.w : q.w ^ 0x7fffffff);
+    return x_lo > mx1 || x_hi < mx0 || y_lo > my1 || y_hi < my0;
 }
 
 // ---- forward ------------------------------------------------------------------------------
+struct FwdState {
+    float col[3];
+    float alpha, sm_sum, sm_max, depth_min;
+    int face_min;
+};
+
+template <int RGB, bool FAST>
+__device__ __forceinline__ void forward_pair(const Params &p, const float *__restrict__ r, const Pixel &px,
+                                             const float *__restrict__ textures, int b, FwdState &s)
+{
+    float bx0, bx1, by0, by1;
+    load_bbox(r, bx0, bx1, by0, by1);
+    if (px.xp > bx1 || px.xp < bx0 || px.yp > by1 || px.yp < by0) return;
+    Face f;
+    load_face(r, f);
+    Frag fr;
+    if (!eval_frag<FAST>(p, f, px.xp, px.yp, fr)) return;
+    const int alpha_mode = FAST ? SCP_ALPHA_PROD : p.alpha_mode;
+
+    // alpha accumulates before the depth test (kernel.cu:408-417)
+    if (alpha_mode == SCP_ALPHA_PROD) s.alpha *= 1.f - fr.frag;
+    else if (alpha_mode == SCP_ALPHA_SUM) s.alpha += fr.frag;
+    else if (fr.frag > 0.5f) s.alpha = 1.f;
+
+    float wc[3];
+    const float zp = clip_and_depth(f, fr.w, wc);
+    if (zp < p.near_ || zp > p.far_) return;
+
+    if (RGB == SCP_RGB_HARD) {
+        if (zp < s.depth_min && inside_closed(fr.w) && (p.double_side || f.front != 0.f)) {
+            s.depth_min = zp;
+            s.face_min = f.idx;
+            sample_color<FAST>(p, f, wc, textures, b, s.col);
+        }
+    } else if (f.front != 0.f || p.double_side) {
+        const float zn = (p.far_ - zp) * p.inv_depth_range;
+        float rescale = 1.f;
+        if (zn > s.sm_max) {
+            rescale = __expf((s.sm_max - zn) * p.inv_gamma);
+            s.sm_max = zn;
+        }
+        const float ez = __expf((zn - s.sm_max) * p.inv_gamma) * fr.frag;
+        s.sm_sum = rescale * s.sm_sum + ez;
+        float c[3];
+        sample_color<FAST>(p, f, wc, textures, b, c);
+#pragma unroll
+        for (int k = 0; k < 3; k++) s.col[k] = rescale * s.col[k] + ez * c[k];
+    }
+}
+
 template <int RGB, bool FAST>
 __global__ void __launch_bounds__(NTHREADS) forward_kernel(Params p, const float4 *__restrict__ bbox,
                                                           const float *__restrict__ rec,
+                                                          const int *__restrict__ img_bbox,
                                                           const float *__restrict__ textures,
                                                           float *__restrict__ aggrs_info,
                                                           float *__restrict__ soft_colors)
 {
-    __shared__ __align__(16) float s_rec[LIST_CAP * REC];
-    __shared__ int s_list[NTHREADS];
-    __shared__ int s_warp_cnt[NTHREADS / 32];
+    __shared__ int s_list[LIST_CAP];
+    __shared__ int s_cnt[SCAN * NWARPS];
 
-    const int b = blockIdx.y;
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
     const size_t plane = (size_t)p.is * p.is;
     Pixel px;
     float x_lo, x_hi, y_lo, y_hi;
     tile_setup(p, px, x_lo, x_hi, y_lo, y_hi);
     const int alpha_mode = FAST ? SCP_ALPHA_PROD : p.alpha_mode;
 
-    float col[3] = { 0.f, 0.f, 0.f };
-    float alpha = alpha_mode == SCP_ALPHA_PROD ? 1.f : 0.f;
-    float sm_sum = expf(p.eps / p.gamma), sm_max = p.eps;
-    float depth_min = 10000000.f;
-    int face_min = -1;
+    FwdState s;
+    s.col[0] = s.col[1] = s.col[2] = 0.f;
+    s.alpha = alpha_mode == SCP_ALPHA_PROD ? 1.f : 0.f;
+    s.sm_sum = __expf(p.eps * p.inv_gamma);
+    s.sm_max = p.eps;
+    s.depth_min = 10000000.f;
+    s.face_min = -1;
     if (px.valid) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const float bg = soft_colors[((size_t)b * 4 + k) * plane + px.pn];
-            col[k] = RGB == SCP_RGB_HARD ? bg : bg * sm_sum;
+            s.col[k] = RGB == SCP_RGB_HARD ? bg : bg * s.sm_sum;
         }
     }
 
-    for (int base = 0; base < p.nf; base += NTHREADS) {
-        const int n = cull_chunk(p, bbox, b, base, x_lo, x_hi, y_lo, y_hi, s_list, s_warp_cnt);
-        for (int start = 0; start < n; start += LIST_CAP) {
-            const int m = min(LIST_CAP, n - start);
-            stage_records(rec, b, p.nf, s_list, start, m, s_rec);
-            __syncthreads();
-            if (px.valid) {
-                for (int j = 0; j < m; j++) {
-                    const float *r = s_rec + j * REC;
-                    float bx0, bx1, by0, by1;
-                    load_bbox(r, bx0, bx1, by0, by1);
-                    if (px.xp > bx1 || px.xp < bx0 || px.yp > by1 || px.yp < by0) continue;
-                    Face f;
-                    load_face(r, f);
-                    Frag fr;
-                    if (!eval_frag<FAST>(p, f, px.xp, px.yp, fr)) continue;
-
-                    // alpha accumulates before the depth test (kernel.cu:408-417)
-                    if (alpha_mode == SCP_ALPHA_PROD) alpha *= 1.f - fr.frag;
-                    else if (alpha_mode == SCP_ALPHA_SUM) alpha += fr.frag;
-                    else if (fr.frag > 0.5f) alpha = 1.f;
-
-                    float wc[3];
-                    const float zp = clip_and_depth(f, fr.w, wc);
-                    if (zp < p.near_ || zp > p.far_) continue;
-
-                    if (RGB == SCP_RGB_HARD) {
-                        if (zp < depth_min && inside_closed(fr.w) && (p.double_side || f.front != 0.f)) {
-                            depth_min = zp;
-                            face_min = f.idx;
-                            sample_color<FAST>(p, f, wc, textures, b, col);
-                        }
-                    } else if (f.front != 0.f || p.double_side) {
-                        const float zn = (p.far_ - zp) / (p.far_ - p.near_);
-                        float rescale = 1.f;
-                        if (zn > sm_max) {
-                            rescale = expf((sm_max - zn) / p.gamma);
-                            sm_max = zn;
-                        }
-                        const float ez = expf((zn - sm_max) / p.gamma);
-                        sm_sum = rescale * sm_sum + ez * fr.frag;
-                        float c[3];
-                        sample_color<FAST>(p, f, wc, textures, b, c);
-#pragma unroll
-                        for (int k = 0; k < 3; k++) col[k] = rescale * col[k] + ez * fr.frag * c[k];
-                    }
+    if (!tile_outside_mesh(img_bbox, b, x_lo, x_hi, y_lo, y_hi)) {
+        int base = 0;
+        while (base < p.nf) {
+            int n = 0;
+            while (base < p.nf && n + SCAN * NTHREADS <= LIST_CAP) {
+                n = cull_round(p, bbox, b, base, x_lo, x_hi, y_lo, y_hi, n, s_list, s_cnt);
+                base += SCAN * NTHREADS;
+            }
+            // warp-private pass: cull the tile list against the warp's 8x4 block, 32 faces at a time
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int fi = i0 + lane < n ? s_list[i0 + lane] : -1;
+                bool hit = false;
+                if (fi >= 0) {
+                    const float4 bb = __ldg(bbox + (size_t)b * p.nf + fi);
+                    hit = !(px.wx_lo > bb.y || px.wx_hi < bb.x || px.wy_lo > bb.w || px.wy_hi < bb.z);
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, hit);
+                while (todo) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int fsel = __shfl_sync(0xffffffffu, fi, j);
+                    if (px.valid) forward_pair<RGB, FAST>(p, rec + ((size_t)b * p.nf + fsel) * REC, px, textures, b, s);
                 }
             }
-            __syncthreads();
+            if (base < p.nf) __syncthreads();  // the list is about to be rebuilt
         }
     }
 
     if (!px.valid) return;
     float a_out;
-    if (alpha_mode == SCP_ALPHA_PROD) a_out = 1.f - alpha;
-    else if (alpha_mode == SCP_ALPHA_SUM) a_out = alpha / p.nf;
-    else a_out = alpha;
+    if (alpha_mode == SCP_ALPHA_PROD) a_out = 1.f - s.alpha;
+    else if (alpha_mode == SCP_ALPHA_SUM) a_out = s.alpha / p.nf;
+    else a_out = s.alpha;
     soft_colors[((size_t)b * 4 + 3) * plane + px.pn] = a_out;
     if (RGB == SCP_RGB_HARD) {
-        if (face_min != -1) {
+        if (s.face_min != -1) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) soft_colors[((size_t)b * 4 + k) * plane + px.pn] = col[k];
+            for (int k = 0; k < 3; k++) soft_colors[((size_t)b * 4 + k) * plane + px.pn] = s.col[k];
         }
-        aggrs_info[((size_t)b * 2 + 0) * plane + px.pn] = depth_min;
-        aggrs_info[((size_t)b * 2 + 1) * plane + px.pn] = (float)face_min;
+        aggrs_info[((size_t)b * 2 + 0) * plane + px.pn] = s.depth_min;
+        aggrs_info[((size_t)b * 2 + 1) * plane + px.pn] = (float)s.face_min;
     } else {
+        const float rs = 1.f / s.sm_sum;
 #pragma unroll
-        for (int k = 0; k < 3; k++) soft_colors[((size_t)b * 4 + k) * plane + px.pn] = col[k] / sm_sum;
-        aggrs_info[((size_t)b * 2 + 0) * plane + px.pn] = sm_sum;
-        aggrs_info[((size_t)b * 2 + 1) * plane + px.pn] = sm_max;
+        for (int k = 0; k < 3; k++) soft_colors[((size_t)b * 4 + k) * plane + px.pn] = s.col[k] * rs;
+        aggrs_info[((size_t)b * 2 + 0) * plane + px.pn] = s.sm_sum;
+        aggrs_info[((size_t)b * 2 + 1) * plane + px.pn] = s.sm_max;
     }
 }
 
 // ---- backward -----------------------------------------------------------------------------
+// Folded butterfly: 18 per-lane values -> after 20 shuffles each lane holds the warp total of ONE
+// value (index returned in `idx`; lanes holding padding get idx >= 18 and a zero total).
+__device__ __forceinline__ float fold18(float (&v)[18], int lane, int &idx)
+{
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+    float a[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {  // 18 -> 9
+        const float send = b4 ? v[i] : v[9 + i], keep = b4 ? v[9 + i] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    float c[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {  // 9 -> 5 (upper half: entries 5..8, padded)
+        const float hi = i < 4 ? a[5 + i] : 0.f;
+        const float send = b3 ? a[i] : hi, keep = b3 ? hi : a[i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float d[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {  // 5 -> 3 (upper: 3..4, padded)
+        const float hi = i < 2 ? c[3 + i] : 0.f;
+        const float send = b2 ? c[i] : hi, keep = b2 ? hi : c[i];
+        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    float e[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {  // 3 -> 2 (upper: 2, padded)
+        const float hi = i < 1 ? d[2 + i] : 0.f;
+        const float send = b1 ? d[i] : hi, keep = b1 ? hi : d[i];
+        e[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const float send = b0 ? e[0] : e[1], keep = b0 ? e[1] : e[0];
+    const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    // position inside each level; invalid (padding) when a level index runs past its size
+    const int i1 = b0 ? 1 : 0;                 // within e (size 2)
+    const int i2 = (b1 ? 2 : 0) + i1;          // within d (size 3)
+    const int i3 = (b2 ? 3 : 0) + i2;          // within c (size 5)
+    const int i4 = (b3 ? 5 : 0) + i3;          // within a (size 9)
+    const bool ok = (!b1 || i1 < 1) && (!b2 || i2 < 2) && (!b3 || i3 < 4);
+    idx = ok ? (b4 ? 9 : 0) + i4 : 18;
+    return tot;
+}
+
+template <int RGB, bool FAST>
+__device__ __forceinline__ bool backward_pair(const Params &p, const float *__restrict__ r, const Pixel &px,
+                                              const float *__restrict__ textures, int b, const float *g,
+                                              const float *out, float sm_sum, float sm_max, float *grad_textures,
+                                              float (&gv)[18])
+{
+    float bx0, bx1, by0, by1;
+    load_bbox(r, bx0, bx1, by0, by1);
+    if (px.xp > bx1 || px.xp < bx0 || px.yp > by1 || px.yp < by0) return false;
+    Face f;
+    load_face(r, f);
+    Frag fr;
+    if (!eval_frag<FAST>(p, f, px.xp, px.yp, fr)) return false;
+    const int alpha_mode = FAST ? SCP_ALPHA_PROD : p.alpha_mode;
+    const int dist_mode = FAST ? SCP_DIST_EUCLIDEAN : p.dist_mode;
+
+    float Gxy = g[3];
+    if (alpha_mode == SCP_ALPHA_SUM) Gxy /= p.nf;
+    else if (alpha_mode == SCP_ALPHA_PROD) Gxy *= __fdividef(1.f - out[3], fmaxf(1.f - fr.frag, 1e-6f));
+    float wc[3];
+    const float zp = clip_and_depth(f, fr.w, wc);
+    if (zp < p.near_ || zp > p.far_) return false;  // face dropped incl. its alpha gradient (kernel.cu:599)
+
+    float *gt = gv + 9;
+    if (RGB == SCP_RGB_HARD) {
+        if ((float)f.idx == sm_max) {  // aggrs_info[1] holds the winning face index in hard mode
+            if (p.tex_mode == SCP_TEX_VERTEX) {
+#pragma unroll
+                for (int v = 0; v < 3; v++)
+#pragma unroll
+                    for (int k = 0; k < 3; k++) gt[3 * v + k] = wc[v] * g[k];
+            } else if (p.T == 1) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) gt[k] = g[k];
+            } else {
+                float *dst = grad_textures + ((size_t)b * p.nf + f.idx) * p.T * 3 + surface_texel(wc, p.R) * 3;
+#pragma unroll
+                for (int k = 0; k < 3; k++) atomicAdd(dst + k, g[k]);
+            }
+        }
+    } else if (f.front != 0.f || p.double_side) {
+        const float zn = (p.far_ - zp) * p.inv_depth_range;
+        const float s = __fdividef(fr.frag * __expf((zn - sm_max) * p.inv_gamma), sm_sum);
+        float c[3];
+        sample_color<FAST>(p, f, wc, textures, b, c);
+        float Q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) Q += g[k] * (c[k] - out[k]);
+        if (p.tex_mode == SCP_TEX_VERTEX) {
+#pragma unroll
+            for (int v = 0; v < 3; v++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) gt[3 * v + k] = s * (wc[v] * g[k]);
+        } else if (p.T == 1) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) gt[k] = s * g[k];
+        } else {
+            float *dst = grad_textures + ((size_t)b * p.nf + f.idx) * p.T * 3 + surface_texel(wc, p.R) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; k++) atomicAdd(dst + k, s * g[k]);
+        }
+        Q *= s;
+        Gxy += __fdividef(Q, fr.frag);
+        const float Gz = Q * p.inv_gamma / (p.near_ - p.far_) * zp * zp;
+#pragma unroll
+        for (int v = 0; v < 3; v++) gv[3 * v + 2] = Gz * wc[v] * f.rz[v] * f.rz[v];
+    }
+    Gxy *= fr.frag * (1.f - fr.frag) * p.inv_sigma;  // sigmoid'
+    if (dist_mode == SCP_DIST_EUCLIDEAN) {
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            const float s2 = 2.f * fr.sign * Gxy * fr.c[v];
+            gv[3 * v + 0] = s2 * fr.dx;
+            gv[3 * v + 1] = s2 * fr.dy;
+        }
+    } else if (dist_mode == SCP_DIST_BARYCENTRIC) {
+        // kernel.cu:161-175
+        const float *t = fr.c;
+        const int q = t[0] > t[1] ? (t[1] > t[2] ? 2 : 1) : (t[0] > t[2] ? 2 : 0);
+        const float sc = 2.f * sqrtf(fabsf(fr.dis));
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+            const float iq = q == 0 ? f.inv[l] : (q == 1 ? f.inv[3 + l] : f.inv[6 + l]);
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+                const float acc = -iq * f.inv[3 * v + 0] * px.xp + -iq * f.inv[3 * v + 1] * px.yp +
+                                  -iq * f.inv[3 * v + 2];
+                gv[3 * v + l] = acc * Gxy * sc;
+            }
+        }
+    }
+    return true;
+}
+
 template <int RGB, bool FAST>
 __global__ void __launch_bounds__(NTHREADS) backward_kernel(Params p, const float4 *__restrict__ bbox,
                                                            const float *__restrict__ rec,
+                                                           const int *__restrict__ img_bbox,
                                                            const float *__restrict__ textures,
                                                            const float *__restrict__ soft_colors,
                                                            const float *__restrict__ aggrs_info,
                                                            const float *__restrict__ grad_soft_colors,
                                                            float *grad_faces, float *grad_textures)
 {
-    __shared__ __align__(16) float s_rec[LIST_CAP * REC];
-    __shared__ float s_grad[LIST_CAP * NGRAD];
-    __shared__ int s_list[NTHREADS];
-    __shared__ int s_warp_cnt[NTHREADS / 32];
+    __shared__ int s_list[LIST_CAP];
+    __shared__ int s_cnt[SCAN * NWARPS];
 
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
     const size_t plane = (size_t)p.is * p.is;
     Pixel px;
     float x_lo, x_hi, y_lo, y_hi;
     tile_setup(p, px, x_lo, x_hi, y_lo, y_hi);
-    const int alpha_mode = FAST ? SCP_ALPHA_PROD : p.alpha_mode;
-    const int dist_mode = FAST ? SCP_DIST_EUCLIDEAN : p.dist_mode;
-    // vertex textures and 1-texel surface textures accumulate through shared memory; larger
-    // surface tables (never used by this repo's renders) go straight to global atomics
-    const bool tex_in_rec = p.T * 3 <= 9;
+    if (tile_outside_mesh(img_bbox, b, x_lo, x_hi, y_lo, y_hi)) return;
+    // vertex textures and 1-texel surface textures ride in the 18-value fold; larger surface tables
+    // (never used by this repo's renders) go straight to global atomics inside backward_pair
+    const int ntex = p.T * 3 <= 9 ? p.T * 3 : 0;
 
     float g[4] = { 0.f, 0.f, 0.f, 0.f }, out[4] = { 0.f, 0.f, 0.f, 0.f };
     float sm_sum = 1.f, sm_max = 0.f;
@@ -507,142 +724,51 @@ __global__ void __launch_bounds__(NTHREADS) backward_kernel(Params p, const floa
         sm_sum = aggrs_info[((size_t)b * 2 + 0) * plane + px.pn];
         sm_max = aggrs_info[((size_t)b * 2 + 1) * plane + px.pn];
     }
+    const bool lane_grad = px.valid && (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f || g[3] != 0.f);
     // a tile whose incoming gradient is identically zero contributes nothing
-    const bool any_grad = __syncthreads_or(px.valid && (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f || g[3] != 0.f));
-    if (!any_grad) return;
+    if (!__syncthreads_or(lane_grad)) return;
+    const bool warp_grad = __any_sync(0xffffffffu, lane_grad);
 
-    for (int base = 0; base < p.nf; base += NTHREADS) {
-        const int n = cull_chunk(p, bbox, b, base, x_lo, x_hi, y_lo, y_hi, s_list, s_warp_cnt);
-        for (int start = 0; start < n; start += LIST_CAP) {
-            const int m = min(LIST_CAP, n - start);
-            stage_records(rec, b, p.nf, s_list, start, m, s_rec);
-            for (int i = tid; i < m * NGRAD; i += NTHREADS) s_grad[i] = 0.f;
-            __syncthreads();
-            for (int j = 0; j < m; j++) {
-                const float *r = s_rec + j * REC;
-                float gv[9], gt[9];
-#pragma unroll
-                for (int k = 0; k < 9; k++) gv[k] = gt[k] = 0.f;
-                bool active = false;
-                float bx0, bx1, by0, by1;
-                load_bbox(r, bx0, bx1, by0, by1);
-                if (px.valid && !(px.xp > bx1 || px.xp < bx0 || px.yp > by1 || px.yp < by0)) {
-                    Face f;
-                    load_face(r, f);
-                    Frag fr;
-                    if (eval_frag<FAST>(p, f, px.xp, px.yp, fr)) {
-                        float Gxy = 0.f;
-                        float Ga = g[3];
-                        if (alpha_mode == SCP_ALPHA_SUM) Ga /= p.nf;
-                        else if (alpha_mode == SCP_ALPHA_PROD) Ga *= (1.f - out[3]) / fmaxf(1.f - fr.frag, 1e-6f);
-                        Gxy += Ga;
-                        float wc[3];
-                        const float zp = clip_and_depth(f, fr.w, wc);
-                        if (!(zp < p.near_ || zp > p.far_)) {  // else: face dropped incl. its alpha gradient
-                            active = true;
-                            if (RGB == SCP_RGB_HARD) {
-                                if ((float)f.idx == sm_max) {
-                                    if (p.tex_mode == SCP_TEX_VERTEX) {
-#pragma unroll
-                                        for (int v = 0; v < 3; v++)
-#pragma unroll
-                                            for (int k = 0; k < 3; k++) gt[3 * v + k] = wc[v] * g[k];
-                                    } else if (p.T == 1) {
-#pragma unroll
-                                        for (int k = 0; k < 3; k++) gt[k] = g[k];
-                                    } else {
-                                        float *dst = grad_textures + ((size_t)b * p.nf + f.idx) * p.T * 3 +
-                                                     surface_texel(wc, p.R) * 3;
-#pragma unroll
-                                        for (int k = 0; k < 3; k++) atomicAdd(dst + k, g[k]);
-                                    }
-                                }
-                            } else if (f.front != 0.f || p.double_side) {
-                                const float zn = (p.far_ - zp) / (p.far_ - p.near_);
-                                const float s = fr.frag * expf((zn - sm_max) / p.gamma) / sm_sum;
-                                float c[3];
-                                sample_color<FAST>(p, f, wc, textures, b, c);
-                                float Q = 0.f;
-#pragma unroll
-                                for (int k = 0; k < 3; k++) Q += g[k] * (c[k] - out[k]);
-                                if (p.tex_mode == SCP_TEX_VERTEX) {
-#pragma unroll
-                                    for (int v = 0; v < 3; v++)
-#pragma unroll
-                                        for (int k = 0; k < 3; k++) gt[3 * v + k] = s * (wc[v] * g[k]);
-                                } else if (p.T == 1) {
-#pragma unroll
-                                    for (int k = 0; k < 3; k++) gt[k] = s * g[k];
-                                } else {
-                                    float *dst = grad_textures + ((size_t)b * p.nf + f.idx) * p.T * 3 +
-                                                 surface_texel(wc, p.R) * 3;
-#pragma unroll
-                                    for (int k = 0; k < 3; k++) atomicAdd(dst + k, s * g[k]);
-                                }
-                                Q *= s;
-                                Gxy += Q / fr.frag;
-                                const float Gz = Q / p.gamma / (p.near_ - p.far_) * zp * zp;
-#pragma unroll
-                                for (int v = 0; v < 3; v++) gv[3 * v + 2] = Gz * wc[v] / f.z[v] / f.z[v];
-                            }
-                            Gxy *= fr.frag * (1.f - fr.frag) / p.sigma;  // sigmoid'
-                            if (dist_mode == SCP_DIST_EUCLIDEAN) {
-#pragma unroll
-                                for (int v = 0; v < 3; v++) {
-                                    const float s2 = 2.f * fr.sign * Gxy * fr.c[v];
-                                    gv[3 * v + 0] = s2 * fr.dx;
-                                    gv[3 * v + 1] = s2 * fr.dy;
-                                }
-                            } else if (dist_mode == SCP_DIST_BARYCENTRIC) {
-                                // kernel.cu:161-175
-                                const float *t = fr.c;
-                                const int q = t[0] > t[1] ? (t[1] > t[2] ? 2 : 1) : (t[0] > t[2] ? 2 : 0);
-                                const float sc = 2.f * sqrtf(fabsf(fr.dis));
-#pragma unroll
-                                for (int l = 0; l < 2; l++) {
-                                    const float iq = q == 0 ? f.inv[l] : (q == 1 ? f.inv[3 + l] : f.inv[6 + l]);
-#pragma unroll
-                                    for (int v = 0; v < 3; v++) {
-                                        const float acc = -iq * f.inv[3 * v + 0] * px.xp +
-                                                          -iq * f.inv[3 * v + 1] * px.yp + -iq * f.inv[3 * v + 2];
-                                        gv[3 * v + l] = acc * Gxy * sc;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-                // warp reduction, then one shared-memory atomic per value per warp
-                if (__any_sync(0xffffffffu, active)) {
-                    float *acc = s_grad + j * NGRAD;
-#pragma unroll
-                    for (int k = 0; k < 9; k++) {
-                        if (RGB == SCP_RGB_HARD && (k % 3) == 2) continue;  // no depth gradient in hard mode
-                        const float v = warp_sum(gv[k]);
-                        if (lane == 0 && v != 0.f) atomicAdd(acc + k, v);
-                    }
-                    if (tex_in_rec) {
-#pragma unroll
-                        for (int k = 0; k < 9; k++) {
-                            const float v = warp_sum(gt[k]);
-                            if (lane == 0 && v != 0.f) atomicAdd(acc + 9 + k, v);
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            // flush: one global atomic per touched value per tile
-            for (int i = tid; i < m * NGRAD; i += NTHREADS) {
-                const float v = s_grad[i];
-                if (v != 0.f) {
-                    const int j = i / NGRAD, k = i - j * NGRAD;
-                    const size_t fg = (size_t)b * p.nf + s_list[start + j];
-                    if (k < 9) atomicAdd(grad_faces + fg * 9 + k, v);
-                    else if (k - 9 < p.T * 3) atomicAdd(grad_textures + fg * p.T * 3 + (k - 9), v);
-                }
-            }
-            __syncthreads();
+    int base = 0;
+    while (base < p.nf) {
+        int n = 0;
+        while (base < p.nf && n + SCAN * NTHREADS <= LIST_CAP) {
+            n = cull_round(p, bbox, b, base, x_lo, x_hi, y_lo, y_hi, n, s_list, s_cnt);
+            base += SCAN * NTHREADS;
         }
+        if (warp_grad) {
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int fi = i0 + lane < n ? s_list[i0 + lane] : -1;
+                bool hit = false;
+                if (fi >= 0) {
+                    const float4 bb = __ldg(bbox + (size_t)b * p.nf + fi);
+                    hit = !(px.wx_lo > bb.y || px.wx_hi < bb.x || px.wy_lo > bb.w || px.wy_hi < bb.z);
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, hit);
+                while (todo) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int fsel = __shfl_sync(0xffffffffu, fi, j);
+                    float gv[18];
+#pragma unroll
+                    for (int k = 0; k < 18; k++) gv[k] = 0.f;
+                    bool active = false;
+                    if (lane_grad)
+                        active = backward_pair<RGB, FAST>(p, rec + ((size_t)b * p.nf + fsel) * REC, px, textures, b, g,
+                                                          out, sm_sum, sm_max, grad_textures, gv);
+                    if (__any_sync(0xffffffffu, active)) {
+                        int idx;
+                        const float tot = fold18(gv, lane, idx);
+                        if (tot != 0.f) {
+                            const size_t fg = (size_t)b * p.nf + fsel;
+                            if (idx < 9) atomicAdd(grad_faces + fg * 9 + idx, tot);
+                            else if (idx - 9 < ntex) atomicAdd(grad_textures + fg * ntex + (idx - 9), tot);
+                        }
+                    }
+                }
+            }
+        }
+        if (base < p.nf) __syncthreads();
     }
 }
 
@@ -661,6 +787,9 @@ static bool make_params(Params &p, int B, int nf, int T, int is, float near_, fl
     p.near_ = near_; p.far_ = far_; p.eps = eps; p.sigma = sigma; p.gamma = gamma;
     p.threshold = dist_eps * sigma;
     p.margin = sqrtf(p.threshold);
+    p.inv_sigma = (float)(1.0 / (double)sigma);
+    p.inv_gamma = (float)(1.0 / (double)gamma);
+    p.inv_depth_range = (float)(1.0 / ((double)far_ - (double)near_));
     p.dist_mode = dist_mode; p.rgb_mode = rgb_mode; p.alpha_mode = alpha_mode; p.tex_mode = tex_mode;
     p.double_side = double_side;
     return true;
@@ -668,6 +797,7 @@ static bool make_params(Params &p, int B, int nf, int T, int is, float near_, fl
 
 static size_t bbox_bytes(int B, int nf) { return (((size_t)B * nf * sizeof(float4)) + 255) / 256 * 256; }
 static size_t rec_bytes(int B, int nf) { return (size_t)B * nf * REC * sizeof(float); }
+static size_t imgbb_bytes(int B) { return (((size_t)B * 4 * sizeof(int)) + 255) / 256 * 256; }
 
 }  // namespace softras
 }  // namespace scp
@@ -677,7 +807,7 @@ using namespace scp::softras;
 extern "C" size_t scp_softras_workspace_bytes(int B, int nf)
 {
     if (B <= 0 || nf <= 0) return 0;
-    return bbox_bytes(B, nf) + rec_bytes(B, nf);
+    return bbox_bytes(B, nf) + rec_bytes(B, nf) + imgbb_bytes(B);
 }
 
 extern "C" int scp_softras_forward(const float *faces, const float *textures, float *faces_info, float *aggrs_info,
@@ -700,16 +830,19 @@ extern "C" int scp_softras_forward(const float *faces, const float *textures, fl
     cudaStream_t st = (cudaStream_t)stream;
     float4 *bbox = (float4 *)workspace;
     float *rec = (float *)((char *)workspace + bbox_bytes(B, nf));
+    int *img_bbox = (int *)((char *)rec + rec_bytes(B, nf));
     const long nfaces = (long)B * nf;
-    pack_kernel<<<(unsigned)((nfaces + 255) / 256), 256, 0, st>>>(p, faces, textures, faces_info, 1, bbox, rec);
+    cudaMemsetAsync(img_bbox, 0x7f, (size_t)B * 4 * sizeof(int), st);
+    pack_kernel<<<(unsigned)((nfaces + 255) / 256), 256, 0, st>>>(p, faces, textures, faces_info, 1, bbox, rec,
+                                                                 img_bbox);
     const dim3 grid(p.tiles_x * p.tiles_x, B);
     const bool fast = func_id_dist == SCP_DIST_EUCLIDEAN && func_id_alpha == SCP_ALPHA_PROD;
     if (func_id_rgb == SCP_RGB_HARD) {
-        if (fast) forward_kernel<SCP_RGB_HARD, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, textures, aggrs_info, soft_colors);
-        else forward_kernel<SCP_RGB_HARD, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, textures, aggrs_info, soft_colors);
+        if (fast) forward_kernel<SCP_RGB_HARD, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors);
+        else forward_kernel<SCP_RGB_HARD, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors);
     } else {
-        if (fast) forward_kernel<SCP_RGB_SOFTMAX, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, textures, aggrs_info, soft_colors);
-        else forward_kernel<SCP_RGB_SOFTMAX, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, textures, aggrs_info, soft_colors);
+        if (fast) forward_kernel<SCP_RGB_SOFTMAX, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors);
+        else forward_kernel<SCP_RGB_SOFTMAX, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors);
     }
     return scp::check_launch("scp_softras_forward");
 }
@@ -735,17 +868,19 @@ extern "C" int scp_softras_backward(const float *faces, const float *textures, c
     cudaStream_t st = (cudaStream_t)stream;
     float4 *bbox = (float4 *)workspace;
     float *rec = (float *)((char *)workspace + bbox_bytes(B, nf));
+    int *img_bbox = (int *)((char *)rec + rec_bytes(B, nf));
     const long nfaces = (long)B * nf;
+    cudaMemsetAsync(img_bbox, 0x7f, (size_t)B * 4 * sizeof(int), st);
     pack_kernel<<<(unsigned)((nfaces + 255) / 256), 256, 0, st>>>(p, faces, textures, const_cast<float *>(faces_info),
-                                                                 0, bbox, rec);
+                                                                 0, bbox, rec, img_bbox);
     const dim3 grid(p.tiles_x * p.tiles_x, B);
     const bool fast = func_id_dist == SCP_DIST_EUCLIDEAN && func_id_alpha == SCP_ALPHA_PROD;
     if (func_id_rgb == SCP_RGB_HARD) {
-        if (fast) backward_kernel<SCP_RGB_HARD, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
-        else backward_kernel<SCP_RGB_HARD, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+        if (fast) backward_kernel<SCP_RGB_HARD, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+        else backward_kernel<SCP_RGB_HARD, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
     } else {
-        if (fast) backward_kernel<SCP_RGB_SOFTMAX, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
-        else backward_kernel<SCP_RGB_SOFTMAX, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+        if (fast) backward_kernel<SCP_RGB_SOFTMAX, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+        else backward_kernel<SCP_RGB_SOFTMAX, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
     }
     return scp::check_launch("scp_softras_backward");
 }
