@@ -78,6 +78,40 @@ int scp_softras_backward(const float *faces, const float *textures, const float 
                          int texture_sample_type, int double_side, void *workspace, size_t workspace_bytes,
                          void *stream);
 
+/* ---- dense 2D<->3D correspondence (Correspondence.match) --------------------------------- */
+
+/* Scratch bytes of scp_corr_match_forward (per-row-block column partials). */
+size_t scp_corr_workspace_bytes(int B, int hf, int wf, int N);
+
+/*
+ * Correspondence.match (model/module/correspondence.py:36-73), training path.
+ *   img_feat[B,C,hf*wf] (unit norm over C), mesh_feat[B,N,C] (unit norm over C), mask_down[B,hf*wf]
+ *   (nearest down-sampled mask, 0 = background), pred_v[B,N,3], meshgrid[2,hf*wf], tau = tau_img = tau_mesh.
+ * Outputs (any of the two pointcorr pointers may be NULL):
+ *   pointcorr_full[B,hf*wf,N]            masked similarity (background rows = -1e5)
+ *   pointcorr_pool[B,(hf/2)*(wf/2),N]    its 2x2 mean = F.interpolate(bilinear, 1/2) used by
+ *                                        pretrained_corr.py:120-123
+ *   match[B,hf*wf,3], imatch[B,2,N]      soft 3D point per pixel / soft 2D location per vertex
+ *   rsum[B,hf*wf], csum[B,N]             softmax denominators w.r.t. the reference point tau*1 (saved
+ *                                        for the backward; features must be L2-normalised so S <= 1)
+ * Supported shapes: C == 64, wf in {8,16,32,64}, hf*wf a multiple of 128 with 128/wf even.
+ */
+int scp_corr_match_forward(const float *img_feat, const float *mesh_feat, const float *mask_down,
+                           const float *pred_v, const float *meshgrid, float tau, int B, int hf, int wf, int N,
+                           int C, float *pointcorr_full, float *pointcorr_pool, float *match, float *imatch,
+                           float *rsum, float *csum, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Backward of the above (autograd of correspondence.py:42-53 in the reference): gradients w.r.t.
+ * img_feat and mesh_feat from g_match[B,hf*wf,3], g_imatch[B,2,N] and (optional, may be NULL)
+ * g_pointcorr_pool / g_pointcorr_full.  The similarity tile is recomputed, nothing P x N is read back.
+ */
+int scp_corr_match_backward(const float *img_feat, const float *mesh_feat, const float *mask_down,
+                            const float *pred_v, const float *meshgrid, float tau, int B, int hf, int wf, int N,
+                            int C, const float *match, const float *imatch, const float *rsum, const float *csum,
+                            const float *g_match, const float *g_imatch, const float *g_pointcorr_pool,
+                            const float *g_pointcorr_full, float *g_img_feat, float *g_mesh_feat, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

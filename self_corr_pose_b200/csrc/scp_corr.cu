@@ -1,0 +1,641 @@
+// Dense 2D<->3D feature correspondence (Correspondence.match of the reference,
+// model/module/correspondence.py:36-73) as fused sm_100a kernels, forward + backward.
+//
+//   S[p,n]   = <mesh_feat[n,:], img_feat[:,p]>, rows of background pixels := -1e5      (:42-44)
+//   Pm       = softmax(tau*S, dim=p)   imatch[:,n] = sum_p meshgrid[:,p] Pm[p,n]        (:47,52)
+//   Pi       = softmax(tau*S, dim=n)   match[p,:]  = sum_n Pi[p,n] pred_v[n,:]          (:48,53)
+//
+// The reference materialises S and both softmaxes ((B,P,N) fp32 each, 16-21 MB per image) plus
+// a (B,P,N,3) broadcast product.  Here one CTA owns 128 pixels (two rows of the 64x64 map, ordered
+// as 8x2 patches so that the 2x2 down-sampling used by the pre-training cycle loss completes
+// inside a thread quad), streams the vertices in tiles of 64, forms the S tile on the tensor
+// cores (m16n8k8 TF32 with the 3-term split, ~fp32 accuracy; K = 64 only) and reduces it in
+// registers: ONE exp per element serves both softmaxes (reference point tau*1: features are
+// L2-normalised, so S <= 1), row sums stay in the thread, column sums are folded across the warp
+// and written as per-row-block partials that a small second kernel combines.  S itself is
+// written at most once (full, eval mode) or only as its 2x2 mean (training).  The backward
+// recomputes the S tile instead of reading saved softmaxes and runs the two gradient products on
+// the tensor cores as well.
+#include "../../include/scp_b200.h"
+#include "scp_common.cuh"
+#include "scp_mma.cuh"
+
+namespace scp {
+namespace corr {
+
+constexpr int C = 64;        // feature channels (n_corr_feat of every shipped config)
+constexpr int BM = 128;      // pixels per row block
+constexpr int BN = 64;       // vertices per tile
+constexpr int NT = 256;
+constexpr int AS = BM + 8;   // As[c][r]   (k-major A operand)
+constexpr int BS = C + 4;    // Bs[n][c]
+constexpr int DS = BN + 4;   // Ds[r][n]
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct Geo {
+    int B, P, N, hf, wf, npblk, ntile;
+    float tau;
+};
+
+// MMA row r (0..127) of row block `pblk` -> pixel index.  16-row MMA tiles are 8(x) x 2(y) patches:
+// rows q and q+8 of a tile are vertical neighbours, rows q and q^1 horizontal neighbours.
+__device__ __forceinline__ int row_pixel(const Geo &g, int pblk, int r, int &pool_idx)
+{
+    const int j = r >> 4, q = r & 15;
+    const int tiles_per_pair = g.wf >> 3;
+    const int pair = j / tiles_per_pair, xt = j - pair * tiles_per_pair;
+    const int y = pblk * (BM / g.wf) + 2 * pair + (q >> 3);
+    const int x = 8 * xt + (q & 7);
+    pool_idx = (y >> 1) * (g.wf >> 1) + (x >> 1);
+    return y * g.wf + x;
+}
+
+// ---- tile loaders --------------------------------------------------------------------------
+// As[c][r] <- img_feat[b][c][pixel(r)]: 32-byte runs (8 consecutive x), two cp.async each
+__device__ __forceinline__ void load_A(const Geo &g, float *As, const float *__restrict__ img_b, int pblk)
+{
+    for (int i = threadIdx.x; i < C * (BM / 4); i += NT) {
+        const int c = i / (BM / 4), r4 = (i - c * (BM / 4)) * 4;
+        int pool;
+        const int p = row_pixel(g, pblk, r4, pool);
+        cp_async16(As + c * AS + r4, img_b + (size_t)c * g.P + p);
+    }
+}
+
+// Bs[n][c] <- mesh_feat[b][n0+n][c], rows past N zero-filled
+__device__ __forceinline__ void load_B(const Geo &g, float *Bs, const float *__restrict__ mesh_b, int n0)
+{
+    for (int i = threadIdx.x; i < BN * (C / 4); i += NT) {
+        const int n = i / (C / 4), c4 = (i - n * (C / 4)) * 4;
+        if (n0 + n < g.N) cp_async16(Bs + n * BS + c4, mesh_b + (size_t)(n0 + n) * C + c4);
+        else *reinterpret_cast<float4 *>(Bs + n * BS + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ---- S tile on the tensor cores: acc[mi][ni] (warp tile 32 rows x 32 cols, K = 64) ----------
+__device__ __forceinline__ void mma_S(float (&acc)[2][4][4], const float *As, const float *Bs, int wm, int wn,
+                                      int g, int t)
+{
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc[mi][ni][k] = 0.f;
+#pragma unroll
+    for (int k0 = 0; k0 < C; k0 += 8) {
+        uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+            const float *a = As + (k0 + t) * AS + 32 * wm + 16 * mi + g;
+            split_tf32(a[0], ah[mi][0], al[mi][0]);
+            split_tf32(a[8], ah[mi][1], al[mi][1]);
+            split_tf32(a[4 * AS], ah[mi][2], al[mi][2]);
+            split_tf32(a[4 * AS + 8], ah[mi][3], al[mi][3]);
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            const float *b = Bs + (32 * wn + 8 * ni + g) * BS + k0 + t;
+            split_tf32(b[0], bh[ni][0], bl[ni][0]);
+            split_tf32(b[4], bh[ni][1], bl[ni][1]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                mma_tf32(acc[mi][ni], al[mi], bh[ni]);
+                mma_tf32(acc[mi][ni], ah[mi], bl[ni]);
+                mma_tf32(acc[mi][ni], ah[mi], bh[ni]);
+            }
+    }
+}
+
+// ---- forward --------------------------------------------------------------------------------
+// dynamic shared memory layout (floats)
+constexpr int F_AS = 0;
+constexpr int F_BS = F_AS + C * AS;              // 2 buffers
+constexpr int F_VS = F_BS + 2 * BN * BS;         // 2 buffers of [BN][4]: x, y, z, valid
+constexpr int F_COL = F_VS + 2 * BN * 4;         // [4 wm][BN][4]
+constexpr int F_ROW = F_COL + 4 * BN * 4;        // [2 wn][BM][4]
+constexpr int F_INFO = F_ROW + 2 * BM * 4;       // mask[BM], gx[BM], gy[BM], pixel[BM] (int)
+constexpr int F_TOTAL = F_INFO + 4 * BM;
+
+__device__ __forceinline__ void load_V(const Geo &g, float *Vs, const float *__restrict__ v_b, int n0)
+{
+    if (threadIdx.x < BN) {
+        const int n = n0 + threadIdx.x;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < g.N) q = make_float4(v_b[3 * n], v_b[3 * n + 1], v_b[3 * n + 2], 1.f);
+        *reinterpret_cast<float4 *>(Vs + 4 * threadIdx.x) = q;
+    }
+}
+
+__global__ void __launch_bounds__(NT, 2)
+corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__restrict__ mesh_feat,
+                const float *__restrict__ mask_down, const float *__restrict__ pred_v,
+                const float *__restrict__ meshgrid, float *__restrict__ pc_full, float *__restrict__ pc_pool,
+                float *__restrict__ match, float *__restrict__ rsum, float *__restrict__ colpart)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *As = sm + F_AS, *Bs = sm + F_BS, *Vs = sm + F_VS, *s_col = sm + F_COL, *s_row = sm + F_ROW;
+    float *s_mask = sm + F_INFO, *s_gx = s_mask + BM, *s_gy = s_gx + BM;
+    int *s_pix = reinterpret_cast<int *>(s_gy + BM);
+
+    const int pblk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3, wm = warp & 3, wn = warp >> 2;
+    const float *img_b = img_feat + (size_t)b * C * geo.P;
+    const float *mesh_b = mesh_feat + (size_t)b * geo.N * C;
+    const float *v_b = pred_v + (size_t)b * geo.N * 3;
+    const float kexp = geo.tau * LOG2E;
+
+    load_A(geo, As, img_b, pblk);
+    load_B(geo, Bs, mesh_b, 0);
+    cp_async_commit();
+    load_V(geo, Vs, v_b, 0);
+    if (tid < BM) {
+        int pool;
+        const int p = row_pixel(geo, pblk, tid, pool);
+        s_pix[tid] = p;
+        s_mask[tid] = mask_down[(size_t)b * geo.P + p];
+        s_gx[tid] = meshgrid[p];
+        s_gy[tid] = meshgrid[geo.P + p];
+    }
+    __syncthreads();
+
+    // this thread's four rows: ri = 2*mi + h  ->  r = 32*wm + 16*mi + 8*h + g
+    float rmask[4], rgx[4], rgy[4];
+    int rpix[4], rpool[2];
+#pragma unroll
+    for (int ri = 0; ri < 4; ri++) {
+        const int r = 32 * wm + 16 * (ri >> 1) + 8 * (ri & 1) + g;
+        rmask[ri] = s_mask[r]; rgx[ri] = s_gx[r]; rgy[ri] = s_gy[r]; rpix[ri] = s_pix[r];
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++) {
+        int pool;
+        row_pixel(geo, pblk, 32 * wm + 16 * mi + g, pool);
+        rpool[mi] = pool;
+    }
+    float rl[4] = { 0.f, 0.f, 0.f, 0.f }, rax[4] = { 0.f, 0.f, 0.f, 0.f }, ray[4] = { 0.f, 0.f, 0.f, 0.f },
+          raz[4] = { 0.f, 0.f, 0.f, 0.f };
+
+    for (int it = 0; it < geo.ntile; it++) {
+        const int n0 = it * BN;
+        float *Bt = Bs + (it & 1) * BN * BS, *Vt = Vs + (it & 1) * BN * 4;
+        cp_async_wait<0>();
+        __syncthreads();  // tile `it` has landed; every warp is done with iteration it-1
+        if (it + 1 < geo.ntile) {  // prefetch overlaps the MMAs below
+            load_B(geo, Bs + ((it + 1) & 1) * BN * BS, mesh_b, n0 + BN);
+            cp_async_commit();
+            load_V(geo, Vs + ((it + 1) & 1) * BN * 4, v_b, n0 + BN);
+        }
+
+        float acc[2][4][4];
+        mma_S(acc, As, Bt, wm, wn, g, t);
+
+        float cv[24];  // column partials: [c = 2*ni + j][sum e, sum e*gx, sum e*gy]
+#pragma unroll
+        for (int k = 0; k < 24; k++) cv[k] = 0.f;
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int cl = 32 * wn + 8 * ni + 2 * t + j;
+                const float4 vq = *reinterpret_cast<const float4 *>(Vt + 4 * cl);
+                const bool valid = vq.w != 0.f;
+                const int n = n0 + cl;
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++) {
+                    float sm2[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int ri = 2 * mi + h;
+                        const bool masked = rmask[ri] == 0.f;
+                        const float s = masked ? -1e5f : acc[mi][ni][2 * h + j];
+                        sm2[h] = s;
+                        const float e = (valid && !masked) ? exp2f((s - 1.f) * kexp) : 0.f;
+                        const float er = valid ? (masked ? 1.f : e) : 0.f;  // background rows: uniform softmax
+                        rl[ri] += er; rax[ri] += er * vq.x; ray[ri] += er * vq.y; raz[ri] += er * vq.z;
+                        cv[(2 * ni + j) * 3 + 0] += e;
+                        cv[(2 * ni + j) * 3 + 1] += e * rgx[ri];
+                        cv[(2 * ni + j) * 3 + 2] += e * rgy[ri];
+                        if (pc_full != nullptr && valid) pc_full[((size_t)b * geo.P + rpix[ri]) * geo.N + n] = s;
+                    }
+                    if (pc_pool != nullptr) {
+                        float q = sm2[0] + sm2[1];
+                        q += __shfl_xor_sync(0xffffffffu, q, 4);   // horizontal neighbour (g ^ 1)
+                        if (valid && !(g & 1))
+                            pc_pool[((size_t)b * (geo.P >> 2) + rpool[mi]) * geo.N + n] = 0.25f * q;
+                    }
+                }
+            }
+        }
+        // fold the 24 column partials across the 8 row-lanes: 24 -> 12 -> 6 -> 3, lane (g,t) ends
+        // with column c = g of its t-group, i.e. tile column 32*wn + 8*(g>>1) + 2*t + (g&1)
+        {
+            float a12[12], a6[6], a3[3];
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const float send = b4 ? cv[i] : cv[12 + i], keep = b4 ? cv[12 + i] : cv[i];
+                a12[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const float send = b3 ? a12[i] : a12[6 + i], keep = b3 ? a12[6 + i] : a12[i];
+                a6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const float send = b2 ? a6[i] : a6[3 + i], keep = b2 ? a6[3 + i] : a6[i];
+                a3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            const int cl = 32 * wn + 8 * (g >> 1) + 2 * t + (g & 1);
+            *reinterpret_cast<float4 *>(s_col + (wm * BN + cl) * 4) = make_float4(a3[0], a3[1], a3[2], 0.f);
+        }
+        __syncthreads();
+        if (tid < BN * 3) {
+            const int cl = tid / 3, k = tid - cl * 3;
+            if (n0 + cl < geo.N) {
+                const float v = s_col[(0 * BN + cl) * 4 + k] + s_col[(1 * BN + cl) * 4 + k] +
+                                s_col[(2 * BN + cl) * 4 + k] + s_col[(3 * BN + cl) * 4 + k];
+                colpart[(((size_t)b * geo.npblk + pblk) * geo.N + n0 + cl) * 4 + k] = v;
+            }
+        }
+    }
+
+    // rows: combine the 4 t-lanes, then the two column-halves (wn) through shared memory
+#pragma unroll
+    for (int ri = 0; ri < 4; ri++) {
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            rl[ri] += __shfl_xor_sync(0xffffffffu, rl[ri], o);
+            rax[ri] += __shfl_xor_sync(0xffffffffu, rax[ri], o);
+            ray[ri] += __shfl_xor_sync(0xffffffffu, ray[ri], o);
+            raz[ri] += __shfl_xor_sync(0xffffffffu, raz[ri], o);
+        }
+        if (t == 0) {
+            const int r = 32 * wm + 16 * (ri >> 1) + 8 * (ri & 1) + g;
+            *reinterpret_cast<float4 *>(s_row + (wn * BM + r) * 4) = make_float4(rl[ri], rax[ri], ray[ri], raz[ri]);
+        }
+    }
+    __syncthreads();
+    if (tid < BM) {
+        const float4 a = *reinterpret_cast<const float4 *>(s_row + tid * 4);
+        const float4 c = *reinterpret_cast<const float4 *>(s_row + (BM + tid) * 4);
+        const float l = a.x + c.x, inv = 1.f / l;
+        const size_t p = (size_t)b * geo.P + s_pix[tid];
+        match[p * 3 + 0] = (a.y + c.y) * inv;
+        match[p * 3 + 1] = (a.z + c.z) * inv;
+        match[p * 3 + 2] = (a.w + c.w) * inv;
+        rsum[p] = l;
+    }
+}
+
+// combine the per-row-block column partials: csum[n], imatch[:,n]
+__global__ void corr_colreduce_kernel(Geo geo, const float *__restrict__ colpart,
+                                      const float *__restrict__ meshgrid, float *__restrict__ imatch,
+                                      float *__restrict__ csum)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (n >= geo.N) return;
+    float s = 0.f, gx = 0.f, gy = 0.f;
+    for (int k = 0; k < geo.npblk; k++) {
+        const float4 q = *reinterpret_cast<const float4 *>(colpart + (((size_t)b * geo.npblk + k) * geo.N + n) * 4);
+        s += q.x; gx += q.y; gy += q.z;
+    }
+    float ix, iy;
+    if (s > 0.f) {
+        ix = gx / s; iy = gy / s;
+    } else {  // every pixel is background: the reference's softmax is uniform over all P pixels
+        float mx = 0.f, my = 0.f;
+        for (int p = 0; p < geo.P; p++) { mx += meshgrid[p]; my += meshgrid[geo.P + p]; }
+        ix = mx / geo.P; iy = my / geo.P;
+    }
+    imatch[((size_t)b * 2 + 0) * geo.N + n] = ix;
+    imatch[((size_t)b * 2 + 1) * geo.N + n] = iy;
+    csum[(size_t)b * geo.N + n] = s;
+}
+
+// ---- backward -------------------------------------------------------------------------------
+// dS[p,n] = mask[p] * ( tau*Pi*(gm[p].v[n] - gm[p].match[p]) + tau*Pm*(gi[:,n].grid[:,p] - gi[:,n].imatch[:,n])
+//                       + 0.25*g_pool[pool(p),n] + g_full[p,n] ),  Pi = e/rsum[p], Pm = e/csum[n]
+// row parameters (8 floats): mask, gx, gy, tau/rsum, gm.x, gm.y, gm.z, gm.match
+// col parameters (8 floats): v.x, v.y, v.z, tau/csum, gi.x, gi.y, gi.imatch, valid
+struct BwdArgs {
+    const float *img_feat, *mesh_feat, *mask_down, *pred_v, *meshgrid;
+    const float *match, *imatch, *rsum, *csum;
+    const float *g_match, *g_imatch, *g_pool, *g_full;
+    float *g_img_feat, *g_mesh_feat;
+};
+
+__device__ __forceinline__ void load_rowparams(const Geo &geo, const BwdArgs &a, int b, int pblk, float *Rp,
+                                               int *s_pix, int *s_pool)
+{
+    if (threadIdx.x < BM) {
+        const int r = threadIdx.x;
+        int pool;
+        const int p = row_pixel(geo, pblk, r, pool);
+        const size_t bp = (size_t)b * geo.P + p;
+        const float mk = a.mask_down[bp];
+        const float gx = a.meshgrid[p], gy = a.meshgrid[geo.P + p];
+        const float l = a.rsum[bp];
+        const float g0 = a.g_match[bp * 3], g1 = a.g_match[bp * 3 + 1], g2 = a.g_match[bp * 3 + 2];
+        const float dot = g0 * a.match[bp * 3] + g1 * a.match[bp * 3 + 1] + g2 * a.match[bp * 3 + 2];
+        float4 *dst = reinterpret_cast<float4 *>(Rp + 8 * r);
+        dst[0] = make_float4(mk, gx, gy, geo.tau / l);
+        dst[1] = make_float4(g0, g1, g2, dot);
+        s_pix[r] = p;
+        s_pool[r] = pool;
+    }
+}
+
+__device__ __forceinline__ void load_colparams(const Geo &geo, const BwdArgs &a, int b, int n0, float *Cp)
+{
+    if (threadIdx.x < BN) {
+        const int n = n0 + threadIdx.x;
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+        if (n < geo.N) {
+            const float *v = a.pred_v + ((size_t)b * geo.N + n) * 3;
+            const float cs = a.csum[(size_t)b * geo.N + n];
+            const float gi0 = a.g_imatch[((size_t)b * 2 + 0) * geo.N + n], gi1 = a.g_imatch[((size_t)b * 2 + 1) * geo.N + n];
+            const float im0 = a.imatch[((size_t)b * 2 + 0) * geo.N + n], im1 = a.imatch[((size_t)b * 2 + 1) * geo.N + n];
+            q0 = make_float4(v[0], v[1], v[2], cs > 0.f ? geo.tau / cs : 0.f);
+            q1 = make_float4(gi0, gi1, gi0 * im0 + gi1 * im1, 1.f);
+        }
+        float4 *dst = reinterpret_cast<float4 *>(Cp + 8 * threadIdx.x);
+        dst[0] = q0;
+        dst[1] = q1;
+    }
+}
+
+// turns the S tile in acc into dS (in place) and stores it to Ds[r][n_local]
+__device__ __forceinline__ void make_dS(const Geo &geo, const BwdArgs &a, int b, int n0, float (&acc)[2][4][4],
+                                        const float *Rp, const float *Cp, const int *s_pix, const int *s_pool,
+                                        float *Ds, int wm, int wn, int g, int t)
+{
+    const float kexp = geo.tau * LOG2E;
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int r = 32 * wm + 16 * mi + 8 * h + g;
+            const float4 r0 = *reinterpret_cast<const float4 *>(Rp + 8 * r);
+            const float4 r1 = *reinterpret_cast<const float4 *>(Rp + 8 * r + 4);
+            const bool masked = r0.x == 0.f;
+            const int pix = s_pix[r], pool = s_pool[r];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                float d2[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int cl = 32 * wn + 8 * ni + 2 * t + j;
+                    const float4 c0 = *reinterpret_cast<const float4 *>(Cp + 8 * cl);
+                    const float4 c1 = *reinterpret_cast<const float4 *>(Cp + 8 * cl + 4);
+                    float d = 0.f;
+                    if (!masked && c1.w != 0.f) {
+                        const float e = exp2f((acc[mi][ni][2 * h + j] - 1.f) * kexp);
+                        const float row_term = r0.w * (r1.x * c0.x + r1.y * c0.y + r1.z * c0.z - r1.w);
+                        const float col_term = c0.w * (c1.x * r0.y + c1.y * r0.z - c1.z);
+                        d = e * (row_term + col_term);
+                        const int n = n0 + cl;
+                        if (a.g_pool != nullptr) d += 0.25f * a.g_pool[((size_t)b * (geo.P >> 2) + pool) * geo.N + n];
+                        if (a.g_full != nullptr) d += a.g_full[((size_t)b * geo.P + pix) * geo.N + n];
+                    }
+                    d2[j] = d;
+                }
+                *reinterpret_cast<float2 *>(Ds + r * DS + 32 * wn + 8 * ni + 2 * t) = make_float2(d2[0], d2[1]);
+            }
+        }
+    }
+}
+
+// backward, row-block CTAs: g_img_feat[c][p] = sum_n dS[p][n] mesh_feat[n][c]
+constexpr int R_AS = 0;
+constexpr int R_BS = R_AS + C * AS;          // 2 buffers
+constexpr int R_DS = R_BS + 2 * BN * BS;
+constexpr int R_RP = R_DS + BM * DS;         // [BM][8]
+constexpr int R_CP = R_RP + BM * 8;          // 2 buffers [BN][8]
+constexpr int R_IX = R_CP + 2 * BN * 8;      // pix[BM], pool[BM] (int)
+constexpr int R_TOTAL = R_IX + 2 * BM;
+
+__global__ void __launch_bounds__(NT, 2) corr_bwd_rows_kernel(Geo geo, BwdArgs a)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *As = sm + R_AS, *Bs = sm + R_BS, *Ds = sm + R_DS, *Rp = sm + R_RP, *Cp = sm + R_CP;
+    int *s_pix = reinterpret_cast<int *>(sm + R_IX), *s_pool = s_pix + BM;
+
+    const int pblk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3, wm = warp & 3, wn = warp >> 2;
+    const float *img_b = a.img_feat + (size_t)b * C * geo.P;
+    const float *mesh_b = a.mesh_feat + (size_t)b * geo.N * C;
+
+    load_A(geo, As, img_b, pblk);
+    load_B(geo, Bs, mesh_b, 0);
+    cp_async_commit();
+    load_rowparams(geo, a, b, pblk, Rp, s_pix, s_pool);
+    load_colparams(geo, a, b, 0, Cp);
+
+    float out[2][4][4];  // g_img tile: rows = pixels (32 per warp), cols = channels (32 per warp)
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ci = 0; ci < 4; ci++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) out[mi][ci][k] = 0.f;
+
+    for (int it = 0; it < geo.ntile; it++) {
+        const int n0 = it * BN;
+        float *Bt = Bs + (it & 1) * BN * BS, *Ct = Cp + (it & 1) * BN * 8;
+        cp_async_wait<0>();
+        __syncthreads();  // tile `it` has landed; every warp is done with iteration it-1 (Ds, Bt reads)
+        if (it + 1 < geo.ntile) {
+            load_B(geo, Bs + ((it + 1) & 1) * BN * BS, mesh_b, n0 + BN);
+            cp_async_commit();
+            load_colparams(geo, a, b, n0 + BN, Cp + ((it + 1) & 1) * BN * 8);
+        }
+        float acc[2][4][4];
+        mma_S(acc, As, Bt, wm, wn, g, t);
+        make_dS(geo, a, b, n0, acc, Rp, Ct, s_pix, s_pool, Ds, wm, wn, g, t);
+        __syncthreads();
+        // out[p][c] += dS[p][k=n] * mesh[k=n][c]   (A = Ds row-major, B[k][col] = Bt[k][col])
+#pragma unroll
+        for (int k0 = 0; k0 < BN; k0 += 8) {
+            uint32_t af[2][4], bf[4][2];
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const float *p = Ds + (32 * wm + 16 * mi + g) * DS + k0 + t;
+                af[mi][0] = f2tf32(p[0]); af[mi][1] = f2tf32(p[8 * DS]);
+                af[mi][2] = f2tf32(p[4]); af[mi][3] = f2tf32(p[8 * DS + 4]);
+            }
+#pragma unroll
+            for (int ci = 0; ci < 4; ci++) {
+                const float *p = Bt + (k0 + t) * BS + 32 * wn + 8 * ci + g;
+                bf[ci][0] = f2tf32(p[0]); bf[ci][1] = f2tf32(p[4 * BS]);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                for (int ci = 0; ci < 4; ci++) mma_tf32(out[mi][ci], af[mi], bf[ci]);
+        }
+    }
+    // g_img_feat[b][c][pixel(r)]
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int pix = s_pix[32 * wm + 16 * mi + 8 * h + g];
+#pragma unroll
+            for (int ci = 0; ci < 4; ci++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int c = 32 * wn + 8 * ci + 2 * t + j;
+                    a.g_img_feat[((size_t)b * C + c) * geo.P + pix] = out[mi][ci][2 * h + j];
+                }
+        }
+}
+
+// backward, vertex-block CTAs: g_mesh_feat[n][c] = sum_p dS[p][n] img_feat[c][p]
+constexpr int V_AS = 0;
+constexpr int V_BS = V_AS + C * AS;
+constexpr int V_DS = V_BS + BN * BS;
+constexpr int V_RP = V_DS + BM * DS;
+constexpr int V_CP = V_RP + BM * 8;
+constexpr int V_IX = V_CP + BN * 8;
+constexpr int V_TOTAL = V_IX + 2 * BM;
+
+__global__ void __launch_bounds__(NT, 2) corr_bwd_cols_kernel(Geo geo, BwdArgs a)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *As = sm + V_AS, *Bs = sm + V_BS, *Ds = sm + V_DS, *Rp = sm + V_RP, *Cp = sm + V_CP;
+    int *s_pix = reinterpret_cast<int *>(sm + V_IX), *s_pool = s_pix + BM;
+
+    const int nblk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, n0 = nblk * BN;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3, wm = warp & 3, wn = warp >> 2;
+    const float *img_b = a.img_feat + (size_t)b * C * geo.P;
+    const float *mesh_b = a.mesh_feat + (size_t)b * geo.N * C;
+
+    load_B(geo, Bs, mesh_b, n0);
+    load_colparams(geo, a, b, n0, Cp);
+
+    float out[4][4];  // g_mesh tile: rows = vertices (16 per warp: wm), cols = channels (32 per warp: wn)
+#pragma unroll
+    for (int ci = 0; ci < 4; ci++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) out[ci][k] = 0.f;
+
+    for (int pblk = 0; pblk < geo.npblk; pblk++) {
+        __syncthreads();  // previous iteration finished reading As / Ds / Rp
+        load_A(geo, As, img_b, pblk);
+        cp_async_commit();
+        load_rowparams(geo, a, b, pblk, Rp, s_pix, s_pool);
+        cp_async_wait<0>();
+        __syncthreads();
+        float acc[2][4][4];
+        mma_S(acc, As, Bs, wm, wn, g, t);
+        make_dS(geo, a, b, n0, acc, Rp, Cp, s_pix, s_pool, Ds, wm, wn, g, t);
+        __syncthreads();
+        // out[n][c] += dS^T[n][k=p] * img[k=p][c]   (A[row][k] = Ds[k][row], B[k][col] = As[col][k])
+#pragma unroll 4
+        for (int k0 = 0; k0 < BM; k0 += 8) {
+            uint32_t af[4], bf[4][2];
+            const float *p = Ds + (k0 + t) * DS + 16 * wm + g;
+            af[0] = f2tf32(p[0]); af[1] = f2tf32(p[8]);
+            af[2] = f2tf32(p[4 * DS]); af[3] = f2tf32(p[4 * DS + 8]);
+#pragma unroll
+            for (int ci = 0; ci < 4; ci++) {
+                const float *q = As + (32 * wn + 8 * ci + g) * AS + k0 + t;
+                bf[ci][0] = f2tf32(q[0]); bf[ci][1] = f2tf32(q[4]);
+            }
+#pragma unroll
+            for (int ci = 0; ci < 4; ci++) mma_tf32(out[ci], af, bf[ci]);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int n = n0 + 16 * wm + 8 * h + g;
+        if (n < geo.N) {
+#pragma unroll
+            for (int ci = 0; ci < 4; ci++) {
+                const int c = 32 * wn + 8 * ci + 2 * t;
+                *reinterpret_cast<float2 *>(a.g_mesh_feat + ((size_t)b * geo.N + n) * C + c) =
+                    make_float2(out[ci][2 * h], out[ci][2 * h + 1]);
+            }
+        }
+    }
+}
+
+static bool make_geo(Geo &g, int B, int hf, int wf, int N, int Cc, float tau)
+{
+    if (B <= 0 || B > 65535 || N <= 0 || Cc != C) return false;
+    if (!(wf == 8 || wf == 16 || wf == 32 || wf == 64) || hf <= 0) return false;
+    if ((hf * wf) % BM != 0 || ((BM / wf) & 1)) return false;
+    g.B = B; g.P = hf * wf; g.N = N; g.hf = hf; g.wf = wf; g.tau = tau;
+    g.npblk = g.P / BM;
+    g.ntile = (N + BN - 1) / BN;
+    return true;
+}
+
+}  // namespace corr
+}  // namespace scp
+
+using namespace scp::corr;
+
+extern "C" size_t scp_corr_workspace_bytes(int B, int hf, int wf, int N)
+{
+    if (B <= 0 || hf <= 0 || wf <= 0 || N <= 0) return 0;
+    return (size_t)B * ((size_t)hf * wf / BM) * N * 4 * sizeof(float);
+}
+
+extern "C" int scp_corr_match_forward(const float *img_feat, const float *mesh_feat, const float *mask_down,
+                                      const float *pred_v, const float *meshgrid, float tau, int B, int hf, int wf,
+                                      int N, int Cc, float *pointcorr_full, float *pointcorr_pool, float *match,
+                                      float *imatch, float *rsum, float *csum, void *workspace,
+                                      size_t workspace_bytes, void *stream)
+{
+    Geo geo;
+    if (!make_geo(geo, B, hf, wf, N, Cc, tau)) {
+        scp::set_last_error("scp_corr_match_forward: unsupported shape (B=%d hf=%d wf=%d N=%d C=%d; need C=64, "
+                            "wf in {8,16,32,64}, hf*wf %% 128 == 0)", B, hf, wf, N, Cc);
+        return -1;
+    }
+    if (!workspace || workspace_bytes < scp_corr_workspace_bytes(B, hf, wf, N)) {
+        scp::set_last_error("scp_corr_match_forward: workspace too small");
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = F_TOTAL * sizeof(float);
+    cudaFuncSetAttribute(corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    corr_fwd_kernel<<<dim3(geo.npblk, B), NT, smem, st>>>(geo, img_feat, mesh_feat, mask_down, pred_v, meshgrid,
+                                                         pointcorr_full, pointcorr_pool, match, rsum,
+                                                         (float *)workspace);
+    corr_colreduce_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(geo, (const float *)workspace, meshgrid, imatch,
+                                                                   csum);
+    return scp::check_launch("scp_corr_match_forward");
+}
+
+extern "C" int scp_corr_match_backward(const float *img_feat, const float *mesh_feat, const float *mask_down,
+                                       const float *pred_v, const float *meshgrid, float tau, int B, int hf, int wf,
+                                       int N, int Cc, const float *match, const float *imatch, const float *rsum,
+                                       const float *csum, const float *g_match, const float *g_imatch,
+                                       const float *g_pointcorr_pool, const float *g_pointcorr_full,
+                                       float *g_img_feat, float *g_mesh_feat, void *stream)
+{
+    Geo geo;
+    if (!make_geo(geo, B, hf, wf, N, Cc, tau)) {
+        scp::set_last_error("scp_corr_match_backward: unsupported shape");
+        return -1;
+    }
+    BwdArgs a;
+    a.img_feat = img_feat; a.mesh_feat = mesh_feat; a.mask_down = mask_down; a.pred_v = pred_v; a.meshgrid = meshgrid;
+    a.match = match; a.imatch = imatch; a.rsum = rsum; a.csum = csum;
+    a.g_match = g_match; a.g_imatch = g_imatch; a.g_pool = g_pointcorr_pool; a.g_full = g_pointcorr_full;
+    a.g_img_feat = g_img_feat; a.g_mesh_feat = g_mesh_feat;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem_r = R_TOTAL * sizeof(float), smem_v = V_TOTAL * sizeof(float);
+    cudaFuncSetAttribute(corr_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+    cudaFuncSetAttribute(corr_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
+    corr_bwd_rows_kernel<<<dim3(geo.npblk, B), NT, smem_r, st>>>(geo, a);
+    corr_bwd_cols_kernel<<<dim3(geo.ntile, B), NT, smem_v, st>>>(geo, a);
+    return scp::check_launch("scp_corr_match_backward");
+}

@@ -1,0 +1,96 @@
+"""Dense 2D<->3D correspondence between image features and mesh-vertex features.
+
+API of the reference's model/module/correspondence.py (`Correspondence(opts)`, `match` :36-73,
+`compute_rotation_cycle_loss` :76-113); the P x N similarity, both softmaxes and the two weighted sums
+run in the fused sm_100a kernels of ops/corr_match.py instead of materialised torch ops.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+import torchvision
+from torchvision.transforms import InterpolationMode
+
+from ...ops.corr_match import corr_match
+
+
+def make_meshgrid(hf, wf, device):
+    """(2, hf*wf) pixel-centre grid, x fastest, BOTH axes divided by wf/2 as in correspondence.py:31-33."""
+    ys, xs = torch.meshgrid(torch.arange(hf, dtype=torch.float32), torch.arange(wf, dtype=torch.float32),
+                            indexing='ij')
+    grid = torch.stack([xs.reshape(-1), ys.reshape(-1)], 0) + 0.5
+    return (grid / (wf / 2) - 1).to(device)
+
+
+class Correspondence:
+
+    def __init__(self, opts, device=None):
+        self.opts = opts
+        self.tau_img, self.tau_mesh = opts.tau_img, opts.tau_mesh
+        if self.tau_img != self.tau_mesh:
+            raise NotImplementedError('the fused correspondence kernel shares one exponential between the two '
+                                      'softmaxes and needs tau_img == tau_mesh (true for every shipped config)')
+        self.k_img, self.k_mesh = opts.topk_img, opts.topk_mesh
+        self.hf, self.wf = opts.corr_h, opts.corr_w
+        self.meshgrid = make_meshgrid(self.hf, self.wf, device if device is not None else 'cuda')
+
+    def match(self, img_feat, mesh_feat, mask, pred_v, pooled=False):
+        """Returns (pointcorr, match, imatch, match_conf).  `pooled=True` (used by MeshNet.forward in
+        training, where the only consumer is the pre-training cycle loss) returns the 2x2-averaged
+        pointcorr (B, P/4, N) instead of the full (B, P, N) map."""
+        bsz, h, w = mask.shape
+        opts = self.opts
+        mask_down = F.interpolate(mask[:, None], (self.hf, self.wf), mode='nearest').reshape(bsz, -1) * 1.0
+        pc_full, pc_pool, match, imatch = corr_match(img_feat, mesh_feat, mask_down, pred_v.detach(),
+                                                     self.meshgrid, self.tau_img, self.hf, self.wf,
+                                                     want_full=not pooled, want_pool=pooled)
+        pointcorr = pc_pool if pooled else pc_full
+
+        if opts.train:
+            match_conf = None
+        else:  # forward-backward consistency confidence, evaluation only (correspondence.py:57-69)
+            with torch.no_grad():
+                near = (match[:, None] - pred_v[:, :, None]).norm(2, -1).argmin(1).view(bsz, -1)  # b,h*w
+                ipred = torch.gather(imatch.permute(0, 2, 1), 1, near[:, :, None].expand(-1, -1, 2))
+                fberr = (self.meshgrid.permute(1, 0)[None] - ipred).norm(2, -1).view(bsz, 1, self.hf, self.wf)
+                match_conf = (-5 * fberr).exp()
+            match_conf = F.interpolate(match_conf, (h, w), mode='bilinear', align_corners=False).detach()
+            conf_mean = min(match_conf[mask[:, None] > 0].mean().item(), 0.5)
+            match_conf[match_conf < conf_mean] = 0
+
+        match = F.interpolate(match.reshape(bsz, self.hf, self.wf, 3).permute(0, 3, 1, 2), (h, w), mode='nearest')
+        return pointcorr, match, imatch, match_conf
+
+    def compute_rotation_cycle_loss(self, src_img, src_mask, src_img_feat, encoder):
+        bsz = src_img.shape[0]
+        hf2, wf2 = self.hf // 2, self.wf // 2
+        angle = torch.empty(1).uniform_(0., 360.).item()
+        grid = self.meshgrid.reshape(2, self.hf, self.wf)[None].repeat(bsz, 1, 1, 1)
+        grid = F.interpolate(grid, (hf2, wf2), mode='bilinear')
+
+        src_mask = src_mask[:, None]
+        rotate = torchvision.transforms.functional.rotate
+        tgt_img = rotate(src_img, angle, interpolation=InterpolationMode.BILINEAR)
+        tgt_mask = rotate(src_mask, angle, interpolation=InterpolationMode.NEAREST)
+        cycle_match_gt = rotate(grid, angle, interpolation=InterpolationMode.NEAREST).reshape(bsz, 2, -1)
+
+        _, tgt_img_feat = encoder.encode_img(tgt_img)
+        C = self.opts.n_corr_feat
+        tgt_img_feat = F.normalize(tgt_img_feat.reshape(bsz, C, -1), 2, 1)
+
+        src_mask_down = F.interpolate(src_mask, (hf2, wf2), mode='nearest').reshape(bsz, -1) * 1.0
+        tgt_mask_down = F.interpolate(tgt_mask, (hf2, wf2), mode='nearest').reshape(bsz, -1) * 1.0
+        tgt_f = F.interpolate(tgt_img_feat.reshape(bsz, C, self.hf, self.wf), (hf2, wf2), mode='nearest')
+        src_f = F.interpolate(src_img_feat.reshape(bsz, C, self.hf, self.wf), (hf2, wf2), mode='nearest')
+
+        # (src pixel) x (tgt pixel) similarity, softmax over src pixels, grid-weighted sum: the same fused
+        # kernel as `match` with the target pixels playing the role of the vertices
+        grid_flat = grid[0].reshape(2, -1).contiguous()
+        tgt_rows = tgt_f.reshape(bsz, C, -1).permute(0, 2, 1).contiguous()
+        dummy_v = torch.zeros(bsz, tgt_rows.shape[1], 3, device=src_img.device)
+        _, _, _, cycle_match = corr_match(src_f.reshape(bsz, C, -1), tgt_rows, src_mask_down, dummy_v, grid_flat,
+                                          self.tau_mesh, hf2, wf2, want_full=False, want_pool=False)
+        # masked target columns: the reference's softmax is uniform there -> mean of the grid
+        cycle_match = torch.where(tgt_mask_down[:, None] > 0, cycle_match,
+                                  grid_flat.mean(1)[None, :, None].expand_as(cycle_match))
+        cycle_loss = ((cycle_match - cycle_match_gt).norm(2, 1) * tgt_mask_down).mean()
+        return cycle_loss, cycle_match, cycle_match_gt, tgt_mask_down

@@ -1,0 +1,70 @@
+"""Renderer: the four SoftRas renders of one training step and the quantities derived from them.
+
+API of the reference's model/module/renderer.py:9-73 (`Renderer(opts, mesh)`, `render_all`,
+`render_mean_mesh`); renderer settings are those of renderer.py:13-27.
+"""
+import torch
+import torch.nn.functional as F
+
+from ... import soft_renderer as sr
+from ..util.loss_utils import render, pinhole_cam
+
+
+def _soft_renderer(img_size, sigma, gamma, rgb):
+    return sr.SoftRenderer(image_size=img_size, sigma_val=sigma, gamma_val=gamma, camera_mode='look_at',
+                           perspective=False, aggr_func_rgb=rgb, light_mode='vertex',
+                           light_intensity_ambient=1., light_intensity_directionals=0.)
+
+
+class Renderer:
+
+    def __init__(self, opts, mesh):
+        self.opts = opts
+        self.mesh = mesh
+        size = opts.img_size
+        self.renderer_mask = _soft_renderer(size, 1e-4, 1e-4, 'hard')
+        self.renderer_depth = _soft_renderer(size, 1e-4, 1e-4, 'softmax')
+        self.renderer_softtex = _soft_renderer(size, 1e-3, 1e-2, 'softmax')
+        self.renderer_hardtex = _soft_renderer(size, 1e-4, 1e-3, 'hard')
+        self.renderer_depth.rasterizer.background_color = [1, 1, 1]
+        self.renderer_softtex.rasterizer.background_color = [1, 1, 1]
+
+    def render_mean_mesh(self, foc_crop, pp_crop, rotation, translation):
+        bsz = rotation.shape[0]
+        mean_v = self.mesh.mean_v[None].repeat(bsz, 1, 1)
+        faces = self.mesh.faces[None].repeat(bsz, 1, 1)
+        return render(self.renderer_depth, mean_v, faces, None, foc_crop, pp_crop, rotation, translation,
+                      rotation_detach=True, translation_detach=True, render_depth=True)
+
+    def render_all(self, pred_v, faces, tex, foc_crop, pp_crop, rotation, translation, scale=None):
+        texture_type = getattr(self.mesh, 'texture_type', 'vertex')
+        mask_render = render(self.renderer_mask, pred_v, faces, None, foc_crop, pp_crop, rotation, translation,
+                             render_mask=True, texture_type='vertex')[:, -1]
+        if tex is not None:
+            tex_render = render(self.renderer_softtex, pred_v, faces, tex, foc_crop, pp_crop, rotation,
+                                translation, texture_type=texture_type)
+            tex_mask, tex_render = tex_render[:, -1], tex_render[:, :3]
+        else:
+            tex_mask = tex_render = None
+
+        depth_render = render(self.renderer_depth, pred_v, faces, None, foc_crop, pp_crop, rotation, translation,
+                              render_depth=True, texture_type='vertex')
+        if not self.opts.use_depth:
+            depth_render = depth_render.detach()
+        depth_mask = depth_render[:, 3]
+        depth_render = depth_render[:, 2].clone()
+
+        # NOCS map: hard RGB with the canonical (detached) coordinates as vertex colours
+        match_gt = render(self.renderer_hardtex, pred_v.detach(), faces, pred_v.detach(), foc_crop, pp_crop,
+                          rotation, translation, texture_type='vertex')
+        match_mask, match_gt = match_gt[:, -1], match_gt[:, :3]
+
+        # projected vertices (no y-flip), visibility weight from the rendered depth
+        imatch_gt = pred_v.detach().bmm(rotation) + translation
+        imatch_depth = imatch_gt[:, :, 2].clone()
+        imatch_gt = pinhole_cam(imatch_gt, pp_crop, foc_crop)[:, :, :2].permute(0, 2, 1)  # b,2,n
+        imatch_depth_gt = F.grid_sample(depth_render[:, None], imatch_gt.permute(0, 2, 1)[:, None],
+                                        align_corners=False)[:, 0, 0]
+        depth_weight = (5 * -F.relu(imatch_depth - imatch_depth_gt)).exp().detach()
+        return (mask_render, tex_render, depth_render, match_gt, imatch_gt, tex_mask, depth_mask, match_mask,
+                depth_weight)

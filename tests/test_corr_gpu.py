@@ -1,0 +1,113 @@
+"""GPU parity: fused correspondence kernels (through the C ABI / CorrMatchFunction) vs the CPU oracle
+(oracle/corr.py, pinned to the reference modules).  Tolerance 1e-3 relative, norm-wise and element-wise."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+import torchvision
+from torchvision.transforms import InterpolationMode
+from types import SimpleNamespace
+
+from oracle import corr as ocorr
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'corr_golden.npz'))
+T = lambda k: torch.from_numpy(np.asarray(G[k]))
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def frac(a, b, rtol=1e-3, atol=1e-5):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float(((a - b).abs() <= atol + rtol * b.abs()).double().mean())
+
+
+def make_inputs(B, hf, wf, N, C=64, H=None, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    H = H or 4 * hf
+    img_feat = F.normalize(torch.randn(B, C, hf * wf, generator=g), 2, 1)
+    mesh_feat = F.normalize(torch.relu(torch.randn(B, N, C, generator=g)), 2, -1)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, H), indexing='ij')
+    mask = torch.stack([(((xx - 0.1 * b) ** 2 + yy ** 2) < 0.6 ** 2).float() for b in range(B)])
+    pred_v = torch.randn(B, N, 3, generator=g)
+    return img_feat, mesh_feat, mask, pred_v
+
+
+def pooled(pc, hf, wf):
+    B, P, N = pc.shape
+    return F.interpolate(pc.permute(0, 2, 1).reshape(B, N, hf, wf), (hf // 2, wf // 2), mode='bilinear') \
+        .reshape(B, N, -1).permute(0, 2, 1)
+
+
+def oracle_fwd_bwd(img_feat, mesh_feat, mask, pred_v, hf, wf, w_match, w_imatch, w_pool, dtype=torch.float32):
+    img_feat = img_feat.to(dtype).requires_grad_(True)
+    mesh_feat = mesh_feat.to(dtype).requires_grad_(True)
+    pc, match_up, imatch, match3d = ocorr.match(img_feat, mesh_feat, mask.to(dtype), pred_v.to(dtype), hf, wf)
+    pool = pooled(pc, hf, wf)
+    loss = (match3d * w_match.to(dtype)).sum() + (imatch * w_imatch.to(dtype)).sum() + (pool * w_pool.to(dtype)).sum()
+    loss.backward()
+    return pc.detach(), pool.detach(), match3d.detach(), imatch.detach(), img_feat.grad, mesh_feat.grad
+
+
+@pytest.mark.parametrize('B,hf,wf,N', [(2, 16, 16, 70), (2, 32, 32, 1280), (2, 64, 64, 995), (1, 64, 64, 64)])
+def test_corr_match_forward_backward(B, hf, wf, N):
+    from self_corr_pose_b200.ops.corr_match import corr_match
+    from self_corr_pose_b200.model.module.correspondence import make_meshgrid
+    img_feat, mesh_feat, mask, pred_v = make_inputs(B, hf, wf, N)
+    g = torch.Generator().manual_seed(1)
+    w_match = torch.randn(B, hf * wf, 3, generator=g)
+    w_imatch = torch.randn(B, 2, N, generator=g)
+    w_pool = torch.randn(B, hf * wf // 4, N, generator=g) * 0.01
+    o = oracle_fwd_bwd(img_feat, mesh_feat, mask, pred_v, hf, wf, w_match, w_imatch, w_pool)
+    o64 = oracle_fwd_bwd(img_feat, mesh_feat, mask, pred_v, hf, wf, w_match, w_imatch, w_pool, torch.float64)
+
+    mask_down = F.interpolate(mask[:, None], (hf, wf), mode='nearest').reshape(B, -1)
+    grid = make_meshgrid(hf, wf, 'cuda')
+    torch.testing.assert_close(grid.cpu(), ocorr.meshgrid(hf, wf), rtol=0, atol=0)
+    a = img_feat.cuda().requires_grad_(True)
+    m = mesh_feat.cuda().requires_grad_(True)
+    pc_full, pc_pool, match, imatch = corr_match(a, m, mask_down.cuda(), pred_v.cuda(), grid, 10.0, hf, wf,
+                                                 want_full=True, want_pool=True)
+    loss = (match * w_match.cuda()).sum() + (imatch * w_imatch.cuda()).sum() + (pc_pool * w_pool.cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    got = (pc_full, pc_pool, match, imatch, a.grad, m.grad)
+    names = ('pointcorr', 'pointcorr_pool', 'match', 'imatch', 'g_img_feat', 'g_mesh_feat')
+    report = {}
+    for name, x, ref, ref64 in zip(names, got, o, o64):
+        report[name] = (rel(x, ref64), rel(ref, ref64), frac(x, ref))
+    print('PARITY corr B%d P%d N%d ' % (B, hf * wf, N) +
+          ' '.join('%s=%.2e(oracle32 %.1e, frac %.4f)' % (k, *v) for k, v in report.items()))
+    for name, (r, r32, fr) in report.items():
+        assert r < 1e-3, (name, r)
+        assert fr >= 0.999 or name.startswith('g_'), (name, fr)
+    # masked rows are exactly -1e5, like the reference
+    assert torch.equal(pc_full.cpu()[o[0] == -1e5], o[0][o[0] == -1e5])
+
+
+def test_module_match_and_rotation_cycle_golden():
+    """Correspondence.match / compute_rotation_cycle_loss modules on the golden inputs of the reference run."""
+    from self_corr_pose_b200.model.module.correspondence import Correspondence
+    opts = SimpleNamespace(tau_img=10., tau_mesh=10., topk_img=100, topk_mesh=100, corr_h=16, corr_w=16,
+                           train=True, n_corr_feat=64, img_size=64)
+    corr = Correspondence(opts)
+    img_feat, mesh_feat, mask, pred_v = (T(k).cuda() for k in ('m_img_feat', 'm_mesh_feat', 'm_mask', 'm_pred_v'))
+    pc, match, imatch, conf = corr.match(img_feat, mesh_feat, mask, pred_v)
+    assert conf is None
+    assert rel(pc, T('m_pointcorr')) < 1e-5 and rel(match, T('m_match')) < 1e-3 and rel(imatch, T('m_imatch')) < 1e-3
+    assert frac(match, T('m_match')) >= 0.999 and frac(imatch, T('m_imatch')) >= 0.999
+
+    tgt_raw = T('r_tgt_feat_raw').cuda()
+
+    class FakeEncoder:
+        def encode_img(self, img):
+            return None, tgt_raw
+    torch.manual_seed(11)   # same CPU draw as the golden script -> same angle
+    loss, cm, gt, tmd = corr.compute_rotation_cycle_loss(T('r_src_img').cuda(), mask, img_feat, FakeEncoder())
+    assert torch.equal(gt.cpu(), T('r_cycle_match_gt')) and torch.equal(tmd.cpu(), T('r_tgt_mask_down'))
+    assert rel(cm, T('r_cycle_match')) < 1e-3 and abs(float(loss) - float(G['r_loss'])) < 1e-3 * float(G['r_loss'])
