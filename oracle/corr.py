@@ -28,7 +28,7 @@ def match(img_feat, mesh_feat, mask, pred_v, hf, wf, tau_img=10., tau_mesh=10.):
     pointcorr = pointcorr * (mask_down[:, :, None] > 0) - 1e5 * (mask_down[:, :, None] == 0)
     pointcorr_mesh = torch.softmax(tau_mesh * pointcorr, dim=1)
     pointcorr_img = torch.softmax(tau_img * pointcorr, dim=2)
-    grid = meshgrid(hf, wf)[None].repeat(bsz, 1, 1)
+    grid = meshgrid(hf, wf)[None].repeat(bsz, 1, 1).to(pointcorr.dtype)
     imatch = grid.bmm(pointcorr_mesh)
     match3d = (pointcorr_img[:, :, :, None] * pred_v.detach()[:, None, :, :]).sum(2)
     match_up = F.interpolate(match3d.reshape(bsz, hf, wf, 3).permute(0, 3, 1, 2), (h, w), mode='nearest')

@@ -45,8 +45,8 @@ def pooled(pc, hf, wf):
 
 
 def oracle_fwd_bwd(img_feat, mesh_feat, mask, pred_v, hf, wf, w_match, w_imatch, w_pool, dtype=torch.float32):
-    img_feat = img_feat.to(dtype).requires_grad_(True)
-    mesh_feat = mesh_feat.to(dtype).requires_grad_(True)
+    img_feat = img_feat.detach().clone().to(dtype).requires_grad_(True)
+    mesh_feat = mesh_feat.detach().clone().to(dtype).requires_grad_(True)
     pc, match_up, imatch, match3d = ocorr.match(img_feat, mesh_feat, mask.to(dtype), pred_v.to(dtype), hf, wf)
     pool = pooled(pc, hf, wf)
     loss = (match3d * w_match.to(dtype)).sum() + (imatch * w_imatch.to(dtype)).sum() + (pool * w_pool.to(dtype)).sum()
@@ -90,8 +90,8 @@ def test_corr_match_forward_backward(B, hf, wf, N):
     assert torch.equal(pc_full.cpu()[o[0] == -1e5], o[0][o[0] == -1e5])
 
 
-def test_module_match_and_rotation_cycle_golden():
-    """Correspondence.match / compute_rotation_cycle_loss modules on the golden inputs of the reference run."""
+def test_module_match_golden():
+    """Correspondence.match module on the golden inputs of the reference run."""
     from self_corr_pose_b200.model.module.correspondence import Correspondence
     opts = SimpleNamespace(tau_img=10., tau_mesh=10., topk_img=100, topk_mesh=100, corr_h=16, corr_w=16,
                            train=True, n_corr_feat=64, img_size=64)
@@ -102,12 +102,49 @@ def test_module_match_and_rotation_cycle_golden():
     assert rel(pc, T('m_pointcorr')) < 1e-5 and rel(match, T('m_match')) < 1e-3 and rel(imatch, T('m_imatch')) < 1e-3
     assert frac(match, T('m_match')) >= 0.999 and frac(imatch, T('m_imatch')) >= 0.999
 
-    tgt_raw = T('r_tgt_feat_raw').cuda()
+
+def test_rotation_cycle_vs_oracle():
+    """compute_rotation_cycle_loss on a 32x32 map (the kernel needs >= 128 pixels per map; the 16x16 golden
+    case pins the oracle on the CPU) against oracle.rotation_cycle, forward and gradients."""
+    from self_corr_pose_b200.model.module.correspondence import Correspondence
+    hf = wf = 32
+    B, C, H = 2, 64, 128
+    opts = SimpleNamespace(tau_img=10., tau_mesh=10., topk_img=100, topk_mesh=100, corr_h=hf, corr_w=wf,
+                           train=True, n_corr_feat=C, img_size=H)
+    corr = Correspondence(opts)
+    img_feat, _, mask, _ = make_inputs(B, hf, wf, 8, H=H, seed=4)
+    g = torch.Generator().manual_seed(5)
+    src_img = torch.rand(B, 3, H, H, generator=g)
+    tgt_raw = torch.randn(B, C, hf, wf, generator=g)
 
     class FakeEncoder:
+        def __init__(self, t):
+            self.t = t
+
         def encode_img(self, img):
-            return None, tgt_raw
-    torch.manual_seed(11)   # same CPU draw as the golden script -> same angle
-    loss, cm, gt, tmd = corr.compute_rotation_cycle_loss(T('r_src_img').cuda(), mask, img_feat, FakeEncoder())
-    assert torch.equal(gt.cpu(), T('r_cycle_match_gt')) and torch.equal(tmd.cpu(), T('r_tgt_mask_down'))
-    assert rel(cm, T('r_cycle_match')) < 1e-3 and abs(float(loss) - float(G['r_loss'])) < 1e-3 * float(G['r_loss'])
+            return None, self.t
+
+    # oracle (CPU)
+    torch.manual_seed(11)
+    angle = torch.empty(1).uniform_(0., 360.).item()
+    rot = torchvision.transforms.functional.rotate
+    tgt_mask = rot(mask[:, None], angle, interpolation=InterpolationMode.NEAREST)
+    grid = ocorr.meshgrid(hf, wf).reshape(2, hf, wf)[None].repeat(B, 1, 1, 1)
+    gt = rot(F.interpolate(grid, (hf // 2, wf // 2), mode='bilinear'), angle,
+             interpolation=InterpolationMode.NEAREST).reshape(B, 2, -1)
+    a_o = img_feat.clone().requires_grad_(True)
+    t_o = tgt_raw.clone().requires_grad_(True)
+    loss_o, cm_o, tmd_o = ocorr.rotation_cycle(a_o, F.normalize(t_o.reshape(B, C, -1), 2, 1), mask[:, None], tgt_mask,
+                                               gt, hf, wf)
+    loss_o.backward()
+
+    a = img_feat.cuda().requires_grad_(True)
+    t = tgt_raw.cuda().requires_grad_(True)
+    torch.manual_seed(11)
+    loss, cm, gt_d, tmd = corr.compute_rotation_cycle_loss(src_img.cuda(), mask.cuda(), a, FakeEncoder(t))
+    loss.backward()
+    assert torch.equal(gt_d.cpu(), gt) and torch.equal(tmd.cpu(), tmd_o)
+    print('PARITY rotcycle loss %.6f vs %.6f cm=%.2e g_src=%.2e g_tgt=%.2e' %
+          (float(loss), float(loss_o), rel(cm, cm_o), rel(a.grad, a_o.grad), rel(t.grad, t_o.grad)))
+    assert abs(float(loss) - float(loss_o)) < 1e-3 * abs(float(loss_o))
+    assert rel(cm, cm_o) < 1e-3 and rel(a.grad, a_o.grad) < 1e-3 and rel(t.grad, t_o.grad) < 1e-3
