@@ -112,6 +112,51 @@ int scp_corr_match_backward(const float *img_feat, const float *mesh_feat, const
                             const float *g_match, const float *g_imatch, const float *g_pointcorr_pool,
                             const float *g_pointcorr_full, float *g_img_feat, float *g_mesh_feat, void *stream);
 
+/* ---- frozen DINO ViT-S/8: layer-k key features ----------------------------------------------- */
+/* Replaces DINO.forward (model/module/network/dino.py:102-109) / VisionTransformer.get_specific_tokens
+ * (third-party/zsp/zsp/method/vision_transformer_flexible.py:249-262): embed 384, 6 heads x 64, MLP 1536,
+ * patch 8, LayerNorm eps 1e-6, exact GELU.  Linear weights are bf16 [out][in] (row-major, as nn.Linear
+ * stores them), everything else fp32.  All pointers are device pointers. */
+#define SCP_VIT_MAX_BLOCKS 12
+
+typedef struct scp_vit_block {
+    const float *ln1_w, *ln1_b;     /* [384] */
+    const void *qkv_w;              /* bf16 [1152][384] */
+    const float *qkv_b;             /* [1152] */
+    const void *proj_w;             /* bf16 [384][384] */
+    const float *proj_b;            /* [384] */
+    const float *ln2_w, *ln2_b;     /* [384] */
+    const void *fc1_w;              /* bf16 [1536][384] */
+    const float *fc1_b;             /* [1536] */
+    const void *fc2_w;              /* bf16 [384][1536] */
+    const float *fc2_b;             /* [384] */
+} scp_vit_block;
+
+typedef struct scp_vit_weights {
+    const void *patch_w;            /* bf16 [384][192]: conv weight (384,3,8,8) flattened */
+    const float *patch_b;           /* [384] */
+    const float *cls_pos0;          /* [384]  = cls_token + pos_embed[0] */
+    const float *pos;               /* [np][384] patch position embeddings ALREADY resampled to the np = (H/8)*(W/8)
+                                       grid (vision_transformer_flexible.py:192-212) */
+    scp_vit_block blocks[SCP_VIT_MAX_BLOCKS];
+} scp_vit_weights;
+
+size_t scp_vit_workspace_bytes(int B, int H, int W);
+
+/*
+ * feat[B][384][H/8][W/8] (fp32) = keys of block `n_blocks` (0-based; the reference uses 9) without the CLS
+ * token, channel = head*64 + d, after running blocks 0..n_blocks-1 on img[B][3][H][W] (fp32, raw [0,1] RGB).
+ */
+int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float *feat, int B, int H, int W, int n_blocks,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* Building blocks of the above, exported for unit tests and reuse:
+ *   C[M][N] (fp32) = A[M][K] (bf16) * W[N][K]^T (bf16) + bias[N] (may be NULL); N % 128 == 0, K % 64 == 0.
+ *   Persistent tcgen05/TMEM GEMM fed by TMA. */
+int scp_gemm_bf16_tn(const void *A, const void *W, const float *bias, float *C, int M, int N, int K, void *stream);
+/* o[B][T][384] = softmax(q k^T / 8) v per head; q,k,v bf16 [B*6][T][64] (vision_transformer_flexible.py:85-101). */
+int scp_attention_bf16(const void *q, const void *k, const void *v, void *o, int B, int T, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,25 @@ _SIGNATURES = {
     'scp_corr_match_backward': ([_f] * 5 + [_fl, _i, _i, _i, _i, _i] + [_f] * 10 + [_f], _i),
 }
 
+
+
+class VitBlock(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('ln1_w', 'ln1_b', 'qkv_w', 'qkv_b', 'proj_w', 'proj_b', 'ln2_w', 'ln2_b',
+                                               'fc1_w', 'fc1_b', 'fc2_w', 'fc2_b')]
+
+
+class VitWeights(ctypes.Structure):
+    _fields_ = [('patch_w', ctypes.c_void_p), ('patch_b', ctypes.c_void_p), ('cls_pos0', ctypes.c_void_p),
+                ('pos', ctypes.c_void_p), ('blocks', VitBlock * 12)]
+
+
+_SIGNATURES.update({
+    'scp_gemm_bf16_tn': ([_f, _f, _f, _f, _i, _i, _i, _f], _i),
+    'scp_attention_bf16': ([_f, _f, _f, _f, _i, _i, _f], _i),
+    'scp_vit_workspace_bytes': ([_i, _i, _i], _sz),
+    'scp_vit_s8_keys': ([ctypes.POINTER(VitWeights), _f, _f, _i, _i, _i, _i, _f, _sz, _f], _i),
+})
+
 _lib = None
 
 

@@ -1,0 +1,192 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (bf16 in, fp32
+// accumulate in TMEM), with a functor epilogue that receives 32 consecutive columns of one row.
+//
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128-byte swizzled K-major tiles, mbarrier expect_tx)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane: tcgen05.mma cta_group::1, M=128, N=128, K=16)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b.x32 -> registers -> functor -> global)
+// Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue),
+// and a static round-robin tile schedule (tile = blockIdx.x + i * gridDim.x), one CTA per SM.
+#pragma once
+#include "scp_common.cuh"
+#include "scp_tc5.cuh"
+
+namespace scp {
+namespace gemm {
+
+constexpr int BM = 128, BN = 128, BK = 64;          // BK * sizeof(bf16) = 128 B = one swizzle atom row
+constexpr int STAGES = 6;
+constexpr int ACC_STAGES = 2;
+constexpr int NTHREADS = 192;
+constexpr int STAGE_BYTES = (BM + BN) * BK * 2;     // 32 KiB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = ACC_STAGES * BN;          // 256
+
+struct Shape {
+    int M, N, K;
+};
+
+// Epi: struct with  __device__ void operator()(int row, int col0, const float (&acc)[32]) const;
+template <class Epi>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    Shape s, Epi epi)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + ACC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (s.M + BM - 1) / BM, tiles_n = s.N / BN, ntiles = tiles_m * tiles_n, nkb = s.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        tc5::tma_prefetch_desc(&tmap_a);
+        tc5::tma_prefetch_desc(&tmap_w);
+        for (int i = 0; i < STAGES; i++) { tc5::mbar_init(full + i, 1); tc5::mbar_init(empty + i, 1); }
+        for (int i = 0; i < ACC_STAGES; i++) { tc5::mbar_init(tfull + i, 1); tc5::mbar_init(tempty + i, 4); }
+        tc5::mbar_fence_init();
+    }
+    if (warp == 1) tc5::tmem_alloc(tmem_slot, TMEM_COLS);
+    tc5::tc_fence_before();
+    __syncthreads();
+    tc5::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;   // n fastest: A tile reused from L2
+                for (int kb = 0; kb < nkb; kb++) {
+                    tc5::mbar_wait(empty + stage, phase ^ 1);
+                    uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + BM * BK * 2;
+                    tc5::mbar_expect_tx(full + stage, STAGE_BYTES);
+                    tc5::tma_load_2d(sa, &tmap_a, full + stage, kb * BK, m_blk * BM);
+                    tc5::tma_load_2d(sb, &tmap_w, full + stage, kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc5::umma_idesc_bf16(BM, BN);
+            int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                tc5::mbar_wait(tempty + acc, acc_phase ^ 1);       // epilogue has drained this accumulator
+                tc5::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < nkb; kb++) {
+                    tc5::mbar_wait(full + stage, phase);           // TMA bytes have landed
+                    tc5::tc_fence_after();
+                    const uint32_t sa = tc5::smem_u32(smem + stage * STAGE_BYTES), sb = sa + BM * BK * 2;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++) {
+                        // advance 16 elements (32 B) along K inside the 128-byte swizzle atom
+                        tc5::umma_bf16(d_tmem, tc5::umma_desc_sw128(sa + k * 32), tc5::umma_desc_sw128(sb + k * 32), idesc,
+                                       (kb | k) != 0);
+                    }
+                    tc5::umma_commit(empty + stage);               // frees the smem slot when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc5::umma_commit(tfull + acc);                     // accumulator complete -> epilogue
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
+        const int quarter = warp & 3;
+        int acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+            tc5::mbar_wait(tfull + acc, acc_phase);
+            tc5::tc_fence_after();
+            const int row = m_blk * BM + quarter * 32 + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tc5::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, v);
+                if (row < s.M) epi(row, n_blk * BN + c0, v);
+            }
+            tc5::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc5::mbar_arrive(tempty + acc);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc5::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc5::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// row-major bf16 matrix [rows][inner] (inner contiguous, row pitch `pitch_elems`), box = 64 x 128, SWIZZLE_128B
+inline bool make_tmap_bf16(CUtensorMap *m, const void *ptr, uint64_t inner, uint64_t rows, uint64_t pitch_elems)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = { inner, rows };
+    const cuuint64_t strides[1] = { pitch_elems * 2 };
+    const cuuint32_t box[2] = { (cuuint32_t)BK, (cuuint32_t)BM };
+    const cuuint32_t estr[2] = { 1, 1 };
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline int num_sms()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+// A[M,K] (pitch lda), W[N,K] (pitch ldw); N % 128 == 0, K % 64 == 0
+template <class Epi>
+int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, const Epi &epi, cudaStream_t st)
+{
+    if (M <= 0 || N % BN != 0 || K % BK != 0) {
+        set_last_error("tcgen05 gemm: unsupported shape M=%d N=%d K=%d", M, N, K);
+        return -1;
+    }
+    CUtensorMap ta, tw;
+    if (!make_tmap_bf16(&ta, A, K, M, lda) || !make_tmap_bf16(&tw, W, K, N, ldw)) {
+        set_last_error("tcgen05 gemm: cuTensorMapEncodeTiled failed");
+        return -1;
+    }
+    static bool attr_done = false;  // per template instantiation
+    if (!attr_done) {
+        cudaFuncSetAttribute(gemm_bf16_tn_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        attr_done = true;
+    }
+    const int ntiles = ((M + BM - 1) / BM) * (N / BN);
+    const int grid = ntiles < num_sms() ? ntiles : num_sms();
+    Shape s{ M, N, K };
+    gemm_bf16_tn_kernel<Epi><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tw, s, epi);
+    return 0;
+}
+
+}  // namespace gemm
+}  // namespace scp

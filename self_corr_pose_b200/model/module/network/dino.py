@@ -1,0 +1,129 @@
+"""Frozen DINO ViT-S/8 feature extractor on the sm_100a tcgen05 kernels.
+
+API of the reference's model/module/network/dino.py (`DINO()`, `forward(img) -> (b, 384, h/8, w/8)`), with
+`self.model` holding the parameters under the reference checkpoint's names so that
+`pretrain_corr_net.net.model.*` keys load unchanged.  No checkpoint is available offline: unless
+`pretrain/dino_deitsmall8_pretrain.pth` exists, seeded synthetic weights are used (vit_weights.py).
+"""
+import ctypes
+import math
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .... import _lib
+from . import vit_weights as VW
+
+
+class ViTSmall8Params(nn.Module):
+    """Parameter container with the names of vision_transformer_flexible.VisionTransformer (vit_small, patch 8)."""
+
+    def __init__(self, state_dict=None):
+        super().__init__()
+        sd = state_dict if state_dict is not None else VW.synthetic_state_dict(0)
+        for name, shape in VW.vit_small_shapes().items():
+            t = sd[name].detach().clone().float()
+            assert tuple(t.shape) == tuple(shape), (name, t.shape, shape)
+            self._register(name, t)
+
+    def _register(self, dotted, tensor):
+        mod = self
+        parts = dotted.split('.')
+        for p in parts[:-1]:
+            if not hasattr(mod, p):
+                mod.add_module(p, nn.Module())
+            mod = getattr(mod, p)
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+def resampled_pos_embed(pos_embed, w_patches, h_patches):
+    """interpolate_pos_encoding (vision_transformer_flexible.py:192-212): bicubic with scale (n+0.1)/n0."""
+    n0 = pos_embed.shape[1] - 1
+    if w_patches * h_patches == n0 and w_patches == h_patches:
+        return pos_embed[0]
+    dim = pos_embed.shape[-1]
+    s0 = int(math.sqrt(n0))
+    patch = F.interpolate(pos_embed[:, 1:].reshape(1, s0, s0, dim).permute(0, 3, 1, 2).float().cpu(),
+                          scale_factor=((w_patches + 0.1) / s0, (h_patches + 0.1) / s0), mode='bicubic')
+    assert patch.shape[-2] == w_patches and patch.shape[-1] == h_patches
+    patch = patch.permute(0, 2, 3, 1).reshape(-1, dim).to(pos_embed.device)
+    return torch.cat((pos_embed[0, :1], patch), dim=0)
+
+
+class DINO(nn.Module):
+    feat_layer = 9
+    patch_size = 8
+    pretrain_path = 'pretrain/dino_deitsmall8_pretrain.pth'
+
+    def __init__(self, state_dict=None):
+        super().__init__()
+        if state_dict is None and os.path.exists(self.pretrain_path):
+            state_dict = torch.load(self.pretrain_path, map_location='cpu')
+        self.model = ViTSmall8Params(state_dict)
+        self._packed = {}
+
+    def _apply(self, fn, *a, **k):
+        self._packed = {}
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._packed = {}
+        return super().load_state_dict(*a, **k)
+
+    def _pack(self, H, W, device):
+        """bf16 GEMM weights, fp32 vectors and the resampled position embedding, as the C-ABI struct."""
+        key = (H, W, str(device))
+        if key in self._packed:
+            return self._packed[key]
+        sd = {k: v.detach().to(device) for k, v in self.model.state_dict().items()}
+        keep = []
+
+        def f32(t):
+            t = t.float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def b16(t):
+            t = t.to(torch.bfloat16).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        pos = resampled_pos_embed(sd['pos_embed'], W // 8, H // 8)
+        w = _lib.VitWeights()
+        w.patch_w = b16(sd['patch_embed.proj.weight'].reshape(VW.EMBED, -1))
+        w.patch_b = f32(sd['patch_embed.proj.bias'])
+        w.cls_pos0 = f32(sd['cls_token'].reshape(-1) + pos[0])
+        w.pos = f32(pos[1:])
+        for i in range(VW.DEPTH):
+            p = 'blocks.%d.' % i
+            blk = w.blocks[i]
+            blk.ln1_w, blk.ln1_b = f32(sd[p + 'norm1.weight']), f32(sd[p + 'norm1.bias'])
+            blk.qkv_w, blk.qkv_b = b16(sd[p + 'attn.qkv.weight']), f32(sd[p + 'attn.qkv.bias'])
+            blk.proj_w, blk.proj_b = b16(sd[p + 'attn.proj.weight']), f32(sd[p + 'attn.proj.bias'])
+            blk.ln2_w, blk.ln2_b = f32(sd[p + 'norm2.weight']), f32(sd[p + 'norm2.bias'])
+            blk.fc1_w, blk.fc1_b = b16(sd[p + 'mlp.fc1.weight']), f32(sd[p + 'mlp.fc1.bias'])
+            blk.fc2_w, blk.fc2_b = b16(sd[p + 'mlp.fc2.weight']), f32(sd[p + 'mlp.fc2.bias'])
+        self._packed[key] = (w, keep)
+        return self._packed[key]
+
+    @torch.no_grad()
+    def forward(self, img, layer=None):
+        """img (b,3,H,W) raw [0,1] RGB -> layer-9 key features (b, 384, H/8, W/8); frozen, no autograd."""
+        if not img.is_cuda:
+            raise TypeError('DINO supports only CUDA tensors (no CPU path)')
+        layer = self.feat_layer if layer is None else layer
+        B, _, H, W = img.shape
+        dev = img.device
+        w, _keep = self._pack(H, W, dev)
+        img = img.detach().float().contiguous()
+        feat = torch.empty(B, VW.EMBED, H // 8, W // 8, dtype=torch.float32, device=dev)
+        L = _lib.lib()
+        ws_bytes = L.scp_vit_workspace_bytes(B, H, W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.scp_vit_s8_keys(ctypes.byref(w), _lib.ptr(img), _lib.ptr(feat), B, H, W, layer, _lib.ptr(ws),
+                                   ws_bytes, _lib.stream_ptr(dev))
+        _lib.check(rc, 'scp_vit_s8_keys')
+        return feat

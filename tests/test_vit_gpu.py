@@ -1,0 +1,74 @@
+"""GPU parity of the ViT pieces: tcgen05 GEMM, flash attention, and the whole layer-9 key extractor against
+the CPU oracle (oracle/vit.py, pinned to the reference ViT).  Operands are bf16 on the tensor cores, so the
+features are compared norm-wise (tolerances stated per check) and at the consumer: the arg-max matches that
+PretrainedCorrespondence.match derives from them."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit as ovit
+from oracle import corr as ocorr
+from self_corr_pose_b200.model.module.network.vit_weights import synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (300, 384, 192), (2050, 1152, 384), (1025, 384, 1536)])
+def test_tcgen05_gemm(M, N, K):
+    from self_corr_pose_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    W = torch.randn(N, K, generator=g).to(torch.bfloat16).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    C = torch.empty(M, N, device='cuda')
+    rc = _lib.lib().scp_gemm_bf16_tn(_lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(C), M, N, K, _lib.stream_ptr())
+    _lib.check(rc, 'scp_gemm_bf16_tn')
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() + bias.double()
+    r = rel(C, ref)
+    print('PARITY gemm %dx%dx%d rel=%.2e' % (M, N, K, r))
+    assert r < 1e-5    # exact bf16 products, fp32 accumulation
+
+
+@pytest.mark.parametrize('B,T', [(1, 64), (2, 65), (1, 1025)])
+def test_attention(B, T):
+    from self_corr_pose_b200 import _lib
+    g = torch.Generator().manual_seed(1)
+    q, k, v = (torch.randn(B * 6, T, 64, generator=g).to(torch.bfloat16).cuda() for _ in range(3))
+    o = torch.empty(B, T, 384, dtype=torch.bfloat16, device='cuda')
+    rc = _lib.lib().scp_attention_bf16(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), B, T, _lib.stream_ptr())
+    _lib.check(rc, 'scp_attention_bf16')
+    torch.cuda.synchronize()
+    attn = ((q.double() @ k.double().transpose(1, 2)) * 0.125).softmax(-1) @ v.double()      # (B*6,T,64)
+    ref = attn.reshape(B, 6, T, 64).permute(0, 2, 1, 3).reshape(B, T, 384)
+    r = rel(o.float(), ref)
+    print('PARITY attention B%d T%d rel=%.2e' % (B, T, r))
+    assert r < 1e-2    # P and the output are rounded to bf16 (2^-9 relative)
+
+
+@pytest.mark.parametrize('B,size', [(2, 64), (2, 256)])
+def test_dino_features_vs_oracle(B, size):
+    from self_corr_pose_b200.model.module.network.dino import DINO
+    sd = synthetic_state_dict(0)
+    net = DINO(sd).cuda()
+    g = torch.Generator().manual_seed(2)
+    img = torch.rand(B, 3, size, size, generator=g)
+    feat = net(img.cuda()).cpu()
+    ref = ovit.dino_features(sd, img)
+    r = rel(feat, ref)
+    # consumer-level check: mutual arg-max matches between the two images (pretrained_corr.py:85-89)
+    fs = size // 8
+    def argmatch(f):
+        s = f[0].reshape(384, -1).t() @ f[1].reshape(384, -1)
+        return s.max(0).indices, s.max(1).indices
+    bw, fw = argmatch(feat)
+    bw_o, fw_o = argmatch(ref)
+    agree = float(((bw == bw_o).float().mean() + (fw == fw_o).float().mean()) / 2)
+    print('PARITY dino B%d %dpx feat_rel=%.3e argmax_agree=%.4f' % (B, size, r, agree))
+    assert r < 2e-2        # bf16 operands through 9 blocks
+    assert agree >= 0.95
