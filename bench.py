@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the self-corr-pose hot path (forward + backward) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B_per_gpu] [--impl b200|reference]
+
+A "step" = one pass of the hot path (fused correspondence -> texture sampling -> 4 SoftRas renders ->
+silhouette/texture/depth/match/imatch losses -> DINO ViT-S/8 features + pseudo-matches + pre-training cycle
+loss -> backward to the encoder-output gradients) over one synthetic batch of 256x256 images (BASELINE.json
+configs[2]: batch 64 per GPU, 1280-vertex mesh, 64x64 correspondence map, C = 64).  Prints ONE JSON line.
+
+--impl reference: the reference's formulation of the same step on the host cores (oracle/hotpath_cpu.py: the
+reference has no CPU path of its own), on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=64, help='images per GPU (batch_size x repeat, repeat = 4)')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--mesh', default='uv1280')
+    ap.add_argument('--cpu-batch', type=int, default=2, help='images in the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-kernel-breakdown', action='store_true')
+    return ap.parse_args()
+
+
+def load_mesh(name):
+    from self_corr_pose_b200 import synthetic
+    if name == 'uv1280':
+        return synthetic.uv_sphere()
+    if name.startswith('ico'):
+        return synthetic.icosphere(int(name[3:]))
+    return synthetic.load_prior(name)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit())
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx[0] if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_step_rate(args, opts_kw, label):
+    """Reference formulation on the host cores, bounded sample; returns the cpu_baseline object."""
+    import torch
+    from oracle import hotpath_cpu as H
+    from oracle import softras as osr
+    from self_corr_pose_b200.hotpath import default_opts
+    from self_corr_pose_b200.model.module.network.vit_weights import synthetic_state_dict
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bc = max(2, args.cpu_batch)
+    opts = default_opts(**dict(opts_kw, batch_size=Bc // 2, repeat=2))
+    v, f = load_mesh(args.mesh)
+    data, enc = H.make_batch_cpu(opts, v, f, Bc, seed=0)
+    sd = synthetic_state_dict(0)
+    use_ref = os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'libsoftras_ref_cpu.so'))
+    t0 = time.time()
+    H.step(opts, torch.from_numpy(v), torch.from_numpy(f), data, enc, sd, use_ref=use_ref, all_vit_blocks=False)
+    dt = time.time() - t0
+    return {'value': Bc / dt, 'unit': 'images/sec', 'cores': cores, 'kind': 'reference' if use_ref else 'port',
+            'sample': '%s: 1 step of %d images 256x256 (%s mesh), reference formulation on CPU: torch ops + '
+                      '%s SoftRas over all faces per pixel, DINO ViT on the 4x duplicated pair batch up to layer 9; %.1f s'
+                      % (label, Bc, args.mesh, 'the reference kernel source built for the host (oracle/_ref)' if use_ref
+                         else 'C restatement (oracle/softras_oracle.c)', dt)}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    opts_kw = dict(img_size=256, corr_h=64, corr_w=64)
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        cb, dt = cpu_step_rate(args, opts_kw, 'impl=reference')
+        if i >= args.warmup:
+            vals.append(cb['value'])
+        last = cb
+        if i == 0 and dt * (args.warmup + args.steps) > 240:   # keep the whole run within a few minutes
+            vals = [cb['value']]
+            break
+    v = sum(vals) / len(vals)
+    last['value'] = v
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'images/sec fwd+bwd (feat+corr+render+loss) 256x256', 'value': v,
+        'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': len(vals), 'warmup': args.warmup,
+        'ms_per_step': 1e3 * max(2, args.cpu_batch) / v, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'configs[2] hot path fwd+bwd, CPU sample of %d images' % max(2, args.cpu_batch),
+                   'mesh': args.mesh, 'img_size': 256},
+        'cpu_baseline': last,
+        'e2e': {'value': v, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def kernel_breakdown(torch, hot, data, enc, B, peaks):
+    """CUDA-event times of the individual kernels (each launched alone on the current stream) and their
+    rooflines; returns (dominant roofline object, list)."""
+    from self_corr_pose_b200 import _lib
+    from self_corr_pose_b200.soft_renderer import functional as srf
+    from self_corr_pose_b200.model.util.loss_utils import project_to_screen
+    dev = data[0].device
+    L = _lib.lib()
+    hbm, tf = peaks.get('hbm_gbs', 6650.0), peaks.get('bf16_tflops', 1590.0)
+    which = 'measured' if peaks else 'fallback'
+
+    def timeit(fn, n=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = []
+    img, mask, depth, foc, pp = data
+    img_feat, mesh_feat, pred_v, rot, trans = [t.detach() for t in enc]
+    N = pred_v.shape[1]
+    nf = hot.mesh.faces.shape[0]
+    is_ = hot.opts.img_size
+    # --- SoftRas: soft-texture render (sigma 1e-3), forward and backward kernels
+    with torch.no_grad():
+        sv = project_to_screen(pred_v.clone(), foc, pp, rot, trans)
+        sv = torch.stack((sv[..., 0], sv[..., 1], sv[..., 2] + 2.7320508), -1)
+        fv = srf.face_vertices(sv, hot.mesh.faces[None].repeat(B, 1, 1)).contiguous()
+        tex = srf.face_vertices(torch.rand_like(sv), hot.mesh.faces[None].repeat(B, 1, 1)).contiguous()
+    for name, sigma, gamma, rgb in (('softras_softtex', 1e-3, 1e-2, 'softmax'), ('softras_mask', 1e-4, 1e-4, 'hard')):
+        kw = dict(image_size=is_, background_color=[1, 1, 1], sigma_val=sigma, gamma_val=gamma, aggr_func_rgb=rgb,
+                  texture_type='vertex')
+        fvg = fv.clone().requires_grad_(True)
+        t_f = timeit(lambda: srf.soft_rasterize(fvg, tex, **kw))
+        o = srf.soft_rasterize(fvg, tex, **kw)
+        g = torch.randn_like(o)
+        t_b = timeit(lambda: torch.autograd.grad(o, fvg, g, retain_graph=True))
+        bytes_f = B * (72 * nf + 24 * is_ * is_)
+        bytes_b = B * (144 * nf + 40 * is_ * is_)
+        out.append(dict(kernel=name + '_fwd (pack+forward_kernel)', ms=t_f, bound='hbm', achieved=bytes_f / t_f / 1e6,
+                        peak=hbm, unit='GB/s', launches_per_step=1 if 'softtex' in name else 3))
+        out.append(dict(kernel=name + '_bwd (pack+backward_kernel)', ms=t_b, bound='hbm', achieved=bytes_b / t_b / 1e6,
+                        peak=hbm, unit='GB/s', launches_per_step=1 if 'softtex' in name else 2))
+    # --- correspondence
+    from self_corr_pose_b200.ops.corr_match import corr_match
+    import torch.nn.functional as F
+    hf, wf = hot.opts.corr_h, hot.opts.corr_w
+    P, C = hf * wf, hot.opts.n_corr_feat
+    md = F.interpolate(mask[:, None], (hf, wf), mode='nearest').reshape(B, -1)
+    a = img_feat.clone().requires_grad_(True)
+    m = mesh_feat.clone().requires_grad_(True)
+    fwd = lambda: corr_match(a, m, md, pred_v, hot.corr_net.meshgrid, 10.0, hf, wf, want_full=False, want_pool=True)
+    t_f = timeit(fwd)
+    _, pool, mt, im = fwd()
+    gs = [torch.randn_like(pool), torch.randn_like(mt), torch.randn_like(im)]
+    t_b = timeit(lambda: torch.autograd.grad([pool, mt, im], [a, m], gs, retain_graph=True))
+    bytes_f = B * (4 * (C * P + N * C + P + 3 * N) + 4 * (P * N // 4 + 2 * N + 3 * P))
+    bytes_b = B * 4 * (2 * C * P + 2 * N * C + P * N // 4 + 6 * P + 7 * N)
+    out.append(dict(kernel='corr_fwd_kernel(+colreduce)', ms=t_f, bound='hbm', achieved=bytes_f / t_f / 1e6, peak=hbm,
+                    unit='GB/s', launches_per_step=1))
+    out.append(dict(kernel='corr_bwd_rows+cols', ms=t_b, bound='hbm', achieved=bytes_b / t_b / 1e6, peak=hbm,
+                    unit='GB/s', launches_per_step=1))
+    # --- ViT: whole extractor, the attention kernel and the QKV GEMM alone
+    net = hot.pretrain_corr_net.net
+    t_v = timeit(lambda: net(img), n=3)
+    out.append(dict(kernel='vit_s8_keys (68 launches)', ms=t_v, bound='tensor', achieved=47.62e9 * B / t_v / 1e9,
+                    peak=tf, unit='TFLOP/s', launches_per_step=1))
+    T = (is_ // 8) ** 2 + 1
+    q = torch.randn(B * 6, T, 64, device=dev).to(torch.bfloat16)
+    o = torch.empty(B, T, 384, device=dev, dtype=torch.bfloat16)
+    st = _lib.stream_ptr(dev)
+    t_a = timeit(lambda: L.scp_attention_bf16(_lib.ptr(q), _lib.ptr(q), _lib.ptr(q), _lib.ptr(o), B, T, st))
+    out.append(dict(kernel='attention_kernel', ms=t_a, bound='tensor', achieved=4.0 * T * T * 64 * 6 * B / t_a / 1e9,
+                    peak=tf, unit='TFLOP/s', launches_per_step=9))
+    M = B * T
+    A = torch.randn(M, 384, device=dev).to(torch.bfloat16)
+    W = torch.randn(1152, 384, device=dev).to(torch.bfloat16)
+    Cc = torch.empty(M, 1152, device=dev)
+    t_g = timeit(lambda: L.scp_gemm_bf16_tn(_lib.ptr(A), _lib.ptr(W), None, _lib.ptr(Cc), M, 1152, 384, st))
+    out.append(dict(kernel='gemm_bf16_tn_kernel (qkv shape, fp32 out)', ms=t_g, bound='tensor',
+                    achieved=2.0 * M * 1152 * 384 / t_g / 1e9, peak=tf, unit='TFLOP/s', launches_per_step=9))
+    for k in out:
+        k['frac'] = k['achieved'] / k['peak']
+        k['step_ms'] = k['ms'] * k['launches_per_step']
+    dom = max(out, key=lambda k: k['step_ms'] if 'vit_s8' not in k['kernel'] else 0)
+    roof = {'kernel': dom['kernel'], 'bound': dom['bound'], 'achieved': dom['achieved'], 'peak': dom['peak'],
+            'unit': dom['unit'], 'frac': dom['frac'], 'traffic': None, 'peak_source': which,
+            'ms_per_launch': dom['ms'], 'launches_per_step': dom['launches_per_step']}
+    return roof, out
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    from self_corr_pose_b200 import _lib
+    from self_corr_pose_b200.hotpath import HotPath, default_opts
+    from self_corr_pose_b200.model.module.renderer import Renderer
+    from self_corr_pose_b200 import synthetic
+    _lib.lib()   # fail loudly if the native library is missing
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', init_method='env://', device_id=dev)
+    B = args.batch
+    assert B % 4 == 0
+    opts = default_opts(img_size=256, corr_h=64, corr_w=64, batch_size=B // 4, repeat=4)
+    v, f = load_mesh(args.mesh)
+    mean_v, faces = torch.from_numpy(v), torch.from_numpy(f)
+    hot = HotPath(opts, mean_v, faces, device=dev)
+    data, enc = synthetic.make_batch(opts, v, f, B, device=dev, seed=rank, renderer=Renderer(opts, hot.mesh))
+    shared_grad = torch.zeros(mean_v.numel(), device=dev)   # gradient of the one shared parameter (mean_v)
+
+    def step(d):
+        total, aux = hot.step(d, enc)
+        if world > 1:   # the single gradient all-reduce of the data-parallel step (mean over ranks)
+            shared_grad.copy_(enc[2].grad.sum(0).reshape(-1))
+            dist.all_reduce(shared_grad)
+            shared_grad.div_(world)
+        return total
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    for _ in range(max(3, args.warmup)):
+        loss = step(data)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = timed(lambda: step(data), args.steps)
+    value = B * world * args.steps / (ms / 1e3)
+
+    # end to end through the public call with HOST buffers: H2D of the batch + step + D2H of the loss
+    host = [t.detach().cpu().pin_memory() for t in data]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        d = tuple(t.to(dev, non_blocking=True) for t in host)
+        total = step(d)
+        loss_host.copy_(total.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host)
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    e2e_value = B * world * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    roof, kernels = (None, [])
+    if not args.no_kernel_breakdown:
+        roof, kernels = kernel_breakdown(torch, hot, data, enc, B, peaks)
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu, _ = cpu_step_rate(args, dict(img_size=256, corr_h=64, corr_w=64), 'cpu_baseline')
+    line = {
+        'metric': 'images/sec fwd+bwd (feat+corr+render+loss) 256x256', 'value': value, 'unit': 'images/sec',
+        'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (ViT GEMM operands bf16)',
+        'data': 'synthetic',
+        'config': {'workload': 'configs[2]: hot path fwd+bwd = fused correspondence (P=4096,N=%d,C=64) -> texture -> '
+                               '4 SoftRas renders (nf=%d) -> mask/texture/depth/match/imatch losses -> DINO ViT-S/8 '
+                               'layer-9 keys + pseudo-matches + pre-train cycle loss; encoder outputs are inputs'
+                               % (v.shape[0], f.shape[0]),
+                   'images_per_gpu': B, 'img_size': 256, 'mesh': args.mesh, 'parallelism': 'dp%d' % world,
+                   'l2': 'working set per step (~1 GB) exceeds the 126 MB L2; no explicit flush'},
+        'e2e': {'value': e2e_value, 'unit': 'images/sec', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': hot.GPU_LAUNCHES * args.steps,
+        'clocks': sampler.summary() if sampler else None,
+        'roofline': roof, 'kernels': kernels, 'cpu_baseline': cpu, 'loss': float(loss),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -122,7 +122,7 @@ def pretrain_cycle_loss(pts_src, indices_tgt, mask_k, depth_weight, pointcorr, b
     corr = pointcorr_mesh.bmm(pointcorr_img.permute(0, 2, 1))
     corr = corr / (corr.sum(1, keepdims=True) + 1e-5)
     grid = meshgrid(hf, wf).reshape(2, hf, wf)[None].repeat(bsz, 1, 1, 1)
-    grid = F.interpolate(grid, (h2, w2), mode='bilinear').reshape(bsz, 2, -1)
+    grid = F.interpolate(grid, (h2, w2), mode='bilinear').reshape(bsz, 2, -1).to(corr.dtype)
     match = grid.bmm(corr)
     match = torch.gather(match, -1, indices_tgt[:, None].repeat(1, 2, 1))
     cycle_loss = ((match - pts_src).norm(2, 1) * mask_k).mean()

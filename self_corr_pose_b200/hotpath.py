@@ -1,25 +1,28 @@
 """The per-image self-supervised hot path as one callable: correspondence -> texture -> SoftRas renders
--> silhouette / texture / depth / correspondence / cycle losses, forward + backward.
+-> silhouette / texture / depth / correspondence losses -> DINO pseudo-matches + pre-training cycle loss,
+forward + backward.
 
-This is lines 73-134 of the reference's MeshNet.forward (model/model.py) with the image/mesh encoder
-outputs (`img_feat`, `mesh_feat`, `pred_v`, `rotation`, `translation`) supplied by the caller.  The
-full model (self_corr_pose_b200.model.model.MeshNet) calls the same stages after its encoder.
-
-Stages are enabled as their sm_100a kernels land; a stage that is enabled always runs natively (there is
-no PyTorch fallback for SoftRas / correspondence / ViT inside an enabled stage).
+This is lines 73-134 of the reference's MeshNet.forward (model/model.py) with the image/mesh encoder outputs
+(`img_feat`, `mesh_feat`, `pred_v`, `rotation`, `translation`) supplied by the caller; the terms that need the
+trainable encoder itself (symmetry sampling, the rotation-cycle second encoder pass) belong to the full
+model.  Every stage runs on the sm_100a kernels of this package (SoftRas, fused correspondence, tcgen05 ViT);
+there is no PyTorch fallback for them.
 """
 from types import SimpleNamespace
 
 import torch
 import torch.nn.functional as F
 
+from .model.module.correspondence import Correspondence
+from .model.module.pretrained_corr import PretrainedCorrespondence
 from .model.module.renderer import Renderer
+from .model.module.weights import Weights
 from .model.util import loss_utils as L
 
 
 def default_opts(**over):
     """Flag values of config/laptop_wild6d/base_config.txt + the flag defaults they do not override."""
-    o = dict(img_size=256, batch_size=16, repeat=4, corr_h=64, corr_w=64, n_corr_feat=64, tau_img=10., tau_mesh=10.,
+    o = dict(img_size=256, batch_size=8, repeat=4, corr_h=64, corr_w=64, n_corr_feat=64, tau_img=10., tau_mesh=10.,
              use_depth=True, use_occ=False, train=True, divide_fn='both', pretrain_k=200, total_iters=20000,
              mask_wt=0.15, tex_wt=0.05, depth_wt=0.1, triangle_wt=0.002, pullfar_wt=0.01, deform_wt=0.4,
              symmetry_wt=0.5, camera_wt=0.005, match_wt=0.02, imatch_wt=0.02, decay_ratio=0.1,
@@ -29,38 +32,63 @@ def default_opts(**over):
 
 
 class HotPath:
-    """render stage: Renderer.render_all + the five render/correspondence losses."""
+    """data = (img, mask, depth, foc_crop, pp_crop); enc = (img_feat[B,C,P], mesh_feat[B,N,C], pred_v[B,N,3],
+    rotation[B,3,3], translation[B,1,3]).  forward() -> (total_loss, aux dict with the reference's keys)."""
 
-    def __init__(self, opts, mesh, stages=('softras',)):
+    # kernels of this package launched by one forward+backward (see DESIGN.md): SoftRas 4x(pack+fwd) + 3x(pack+bwd),
+    # correspondence 2 fwd + 2 bwd, ViT 3 + 9*7 + 2
+    GPU_LAUNCHES = 8 + 6 + 4 + 68
+
+    def __init__(self, opts, mean_v, faces, device='cuda'):
         self.opts = opts
-        self.mesh = mesh
-        self.stages = tuple(stages)
-        self.renderer = Renderer(opts, mesh)
+        self.device = device
+        self.mesh = SimpleNamespace(mean_v=mean_v.to(device), faces=faces.to(device), texture_type='vertex')
+        self.weights = Weights(opts)
+        self.corr_net = Correspondence(opts, device)
+        self.pretrain_corr_net = PretrainedCorrespondence(opts, self.mesh, device=device).to(device)
+        self.renderer = Renderer(opts, self.mesh)
+        self.triangle_loss_fn = L.LaplacianLoss(mean_v, faces, average=True).to(device)
+        self.iters = 0
 
     def forward(self, data, enc):
-        """data = (img, mask, depth, foc_crop, pp_crop); enc = dict(pred_v, rotation, translation, tex,
-        match, imatch[, img_feat, mesh_feat]).  Returns (total_loss, aux)."""
-        opts = self.opts
+        opts, wts = self.opts, self.weights
+        wts.schedule(self.iters)
         img, mask, depth, foc_crop, pp_crop = data
-        pred_v, rotation, translation = enc['pred_v'], enc['rotation'], enc['translation']
+        img_feat, mesh_feat, pred_v, rotation, translation = enc
         bsz = img.shape[0]
         faces = self.mesh.faces[None].repeat(bsz, 1, 1)
-        tex, match, imatch = enc['tex'], enc['match'], enc['imatch']
+        mean_v = self.mesh.mean_v[None].repeat(bsz, 1, 1)
+
+        pointcorr, match, imatch, _ = self.corr_net.match(img_feat, mesh_feat, mask, pred_v, pooled=True)
+        # CanonicalMesh.get_texture (model/module/mesh.py:46-51): vertex colours sampled at the soft 2D matches
+        tex = F.grid_sample(img, imatch.permute(0, 2, 1)[:, None], align_corners=False)[:, :, 0].permute(0, 2, 1)
 
         (mask_render, tex_render, depth_render, match_gt, imatch_gt, tex_mask, depth_mask, match_mask,
          depth_weight) = self.renderer.render_all(pred_v, faces, tex, foc_crop, pp_crop, rotation, translation)
 
         aux = {}
-        aux['mask_loss'] = opts.mask_wt * L.compute_mask_loss(img, mask, mask_render).mean(0)
-        aux['texture_loss'] = opts.tex_wt * L.compute_texture_loss(img, mask, tex_render, tex_mask).mean(0)
+        aux['mask_loss'] = wts.mask_wt * L.compute_mask_loss(img, mask, mask_render).mean(0)
+        aux['texture_loss'] = wts.tex_wt * L.compute_texture_loss(img, mask, tex_render, tex_mask).mean(0)
         if opts.use_depth:
             d_loss, _ = L.compute_depth_loss(depth, depth_render, depth_mask, mask)
-            aux['depth_loss'] = opts.depth_wt * d_loss.mean(0)
-        aux['match_loss'] = opts.match_wt * L.compute_match_loss(match, match_gt, match_mask, mask).mean(0)
-        aux['imatch_loss'] = opts.imatch_wt * L.compute_imatch_loss(imatch, imatch_gt, depth_weight).mean(0)
-        aux['pullfar_loss'] = opts.pullfar_wt * F.relu(1 - translation[:, :, -1]).mean()
+            aux['depth_loss'] = wts.depth_wt * d_loss.mean(0)
+        aux['match_loss'] = wts.match_wt * L.compute_match_loss(match, match_gt, match_mask, mask).mean(0)
+        aux['imatch_loss'] = wts.imatch_wt * L.compute_imatch_loss(imatch, imatch_gt, depth_weight).mean(0)
+        aux['triangle_loss'] = wts.triangle_wt * self.triangle_loss_fn(pred_v) * pred_v.shape[1] / 64.
+        aux['pullfar_loss'] = wts.pullfar_wt * F.relu(1 - translation[:, :, -1]).mean()
+        aux['deform_loss'] = wts.deform_wt * F.smooth_l1_loss(pred_v, mean_v, reduction='mean')
+        cyc = self.pretrain_corr_net.compute_cycle_loss(img, mask, depth_weight, pointcorr, pooled=True)
+        aux['cycle_loss_pretrain'] = cyc[0] * wts.cycle_loss_pt_wt
         total = sum(aux.values())
         aux['total_loss'] = total
-        aux['mask_render'] = mask_render
-        aux['depth_weight'] = depth_weight
+        return total, aux
+
+    __call__ = forward
+
+    def step(self, data, enc):
+        """forward + backward; returns (loss tensor, aux).  Gradients land in the .grad of the `enc` leaves."""
+        for t in enc:
+            t.grad = None
+        total, aux = self.forward(data, enc)
+        total.backward()
         return total, aux

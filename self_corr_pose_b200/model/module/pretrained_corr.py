@@ -1,0 +1,110 @@
+"""Pseudo-ground-truth 2D<->2D matches from frozen DINO features and the pre-training cycle loss.
+
+API of the reference's model/module/pretrained_corr.py (`PretrainedCorrespondence(opts, mesh)`, `match` :48-104,
+`compute_cycle_loss` :107-140).  Differences in HOW (results identical up to fp reassociation):
+  * DINO features are computed once per UNIQUE image by the tcgen05 ViT (the reference feeds every image four
+    times under divide_fn='both') and only up to the layer-9 key projection;
+  * the (2B,1024,1024) `corr` matrix of :130-131 is never formed: only its k gathered columns are needed
+    (note A):  match[:,j] = sum_n A[:,n] Pi[j,n] / (sum_n s[n] Pi[j,n] + 1e-5) with
+    A = grid . Pm (2 x N) and s[n] = sum_p Pm[p,n] = [depth_weight_src[n] >= 0.5];
+  * `pointcorr` may arrive already 2x2-averaged (pooled=True) from the fused correspondence kernel.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .network.dino import DINO
+from .correspondence import make_meshgrid
+from ..util.loss_utils import divide_by_frame, divide_by_instance, divide_by_both
+
+
+class PretrainedCorrespondence(nn.Module):
+
+    def __init__(self, opts, mesh=None, pretrained=True, device=None):
+        super().__init__()
+        self.opts = opts
+        self.mesh = mesh
+        self.net = DINO().eval()
+        for p in self.net.parameters():
+            p.requires_grad = False
+        self.img_size = opts.img_size
+        self.feat_size = opts.img_size // 8
+        self.tau_img, self.tau_mesh = opts.tau_img, opts.tau_mesh
+        self.k = opts.pretrain_k
+        self.hf, self.wf = opts.corr_h, opts.corr_w
+        self.meshgrid = make_meshgrid(self.hf, self.wf, device if device is not None else 'cuda')
+        try:
+            self.divide_fn = {'frame': divide_by_frame, 'instance': divide_by_instance,
+                              'both': divide_by_both}[opts.divide_fn]
+        except KeyError:
+            raise ValueError(opts.divide_fn)
+
+    def _match_from_feats(self, src_feat, tgt_feat, src_mask, tgt_mask, grid):
+        bsz = src_feat.shape[0]
+        src_feat = src_feat.reshape(*src_feat.shape[:2], -1)
+        tgt_feat = tgt_feat.reshape(*tgt_feat.shape[:2], -1)
+        fs = self.feat_size
+        src_mask_down = F.interpolate(src_mask[:, None], (fs, fs), mode='nearest').reshape(bsz, -1) * 1.0
+        tgt_mask_down = F.interpolate(tgt_mask[:, None], (fs, fs), mode='nearest').reshape(bsz, -1) * 1.0
+        mask_down = src_mask_down[:, :, None] * tgt_mask_down[:, None, :]
+        pointcorr = src_feat.permute(0, 2, 1).bmm(tgt_feat)
+        pointcorr = pointcorr * (mask_down > 0) - 1e5 * (mask_down == 0)
+        max_bw = pointcorr.max(1).indices
+        max_fw = pointcorr.max(2).indices
+        max_cy = torch.gather(max_fw, -1, max_bw)
+        grid = grid.reshape(bsz, 2, -1)
+        match = torch.gather(grid, -1, max_bw[:, None].expand(-1, 2, -1))
+        cycle = torch.gather(grid, -1, max_cy[:, None].expand(-1, 2, -1))
+        distance = (cycle - grid).norm(2, 1)
+        distance = distance * (tgt_mask_down > 0) + 1e5 * (tgt_mask_down == 0)
+        _, indices = torch.topk(-distance, k=self.k, dim=1)
+        match = torch.gather(match, -1, indices[:, None].expand(-1, 2, -1))
+        grid_k = torch.gather(grid, -1, indices[:, None].expand(-1, 2, -1))
+        match_mask = torch.gather(tgt_mask_down, -1, indices)
+        indices_match = torch.gather(max_bw, -1, indices)
+        return match, grid_k, indices_match, indices, match_mask
+
+    def match(self, src_img, tgt_img, src_mask, tgt_mask, grid):
+        with torch.no_grad():
+            feat = self.net(torch.cat([src_img, tgt_img], dim=0))
+            bsz = src_img.shape[0]
+            return self._match_from_feats(feat[:bsz], feat[bsz:], src_mask, tgt_mask, grid)
+
+    def compute_cycle_loss(self, img, mask, depth_weight, pointcorr, pooled=False, feat=None):
+        opts = self.opts
+        num_verts = pointcorr.shape[-1]
+        bs, rep = opts.batch_size, opts.repeat
+        h2, w2 = self.hf // 2, self.wf // 2
+        img_src, img_tgt = self.divide_fn(img, bs, rep)
+        mask_src, mask_tgt = self.divide_fn(mask, bs, rep)
+        dw_src, dw_tgt = self.divide_fn(depth_weight, bs, rep)
+        bsz = img_src.shape[0]
+        grid = F.interpolate(self.meshgrid.reshape(2, self.hf, self.wf)[None], (h2, w2), mode='bilinear')
+        grid_flat = grid.reshape(2, -1)                                         # 2, h2*w2 (same for every pair)
+
+        with torch.no_grad():   # DINO once per unique image, then paired
+            if feat is None:
+                feat = self.net(img)
+            feat_src, feat_tgt = self.divide_fn(feat, bs, rep)
+            pts_src, pts_tgt, indices_src, indices_tgt, mask_k = self._match_from_feats(
+                feat_src, feat_tgt, mask_src, mask_tgt, grid.expand(bsz, -1, -1, -1))
+
+        if not pooled:  # bilinear 1/2 with align_corners=False == exact 2x2 mean
+            B = pointcorr.shape[0]
+            pointcorr = F.avg_pool2d(pointcorr.permute(0, 2, 1).reshape(B, num_verts, self.hf, self.wf), 2) \
+                .reshape(B, num_verts, h2 * w2).permute(0, 2, 1)
+        # per unique image: Pm = softmax over pixels (used when the image is a source) -> A = grid . Pm
+        Pm = torch.softmax(self.tau_mesh * pointcorr, dim=1)                    # B, h2*w2, N
+        A = torch.matmul(grid_flat[None], Pm)                                   # B, 2, N
+        A_src, _ = self.divide_fn(A, bs, rep)
+        A_src = A_src * (dw_src[:, None] >= 0.5)
+        s_src = (dw_src >= 0.5).to(pointcorr.dtype)                             # = column sums of the gated Pm
+        # target rows needed: the k gathered pixels of every pair
+        _, pc_tgt = self.divide_fn(pointcorr, bs, rep)                          # 2B, h2*w2, N (view/copy of rows)
+        rows = torch.gather(pc_tgt, 1, indices_tgt[:, :, None].expand(-1, -1, num_verts))   # 2B, k, N
+        Pi = torch.softmax(self.tau_img * rows, dim=2) * (dw_tgt[:, None] >= 0.5)
+        num = torch.matmul(A_src, Pi.permute(0, 2, 1))                          # 2B, 2, k
+        den = torch.matmul(s_src[:, None], Pi.permute(0, 2, 1)) + 1e-5          # 2B, 1, k
+        match = num / den
+        cycle_loss = ((match - pts_src).norm(2, 1) * mask_k).mean()
+        return cycle_loss, pts_src, pts_tgt, match, mask_k, img_src, img_tgt

@@ -54,9 +54,13 @@ class Renderer:
         depth_mask = depth_render[:, 3]
         depth_render = depth_render[:, 2].clone()
 
-        # NOCS map: hard RGB with the canonical (detached) coordinates as vertex colours
+        # NOCS map: hard RGB with the canonical (detached) coordinates as vertex colours.  Its gradient w.r.t.
+        # geometry is exactly zero (hard RGB has no xyz gradient, soft_rasterize_cuda_kernel.cu:602; the alpha
+        # channel only feeds a boolean mask, loss_utils.py:318), so the pose is detached too and the backward
+        # launch the reference performs for this render is skipped.
         match_gt = render(self.renderer_hardtex, pred_v.detach(), faces, pred_v.detach(), foc_crop, pp_crop,
-                          rotation, translation, texture_type='vertex')
+                          rotation, translation, rotation_detach=True, translation_detach=True,
+                          texture_type='vertex')
         match_mask, match_gt = match_gt[:, -1], match_gt[:, :3]
 
         # projected vertices (no y-flip), visibility weight from the rendered depth

@@ -99,3 +99,40 @@ def default_intrinsics(B, device='cpu'):
     foc = torch.full((B, 2), 3.7, dtype=torch.float64, device=device)
     pp = torch.zeros(B, 2, dtype=torch.float64, device=device)
     return foc, pp
+
+
+def make_batch(opts, verts, faces, B, device='cuda', seed=0, renderer=None):
+    """Config-2 style synthetic scene batch: per image a random pose; `mask` = hard
+    silhouette and `depth` = rendered depth x 1000 (0 outside) of the prior mesh at a slightly perturbed pose,
+    `img` = vertex-colour render + noise; random unit-norm image / mesh features stand in for the encoder.
+    `renderer`: a model.module.renderer.Renderer used (untimed) to rasterise the ground truth.
+    Returns (data, enc): data = (img, mask, depth, foc_crop, pp_crop), enc = leaf tensors requiring grad."""
+    g = torch.Generator().manual_seed(seed)
+    N = verts.shape[0]
+    v = torch.from_numpy(verts) if not torch.is_tensor(verts) else verts
+    f = torch.from_numpy(faces) if not torch.is_tensor(faces) else faces
+    rot, trans = random_poses(B, g)
+    foc, pp = default_intrinsics(B)
+    pred_v = v[None] + 0.01 * torch.randn(B, N, 3, generator=g)
+    colors = torch.rand(B, N, 3, generator=g)
+    # ground-truth pose: a small perturbation of the predicted one
+    d_rot, _ = random_poses(B, g)
+    rot_gt = rot.bmm(torch.matrix_exp(0.05 * (d_rot - d_rot.transpose(1, 2))))
+    trans_gt = trans + 0.02 * torch.randn(B, 1, 3, generator=g)
+    C, P = opts.n_corr_feat, opts.corr_h * opts.corr_w
+    img_feat = torch.nn.functional.normalize(torch.randn(B, C, P, generator=g), 2, 1)
+    mesh_feat = torch.nn.functional.normalize(torch.relu(torch.randn(B, N, C, generator=g)), 2, -1)
+    noise = 0.05 * torch.rand(B, 3, opts.img_size, opts.img_size, generator=g)
+
+    to = lambda t: t.to(device)
+    with torch.no_grad():
+        fb = to(f)[None].repeat(B, 1, 1)
+        gt_v = to(v)[None].repeat(B, 1, 1)
+        (mask_r, tex_r, depth_r, _, _, _, depth_mask, _, _) = renderer.render_all(
+            gt_v, fb, to(colors), to(foc), to(pp), to(rot_gt), to(trans_gt))
+        mask = (mask_r > 0.5).float()
+        depth = depth_r * 1000.0 * mask
+        img = (tex_r + to(noise)).clamp(0, 1)
+    data = (img.contiguous(), mask.contiguous(), depth.contiguous(), to(foc), to(pp))
+    enc = tuple(to(t).clone().requires_grad_(True) for t in (img_feat, mesh_feat, pred_v, rot, trans))
+    return data, enc
