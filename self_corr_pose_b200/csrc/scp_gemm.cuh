@@ -18,14 +18,21 @@ constexpr int STAGES = 6;
 constexpr int ACC_STAGES = 2;
 constexpr int NTHREADS = 192;
 constexpr int STAGE_BYTES = (BM + BN) * BK * 2;     // 32 KiB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STG_FLOATS = 32 * 33;                   // per-epilogue-warp transpose buffer (padded)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * STG_FLOATS * 4;
 constexpr int TMEM_COLS = ACC_STAGES * BN;          // 256
 
 struct Shape {
     int M, N, K;
 };
 
-// Epi: struct with  __device__ void operator()(int row, int col0, const float (&acc)[32]) const;
+// Epi: struct with
+//   static constexpr bool kStaged;
+//   kStaged == true : __device__ void elem(int row, int col, float acc) const;  called with lane = column, so a
+//                     warp touches 32 consecutive columns of ONE row per instruction (coalesced); the 32x32
+//                     accumulator chunk is transposed through a padded shared-memory buffer first
+//   kStaged == false: __device__ void operator()(int row, int col0, const float (&acc)[32]) const;  lane = row
+//                     (for outputs that are contiguous along the rows, e.g. the transposed feature store)
 template <class Epi>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -36,6 +43,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + ACC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2 * ACC_STAGES);
+    float *stage_buf = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (s.M + BM - 1) / BM, tiles_n = s.N / BN, ntiles = tiles_m * tiles_n, nkb = s.K / BK;
@@ -103,12 +111,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
             tc5::mbar_wait(tfull + acc, acc_phase);
             tc5::tc_fence_after();
-            const int row = m_blk * BM + quarter * 32 + lane;
+            const int row0 = m_blk * BM + quarter * 32;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 float v[32];
                 tc5::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, v);
-                if (row < s.M) epi(row, n_blk * BN + c0, v);
+                if constexpr (Epi::kStaged) {
+                    float *stg = stage_buf + (warp - 2) * STG_FLOATS;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) stg[lane * 33 + j] = v[j];
+                    __syncwarp();
+                    const int col = n_blk * BN + c0 + lane;
+                    const int nrows = min(32, s.M - row0);
+#pragma unroll 8
+                    for (int r = 0; r < nrows; r++) epi.elem(row0 + r, col, stg[r * 33 + lane]);
+                    __syncwarp();
+                } else {
+                    if (row0 + lane < s.M) epi(row0 + lane, n_blk * BN + c0, v);
+                }
             }
             tc5::tc_fence_before();
             __syncwarp();

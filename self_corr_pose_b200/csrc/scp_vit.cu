@@ -83,74 +83,51 @@ __global__ void layernorm_kernel(const float *__restrict__ x, const float *__res
     }
 }
 
-// ---- GEMM epilogues: (row, col0, acc[32]) ---------------------------------------------------------------
+// ---- GEMM epilogues (see scp_gemm.cuh: staged = lane is the column, coalesced along a row) ---------------
 struct EpiPatch {  // tokens: x[b][1+p][:] = acc + bias + pos[p]
+    static constexpr bool kStaged = true;
     float *x; const float *bias, *pos; int np, T;
-    __device__ void operator()(int row, int col0, const float (&a)[32]) const
+    __device__ __forceinline__ void elem(int row, int col, float a) const
     {
         const int b = row / np, p = row - b * np;
-        float *dst = x + ((long)b * T + 1 + p) * D + col0;
-        const float *ps = pos + (long)p * D + col0;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            const float4 bb = *reinterpret_cast<const float4 *>(bias + col0 + i), pp = *reinterpret_cast<const float4 *>(ps + i);
-            *reinterpret_cast<float4 *>(dst + i) = make_float4(a[i] + bb.x + pp.x, a[i + 1] + bb.y + pp.y,
-                                                              a[i + 2] + bb.z + pp.z, a[i + 3] + bb.w + pp.w);
-        }
+        x[((long)b * T + 1 + p) * D + col] = a + __ldg(bias + col) + __ldg(pos + (long)p * D + col);
     }
 };
 
 struct EpiQKV {  // head-major split: q/k/v[b][h][t][64] bf16
+    static constexpr bool kStaged = true;
     bf16 *q, *k, *v; const float *bias; int T;
-    __device__ void operator()(int row, int col0, const float (&a)[32]) const
+    __device__ __forceinline__ void elem(int row, int col, float a) const
     {
-        const int which = col0 / D, c = col0 - which * D, h = c / HD, d0 = c - h * HD;
+        const int which = col / D, c = col - which * D, h = c >> 6, d = c & 63;
         const int b = row / T, t = row - b * T;
-        bf16 *dst = (which == 0 ? q : (which == 1 ? k : v)) + (((long)b * HEADS + h) * T + t) * HD + d0;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-            __align__(16) bf16 o[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) o[j] = __float2bfloat16(a[i + j] + bias[col0 + i + j]);
-            *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(o);
-        }
+        bf16 *dst = which == 0 ? q : (which == 1 ? k : v);
+        dst[(((long)b * HEADS + h) * T + t) * HD + d] = __float2bfloat16(a + __ldg(bias + col));
     }
 };
 
-struct EpiResidual {  // x[row][:] += acc + bias   (fp32 residual stream, in place)
+struct EpiResidual {  // x[row][:] += acc + bias   (fp32 residual stream, in place; one owner per element)
+    static constexpr bool kStaged = true;
     float *x; const float *bias;
-    __device__ void operator()(int row, int col0, const float (&a)[32]) const
+    __device__ __forceinline__ void elem(int row, int col, float a) const
     {
-        float *dst = x + (long)row * D + col0;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            const float4 bb = *reinterpret_cast<const float4 *>(bias + col0 + i);
-            float4 r = *reinterpret_cast<float4 *>(dst + i);
-            r.x += a[i] + bb.x; r.y += a[i + 1] + bb.y; r.z += a[i + 2] + bb.z; r.w += a[i + 3] + bb.w;
-            *reinterpret_cast<float4 *>(dst + i) = r;
-        }
+        float *p = x + (long)row * D + col;
+        *p = *p + a + __ldg(bias + col);
     }
 };
 
 struct EpiGelu {  // h[row][:] = gelu_erf(acc + bias)  bf16
+    static constexpr bool kStaged = true;
     bf16 *h; const float *bias; int ld;
-    __device__ void operator()(int row, int col0, const float (&a)[32]) const
+    __device__ __forceinline__ void elem(int row, int col, float a) const
     {
-        bf16 *dst = h + (long)row * ld + col0;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-            __align__(16) bf16 o[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float z = a[i + j] + bias[col0 + i + j];
-                o[j] = __float2bfloat16(0.5f * z * (1.f + erff(z * 0.70710678118654752f)));
-            }
-            *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(o);
-        }
+        const float z = a + __ldg(bias + col);
+        h[(long)row * ld + col] = __float2bfloat16(0.5f * z * (1.f + erff(z * 0.70710678118654752f)));
     }
 };
 
 struct EpiKeys {  // feat[b][col][t-1] = acc + bias for patch tokens (CLS dropped); (b, 384, hp, wp) fp32
+    static constexpr bool kStaged = false;   // output is contiguous along the rows (tokens): lane = row
     float *feat; const float *bias; int T;
     __device__ void operator()(int row, int col0, const float (&a)[32]) const
     {
@@ -163,12 +140,11 @@ struct EpiKeys {  // feat[b][col][t-1] = acc + bias for patch tokens (CLS droppe
 };
 
 struct EpiPlain {  // C[row][:] = acc (+ bias)   fp32, used by the exported test GEMM
+    static constexpr bool kStaged = true;
     float *c; const float *bias; int ld;
-    __device__ void operator()(int row, int col0, const float (&a)[32]) const
+    __device__ __forceinline__ void elem(int row, int col, float a) const
     {
-        float *dst = c + (long)row * ld + col0;
-#pragma unroll
-        for (int i = 0; i < 32; i++) dst[i] = a[i] + (bias ? bias[col0 + i] : 0.f);
+        c[(long)row * ld + col] = a + (bias ? __ldg(bias + col) : 0.f);
     }
 };
 
