@@ -3,7 +3,8 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, 128-byte swizzled K-major tiles, mbarrier expect_tx)
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane: tcgen05.mma cta_group::1, M=128, N=128, K=16)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b.x32 -> registers -> functor -> global)
+//   warps 2..9  : epilogue (tcgen05.ld 32x32b.x32 -> registers -> smem transpose -> functor -> global);
+//                 warp w owns TMEM lanes 32*(w%4).. and the column half (w-2)/4 of the 128-wide tile
 // Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue),
 // and a static round-robin tile schedule (tile = blockIdx.x + i * gridDim.x), one CTA per SM.
 #pragma once
@@ -16,10 +17,11 @@ namespace gemm {
 constexpr int BM = 128, BN = 128, BK = 64;          // BK * sizeof(bf16) = 128 B = one swizzle atom row
 constexpr int STAGES = 6;
 constexpr int ACC_STAGES = 2;
-constexpr int NTHREADS = 192;
+constexpr int EPI_WARPS = 8;                          // two warps per TMEM lane quarter, 64 columns each
+constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 constexpr int STAGE_BYTES = (BM + BN) * BK * 2;     // 32 KiB
 constexpr int STG_FLOATS = 32 * 33;                   // per-epilogue-warp transpose buffer (padded)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * STG_FLOATS * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_WARPS * STG_FLOATS * 4;
 constexpr int TMEM_COLS = ACC_STAGES * BN;          // 256
 
 struct Shape {
@@ -28,9 +30,10 @@ struct Shape {
 
 // Epi: struct with
 //   static constexpr bool kStaged;
-//   kStaged == true : __device__ void elem(int row, int col, float acc) const;  called with lane = column, so a
-//                     warp touches 32 consecutive columns of ONE row per instruction (coalesced); the 32x32
-//                     accumulator chunk is transposed through a padded shared-memory buffer first
+//   kStaged == true : __device__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const;
+//                     called per 32x32 accumulator chunk after it has been transposed through a padded
+//                     shared-memory buffer: value of (row0 + r, col) is stg[r * 33 + lane], lane = column, so a
+//                     warp touches 32 consecutive columns of ONE row per instruction (coalesced)
 //   kStaged == false: __device__ void operator()(int row, int col0, const float (&acc)[32]) const;  lane = row
 //                     (for outputs that are contiguous along the rows, e.g. the transposed feature store)
 template <class Epi>
@@ -52,7 +55,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tc5::tma_prefetch_desc(&tmap_a);
         tc5::tma_prefetch_desc(&tmap_w);
         for (int i = 0; i < STAGES; i++) { tc5::mbar_init(full + i, 1); tc5::mbar_init(empty + i, 1); }
-        for (int i = 0; i < ACC_STAGES; i++) { tc5::mbar_init(tfull + i, 1); tc5::mbar_init(tempty + i, 4); }
+        for (int i = 0; i < ACC_STAGES; i++) { tc5::mbar_init(tfull + i, 1); tc5::mbar_init(tempty + i, EPI_WARPS); }
         tc5::mbar_fence_init();
     }
     if (warp == 1) tc5::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -104,8 +107,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else {
-        // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
-        const int quarter = warp & 3;
+        // ===== epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        float *stg = stage_buf + (warp - 2) * STG_FLOATS;
         int acc = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
@@ -113,18 +117,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tc5::tc_fence_after();
             const int row0 = m_blk * BM + quarter * 32;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                 float v[32];
                 tc5::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, v);
                 if constexpr (Epi::kStaged) {
-                    float *stg = stage_buf + (warp - 2) * STG_FLOATS;
 #pragma unroll
                     for (int j = 0; j < 32; j++) stg[lane * 33 + j] = v[j];
                     __syncwarp();
-                    const int col = n_blk * BN + c0 + lane;
                     const int nrows = min(32, s.M - row0);
-#pragma unroll 8
-                    for (int r = 0; r < nrows; r++) epi.elem(row0 + r, col, stg[r * 33 + lane]);
+                    if (nrows > 0) epi.chunk(row0, nrows, n_blk * BN + c0 + lane, stg, lane);
                     __syncwarp();
                 } else {
                     if (row0 + lane < s.M) epi(row0 + lane, n_blk * BN + c0, v);

@@ -87,42 +87,65 @@ __global__ void layernorm_kernel(const float *__restrict__ x, const float *__res
 struct EpiPatch {  // tokens: x[b][1+p][:] = acc + bias + pos[p]
     static constexpr bool kStaged = true;
     float *x; const float *bias, *pos; int np, T;
-    __device__ __forceinline__ void elem(int row, int col, float a) const
+    __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
-        const int b = row / np, p = row - b * np;
-        x[((long)b * T + 1 + p) * D + col] = a + __ldg(bias + col) + __ldg(pos + (long)p * D + col);
+        int b = row0 / np, p = row0 - b * np;
+        const float bb = __ldg(bias + col);
+        for (int r = 0; r < nrows; r++) {
+            x[((long)b * T + 1 + p) * D + col] = stg[r * 33 + lane] + bb + __ldg(pos + (long)p * D + col);
+            if (++p == np) { p = 0; b++; }
+        }
     }
 };
 
 struct EpiQKV {  // head-major split: q/k/v[b][h][t][64] bf16
     static constexpr bool kStaged = true;
     bf16 *q, *k, *v; const float *bias; int T;
-    __device__ __forceinline__ void elem(int row, int col, float a) const
+    __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
         const int which = col / D, c = col - which * D, h = c >> 6, d = c & 63;
-        const int b = row / T, t = row - b * T;
-        bf16 *dst = which == 0 ? q : (which == 1 ? k : v);
-        dst[(((long)b * HEADS + h) * T + t) * HD + d] = __float2bfloat16(a + __ldg(bias + col));
+        int b = row0 / T, t = row0 - b * T;
+        bf16 *base = (which == 0 ? q : (which == 1 ? k : v)) + (long)h * T * HD + d;
+        const float bb = __ldg(bias + col);
+#pragma unroll 4
+        for (int r = 0; r < nrows; r++) {
+            base[((long)b * HEADS * T + t) * HD] = __float2bfloat16(stg[r * 33 + lane] + bb);
+            if (++t == T) { t = 0; b++; }
+        }
     }
 };
 
 struct EpiResidual {  // x[row][:] += acc + bias   (fp32 residual stream, in place; one owner per element)
     static constexpr bool kStaged = true;
     float *x; const float *bias;
-    __device__ __forceinline__ void elem(int row, int col, float a) const
+    __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
-        float *p = x + (long)row * D + col;
-        *p = *p + a + __ldg(bias + col);
+        float *p = x + (long)row0 * D + col;
+        const float bb = __ldg(bias + col);
+        int r = 0;
+        for (; r + 8 <= nrows; r += 8) {   // batch the loads: 8 independent requests in flight per lane
+            float old[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) old[j] = __ldcg(p + (long)(r + j) * D);
+#pragma unroll
+            for (int j = 0; j < 8; j++) p[(long)(r + j) * D] = old[j] + stg[(r + j) * 33 + lane] + bb;
+        }
+        for (; r < nrows; r++) p[(long)r * D] = __ldcg(p + (long)r * D) + stg[r * 33 + lane] + bb;
     }
 };
 
 struct EpiGelu {  // h[row][:] = gelu_erf(acc + bias)  bf16
     static constexpr bool kStaged = true;
     bf16 *h; const float *bias; int ld;
-    __device__ __forceinline__ void elem(int row, int col, float a) const
+    __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
-        const float z = a + __ldg(bias + col);
-        h[(long)row * ld + col] = __float2bfloat16(0.5f * z * (1.f + erff(z * 0.70710678118654752f)));
+        bf16 *p = h + (long)row0 * ld + col;
+        const float bb = __ldg(bias + col);
+#pragma unroll 4
+        for (int r = 0; r < nrows; r++) {
+            const float z = stg[r * 33 + lane] + bb;
+            p[(long)r * ld] = __float2bfloat16(0.5f * z * (1.f + erff(z * 0.70710678118654752f)));
+        }
     }
 };
 
@@ -142,9 +165,10 @@ struct EpiKeys {  // feat[b][col][t-1] = acc + bias for patch tokens (CLS droppe
 struct EpiPlain {  // C[row][:] = acc (+ bias)   fp32, used by the exported test GEMM
     static constexpr bool kStaged = true;
     float *c; const float *bias; int ld;
-    __device__ __forceinline__ void elem(int row, int col, float a) const
+    __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
-        c[(long)row * ld + col] = a + (bias ? __ldg(bias + col) : 0.f);
+        const float bb = bias ? __ldg(bias + col) : 0.f;
+        for (int r = 0; r < nrows; r++) c[(long)(row0 + r) * ld + col] = stg[r * 33 + lane] + bb;
     }
 };
 
