@@ -252,14 +252,16 @@ def main():
     mean_v, faces = torch.from_numpy(v), torch.from_numpy(f)
     hot = HotPath(opts, mean_v, faces, device=dev)
     data, enc = synthetic.make_batch(opts, v, f, B, device=dev, seed=rank, renderer=Renderer(opts, hot.mesh))
-    shared_grad = torch.zeros(mean_v.numel(), device=dev)   # gradient of the one shared parameter (mean_v)
+    from self_corr_pose_b200.dist import FlatGradReducer
+    # the one parameter shared across the batch on this path: the canonical mesh (pred_v = mean_v + deformation)
+    mean_v_param = torch.nn.Parameter(mean_v.clone().to(dev))
+    reducer = FlatGradReducer([mean_v_param])
 
     def step(d):
         total, aux = hot.step(d, enc)
-        if world > 1:   # the single gradient all-reduce of the data-parallel step (mean over ranks)
-            shared_grad.copy_(enc[2].grad.sum(0).reshape(-1))
-            dist.all_reduce(shared_grad)
-            shared_grad.div_(world)
+        if world > 1:   # the single flat-buffer gradient all-reduce of the data-parallel step (mean over ranks)
+            mean_v_param.grad = enc[2].grad.sum(0)
+            reducer.reduce()
         return total
 
     def timed(fn, k):

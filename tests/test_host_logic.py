@@ -1,0 +1,130 @@
+"""CPU: host-side logic -- C-ABI exports, loss/camera helpers against the reference statements, data-parallel
+gradient reduction over gloo (world size 2), batch sharding."""
+import ctypes
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from self_corr_pose_b200 import build
+    lib_path = build.build()
+    lib = ctypes.CDLL(lib_path)
+    header = open(os.path.join(ROOT, 'include', 'scp_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    names = sorted(set(re.findall(r'\b(scp_[a-z0-9_]+)\s*\(', header)))
+    assert len(names) >= 10, names
+    for n in names:
+        assert hasattr(lib, n), 'libscp_b200.so does not export %s' % n
+    lib.scp_abi_version.restype = ctypes.c_int
+    assert lib.scp_abi_version() == 1
+    # size queries are pure host code
+    lib.scp_softras_workspace_bytes.restype = ctypes.c_size_t
+    assert lib.scp_softras_workspace_bytes(2, 100) >= 2 * 100 * (16 + 192)
+    lib.scp_vit_workspace_bytes.restype = ctypes.c_size_t
+    assert lib.scp_vit_workspace_bytes(1, 256, 256) > 1025 * 384 * 4
+    assert lib.scp_vit_workspace_bytes(1, 250, 256) == 0
+
+
+def test_product_fails_loudly_without_cuda():
+    from self_corr_pose_b200.soft_renderer import functional as srf
+    from self_corr_pose_b200.ops.corr_match import corr_match
+    from self_corr_pose_b200.model.module.network.dino import DINO
+    with pytest.raises(TypeError):
+        srf.soft_rasterize(torch.zeros(1, 1, 3, 3), torch.zeros(1, 1, 1, 3))
+    with pytest.raises(TypeError):
+        corr_match(torch.zeros(1, 64, 128), torch.zeros(1, 8, 64), torch.zeros(1, 128), torch.zeros(1, 8, 3),
+                   torch.zeros(2, 128), 10., 8, 16)
+    if not torch.cuda.is_available():
+        with pytest.raises(TypeError):
+            DINO()(torch.zeros(1, 3, 64, 64))
+
+
+def test_loss_helpers_match_reference_statements():
+    """mask pyramid pools along rows only; divide_by_* pairing; pinhole camera in fp64 intrinsics."""
+    from self_corr_pose_b200.model.util import loss_utils as L
+    from oracle import corr as ocorr
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(8, 3, 5, generator=g)
+    for name in ('frame', 'instance', 'both'):
+        a = getattr(L, 'divide_by_' + name)(x, 2, 4)
+        b = ocorr.DIVIDE[name](x, 2, 4)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    m, mp_ = torch.rand(2, 32, 32, generator=g), torch.rand(2, 32, 32, generator=g)
+    got = L.compute_mask_loss(None, m, mp_)
+    want = 0
+    for i in range(5):   # explicit 1-D pooling along the last axis
+        k = 2 ** i
+        d = (mp_.reshape(2, 32, 32 // k, k).mean(-1) - m.reshape(2, 32, 32 // k, k).mean(-1)).pow(2)
+        want = want + d.repeat_interleave(k, dim=2)
+    torch.testing.assert_close(got, 0.2 * want.mean((1, 2)), rtol=1e-5, atol=1e-7)
+    v = torch.rand(2, 7, 3, generator=g) + torch.tensor([0., 0., 2.])
+    foc = torch.tensor([[3.7, 3.6], [3.5, 3.4]], dtype=torch.float64)
+    pp = torch.tensor([[0.01, -0.02], [0.0, 0.03]], dtype=torch.float64)
+    out = L.pinhole_cam(v.clone(), pp, foc)
+    ref = v.clone().double()
+    ref[:, :, 0] = pp[:, 0:1] + v[:, :, 0].double() * foc[:, 0:1] / v[:, :, 2].double()
+    ref[:, :, 1] = pp[:, 1:2] + v[:, :, 1].double() * foc[:, 1:2] / v[:, :, 2].double()
+    torch.testing.assert_close(out, ref.float(), rtol=0, atol=0)
+
+
+def test_weights_schedule():
+    from self_corr_pose_b200.hotpath import default_opts
+    from self_corr_pose_b200.model.module.weights import Weights
+    w = Weights(default_opts())
+    w.schedule(0)
+    assert w.triangle_wt == pytest.approx(0.002) and w.match_wt == pytest.approx(0.002)   # match starts at decay*wt
+    w.schedule(20000)
+    assert w.triangle_wt == pytest.approx(0.0002) and w.match_wt == pytest.approx(0.02)
+
+
+def test_shard_batch():
+    from self_corr_pose_b200.dist import shard_batch
+    assert list(shard_batch(256, 4, 3, 8)) == list(range(96, 128))
+    with pytest.raises(ValueError):
+        shard_batch(30, 4, 0, 8)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    from self_corr_pose_b200.dist import FlatGradReducer
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    torch.manual_seed(0)
+    w = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7)), torch.nn.Parameter(torch.randn(2))]
+    x = torch.full((5, 3), float(rank + 1))
+    loss = (w[0] * x).sum() + (w[1] ** 2).sum() * (rank + 1)      # w[2] gets no gradient on any rank
+    loss.backward()
+    FlatGradReducer(w).reduce()
+    out[rank] = [p.grad.clone() for p in w]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    torch.manual_seed(0)
+    w0, w1 = torch.randn(5, 3), torch.randn(7)
+    exp0 = torch.full((5, 3), 1.5)            # mean of rank-wise gradients 1 and 2
+    exp1 = 2 * w1 * 1.5
+    for r in range(world):
+        torch.testing.assert_close(out[r][0], exp0)
+        torch.testing.assert_close(out[r][1], exp1)
+        torch.testing.assert_close(out[r][2], torch.zeros(2))
