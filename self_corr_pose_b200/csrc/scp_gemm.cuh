@@ -15,13 +15,15 @@ namespace scp {
 namespace gemm {
 
 constexpr int BM = 128, BN = 128, BK = 64;          // BK * sizeof(bf16) = 128 B = one swizzle atom row
-constexpr int STAGES = 6;
+constexpr int STAGES = 5;
 constexpr int ACC_STAGES = 2;
 constexpr int EPI_WARPS = 8;                          // two warps per TMEM lane quarter, 64 columns each
 constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 constexpr int STAGE_BYTES = (BM + BN) * BK * 2;     // 32 KiB
-constexpr int STG_FLOATS = 32 * 33;                   // per-epilogue-warp transpose buffer (padded)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_WARPS * STG_FLOATS * 4;
+constexpr int STG_FLOATS = 32 * 33;                   // per-epilogue-warp transpose buffer (padded) ...
+constexpr int TMA_TILE_BYTES = 32 * 32 * 4;           // ... or a 32x32 fp32 box in TMA SWIZZLE_128B layout (same region)
+constexpr int EPI_BYTES = EPI_WARPS * STG_FLOATS * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
 constexpr int TMEM_COLS = ACC_STAGES * BN;          // 256
 
 struct Shape {
@@ -36,17 +38,21 @@ struct Shape {
 //                     warp touches 32 consecutive columns of ONE row per instruction (coalesced)
 //   kStaged == false: __device__ void operator()(int row, int col0, const float (&acc)[32]) const;  lane = row
 //                     (for outputs that are contiguous along the rows, e.g. the transposed feature store)
+//   static constexpr bool kTmaReduceAdd (optional third mode, takes precedence): C[tile] += acc + bias[col] through
+//                     cp.reduce.async.bulk.tensor (.add, fp32) from a swizzled smem box -- the read-modify-write of
+//                     the residual stream happens at L2, the SM issues no loads; needs `const float *bias` member
 template <class Epi>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                    Shape s, Epi epi)
+                    const __grid_constant__ CUtensorMap tmap_c, Shape s, Epi epi)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint8_t *epi_buf = smem + STAGES * STAGE_BYTES;   // 1024-aligned
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_buf + EPI_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + ACC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2 * ACC_STAGES);
-    float *stage_buf = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES + 256);
+    float *stage_buf = reinterpret_cast<float *>(epi_buf);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (s.M + BM - 1) / BM, tiles_n = s.N / BN, ntiles = tiles_m * tiles_n, nkb = s.K / BK;
@@ -120,7 +126,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                 float v[32];
                 tc5::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, v);
-                if constexpr (Epi::kStaged) {
+                if constexpr (Epi::kTmaReduceAdd) {
+                    uint8_t *box = epi_buf + (warp - 2) * TMA_TILE_BYTES;      // 32 rows x 128 B, SWIZZLE_128B
+                    if (lane == 0) tc5::tma_store_wait_read();                  // previous bulk store has read the box
+                    __syncwarp();
+                    const float4 *b4 = reinterpret_cast<const float4 *>(epi.bias + n_blk * BN + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 bb = __ldg(b4 + j);
+                        const float4 o = make_float4(v[4 * j] + bb.x, v[4 * j + 1] + bb.y, v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
+                        *reinterpret_cast<float4 *>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    }
+                    tc5::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && row0 < s.M) {   // rows past M are clipped by the tensor map
+                        tc5::tma_reduce_add_2d(&tmap_c, box, n_blk * BN + c0, row0);
+                        tc5::tma_store_commit();
+                    }
+                } else if constexpr (Epi::kStaged) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) stg[lane * 33 + j] = v[j];
                     __syncwarp();
@@ -135,6 +158,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             __syncwarp();
             if (lane == 0) tc5::mbar_arrive(tempty + acc);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+        if constexpr (Epi::kTmaReduceAdd) {
+            if (lane == 0) tc5::tma_store_wait_all();   // all reduce-adds of this warp have completed
         }
     }
     tc5::tc_fence_before();
@@ -173,6 +199,20 @@ inline bool make_tmap_bf16(CUtensorMap *m, const void *ptr, uint64_t inner, uint
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// row-major fp32 matrix [rows][cols] (pitch in elements), box = 32 x 32, SWIZZLE_128B (reduce-add epilogue target)
+inline bool make_tmap_f32_box32(CUtensorMap *m, const void *ptr, uint64_t cols, uint64_t rows, uint64_t pitch_elems)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = { cols, rows };
+    const cuuint64_t strides[1] = { pitch_elems * 4 };
+    const cuuint32_t box[2] = { 32, 32 };
+    const cuuint32_t estr[2] = { 1, 1 };
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 inline int num_sms()
 {
     static int n = 0;
@@ -185,8 +225,10 @@ inline int num_sms()
 }
 
 // A[M,K] (pitch lda), W[N,K] (pitch ldw); N % 128 == 0, K % 64 == 0
+// c_out / ldc: fp32 output matrix of the kTmaReduceAdd epilogue (ignored otherwise)
 template <class Epi>
-int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, const Epi &epi, cudaStream_t st)
+int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, const Epi &epi, cudaStream_t st,
+           float *c_out = nullptr, int ldc = 0)
 {
     if (M <= 0 || N % BN != 0 || K % BK != 0) {
         set_last_error("tcgen05 gemm: unsupported shape M=%d N=%d K=%d", M, N, K);
@@ -197,6 +239,13 @@ int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, 
         set_last_error("tcgen05 gemm: cuTensorMapEncodeTiled failed");
         return -1;
     }
+    CUtensorMap tc = ta;
+    if constexpr (Epi::kTmaReduceAdd) {
+        if (!c_out || !make_tmap_f32_box32(&tc, c_out, N, M, ldc)) {
+            set_last_error("tcgen05 gemm: output tensor map failed");
+            return -1;
+        }
+    }
     static bool attr_done = false;  // per template instantiation
     if (!attr_done) {
         cudaFuncSetAttribute(gemm_bf16_tn_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -205,7 +254,7 @@ int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, 
     const int ntiles = ((M + BM - 1) / BM) * (N / BN);
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
     Shape s{ M, N, K };
-    gemm_bf16_tn_kernel<Epi><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tw, s, epi);
+    gemm_bf16_tn_kernel<Epi><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tw, tc, s, epi);
     return 0;
 }
 

@@ -83,9 +83,21 @@ __global__ void layernorm_kernel(const float *__restrict__ x, const float *__res
     }
 }
 
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 output rounding of 4e-3): one exp,
+// one reciprocal, five FMAs instead of erff's ~30-instruction branchy polynomial
+__device__ __forceinline__ float erf_as(float x)
+{
+    const float a = fabsf(x);
+    const float t = __fdividef(1.f, 1.f + 0.3275911f * a);
+    const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+    const float y = 1.f - poly * __expf(-a * a);
+    return copysignf(y, x);
+}
+
 // ---- GEMM epilogues (see scp_gemm.cuh: staged = lane is the column, coalesced along a row) ---------------
 struct EpiPatch {  // tokens: x[b][1+p][:] = acc + bias + pos[p]
     static constexpr bool kStaged = true;
+    static constexpr bool kTmaReduceAdd = false;
     float *x; const float *bias, *pos; int np, T;
     __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
@@ -100,6 +112,7 @@ struct EpiPatch {  // tokens: x[b][1+p][:] = acc + bias + pos[p]
 
 struct EpiQKV {  // head-major split: q/k/v[b][h][t][64] bf16
     static constexpr bool kStaged = true;
+    static constexpr bool kTmaReduceAdd = false;
     bf16 *q, *k, *v; const float *bias; int T;
     __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
@@ -115,27 +128,16 @@ struct EpiQKV {  // head-major split: q/k/v[b][h][t][64] bf16
     }
 };
 
-struct EpiResidual {  // x[row][:] += acc + bias   (fp32 residual stream, in place; one owner per element)
-    static constexpr bool kStaged = true;
-    float *x; const float *bias;
-    __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
-    {
-        float *p = x + (long)row0 * D + col;
-        const float bb = __ldg(bias + col);
-        int r = 0;
-        for (; r + 8 <= nrows; r += 8) {   // batch the loads: 8 independent requests in flight per lane
-            float old[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) old[j] = __ldcg(p + (long)(r + j) * D);
-#pragma unroll
-            for (int j = 0; j < 8; j++) p[(long)(r + j) * D] = old[j] + stg[(r + j) * 33 + lane] + bb;
-        }
-        for (; r < nrows; r++) p[(long)r * D] = __ldcg(p + (long)r * D) + stg[r * 33 + lane] + bb;
-    }
+struct EpiResidual {  // x[tile] += acc + bias: fp32 residual stream updated by TMA reduce-add (no SM loads)
+    static constexpr bool kStaged = false;
+    static constexpr bool kTmaReduceAdd = true;
+    const float *bias;
+    __device__ void operator()(int, int, const float (&)[32]) const {}
 };
 
 struct EpiGelu {  // h[row][:] = gelu_erf(acc + bias)  bf16
     static constexpr bool kStaged = true;
+    static constexpr bool kTmaReduceAdd = false;
     bf16 *h; const float *bias; int ld;
     __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
@@ -144,13 +146,14 @@ struct EpiGelu {  // h[row][:] = gelu_erf(acc + bias)  bf16
 #pragma unroll 4
         for (int r = 0; r < nrows; r++) {
             const float z = stg[r * 33 + lane] + bb;
-            p[(long)r * ld] = __float2bfloat16(0.5f * z * (1.f + erff(z * 0.70710678118654752f)));
+            p[(long)r * ld] = __float2bfloat16(0.5f * z * (1.f + erf_as(z * 0.70710678118654752f)));
         }
     }
 };
 
 struct EpiKeys {  // feat[b][col][t-1] = acc + bias for patch tokens (CLS dropped); (b, 384, hp, wp) fp32
     static constexpr bool kStaged = false;   // output is contiguous along the rows (tokens): lane = row
+    static constexpr bool kTmaReduceAdd = false;
     float *feat; const float *bias; int T;
     __device__ void operator()(int row, int col0, const float (&a)[32]) const
     {
@@ -164,6 +167,7 @@ struct EpiKeys {  // feat[b][col][t-1] = acc + bias for patch tokens (CLS droppe
 
 struct EpiPlain {  // C[row][:] = acc (+ bias)   fp32, used by the exported test GEMM
     static constexpr bool kStaged = true;
+    static constexpr bool kTmaReduceAdd = false;
     float *c; const float *bias; int ld;
     __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
@@ -411,13 +415,13 @@ extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float
         EpiQKV eq{ qb, kb, vb, bw.qkv_b, T };
         if ((rc = scp::gemm::launch(y, D, bw.qkv_w, D, (int)M, 3 * D, D, eq, st))) return rc;
         attention_kernel<<<dim3((T + AQ - 1) / AQ, B * HEADS), 128, 0, st>>>(qb, kb, vb, ob, T, scale_log2e);
-        EpiResidual ep{ x, bw.proj_b };
-        if ((rc = scp::gemm::launch(ob, D, bw.proj_w, D, (int)M, D, D, ep, st))) return rc;
+        EpiResidual ep{ bw.proj_b };
+        if ((rc = scp::gemm::launch(ob, D, bw.proj_w, D, (int)M, D, D, ep, st, x, D))) return rc;
         layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, bw.ln2_w, bw.ln2_b, y, M);
         EpiGelu eg{ hb, bw.fc1_b, MLP };
         if ((rc = scp::gemm::launch(y, D, bw.fc1_w, D, (int)M, MLP, D, eg, st))) return rc;
-        EpiResidual e2{ x, bw.fc2_b };
-        if ((rc = scp::gemm::launch(hb, MLP, bw.fc2_w, MLP, (int)M, D, MLP, e2, st))) return rc;
+        EpiResidual e2{ bw.fc2_b };
+        if ((rc = scp::gemm::launch(hb, MLP, bw.fc2_w, MLP, (int)M, D, MLP, e2, st, x, D))) return rc;
     }
     // key projection of block `n_blocks` (rows D..2D-1 of its qkv weight) on norm1(x)
     {

@@ -75,36 +75,34 @@ class PretrainedCorrespondence(nn.Module):
         num_verts = pointcorr.shape[-1]
         bs, rep = opts.batch_size, opts.repeat
         h2, w2 = self.hf // 2, self.wf // 2
-        img_src, img_tgt = self.divide_fn(img, bs, rep)
-        mask_src, mask_tgt = self.divide_fn(mask, bs, rep)
-        dw_src, dw_tgt = self.divide_fn(depth_weight, bs, rep)
-        bsz = img_src.shape[0]
+        B = img.shape[0]
+        # pairing as index vectors (divide_by_* applied to arange): big tensors are gathered, never rolled/copied
+        src_idx, tgt_idx = self.divide_fn(torch.arange(B, device=img.device), bs, rep)
+        mask_src, mask_tgt = mask[src_idx], mask[tgt_idx]
+        dw_src, dw_tgt = depth_weight[src_idx], depth_weight[tgt_idx]
+        bsz = src_idx.shape[0]
         grid = F.interpolate(self.meshgrid.reshape(2, self.hf, self.wf)[None], (h2, w2), mode='bilinear')
         grid_flat = grid.reshape(2, -1)                                         # 2, h2*w2 (same for every pair)
 
         with torch.no_grad():   # DINO once per unique image, then paired
             if feat is None:
                 feat = self.net(img)
-            feat_src, feat_tgt = self.divide_fn(feat, bs, rep)
             pts_src, pts_tgt, indices_src, indices_tgt, mask_k = self._match_from_feats(
-                feat_src, feat_tgt, mask_src, mask_tgt, grid.expand(bsz, -1, -1, -1))
+                feat[src_idx], feat[tgt_idx], mask_src, mask_tgt, grid.expand(bsz, -1, -1, -1))
 
         if not pooled:  # bilinear 1/2 with align_corners=False == exact 2x2 mean
-            B = pointcorr.shape[0]
             pointcorr = F.avg_pool2d(pointcorr.permute(0, 2, 1).reshape(B, num_verts, self.hf, self.wf), 2) \
                 .reshape(B, num_verts, h2 * w2).permute(0, 2, 1)
         # per unique image: Pm = softmax over pixels (used when the image is a source) -> A = grid . Pm
         Pm = torch.softmax(self.tau_mesh * pointcorr, dim=1)                    # B, h2*w2, N
         A = torch.matmul(grid_flat[None], Pm)                                   # B, 2, N
-        A_src, _ = self.divide_fn(A, bs, rep)
-        A_src = A_src * (dw_src[:, None] >= 0.5)
+        A_src = A[src_idx] * (dw_src[:, None] >= 0.5)
         s_src = (dw_src >= 0.5).to(pointcorr.dtype)                             # = column sums of the gated Pm
-        # target rows needed: the k gathered pixels of every pair
-        _, pc_tgt = self.divide_fn(pointcorr, bs, rep)                          # 2B, h2*w2, N (view/copy of rows)
-        rows = torch.gather(pc_tgt, 1, indices_tgt[:, :, None].expand(-1, -1, num_verts))   # 2B, k, N
+        # target rows needed: only the k gathered pixels of every pair, straight from the per-image tensor
+        rows = pointcorr[tgt_idx[:, None], indices_tgt]                         # 2B, k, N
         Pi = torch.softmax(self.tau_img * rows, dim=2) * (dw_tgt[:, None] >= 0.5)
         num = torch.matmul(A_src, Pi.permute(0, 2, 1))                          # 2B, 2, k
         den = torch.matmul(s_src[:, None], Pi.permute(0, 2, 1)) + 1e-5          # 2B, 1, k
         match = num / den
         cycle_loss = ((match - pts_src).norm(2, 1) * mask_k).mean()
-        return cycle_loss, pts_src, pts_tgt, match, mask_k, img_src, img_tgt
+        return cycle_loss, pts_src, pts_tgt, match, mask_k, img[src_idx], img[tgt_idx]
