@@ -26,7 +26,13 @@ def default_opts(**over):
              use_depth=True, use_occ=False, train=True, divide_fn='both', pretrain_k=200, total_iters=20000,
              mask_wt=0.15, tex_wt=0.05, depth_wt=0.1, triangle_wt=0.002, pullfar_wt=0.01, deform_wt=0.4,
              symmetry_wt=0.5, camera_wt=0.005, match_wt=0.02, imatch_wt=0.02, decay_ratio=0.1,
-             cycle_loss_wt=0.01, cycle_loss_pretrain_wt=0.02, topk_img=100, topk_mesh=100)
+             cycle_loss_wt=0.01, cycle_loss_pretrain_wt=0.02, topk_img=100, topk_mesh=100,
+             # model / optimiser flags of the same flagfile (used by MeshNet / Trainer)
+             codedim=64, depth_offset=5., rotation_offset=[0.2, 0.0, 0.0, 0.0, -0.2, 0.2], use_scale=False,
+             shape_prior=True, shape_prior_path='config/laptop_wild6d/laptop.obj', prior_deform=True,
+             init_scale=[1, 1, 1], symmetry_idx=1, subdivide=3, no_deform=False, deform_ratio=1.,
+             surface_texture=False, learning_rate=1e-4, vert_lr_ratio=0.01, cam_lr_ratio=0.1, ngpu=1, local_rank=0,
+             model_path='')
     o.update(over)
     return SimpleNamespace(**o)
 

@@ -1,0 +1,77 @@
+"""MeshNet: the full model graph on the B200-native hot path.  API of the reference's model/model.py:41-152
+(`MeshNet(opts)`, `forward(data)` -> (total_loss, aux_output) in training / the 10-tuple in evaluation,
+`load_network`, `.iters`, submodules `mesh, weights, encoder, corr_net, pretrain_corr_net, renderer`).
+The visualisation block (:154-307, logging only) is not reproduced."""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .module.weights import Weights
+from .module.mesh import CanonicalMesh
+from .module.encoder import Encoder
+from .module.correspondence import Correspondence
+from .module.pretrained_corr import PretrainedCorrespondence
+from .module.renderer import Renderer
+from .util import loss_utils as L
+
+
+class MeshNet(nn.Module):
+
+    def __init__(self, opts):
+        super().__init__()
+        self.opts = opts
+        self.mesh = CanonicalMesh(opts)
+        self.weights = Weights(opts)
+        self.encoder = Encoder(opts)
+        self.corr_net = Correspondence(opts)
+        self.pretrain_corr_net = PretrainedCorrespondence(opts, self.mesh, pretrained=True)
+        self.renderer = Renderer(opts, self.mesh)
+        self.iters = 0
+        self.triangle_loss_fn = L.LaplacianLoss(self.mesh.mean_v, self.mesh.faces, average=True)
+
+    def forward(self, data):
+        opts, wts = self.opts, self.weights
+        wts.schedule(self.iters)
+        img, mask, depth, occ, center, length, foc, foc_crop, pp, pp_crop, indices, gt = data
+        bsz = img.shape[0]
+        mean_v = self.mesh.mean_v[None].repeat(bsz, 1, 1)
+        faces = self.mesh.faces[None].repeat(bsz, 1, 1)
+
+        img_feat, mesh_feat, pred_v, rotation, translation, scale = self.encoder(img, mean_v, pp_crop, foc_crop)
+        pointcorr, match, imatch, match_conf = self.corr_net.match(img_feat, mesh_feat, mask, pred_v, pooled=opts.train)
+        tex = self.mesh.get_texture(pred_v, faces, imatch, img)
+        if not opts.train:
+            return pred_v, faces, tex, imatch, match, match_conf, rotation, translation, scale, pointcorr
+
+        (mask_render, tex_render, depth_render, match_gt, imatch_gt, tex_mask, depth_mask, match_mask,
+         depth_weight) = self.renderer.render_all(pred_v, faces, tex, foc_crop, pp_crop, rotation, translation, scale)
+        if opts.use_occ:
+            raise NotImplementedError('use_occ is False in every shipped config')
+        aux = {}
+        aux['mask_loss'] = wts.mask_wt * L.compute_mask_loss(img, mask, mask_render).mean(0)
+        aux['triangle_loss'] = wts.triangle_wt * self.triangle_loss_fn(pred_v) * pred_v.shape[1] / 64.
+        aux['deform_loss'] = wts.deform_wt * F.smooth_l1_loss(pred_v, mean_v, reduction='mean')
+        aux['pullfar_loss'] = wts.pullfar_wt * F.relu(1 - translation[:, :, -1]).mean()
+        aux['symmetry_loss'] = wts.symmetry_wt * self.mesh.compute_symmetry_loss(pred_v, faces)
+        aux['match_loss'] = wts.match_wt * L.compute_match_loss(match, match_gt, match_mask, mask).mean(0)
+        aux['texture_loss'] = wts.tex_wt * L.compute_texture_loss(img, mask, tex_render, tex_mask).mean(0)
+        aux['imatch_loss'] = wts.imatch_wt * L.compute_imatch_loss(imatch, imatch_gt, depth_weight).mean(0)
+        cyc = self.pretrain_corr_net.compute_cycle_loss(img, mask, depth_weight, pointcorr, pooled=True)
+        aux['cycle_loss_pretrain'] = cyc[0] * wts.cycle_loss_pt_wt
+        rot_cyc = self.corr_net.compute_rotation_cycle_loss(img, mask, img_feat, self.encoder)
+        aux['cycle_loss'] = rot_cyc[0] * wts.cycle_loss_wt
+        if opts.use_depth:
+            d_loss, _ = L.compute_depth_loss(depth, depth_render, depth_mask, mask)
+            aux['depth_loss'] = wts.depth_wt * d_loss.mean(0)
+        total_loss = sum(aux.values())
+        aux_output = {'total_loss': total_loss}
+        aux_output.update(aux)
+        return total_loss, aux_output
+
+    def load_network(self, model_path, iter=0):
+        states = torch.load(model_path, map_location='cpu')
+        for name in list(states.keys()):
+            if 'symm_rots' in name or 'triangle_loss_fn' in name or 'flatten_loss_fn' in name:
+                states.pop(name)
+        self.load_state_dict(states, strict=False)

@@ -1,0 +1,112 @@
+"""Canonical category mesh: learnable mean shape, fixed faces, vertex-colour texture lookup, symmetry loss.
+API of the reference's model/module/mesh.py:29-131 (`CanonicalMesh(opts)`: `mean_v`, `faces`, `symm_rots`,
+`get_texture`, `compute_symmetry_loss`).  trimesh / pytorch3d are not available offline: OBJ priors are read with a
+plain parser (the shipped priors are duplicate-free, so `trimesh.load_mesh(process=True)` returns the same arrays)
+and the symmetry regulariser's point sampling + 1-NN search are restated in torch (parity unpinned: the reference
+delegates them to pytorch3d 0.6.1, absent here)."""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import synthetic
+
+
+def read_obj(path):
+    v, f = [], []
+    with open(path) as fh:
+        for line in fh:
+            t = line.split()
+            if not t:
+                continue
+            if t[0] == 'v':
+                v.append([float(x) for x in t[1:4]])
+            elif t[0] == 'f':
+                f.append([int(x.split('/')[0]) - 1 for x in t[1:4]])
+    return np.asarray(v, np.float32), np.asarray(f, np.int64)
+
+
+def get_symm_rots(division):
+    rots = torch.zeros(division, 3, 3)
+    for i in range(division):
+        th = 2 * np.pi / division * i
+        rots[i] = torch.tensor([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]])
+    return rots
+
+
+def sample_points_from_meshes(verts, faces, num_samples):
+    """Area-weighted uniform surface samples, (B, num_samples, 3) (pytorch3d.ops.sample_points_from_meshes semantics)."""
+    B = verts.shape[0]
+    idx = faces.long()
+    v0, v1, v2 = (torch.gather(verts, 1, idx[:, :, k:k + 1].expand(-1, -1, 3)) for k in range(3))
+    areas = 0.5 * torch.cross(v1 - v0, v2 - v0, dim=-1).norm(dim=-1)
+    face_idx = torch.multinomial(areas.detach().clamp_min(1e-12), num_samples, replacement=True)   # B, S
+    u = torch.rand(B, num_samples, 2, device=verts.device)
+    su = u[..., 0].sqrt()
+    w0, w1, w2 = 1 - su, su * (1 - u[..., 1]), su * u[..., 1]
+    pick = lambda t: torch.gather(t, 1, face_idx[:, :, None].expand(-1, -1, 3))
+    return w0[..., None] * pick(v0) + w1[..., None] * pick(v1) + w2[..., None] * pick(v2)
+
+
+def chamfer_single_way(x, y, chunk=16):
+    """mean over x-points of the squared distance to their nearest y-point, averaged over the batch
+    (model/util/chamfer.py chamfer_distance_single_way with the default mean reductions)."""
+    total = x.new_zeros(())
+    for s in range(0, x.shape[0], chunk):
+        d = torch.cdist(x[s:s + chunk], y[s:s + chunk]).pow(2).min(dim=2)[0]     # b, Nx
+        total = total + d.mean(1).sum()
+    return total / x.shape[0]
+
+
+class CanonicalMesh(nn.Module):
+
+    def __init__(self, opts):
+        super().__init__()
+        self.opts = opts
+        self.mean_v, self.faces, self.symm_rots = self.init_shape()
+        self.num_verts, self.num_faces = self.mean_v.shape[0], self.faces.shape[0]
+        if getattr(opts, 'surface_texture', False):
+            raise NotImplementedError('surface textures are off in every shipped config and outside the hot path')
+        self.texture_type = 'vertex'
+
+    def get_texture(self, pred_v, faces, imatch, img):
+        return F.grid_sample(img, imatch.permute(0, 2, 1)[:, None], align_corners=False)[:, :, 0].permute(0, 2, 1)
+
+    def compute_symmetry_loss(self, pred_v, faces, npts=10000):
+        k, bsz = self.symm_rots.shape[0], pred_v.shape[0]
+        v = pred_v[:, None].repeat(1, k, 1, 1).reshape(k * bsz, self.num_verts, 3)
+        f = faces[:, None].repeat(1, k, 1, 1).reshape(k * bsz, self.num_faces, 3)
+        pts = sample_points_from_meshes(v, f, npts)
+        rots = self.symm_rots[None].repeat(bsz, 1, 1, 1).reshape(k * bsz, 3, 3)
+        return chamfer_single_way(v, pts.bmm(rots))
+
+    def _load_prior(self, path):
+        if os.path.exists(path):
+            return read_obj(path)
+        cat = os.path.splitext(os.path.basename(path))[0]
+        return synthetic.load_prior(cat, normalise=False)     # fixture copy of config/<cat>_wild6d/<cat>.obj
+
+    def init_shape(self):
+        opts = self.opts
+        if opts.shape_prior:
+            v, f = self._load_prior(opts.shape_prior_path)
+            verts, faces = torch.from_numpy(v).float(), torch.from_numpy(f)
+            verts = verts - verts.mean(0)
+            verts = verts / verts.abs().max()
+            verts = verts * torch.tensor([float(s) for s in opts.init_scale])
+            learn = opts.prior_deform
+        else:
+            v, f = synthetic.icosphere(opts.subdivide)
+            verts, faces = torch.from_numpy(v).float(), torch.from_numpy(f)
+            verts = verts * torch.tensor([getattr(opts, 'x_scale', 1.), getattr(opts, 'y_scale', 1.), getattr(opts, 'z_scale', 1.)])
+            learn = True
+        if opts.symmetry_idx == 0:
+            symm = get_symm_rots(17)
+        elif opts.symmetry_idx == 1:
+            symm = torch.stack([torch.eye(3), torch.diag(torch.tensor([-1., 1., 1.]))])
+        else:
+            symm = torch.eye(3)[None]
+        return (nn.Parameter(verts.float(), requires_grad=learn), nn.Parameter(faces.long(), requires_grad=False),
+                nn.Parameter(symm, requires_grad=False))

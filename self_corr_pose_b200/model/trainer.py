@@ -1,0 +1,95 @@
+"""Trainer: model set-up, batch reshape, one training step.  API of the reference's model/trainer.py
+(`Trainer(opts)`: `define_model`, `batch_reshape`, `collect_grad`, `save`) plus `step(batch)` = the loop body
+:118-125 with ONE flat-buffer gradient all-reduce between backward and clipping (the mean over ranks that the
+reference's DDP wrapper intends but never performs).  TensorBoard logging / the dataset loop are
+outside the hot path."""
+import os
+
+import torch
+
+from .model import MeshNet
+from .module.optimizers import Optimizers
+from ..dist import FlatGradReducer
+
+
+class Trainer:
+
+    def __init__(self, opts):
+        self.opts = opts
+        self.iters = 0
+
+    @staticmethod
+    def set_bn_eval(m):
+        if m.__class__.__name__ == 'BatchNorm2d':
+            for p in m.parameters():
+                p.requires_grad = False
+
+    def define_model(self):
+        opts = self.opts
+        self.model = MeshNet(opts)
+        if getattr(opts, 'model_path', ''):
+            self.model.load_network(opts.model_path)
+        self.model.apply(self.set_bn_eval)
+        dev = torch.device('cuda', max(getattr(opts, 'local_rank', 0), 0))
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(self.model)
+        self.model = self.model.to(dev)
+        self.device = dev
+        self.optim = Optimizers(opts, self.model)
+        self.reducer = FlatGradReducer([p for n, p in self.model.named_parameters() if 'pretrain_corr_net' not in n])
+        self.model.train()
+        return self.model
+
+    def batch_reshape(self, batch):
+        opts, dev = self.opts, self.device
+        img = batch['img'].float().to(dev, non_blocking=True)
+        mask = batch['mask'].to(dev, non_blocking=True).squeeze(1)
+        depth = batch['depth'].to(dev, non_blocking=True).squeeze(1) if opts.use_depth else None
+        occ = batch['occ'].to(dev).squeeze(1) if opts.use_occ else None
+        foc, pp = batch['foc'].to(dev), batch['pp'].to(dev)
+        # crop intrinsics -> NDC (fp64 end to end, trainer.py:99-101)
+        pp_crop = batch['pp_crop'].to(dev) / (opts.img_size / 2.) - 1.
+        foc_crop = batch['foc_crop'].to(dev) / (opts.img_size / 2.)
+        return (img, mask, depth, occ, batch['center'], batch['length'], foc, foc_crop, pp, pp_crop,
+                batch['idx'].to(dev), None)
+
+    def collect_grad(self):
+        shapenerf, pose = [], []
+        grad_meanv_norm = 0
+        for name, p in self.model.named_parameters():
+            if p.grad is None:
+                continue
+            if 'mean_v' in name:
+                torch.nn.utils.clip_grad_norm_(p, 1.)
+                grad_meanv_norm = p.grad.view(-1).norm(2, -1)
+            elif 'shapenerf' in name:
+                shapenerf.append(p)
+            elif 'pose_predictor' in name:
+                pose.append(p)
+        # one fused NaN check instead of a host sync per parameter (trainer.py:144-147)
+        flat = torch.stack([p.grad.isnan().any() for p in self.model.parameters() if p.grad is not None])
+        if bool(flat.any()):
+            print('bad gradient')
+            self.optim.zero_grad()
+        g_shape = torch.nn.utils.clip_grad_norm_(shapenerf, 1) if shapenerf else 0
+        g_pose = torch.nn.utils.clip_grad_norm_(pose, 0.1) if pose else 0
+        return grad_meanv_norm, g_shape, g_pose
+
+    def step(self, batch):
+        """zero_grad -> forward -> backward -> gradient all-reduce -> clip -> AdamW/OneCycle (trainer.py:118-125)."""
+        self.model.iters = self.iters
+        self.optim.zero_grad()
+        data = self.batch_reshape(batch)
+        total_loss, aux_output = self.model(data)
+        total_loss.mean().backward()
+        self.reducer.reduce()
+        grad = self.collect_grad()
+        self.optim.step(self.iters)
+        self.iters += 1
+        return total_loss, aux_output, grad
+
+    def save(self, prefix, save_dir='.'):
+        if getattr(self.opts, 'local_rank', 0) <= 0:
+            sd = self.model.state_dict()
+            sd['mesh.faces'] = self.model.mesh.faces.cpu()
+            torch.save(sd, os.path.join(save_dir, 'pred_net_{}.pth'.format(prefix)))

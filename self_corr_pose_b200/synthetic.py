@@ -136,3 +136,16 @@ def make_batch(opts, verts, faces, B, device='cuda', seed=0, renderer=None):
     data = (img.contiguous(), mask.contiguous(), depth.contiguous(), to(foc), to(pp))
     enc = tuple(to(t).clone().requires_grad_(True) for t in (img_feat, mesh_feat, pred_v, rot, trans))
     return data, enc
+
+
+def make_trainer_batch(opts, verts, faces, B, device='cuda', seed=0, renderer=None):
+    """The dict a Wild6D dataloader batch would hold (data/dataset_wild6d.py:165-182), synthetic: pixel-unit crop
+    intrinsics in fp64 (focal 3.7*128, principal point 128), mask/depth with a channel axis."""
+    data, _ = make_batch(opts, verts, faces, B, device=device, seed=seed, renderer=renderer)
+    img, mask, depth, foc, pp = data
+    half = opts.img_size / 2.
+    return {'img': img, 'mask': mask[:, None], 'depth': depth[:, None],
+            'center': torch.zeros(B, 2, dtype=torch.int64), 'length': torch.full((B, 2), opts.img_size, dtype=torch.int64),
+            'foc': (foc * half).double(), 'pp': ((pp + 1) * half).double(),
+            'foc_crop': (foc * half).double(), 'pp_crop': ((pp + 1) * half).double(),
+            'idx': torch.arange(B)[:, None]}
