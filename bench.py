@@ -189,7 +189,7 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
     m = mesh_feat.clone().requires_grad_(True)
     fwd = lambda: corr_match(a, m, md, pred_v, hot.corr_net.meshgrid, 10.0, hf, wf, want_full=False, want_pool=True)
     t_f = timeit(fwd)
-    _, pool, mt, im = fwd()
+    _, pool, mt, im, _A = fwd()
     gs = [torch.randn_like(pool), torch.randn_like(mt), torch.randn_like(im)]
     t_b = timeit(lambda: torch.autograd.grad([pool, mt, im], [a, m], gs, retain_graph=True))
     bytes_f = B * (4 * (C * P + N * C + P + 3 * N) + 4 * (P * N // 4 + 2 * N + 3 * P))

@@ -94,23 +94,29 @@ size_t scp_corr_workspace_bytes(int B, int hf, int wf, int N);
  *   match[B,hf*wf,3], imatch[B,2,N]      soft 3D point per pixel / soft 2D location per vertex
  *   rsum[B,hf*wf], csum[B,N]             softmax denominators w.r.t. the reference point tau*1 (saved
  *                                        for the backward; features must be L2-normalised so S <= 1)
+ *   A_pool[B,2,N], csum_pool[B,N]        (optional, may be NULL; need pointcorr_pool) column softmax over the
+ *                                        POOLED similarity times the pooled meshgrid = "grid.bmm(softmax(tau*
+ *                                        pointcorr_src, dim=1))" of pretrained_corr.py:125,131-136, per image
  * Supported shapes: C == 64, wf in {8,16,32,64}, hf*wf a multiple of 128 with 128/wf even.
  */
 int scp_corr_match_forward(const float *img_feat, const float *mesh_feat, const float *mask_down,
                            const float *pred_v, const float *meshgrid, float tau, int B, int hf, int wf, int N,
                            int C, float *pointcorr_full, float *pointcorr_pool, float *match, float *imatch,
-                           float *rsum, float *csum, void *workspace, size_t workspace_bytes, void *stream);
+                           float *rsum, float *csum, float *A_pool, float *csum_pool, void *workspace,
+                           size_t workspace_bytes, void *stream);
 
 /*
  * Backward of the above (autograd of correspondence.py:42-53 in the reference): gradients w.r.t.
  * img_feat and mesh_feat from g_match[B,hf*wf,3], g_imatch[B,2,N] and (optional, may be NULL)
- * g_pointcorr_pool / g_pointcorr_full.  The similarity tile is recomputed, nothing P x N is read back.
+ * g_pointcorr_pool / g_pointcorr_full / g_A_pool (with the saved A_pool, csum_pool).  The similarity tile is
+ * recomputed, nothing P x N is read back.
  */
 int scp_corr_match_backward(const float *img_feat, const float *mesh_feat, const float *mask_down,
                             const float *pred_v, const float *meshgrid, float tau, int B, int hf, int wf, int N,
                             int C, const float *match, const float *imatch, const float *rsum, const float *csum,
                             const float *g_match, const float *g_imatch, const float *g_pointcorr_pool,
-                            const float *g_pointcorr_full, float *g_img_feat, float *g_mesh_feat, void *stream);
+                            const float *g_pointcorr_full, const float *A_pool, const float *csum_pool,
+                            const float *g_A_pool, float *g_img_feat, float *g_mesh_feat, void *stream);
 
 /* ---- frozen DINO ViT-S/8: layer-k key features ----------------------------------------------- */
 /* Replaces DINO.forward (model/module/network/dino.py:102-109) / VisionTransformer.get_specific_tokens

@@ -110,13 +110,36 @@ __device__ __forceinline__ void mma_S(float (&acc)[2][4][4], const float *As, co
     }
 }
 
+// fold 24 per-lane column partials ([c = 2*ni + j][3]) across the 8 row-lanes (lane bits 2..4): 24 -> 12 -> 6 -> 3.
+// Lane (g,t) ends with column c = g of its t-group, i.e. tile column 32*wn + 8*(g>>1) + 2*t + (g&1).
+__device__ __forceinline__ void fold24(const float (&cv)[24], int lane, float (&a3)[3])
+{
+    float a12[12], a6[6];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const float send = b4 ? cv[i] : cv[12 + i], keep = b4 ? cv[12 + i] : cv[i];
+        a12[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const float send = b3 ? a12[i] : a12[6 + i], keep = b3 ? a12[6 + i] : a12[i];
+        a6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float send = b2 ? a6[i] : a6[3 + i], keep = b2 ? a6[3 + i] : a6[i];
+        a3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+}
+
 // ---- forward --------------------------------------------------------------------------------
 // dynamic shared memory layout (floats)
 constexpr int F_AS = 0;
 constexpr int F_BS = F_AS + C * AS;              // 2 buffers
 constexpr int F_VS = F_BS + 2 * BN * BS;         // 2 buffers of [BN][4]: x, y, z, valid
-constexpr int F_COL = F_VS + 2 * BN * 4;         // [4 wm][BN][4]
-constexpr int F_ROW = F_COL + 4 * BN * 4;        // [2 wn][BM][4]
+constexpr int F_COL = F_VS + 2 * BN * 4;         // [2: full-res / pooled][4 wm][BN][4]
+constexpr int F_ROW = F_COL + 2 * 4 * BN * 4;    // [2 wn][BM][4]
 constexpr int F_INFO = F_ROW + 2 * BM * 4;       // mask[BM], gx[BM], gy[BM], pixel[BM] (int)
 constexpr int F_TOTAL = F_INFO + 4 * BM;
 
@@ -134,7 +157,8 @@ __global__ void __launch_bounds__(NT, 2)
 corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__restrict__ mesh_feat,
                 const float *__restrict__ mask_down, const float *__restrict__ pred_v,
                 const float *__restrict__ meshgrid, float *__restrict__ pc_full, float *__restrict__ pc_pool,
-                float *__restrict__ match, float *__restrict__ rsum, float *__restrict__ colpart)
+                float *__restrict__ match, float *__restrict__ rsum, float *__restrict__ colpart,
+                float *__restrict__ colpart_pool)
 {
     extern __shared__ __align__(16) float sm[];
     float *As = sm + F_AS, *Bs = sm + F_BS, *Vs = sm + F_VS, *s_col = sm + F_COL, *s_row = sm + F_ROW;
@@ -176,6 +200,16 @@ corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__rest
         row_pixel(geo, pblk, 32 * wm + 16 * mi + g, pool);
         rpool[mi] = pool;
     }
+    // grid coordinates of the 2x2-pooled pixel of each row pair (bilinear 1/2 of the meshgrid = 2x2 mean)
+    float pgx[2], pgy[2];
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++) {
+        float sx = rgx[2 * mi] + rgx[2 * mi + 1], sy = rgy[2 * mi] + rgy[2 * mi + 1];
+        sx += __shfl_xor_sync(0xffffffffu, sx, 4);
+        sy += __shfl_xor_sync(0xffffffffu, sy, 4);
+        pgx[mi] = 0.25f * sx; pgy[mi] = 0.25f * sy;
+    }
+    const bool want_pool_stats = colpart_pool != nullptr;
     float rl[4] = { 0.f, 0.f, 0.f, 0.f }, rax[4] = { 0.f, 0.f, 0.f, 0.f }, ray[4] = { 0.f, 0.f, 0.f, 0.f },
           raz[4] = { 0.f, 0.f, 0.f, 0.f };
 
@@ -193,9 +227,10 @@ corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__rest
         float acc[2][4][4];
         mma_S(acc, As, Bt, wm, wn, g, t);
 
-        float cv[24];  // column partials: [c = 2*ni + j][sum e, sum e*gx, sum e*gy]
+        float cv[24];   // column partials: [c = 2*ni + j][sum e, sum e*gx, sum e*gy]
+        float cvp[24];  // the same for the 2x2-pooled similarity (column softmax of the pre-training cycle loss)
 #pragma unroll
-        for (int k = 0; k < 24; k++) cv[k] = 0.f;
+        for (int k = 0; k < 24; k++) cv[k] = cvp[k] = 0.f;
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) {
 #pragma unroll
@@ -224,42 +259,40 @@ corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__rest
                     if (pc_pool != nullptr) {
                         float q = sm2[0] + sm2[1];
                         q += __shfl_xor_sync(0xffffffffu, q, 4);   // horizontal neighbour (g ^ 1)
-                        if (valid && !(g & 1))
-                            pc_pool[((size_t)b * (geo.P >> 2) + rpool[mi]) * geo.N + n] = 0.25f * q;
+                        const float pv = 0.25f * q;
+                        if (valid && !(g & 1)) {
+                            pc_pool[((size_t)b * (geo.P >> 2) + rpool[mi]) * geo.N + n] = pv;
+                            if (want_pool_stats) {   // pooled rows containing background pixels underflow to 0
+                                const float ep = exp2f((pv - 1.f) * kexp);
+                                cvp[(2 * ni + j) * 3 + 0] += ep;
+                                cvp[(2 * ni + j) * 3 + 1] += ep * pgx[mi];
+                                cvp[(2 * ni + j) * 3 + 2] += ep * pgy[mi];
+                            }
+                        }
                     }
                 }
             }
         }
-        // fold the 24 column partials across the 8 row-lanes: 24 -> 12 -> 6 -> 3, lane (g,t) ends
-        // with column c = g of its t-group, i.e. tile column 32*wn + 8*(g>>1) + 2*t + (g&1)
         {
-            float a12[12], a6[6], a3[3];
-            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-                const float send = b4 ? cv[i] : cv[12 + i], keep = b4 ? cv[12 + i] : cv[i];
-                a12[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                const float send = b3 ? a12[i] : a12[6 + i], keep = b3 ? a12[6 + i] : a12[i];
-                a6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const float send = b2 ? a6[i] : a6[3 + i], keep = b2 ? a6[3 + i] : a6[i];
-                a3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
+            float a3[3];
             const int cl = 32 * wn + 8 * (g >> 1) + 2 * t + (g & 1);
+            fold24(cv, lane, a3);
             *reinterpret_cast<float4 *>(s_col + (wm * BN + cl) * 4) = make_float4(a3[0], a3[1], a3[2], 0.f);
+            if (want_pool_stats) {
+                fold24(cvp, lane, a3);
+                *reinterpret_cast<float4 *>(s_col + ((4 + wm) * BN + cl) * 4) = make_float4(a3[0], a3[1], a3[2], 0.f);
+            }
         }
         __syncthreads();
         if (tid < BN * 3) {
             const int cl = tid / 3, k = tid - cl * 3;
             if (n0 + cl < geo.N) {
-                const float v = s_col[(0 * BN + cl) * 4 + k] + s_col[(1 * BN + cl) * 4 + k] +
-                                s_col[(2 * BN + cl) * 4 + k] + s_col[(3 * BN + cl) * 4 + k];
-                colpart[(((size_t)b * geo.npblk + pblk) * geo.N + n0 + cl) * 4 + k] = v;
+                const size_t dst = (((size_t)b * geo.npblk + pblk) * geo.N + n0 + cl) * 4 + k;
+                colpart[dst] = s_col[(0 * BN + cl) * 4 + k] + s_col[(1 * BN + cl) * 4 + k] +
+                               s_col[(2 * BN + cl) * 4 + k] + s_col[(3 * BN + cl) * 4 + k];
+                if (want_pool_stats)
+                    colpart_pool[dst] = s_col[(4 * BN + cl) * 4 + k] + s_col[(5 * BN + cl) * 4 + k] +
+                                        s_col[(6 * BN + cl) * 4 + k] + s_col[(7 * BN + cl) * 4 + k];
             }
         }
     }
@@ -293,6 +326,8 @@ corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__rest
 }
 
 // combine the per-row-block column partials: csum[n], imatch[:,n]
+// (launched a second time on the pooled partials with pooled = 1: the uniform fallback then averages the
+// pooled grid, which has the same mean as the full one)
 __global__ void corr_colreduce_kernel(Geo geo, const float *__restrict__ colpart,
                                       const float *__restrict__ meshgrid, float *__restrict__ imatch,
                                       float *__restrict__ csum)
@@ -321,13 +356,16 @@ __global__ void corr_colreduce_kernel(Geo geo, const float *__restrict__ colpart
 // dS[p,n] = mask[p] * ( tau*Pi*(gm[p].v[n] - gm[p].match[p]) + tau*Pm*(gi[:,n].grid[:,p] - gi[:,n].imatch[:,n])
 //                       + 0.25*g_pool[pool(p),n] + g_full[p,n] ),  Pi = e/rsum[p], Pm = e/csum[n]
 // row parameters (8 floats): mask, gx, gy, tau/rsum, gm.x, gm.y, gm.z, gm.match
-// col parameters (8 floats): v.x, v.y, v.z, tau/csum, gi.x, gi.y, gi.imatch, valid
+// col parameters (12 floats): v.x, v.y, v.z, tau/csum | gi.x, gi.y, gi.imatch, valid |
+//                             tau/csum_pool, gA.x, gA.y, gA.A_pool   (pooled column softmax, zeros when unused)
 struct BwdArgs {
     const float *img_feat, *mesh_feat, *mask_down, *pred_v, *meshgrid;
     const float *match, *imatch, *rsum, *csum;
     const float *g_match, *g_imatch, *g_pool, *g_full;
+    const float *A_pool, *csum_pool, *g_A_pool;   // pooled column softmax (may be NULL)
     float *g_img_feat, *g_mesh_feat;
 };
+constexpr int CPS = 12;   // floats per column-parameter record
 
 __device__ __forceinline__ void load_rowparams(const Geo &geo, const BwdArgs &a, int b, int pblk, float *Rp,
                                                int *s_pix, int *s_pool)
@@ -354,58 +392,87 @@ __device__ __forceinline__ void load_colparams(const Geo &geo, const BwdArgs &a,
 {
     if (threadIdx.x < BN) {
         const int n = n0 + threadIdx.x;
-        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
         if (n < geo.N) {
             const float *v = a.pred_v + ((size_t)b * geo.N + n) * 3;
+            const size_t i0 = ((size_t)b * 2 + 0) * geo.N + n, i1 = ((size_t)b * 2 + 1) * geo.N + n;
             const float cs = a.csum[(size_t)b * geo.N + n];
-            const float gi0 = a.g_imatch[((size_t)b * 2 + 0) * geo.N + n], gi1 = a.g_imatch[((size_t)b * 2 + 1) * geo.N + n];
-            const float im0 = a.imatch[((size_t)b * 2 + 0) * geo.N + n], im1 = a.imatch[((size_t)b * 2 + 1) * geo.N + n];
+            const float gi0 = a.g_imatch[i0], gi1 = a.g_imatch[i1];
             q0 = make_float4(v[0], v[1], v[2], cs > 0.f ? geo.tau / cs : 0.f);
-            q1 = make_float4(gi0, gi1, gi0 * im0 + gi1 * im1, 1.f);
+            q1 = make_float4(gi0, gi1, gi0 * a.imatch[i0] + gi1 * a.imatch[i1], 1.f);
+            if (a.g_A_pool != nullptr) {
+                const float cp = a.csum_pool[(size_t)b * geo.N + n];
+                const float ga0 = a.g_A_pool[i0], ga1 = a.g_A_pool[i1];
+                q2 = make_float4(cp > 0.f ? geo.tau / cp : 0.f, ga0, ga1, ga0 * a.A_pool[i0] + ga1 * a.A_pool[i1]);
+            }
         }
-        float4 *dst = reinterpret_cast<float4 *>(Cp + 8 * threadIdx.x);
+        float4 *dst = reinterpret_cast<float4 *>(Cp + CPS * threadIdx.x);
         dst[0] = q0;
         dst[1] = q1;
+        dst[2] = q2;
     }
 }
 
-// turns the S tile in acc into dS (in place) and stores it to Ds[r][n_local]
+// turns the S tile in acc into dS and stores it to Ds[r][n_local]
 __device__ __forceinline__ void make_dS(const Geo &geo, const BwdArgs &a, int b, int n0, float (&acc)[2][4][4],
                                         const float *Rp, const float *Cp, const int *s_pix, const int *s_pool,
                                         float *Ds, int wm, int wn, int g, int t)
 {
     const float kexp = geo.tau * LOG2E;
+    const bool pooled_softmax = a.g_A_pool != nullptr;
 #pragma unroll
     for (int mi = 0; mi < 2; mi++) {
+        const int r_lo = 32 * wm + 16 * mi + g;          // rows r_lo (h = 0) and r_lo + 8 (h = 1): a vertical pair
+        float4 ra[2], rb[2];
+        int pix[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const int r = 32 * wm + 16 * mi + 8 * h + g;
-            const float4 r0 = *reinterpret_cast<const float4 *>(Rp + 8 * r);
-            const float4 r1 = *reinterpret_cast<const float4 *>(Rp + 8 * r + 4);
-            const bool masked = r0.x == 0.f;
-            const int pix = s_pix[r], pool = s_pool[r];
+            ra[h] = *reinterpret_cast<const float4 *>(Rp + 8 * (r_lo + 8 * h));
+            rb[h] = *reinterpret_cast<const float4 *>(Rp + 8 * (r_lo + 8 * h) + 4);
+            pix[h] = s_pix[r_lo + 8 * h];
+        }
+        const int pool = s_pool[r_lo];
+        // pooled grid coordinates of this 2x2 block
+        float pgx = ra[0].y + ra[1].y, pgy = ra[0].z + ra[1].z;
+        pgx += __shfl_xor_sync(0xffffffffu, pgx, 4);
+        pgy += __shfl_xor_sync(0xffffffffu, pgy, 4);
+        pgx *= 0.25f; pgy *= 0.25f;
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) {
-                float d2[2];
+        for (int ni = 0; ni < 4; ni++) {
+            float d2[2][2];
 #pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const int cl = 32 * wn + 8 * ni + 2 * t + j;
-                    const float4 c0 = *reinterpret_cast<const float4 *>(Cp + 8 * cl);
-                    const float4 c1 = *reinterpret_cast<const float4 *>(Cp + 8 * cl + 4);
-                    float d = 0.f;
-                    if (!masked && c1.w != 0.f) {
-                        const float e = exp2f((acc[mi][ni][2 * h + j] - 1.f) * kexp);
-                        const float row_term = r0.w * (r1.x * c0.x + r1.y * c0.y + r1.z * c0.z - r1.w);
-                        const float col_term = c0.w * (c1.x * r0.y + c1.y * r0.z - c1.z);
-                        d = e * (row_term + col_term);
-                        const int n = n0 + cl;
-                        if (a.g_pool != nullptr) d += 0.25f * a.g_pool[((size_t)b * (geo.P >> 2) + pool) * geo.N + n];
-                        if (a.g_full != nullptr) d += a.g_full[((size_t)b * geo.P + pix) * geo.N + n];
-                    }
-                    d2[j] = d;
+            for (int j = 0; j < 2; j++) {
+                const int cl = 32 * wn + 8 * ni + 2 * t + j;
+                const float4 c0 = *reinterpret_cast<const float4 *>(Cp + CPS * cl);
+                const float4 c1 = *reinterpret_cast<const float4 *>(Cp + CPS * cl + 4);
+                const bool valid = c1.w != 0.f;
+                const int n = n0 + cl;
+                // gradient through the pooled similarity: shared by the four pixels of the block
+                float dpool = 0.f;
+                if (a.g_pool != nullptr && valid) dpool = 0.25f * a.g_pool[((size_t)b * (geo.P >> 2) + pool) * geo.N + n];
+                if (pooled_softmax) {
+                    const float4 c2 = *reinterpret_cast<const float4 *>(Cp + CPS * cl + 8);
+                    float q = (ra[0].x == 0.f ? -1e5f : acc[mi][ni][j]) + (ra[1].x == 0.f ? -1e5f : acc[mi][ni][2 + j]);
+                    q += __shfl_xor_sync(0xffffffffu, q, 4);
+                    const float ep = exp2f((0.25f * q - 1.f) * kexp);
+                    if (valid) dpool += 0.25f * ep * c2.x * (c2.y * pgx + c2.z * pgy - c2.w);
                 }
-                *reinterpret_cast<float2 *>(Ds + r * DS + 32 * wn + 8 * ni + 2 * t) = make_float2(d2[0], d2[1]);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    float d = 0.f;
+                    if (ra[h].x != 0.f && valid) {
+                        const float e = exp2f((acc[mi][ni][2 * h + j] - 1.f) * kexp);
+                        const float row_term = ra[h].w * (rb[h].x * c0.x + rb[h].y * c0.y + rb[h].z * c0.z - rb[h].w);
+                        const float col_term = c0.w * (c1.x * ra[h].y + c1.y * ra[h].z - c1.z);
+                        d = e * (row_term + col_term) + dpool;
+                        if (a.g_full != nullptr) d += a.g_full[((size_t)b * geo.P + pix[h]) * geo.N + n];
+                    }
+                    d2[h][j] = d;
+                }
             }
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+                *reinterpret_cast<float2 *>(Ds + (r_lo + 8 * h) * DS + 32 * wn + 8 * ni + 2 * t) = make_float2(d2[h][0], d2[h][1]);
         }
     }
 }
@@ -416,7 +483,7 @@ constexpr int R_BS = R_AS + C * AS;          // 2 buffers
 constexpr int R_DS = R_BS + 2 * BN * BS;
 constexpr int R_RP = R_DS + BM * DS;         // [BM][8]
 constexpr int R_CP = R_RP + BM * 8;          // 2 buffers [BN][8]
-constexpr int R_IX = R_CP + 2 * BN * 8;      // pix[BM], pool[BM] (int)
+constexpr int R_IX = R_CP + 2 * BN * CPS;    // pix[BM], pool[BM] (int)
 constexpr int R_TOTAL = R_IX + 2 * BM;
 
 __global__ void __launch_bounds__(NT, 2) corr_bwd_rows_kernel(Geo geo, BwdArgs a)
@@ -446,13 +513,13 @@ __global__ void __launch_bounds__(NT, 2) corr_bwd_rows_kernel(Geo geo, BwdArgs a
 
     for (int it = 0; it < geo.ntile; it++) {
         const int n0 = it * BN;
-        float *Bt = Bs + (it & 1) * BN * BS, *Ct = Cp + (it & 1) * BN * 8;
+        float *Bt = Bs + (it & 1) * BN * BS, *Ct = Cp + (it & 1) * BN * CPS;
         cp_async_wait<0>();
         __syncthreads();  // tile `it` has landed; every warp is done with iteration it-1 (Ds, Bt reads)
         if (it + 1 < geo.ntile) {
             load_B(geo, Bs + ((it + 1) & 1) * BN * BS, mesh_b, n0 + BN);
             cp_async_commit();
-            load_colparams(geo, a, b, n0 + BN, Cp + ((it + 1) & 1) * BN * 8);
+            load_colparams(geo, a, b, n0 + BN, Cp + ((it + 1) & 1) * BN * CPS);
         }
         float acc[2][4][4];
         mma_S(acc, As, Bt, wm, wn, g, t);
@@ -501,7 +568,7 @@ constexpr int V_BS = V_AS + C * AS;
 constexpr int V_DS = V_BS + BN * BS;
 constexpr int V_RP = V_DS + BM * DS;
 constexpr int V_CP = V_RP + BM * 8;
-constexpr int V_IX = V_CP + BN * 8;
+constexpr int V_IX = V_CP + BN * CPS;
 constexpr int V_TOTAL = V_IX + 2 * BM;
 
 __global__ void __launch_bounds__(NT, 2) corr_bwd_cols_kernel(Geo geo, BwdArgs a)
@@ -584,14 +651,14 @@ using namespace scp::corr;
 extern "C" size_t scp_corr_workspace_bytes(int B, int hf, int wf, int N)
 {
     if (B <= 0 || hf <= 0 || wf <= 0 || N <= 0) return 0;
-    return (size_t)B * ((size_t)hf * wf / BM) * N * 4 * sizeof(float);
+    return 2 * (size_t)B * ((size_t)hf * wf / BM) * N * 4 * sizeof(float);   // full-res + pooled column partials
 }
 
 extern "C" int scp_corr_match_forward(const float *img_feat, const float *mesh_feat, const float *mask_down,
                                       const float *pred_v, const float *meshgrid, float tau, int B, int hf, int wf,
                                       int N, int Cc, float *pointcorr_full, float *pointcorr_pool, float *match,
-                                      float *imatch, float *rsum, float *csum, void *workspace,
-                                      size_t workspace_bytes, void *stream)
+                                      float *imatch, float *rsum, float *csum, float *A_pool, float *csum_pool,
+                                      void *workspace, size_t workspace_bytes, void *stream)
 {
     Geo geo;
     if (!make_geo(geo, B, hf, wf, N, Cc, tau)) {
@@ -606,11 +673,17 @@ extern "C" int scp_corr_match_forward(const float *img_feat, const float *mesh_f
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = F_TOTAL * sizeof(float);
     cudaFuncSetAttribute(corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (A_pool != nullptr && (pointcorr_pool == nullptr || csum_pool == nullptr)) {
+        scp::set_last_error("scp_corr_match_forward: A_pool needs pointcorr_pool and csum_pool");
+        return -1;
+    }
+    float *part = (float *)workspace;
+    float *part_pool = A_pool != nullptr ? part + (size_t)B * geo.npblk * N * 4 : nullptr;
     corr_fwd_kernel<<<dim3(geo.npblk, B), NT, smem, st>>>(geo, img_feat, mesh_feat, mask_down, pred_v, meshgrid,
-                                                         pointcorr_full, pointcorr_pool, match, rsum,
-                                                         (float *)workspace);
-    corr_colreduce_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(geo, (const float *)workspace, meshgrid, imatch,
-                                                                   csum);
+                                                         pointcorr_full, pointcorr_pool, match, rsum, part, part_pool);
+    corr_colreduce_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(geo, part, meshgrid, imatch, csum);
+    if (A_pool != nullptr)
+        corr_colreduce_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(geo, part_pool, meshgrid, A_pool, csum_pool);
     return scp::check_launch("scp_corr_match_forward");
 }
 
@@ -619,6 +692,7 @@ extern "C" int scp_corr_match_backward(const float *img_feat, const float *mesh_
                                        int N, int Cc, const float *match, const float *imatch, const float *rsum,
                                        const float *csum, const float *g_match, const float *g_imatch,
                                        const float *g_pointcorr_pool, const float *g_pointcorr_full,
+                                       const float *A_pool, const float *csum_pool, const float *g_A_pool,
                                        float *g_img_feat, float *g_mesh_feat, void *stream)
 {
     Geo geo;
@@ -630,6 +704,7 @@ extern "C" int scp_corr_match_backward(const float *img_feat, const float *mesh_
     a.img_feat = img_feat; a.mesh_feat = mesh_feat; a.mask_down = mask_down; a.pred_v = pred_v; a.meshgrid = meshgrid;
     a.match = match; a.imatch = imatch; a.rsum = rsum; a.csum = csum;
     a.g_match = g_match; a.g_imatch = g_imatch; a.g_pool = g_pointcorr_pool; a.g_full = g_pointcorr_full;
+    a.A_pool = A_pool; a.csum_pool = csum_pool; a.g_A_pool = (A_pool && csum_pool) ? g_A_pool : nullptr;
     a.g_img_feat = g_img_feat; a.g_mesh_feat = g_mesh_feat;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem_r = R_TOTAL * sizeof(float), smem_v = V_TOTAL * sizeof(float);

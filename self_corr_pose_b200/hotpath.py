@@ -83,7 +83,8 @@ class HotPath:
         aux['triangle_loss'] = wts.triangle_wt * self.triangle_loss_fn(pred_v) * pred_v.shape[1] / 64.
         aux['pullfar_loss'] = wts.pullfar_wt * F.relu(1 - translation[:, :, -1]).mean()
         aux['deform_loss'] = wts.deform_wt * F.smooth_l1_loss(pred_v, mean_v, reduction='mean')
-        cyc = self.pretrain_corr_net.compute_cycle_loss(img, mask, depth_weight, pointcorr, pooled=True)
+        cyc = self.pretrain_corr_net.compute_cycle_loss(img, mask, depth_weight, pointcorr, pooled=True,
+                                                        A=self.corr_net.pool_A)
         aux['cycle_loss_pretrain'] = cyc[0] * wts.cycle_loss_pt_wt
         total = sum(aux.values())
         aux['total_loss'] = total

@@ -57,7 +57,8 @@ class MeshNet(nn.Module):
         aux['match_loss'] = wts.match_wt * L.compute_match_loss(match, match_gt, match_mask, mask).mean(0)
         aux['texture_loss'] = wts.tex_wt * L.compute_texture_loss(img, mask, tex_render, tex_mask).mean(0)
         aux['imatch_loss'] = wts.imatch_wt * L.compute_imatch_loss(imatch, imatch_gt, depth_weight).mean(0)
-        cyc = self.pretrain_corr_net.compute_cycle_loss(img, mask, depth_weight, pointcorr, pooled=True)
+        cyc = self.pretrain_corr_net.compute_cycle_loss(img, mask, depth_weight, pointcorr, pooled=True,
+                                                        A=self.corr_net.pool_A)
         aux['cycle_loss_pretrain'] = cyc[0] * wts.cycle_loss_pt_wt
         rot_cyc = self.corr_net.compute_rotation_cycle_loss(img, mask, img_feat, self.encoder)
         aux['cycle_loss'] = rot_cyc[0] * wts.cycle_loss_wt

@@ -32,6 +32,7 @@ class Correspondence:
         self.k_img, self.k_mesh = opts.topk_img, opts.topk_mesh
         self.hf, self.wf = opts.corr_h, opts.corr_w
         self.meshgrid = make_meshgrid(self.hf, self.wf, device if device is not None else 'cuda')
+        self.pool_A = None
 
     def match(self, img_feat, mesh_feat, mask, pred_v, pooled=False):
         """Returns (pointcorr, match, imatch, match_conf).  `pooled=True` (used by MeshNet.forward in
@@ -40,10 +41,13 @@ class Correspondence:
         bsz, h, w = mask.shape
         opts = self.opts
         mask_down = F.interpolate(mask[:, None], (self.hf, self.wf), mode='nearest').reshape(bsz, -1) * 1.0
-        pc_full, pc_pool, match, imatch = corr_match(img_feat, mesh_feat, mask_down, pred_v.detach(),
-                                                     self.meshgrid, self.tau_img, self.hf, self.wf,
-                                                     want_full=not pooled, want_pool=pooled)
+        pc_full, pc_pool, match, imatch, A_pool = corr_match(img_feat, mesh_feat, mask_down, pred_v.detach(),
+                                                             self.meshgrid, self.tau_img, self.hf, self.wf,
+                                                             want_full=not pooled, want_pool=pooled)
         pointcorr = pc_pool if pooled else pc_full
+        # by-product of the pooled kernel: pooled_grid . softmax(tau * pointcorr_pool, dim=pixels) per image, the
+        # source-side factor of the pre-training cycle loss (PretrainedCorrespondence.compute_cycle_loss(A=...))
+        self.pool_A = A_pool
 
         if opts.train:
             match_conf = None
@@ -87,8 +91,8 @@ class Correspondence:
         grid_flat = grid[0].reshape(2, -1).contiguous()
         tgt_rows = tgt_f.reshape(bsz, C, -1).permute(0, 2, 1).contiguous()
         dummy_v = torch.zeros(bsz, tgt_rows.shape[1], 3, device=src_img.device)
-        _, _, _, cycle_match = corr_match(src_f.reshape(bsz, C, -1), tgt_rows, src_mask_down, dummy_v, grid_flat,
-                                          self.tau_mesh, hf2, wf2, want_full=False, want_pool=False)
+        _, _, _, cycle_match, _ = corr_match(src_f.reshape(bsz, C, -1), tgt_rows, src_mask_down, dummy_v, grid_flat,
+                                             self.tau_mesh, hf2, wf2, want_full=False, want_pool=False)
         # masked target columns: the reference's softmax is uniform there -> mean of the grid
         cycle_match = torch.where(tgt_mask_down[:, None] > 0, cycle_match,
                                   grid_flat.mean(1)[None, :, None].expand_as(cycle_match))

@@ -70,7 +70,7 @@ class PretrainedCorrespondence(nn.Module):
             bsz = src_img.shape[0]
             return self._match_from_feats(feat[:bsz], feat[bsz:], src_mask, tgt_mask, grid)
 
-    def compute_cycle_loss(self, img, mask, depth_weight, pointcorr, pooled=False, feat=None):
+    def compute_cycle_loss(self, img, mask, depth_weight, pointcorr, pooled=False, feat=None, A=None):
         opts = self.opts
         num_verts = pointcorr.shape[-1]
         bs, rep = opts.batch_size, opts.repeat
@@ -78,8 +78,8 @@ class PretrainedCorrespondence(nn.Module):
         B = img.shape[0]
         # pairing as index vectors (divide_by_* applied to arange): big tensors are gathered, never rolled/copied
         src_idx, tgt_idx = self.divide_fn(torch.arange(B, device=img.device), bs, rep)
-        mask_src, mask_tgt = mask[src_idx], mask[tgt_idx]
-        dw_src, dw_tgt = depth_weight[src_idx], depth_weight[tgt_idx]
+        mask_src, mask_tgt = mask.index_select(0, src_idx), mask.index_select(0, tgt_idx)
+        dw_src, dw_tgt = depth_weight.index_select(0, src_idx), depth_weight.index_select(0, tgt_idx)
         bsz = src_idx.shape[0]
         grid = F.interpolate(self.meshgrid.reshape(2, self.hf, self.wf)[None], (h2, w2), mode='bilinear')
         grid_flat = grid.reshape(2, -1)                                         # 2, h2*w2 (same for every pair)
@@ -88,21 +88,26 @@ class PretrainedCorrespondence(nn.Module):
             if feat is None:
                 feat = self.net(img)
             pts_src, pts_tgt, indices_src, indices_tgt, mask_k = self._match_from_feats(
-                feat[src_idx], feat[tgt_idx], mask_src, mask_tgt, grid.expand(bsz, -1, -1, -1))
+                feat.index_select(0, src_idx), feat.index_select(0, tgt_idx), mask_src, mask_tgt,
+                grid.expand(bsz, -1, -1, -1))
 
         if not pooled:  # bilinear 1/2 with align_corners=False == exact 2x2 mean
             pointcorr = F.avg_pool2d(pointcorr.permute(0, 2, 1).reshape(B, num_verts, self.hf, self.wf), 2) \
                 .reshape(B, num_verts, h2 * w2).permute(0, 2, 1)
         # per unique image: Pm = softmax over pixels (used when the image is a source) -> A = grid . Pm
-        Pm = torch.softmax(self.tau_mesh * pointcorr, dim=1)                    # B, h2*w2, N
-        A = torch.matmul(grid_flat[None], Pm)                                   # B, 2, N
-        A_src = A[src_idx] * (dw_src[:, None] >= 0.5)
+        # (A may come pre-computed from the fused correspondence kernel: Correspondence.pool_A)
+        if A is None:
+            Pm = torch.softmax(self.tau_mesh * pointcorr, dim=1)                # B, h2*w2, N
+            A = torch.matmul(grid_flat[None], Pm)                               # B, 2, N
+        A_src = A.index_select(0, src_idx) * (dw_src[:, None] >= 0.5)
         s_src = (dw_src >= 0.5).to(pointcorr.dtype)                             # = column sums of the gated Pm
         # target rows needed: only the k gathered pixels of every pair, straight from the per-image tensor
-        rows = pointcorr[tgt_idx[:, None], indices_tgt]                         # 2B, k, N
+        # (index_select on the flattened rows: its backward is an atomic index_add, not a sorting index_put)
+        flat_rows = (tgt_idx[:, None] * pointcorr.shape[1] + indices_tgt).reshape(-1)
+        rows = pointcorr.reshape(-1, num_verts).index_select(0, flat_rows).reshape(bsz, -1, num_verts)   # 2B, k, N
         Pi = torch.softmax(self.tau_img * rows, dim=2) * (dw_tgt[:, None] >= 0.5)
         num = torch.matmul(A_src, Pi.permute(0, 2, 1))                          # 2B, 2, k
         den = torch.matmul(s_src[:, None], Pi.permute(0, 2, 1)) + 1e-5          # 2B, 1, k
         match = num / den
         cycle_loss = ((match - pts_src).norm(2, 1) * mask_k).mean()
-        return cycle_loss, pts_src, pts_tgt, match, mask_k, img[src_idx], img[tgt_idx]
+        return cycle_loss, pts_src, pts_tgt, match, mask_k, img.index_select(0, src_idx), img.index_select(0, tgt_idx)

@@ -11,7 +11,9 @@ from .. import _lib
 
 class CorrMatchFunction(Function):
     """(img_feat[B,C,P], mesh_feat[B,N,C], mask_down[B,P], pred_v[B,N,3], meshgrid[2,P]) ->
-    (pointcorr_full[B,P,N] | None, pointcorr_pool[B,P/4,N] | None, match[B,P,3], imatch[B,2,N])"""
+    (pointcorr_full[B,P,N] | None, pointcorr_pool[B,P/4,N] | None, match[B,P,3], imatch[B,2,N],
+     A_pool[B,2,N] | None)   -- A_pool = pooled_meshgrid . softmax(tau * pointcorr_pool, dim=pixels), produced with
+    pointcorr_pool (the "grid.bmm(pointcorr_mesh)" factor of the pre-training cycle loss)"""
 
     @staticmethod
     def forward(ctx, img_feat, mesh_feat, mask_down, pred_v, meshgrid, tau, hf, wf, want_full, want_pool):
@@ -30,6 +32,8 @@ class CorrMatchFunction(Function):
         imatch = torch.empty(B, 2, N, **f32)
         rsum = torch.empty(B, P, **f32)
         csum = torch.empty(B, N, **f32)
+        A_pool = torch.empty(B, 2, N, **f32) if want_pool else None
+        csum_pool = torch.empty(B, N, **f32) if want_pool else None
         L = _lib.lib()
         ws_bytes = L.scp_corr_workspace_bytes(B, hf, wf, N)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
@@ -37,15 +41,17 @@ class CorrMatchFunction(Function):
             rc = L.scp_corr_match_forward(
                 _lib.ptr(img_feat), _lib.ptr(mesh_feat), _lib.ptr(mask_down), _lib.ptr(pred_v), _lib.ptr(meshgrid),
                 float(tau), B, hf, wf, N, C, _lib.ptr(pc_full), _lib.ptr(pc_pool), _lib.ptr(match),
-                _lib.ptr(imatch), _lib.ptr(rsum), _lib.ptr(csum), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+                _lib.ptr(imatch), _lib.ptr(rsum), _lib.ptr(csum), _lib.ptr(A_pool), _lib.ptr(csum_pool), _lib.ptr(ws),
+                ws_bytes, _lib.stream_ptr(dev))
         _lib.check(rc, 'scp_corr_match_forward')
         ctx.save_for_backward(img_feat, mesh_feat, mask_down, pred_v, meshgrid, match, imatch, rsum, csum)
+        ctx.pool_saved = (A_pool, csum_pool)
         ctx.geom = (float(tau), B, hf, wf, N, C)
         ctx.set_materialize_grads(False)
-        return pc_full, pc_pool, match, imatch
+        return pc_full, pc_pool, match, imatch, A_pool
 
     @staticmethod
-    def backward(ctx, g_full, g_pool, g_match, g_imatch):
+    def backward(ctx, g_full, g_pool, g_match, g_imatch, g_A):
         img_feat, mesh_feat, mask_down, pred_v, meshgrid, match, imatch, rsum, csum = ctx.saved_tensors
         tau, B, hf, wf, N, C = ctx.geom
         dev = img_feat.device
@@ -54,7 +60,8 @@ class CorrMatchFunction(Function):
             if g is None:
                 return None
             return g.float().contiguous()
-        g_full, g_pool = prep(g_full, None), prep(g_pool, None)
+        g_full, g_pool, g_A = prep(g_full, None), prep(g_pool, None), prep(g_A, None)
+        A_pool, csum_pool = ctx.pool_saved
         g_match = prep(g_match, None) if g_match is not None else torch.zeros_like(match)
         g_imatch = prep(g_imatch, None) if g_imatch is not None else torch.zeros_like(imatch)
         g_img = torch.empty_like(img_feat)
@@ -63,8 +70,8 @@ class CorrMatchFunction(Function):
             rc = _lib.lib().scp_corr_match_backward(
                 _lib.ptr(img_feat), _lib.ptr(mesh_feat), _lib.ptr(mask_down), _lib.ptr(pred_v), _lib.ptr(meshgrid),
                 tau, B, hf, wf, N, C, _lib.ptr(match), _lib.ptr(imatch), _lib.ptr(rsum), _lib.ptr(csum),
-                _lib.ptr(g_match), _lib.ptr(g_imatch), _lib.ptr(g_pool), _lib.ptr(g_full), _lib.ptr(g_img),
-                _lib.ptr(g_mesh), _lib.stream_ptr(dev))
+                _lib.ptr(g_match), _lib.ptr(g_imatch), _lib.ptr(g_pool), _lib.ptr(g_full), _lib.ptr(A_pool),
+                _lib.ptr(csum_pool), _lib.ptr(g_A), _lib.ptr(g_img), _lib.ptr(g_mesh), _lib.stream_ptr(dev))
         _lib.check(rc, 'scp_corr_match_backward')
         return g_img, g_mesh, None, None, None, None, None, None, None, None
 

@@ -44,14 +44,18 @@ def pooled(pc, hf, wf):
         .reshape(B, N, -1).permute(0, 2, 1)
 
 
-def oracle_fwd_bwd(img_feat, mesh_feat, mask, pred_v, hf, wf, w_match, w_imatch, w_pool, dtype=torch.float32):
+def oracle_fwd_bwd(img_feat, mesh_feat, mask, pred_v, hf, wf, w_match, w_imatch, w_pool, w_A, dtype=torch.float32):
     img_feat = img_feat.detach().clone().to(dtype).requires_grad_(True)
     mesh_feat = mesh_feat.detach().clone().to(dtype).requires_grad_(True)
     pc, match_up, imatch, match3d = ocorr.match(img_feat, mesh_feat, mask.to(dtype), pred_v.to(dtype), hf, wf)
     pool = pooled(pc, hf, wf)
-    loss = (match3d * w_match.to(dtype)).sum() + (imatch * w_imatch.to(dtype)).sum() + (pool * w_pool.to(dtype)).sum()
+    # source-side factor of the pre-training cycle loss (pretrained_corr.py:125,131-136): grid . softmax over pixels
+    grid2 = F.interpolate(ocorr.meshgrid(hf, wf).reshape(1, 2, hf, wf), (hf // 2, wf // 2), mode='bilinear').reshape(2, -1)
+    A = torch.matmul(grid2.to(dtype)[None], torch.softmax(10.0 * pool, dim=1))
+    loss = (match3d * w_match.to(dtype)).sum() + (imatch * w_imatch.to(dtype)).sum() + (pool * w_pool.to(dtype)).sum() \
+        + (A * w_A.to(dtype)).sum()
     loss.backward()
-    return pc.detach(), pool.detach(), match3d.detach(), imatch.detach(), img_feat.grad, mesh_feat.grad
+    return pc.detach(), pool.detach(), match3d.detach(), imatch.detach(), A.detach(), img_feat.grad, mesh_feat.grad
 
 
 @pytest.mark.parametrize('B,hf,wf,N', [(2, 16, 16, 70), (2, 32, 32, 1280), (2, 64, 64, 995), (1, 64, 64, 64)])
@@ -63,21 +67,23 @@ def test_corr_match_forward_backward(B, hf, wf, N):
     w_match = torch.randn(B, hf * wf, 3, generator=g)
     w_imatch = torch.randn(B, 2, N, generator=g)
     w_pool = torch.randn(B, hf * wf // 4, N, generator=g) * 0.01
-    o = oracle_fwd_bwd(img_feat, mesh_feat, mask, pred_v, hf, wf, w_match, w_imatch, w_pool)
-    o64 = oracle_fwd_bwd(img_feat, mesh_feat, mask, pred_v, hf, wf, w_match, w_imatch, w_pool, torch.float64)
+    w_A = torch.randn(B, 2, N, generator=g)
+    o = oracle_fwd_bwd(img_feat, mesh_feat, mask, pred_v, hf, wf, w_match, w_imatch, w_pool, w_A)
+    o64 = oracle_fwd_bwd(img_feat, mesh_feat, mask, pred_v, hf, wf, w_match, w_imatch, w_pool, w_A, torch.float64)
 
     mask_down = F.interpolate(mask[:, None], (hf, wf), mode='nearest').reshape(B, -1)
     grid = make_meshgrid(hf, wf, 'cuda')
     torch.testing.assert_close(grid.cpu(), ocorr.meshgrid(hf, wf), rtol=0, atol=0)
     a = img_feat.cuda().requires_grad_(True)
     m = mesh_feat.cuda().requires_grad_(True)
-    pc_full, pc_pool, match, imatch = corr_match(a, m, mask_down.cuda(), pred_v.cuda(), grid, 10.0, hf, wf,
+    pc_full, pc_pool, match, imatch, A_pool = corr_match(a, m, mask_down.cuda(), pred_v.cuda(), grid, 10.0, hf, wf,
                                                  want_full=True, want_pool=True)
-    loss = (match * w_match.cuda()).sum() + (imatch * w_imatch.cuda()).sum() + (pc_pool * w_pool.cuda()).sum()
+    loss = (match * w_match.cuda()).sum() + (imatch * w_imatch.cuda()).sum() + (pc_pool * w_pool.cuda()).sum() \
+        + (A_pool * w_A.cuda()).sum()
     loss.backward()
     torch.cuda.synchronize()
-    got = (pc_full, pc_pool, match, imatch, a.grad, m.grad)
-    names = ('pointcorr', 'pointcorr_pool', 'match', 'imatch', 'g_img_feat', 'g_mesh_feat')
+    got = (pc_full, pc_pool, match, imatch, A_pool, a.grad, m.grad)
+    names = ('pointcorr', 'pointcorr_pool', 'match', 'imatch', 'A_pool', 'g_img_feat', 'g_mesh_feat')
     report = {}
     for name, x, ref, ref64 in zip(names, got, o, o64):
         report[name] = (rel(x, ref64), rel(ref, ref64), frac(x, ref))

@@ -19,16 +19,16 @@ res = {}
 for full in (False, True):
     def fwd():
         return corr_match(img_feat, mesh_feat, mask_down, pred_v, grid, 10.0, hf, wf, want_full=full, want_pool=not full)
-    pf, pp, m, im = fwd()
+    pf, pp, m, im, _A = fwd()
     gpc = torch.randn_like(pf if full else pp); gm = torch.randn_like(m); gi = torch.randn_like(im)
     for _ in range(3):
-        pf, pp, m, im = fwd(); torch.autograd.backward([pf if full else pp, m, im], [gpc, gm, gi])
+        pf, pp, m, im, _A = fwd(); torch.autograd.backward([pf if full else pp, m, im], [gpc, gm, gi])
     torch.cuda.synchronize()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     tf = tb = 0.0
     n = 10
     for _ in range(n):
-        e[0].record(); pf, pp, m, im = fwd(); e[1].record()
+        e[0].record(); pf, pp, m, im, _A = fwd(); e[1].record()
         torch.autograd.backward([pf if full else pp, m, im], [gpc, gm, gi]); e[2].record()
         torch.cuda.synchronize()
         tf += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
