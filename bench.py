@@ -34,6 +34,7 @@ def parse():
     ap.add_argument('--cpu-batch', type=int, default=2, help='images in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-breakdown', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
     return ap.parse_args()
 
 
@@ -257,10 +258,25 @@ def main():
     mean_v_param = torch.nn.Parameter(mean_v.clone().to(dev))
     reducer = FlatGradReducer([mean_v_param])
 
+    graphed = None
+    if not args.no_graph:
+        try:   # whole step (forward + backward, ~900 launches) as ONE CUDA graph over static buffers
+            graphed = hot.capture(data, enc)
+        except Exception as e:   # noqa: BLE001 -- report and continue eagerly
+            print('CUDA graph capture failed, running eagerly: %r' % (e,), file=sys.stderr)
+            graphed = None
+
     def step(d):
-        total, aux = hot.step(d, enc)
+        if graphed is not None:
+            if d is not data:
+                graphed.load(data=d)
+            total = graphed.replay()
+            pred_v_grad = graphed.grads[2]
+        else:
+            total, aux = hot.step(d, enc)
+            pred_v_grad = enc[2].grad
         if world > 1:   # the single flat-buffer gradient all-reduce of the data-parallel step (mean over ranks)
-            mean_v_param.grad = enc[2].grad.sum(0)
+            mean_v_param.grad = pred_v_grad.sum(0)
             reducer.reduce()
         return total
 
@@ -332,7 +348,8 @@ def main():
                                'layer-9 keys + pseudo-matches + pre-train cycle loss; encoder outputs are inputs'
                                % (v.shape[0], f.shape[0]),
                    'images_per_gpu': B, 'img_size': 256, 'mesh': args.mesh, 'parallelism': 'dp%d' % world,
-                   'l2': 'working set per step (~1 GB) exceeds the 126 MB L2; no explicit flush'},
+                   'l2': 'working set per step (~1 GB) exceeds the 126 MB L2; no explicit flush',
+                   'cuda_graph': graphed is not None},
         'e2e': {'value': e2e_value, 'unit': 'images/sec', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': hot.GPU_LAUNCHES * args.steps,

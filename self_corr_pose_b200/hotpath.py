@@ -99,3 +99,44 @@ class HotPath:
         total, aux = self.forward(data, enc)
         total.backward()
         return total, aux
+
+    def capture(self, data, enc, warmup=3):
+        """Captures one whole step (forward + backward, ~900 kernel launches) into a CUDA graph over STATIC copies
+        of `data` / `enc`.  Returns a GraphedStep: `.load(data, enc)` copies new values into the static buffers,
+        `.replay()` runs the step, `.loss` / `.aux` / `.grads` are the static outputs."""
+        static_data = tuple(t.clone() for t in data)
+        static_enc = tuple(t.detach().clone().requires_grad_(True) for t in enc)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(static_data, static_enc)
+        torch.cuda.current_stream().wait_stream(side)
+        for t in static_enc:
+            t.grad = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            total, aux = self.forward(static_data, static_enc)
+            total.backward()
+        return GraphedStep(graph, static_data, static_enc, total, aux)
+
+
+class GraphedStep:
+    def __init__(self, graph, data, enc, loss, aux):
+        self.graph, self.data, self.enc, self.loss, self.aux = graph, data, enc, loss, aux
+
+    @property
+    def grads(self):
+        return tuple(t.grad for t in self.enc)
+
+    def load(self, data=None, enc=None):
+        if data is not None:
+            for dst, src in zip(self.data, data):
+                dst.copy_(src, non_blocking=True)
+        if enc is not None:
+            for dst, src in zip(self.enc, enc):
+                dst.data.copy_(src.detach(), non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.loss

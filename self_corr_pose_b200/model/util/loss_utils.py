@@ -93,8 +93,12 @@ def compute_texture_loss(img, mask, tex_pred, tex_mask):
 
 def compute_depth_loss(depth, depth_pred, depth_mask, mask):
     keep = (mask * depth_mask).detach()
-    # one batch-global scale; the gradient flows through it (Appendix A.8 of SURVEY.md)
-    depth_scale = depth_pred[depth_mask != 0].mean() / depth[mask * depth != 0].mean()
+    # one batch-global scale; the gradient flows through it (Appendix A.8 of SURVEY.md).  The reference takes
+    # the means over boolean-indexed tensors (loss_utils.py:276, a host sync); masked sums give the same value
+    # without the data-dependent shape, so the step can be captured in a CUDA graph.
+    sel_pred = (depth_mask != 0).to(depth_pred.dtype)
+    sel_gt = (mask * depth != 0).to(depth.dtype)
+    depth_scale = ((depth_pred * sel_pred).sum() / sel_pred.sum()) / ((depth * sel_gt).sum() / sel_gt.sum())
     diff = depth_pred - depth_scale * depth
     diff = diff.masked_fill((keep == 0) | (depth == 0), 0)
     loss = diff.pow(2)
