@@ -35,9 +35,21 @@ def vertex_normals(vertices, faces):
     return F.normalize(normals, eps=1e-6, dim=1).reshape(B, nv, 3)
 
 
+_CONST_CACHE = {}
+
+
+def _const(values, device):
+    """Small constant vectors given as python lists (eye, up, light colours): uploaded once per device and cached,
+    so that no host->device copy happens inside a CUDA-graph capture."""
+    key = (tuple(float(v) for v in values), str(device))
+    if key not in _CONST_CACHE:
+        _CONST_CACHE[key] = torch.tensor([float(v) for v in values], dtype=torch.float32, device=device)
+    return _CONST_CACHE[key]
+
+
 def _as_vec(x, device, B):
     if isinstance(x, (list, tuple)):
-        x = torch.tensor(x, dtype=torch.float32, device=device)
+        x = _const(x, device)
     elif isinstance(x, np.ndarray):
         x = torch.from_numpy(x).to(device)
     else:
@@ -76,7 +88,7 @@ def perspective(vertices, angle=30.):
 
 def _as_row(x, device):
     if isinstance(x, (list, tuple)):
-        x = torch.tensor(x, dtype=torch.float32, device=device)
+        x = _const(x, device)
     elif isinstance(x, np.ndarray):
         x = torch.from_numpy(x).float().to(device)
     return x[None, :] if x.ndimension() == 1 else x
