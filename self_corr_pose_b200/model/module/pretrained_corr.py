@@ -46,11 +46,22 @@ class PretrainedCorrespondence(nn.Module):
         fs = self.feat_size
         src_mask_down = F.interpolate(src_mask[:, None], (fs, fs), mode='nearest').reshape(bsz, -1) * 1.0
         tgt_mask_down = F.interpolate(tgt_mask[:, None], (fs, fs), mode='nearest').reshape(bsz, -1) * 1.0
-        mask_down = src_mask_down[:, :, None] * tgt_mask_down[:, None, :]
-        pointcorr = src_feat.permute(0, 2, 1).bmm(tgt_feat)
-        pointcorr = pointcorr * (mask_down > 0) - 1e5 * (mask_down == 0)
-        max_bw = pointcorr.max(1).indices
-        max_fw = pointcorr.max(2).indices
+        # arg-max of the masked similarity in both directions (pretrained_corr.py:85-89) without materialising the
+        # mask product: background entries are exactly -1e5 in the reference, so (a) an unmasked row/column never
+        # picks a masked partner -> a large negative bias on masked partners gives the same arg-max, folded into
+        # the GEMM as two extra channels; (b) a fully masked row/column is constant -> first index (0).
+        neg = -1e5
+        ones = torch.ones_like(src_mask_down)[:, None]
+        a = torch.cat([src_feat, ones, (neg * (src_mask_down == 0))[:, None]], dim=1)           # b, C+2, hw(src)
+        b = torch.cat([tgt_feat, (neg * (tgt_mask_down == 0))[:, None], ones], dim=1)           # b, C+2, hw(tgt)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True      # tensor-core GEMM; the features are bf16-accurate already
+        try:
+            pointcorr = a.permute(0, 2, 1).bmm(b)                                              # b, hw(src), hw(tgt)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        max_bw = pointcorr.max(1).indices * (tgt_mask_down > 0)      # per target pixel: best source pixel
+        max_fw = pointcorr.max(2).indices * (src_mask_down > 0)      # per source pixel: best target pixel
         max_cy = torch.gather(max_fw, -1, max_bw)
         grid = grid.reshape(bsz, 2, -1)
         match = torch.gather(grid, -1, max_bw[:, None].expand(-1, 2, -1))
