@@ -162,6 +162,9 @@ int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float *feat, int
 int scp_gemm_bf16_tn(const void *A, const void *W, const float *bias, float *C, int M, int N, int K, void *stream);
 /* o[B][T][384] = softmax(q k^T / 8) v per head; q,k,v bf16 [B*6][T][64] (vision_transformer_flexible.py:85-101). */
 int scp_attention_bf16(const void *q, const void *k, const void *v, void *o, int B, int T, void *stream);
+/* Same result on the tcgen05 tensor cores (S and O tiles in TMEM, TMA-staged operands); v is passed TRANSPOSED:
+ * vt[B*6][64][Tp] bf16, Tp = T rounded up to a multiple of 8, columns t >= T zero.  Used by scp_vit_s8_keys. */
+int scp_attention_tc5(const void *q, const void *k, const void *vt, void *o, int B, int T, void *stream);
 
 #ifdef __cplusplus
 }

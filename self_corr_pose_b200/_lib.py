@@ -45,6 +45,7 @@ class VitWeights(ctypes.Structure):
 _SIGNATURES.update({
     'scp_gemm_bf16_tn': ([_f, _f, _f, _f, _i, _i, _i, _f], _i),
     'scp_attention_bf16': ([_f, _f, _f, _f, _i, _i, _f], _i),
+    'scp_attention_tc5': ([_f, _f, _f, _f, _i, _i, _f], _i),
     'scp_vit_workspace_bytes': ([_i, _i, _i], _sz),
     'scp_vit_s8_keys': ([ctypes.POINTER(VitWeights), _f, _f, _i, _i, _i, _i, _f, _sz, _f], _i),
 })

@@ -144,6 +144,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         tc5::tma_store_commit();
                     }
                 } else if constexpr (Epi::kStaged) {
+                    if constexpr (Epi::kMixed) {   // some column ranges are contiguous along the rows instead
+                        if (epi.direct(n_blk * BN + c0)) {
+                            if (row0 + lane < s.M) epi(row0 + lane, n_blk * BN + c0, v);
+                            continue;
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; j++) stg[lane * 33 + j] = v[j];
                     __syncwarp();
@@ -186,13 +192,14 @@ inline EncodeTiledFn encode_tiled_fn()
 }
 
 // row-major bf16 matrix [rows][inner] (inner contiguous, row pitch `pitch_elems`), box = 64 x 128, SWIZZLE_128B
-inline bool make_tmap_bf16(CUtensorMap *m, const void *ptr, uint64_t inner, uint64_t rows, uint64_t pitch_elems)
+inline bool make_tmap_bf16(CUtensorMap *m, const void *ptr, uint64_t inner, uint64_t rows, uint64_t pitch_elems,
+                           uint32_t box_rows = BM)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = { inner, rows };
     const cuuint64_t strides[1] = { pitch_elems * 2 };
-    const cuuint32_t box[2] = { (cuuint32_t)BK, (cuuint32_t)BM };
+    const cuuint32_t box[2] = { (cuuint32_t)BK, (cuuint32_t)box_rows };
     const cuuint32_t estr[2] = { 1, 1 };
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -12,10 +12,12 @@
 //   LayerNorm : one warp per token, fp32 statistics, bf16 output feeding the next TMA load
 // Activations: residual stream fp32, GEMM operands bf16, accumulation fp32.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "../../include/scp_b200.h"
 #include "scp_common.cuh"
 #include "scp_gemm.cuh"
+#include "scp_fa.cuh"
 
 namespace scp {
 namespace vit {
@@ -98,6 +100,7 @@ __device__ __forceinline__ float erf_as(float x)
 struct EpiPatch {  // tokens: x[b][1+p][:] = acc + bias + pos[p]
     static constexpr bool kStaged = true;
     static constexpr bool kTmaReduceAdd = false;
+    static constexpr bool kMixed = false;
     float *x; const float *bias, *pos; int np, T;
     __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
@@ -110,9 +113,40 @@ struct EpiPatch {  // tokens: x[b][1+p][:] = acc + bias + pos[p]
     }
 };
 
-struct EpiQKV {  // head-major split: q/k/v[b][h][t][64] bf16
+struct EpiQKV {  // head-major split: q/k[b][h][t][64] bf16, and v TRANSPOSED vT[b][h][64][Tp] (keys contiguous: the
+                 // K-major B operand of the P.V tensor-core product); Tp = T rounded up to 8, pad columns stay zero
     static constexpr bool kStaged = true;
     static constexpr bool kTmaReduceAdd = false;
+    static constexpr bool kMixed = true;
+    bf16 *q, *k, *vt; const float *bias; int T, Tp;
+    __device__ __forceinline__ bool direct(int col0) const { return col0 >= 2 * D; }
+    __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
+    {
+        const int which = col / D, c = col - which * D, h = c >> 6, d = c & 63;
+        int b = row0 / T, t = row0 - b * T;
+        bf16 *base = (which == 0 ? q : k) + (long)h * T * HD + d;
+        const float bb = __ldg(bias + col);
+#pragma unroll 4
+        for (int r = 0; r < nrows; r++) {
+            base[((long)b * HEADS * T + t) * HD] = __float2bfloat16(stg[r * 33 + lane] + bb);
+            if (++t == T) { t = 0; b++; }
+        }
+    }
+    // v columns, lane = row (token): consecutive lanes write consecutive tokens of one vT row
+    __device__ __forceinline__ void operator()(int row, int col0, const float (&a)[32]) const
+    {
+        const int c = col0 - 2 * D, h = c >> 6, d0 = c & 63;
+        const int b = row / T, t = row - b * T;
+        bf16 *dst = vt + (((long)b * HEADS + h) * HD + d0) * Tp + t;
+#pragma unroll
+        for (int i = 0; i < 32; i++) dst[(long)i * Tp] = __float2bfloat16(a[i] + __ldg(bias + col0 + i));
+    }
+};
+
+struct EpiQKVPlain {  // q/k/v[b][h][t][64] bf16 (layout of the mma.sync attention variant)
+    static constexpr bool kStaged = true;
+    static constexpr bool kTmaReduceAdd = false;
+    static constexpr bool kMixed = false;
     bf16 *q, *k, *v; const float *bias; int T;
     __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
@@ -131,6 +165,7 @@ struct EpiQKV {  // head-major split: q/k/v[b][h][t][64] bf16
 struct EpiResidual {  // x[tile] += acc + bias: fp32 residual stream updated by TMA reduce-add (no SM loads)
     static constexpr bool kStaged = false;
     static constexpr bool kTmaReduceAdd = true;
+    static constexpr bool kMixed = false;
     const float *bias;
     __device__ void operator()(int, int, const float (&)[32]) const {}
 };
@@ -138,6 +173,7 @@ struct EpiResidual {  // x[tile] += acc + bias: fp32 residual stream updated by 
 struct EpiGelu {  // h[row][:] = gelu_erf(acc + bias)  bf16
     static constexpr bool kStaged = true;
     static constexpr bool kTmaReduceAdd = false;
+    static constexpr bool kMixed = false;
     bf16 *h; const float *bias; int ld;
     __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
@@ -154,6 +190,7 @@ struct EpiGelu {  // h[row][:] = gelu_erf(acc + bias)  bf16
 struct EpiKeys {  // feat[b][col][t-1] = acc + bias for patch tokens (CLS dropped); (b, 384, hp, wp) fp32
     static constexpr bool kStaged = false;   // output is contiguous along the rows (tokens): lane = row
     static constexpr bool kTmaReduceAdd = false;
+    static constexpr bool kMixed = false;
     float *feat; const float *bias; int T;
     __device__ void operator()(int row, int col0, const float (&a)[32]) const
     {
@@ -168,6 +205,7 @@ struct EpiKeys {  // feat[b][col][t-1] = acc + bias for patch tokens (CLS droppe
 struct EpiPlain {  // C[row][:] = acc (+ bias)   fp32, used by the exported test GEMM
     static constexpr bool kStaged = true;
     static constexpr bool kTmaReduceAdd = false;
+    static constexpr bool kMixed = false;
     float *c; const float *bias; int ld;
     __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
     {
@@ -365,12 +403,42 @@ extern "C" int scp_attention_bf16(const void *q, const void *k, const void *v, v
     return scp::check_launch("scp_attention_bf16");
 }
 
+static int launch_fa(const bf16 *q, const bf16 *k, const bf16 *vt, bf16 *o, int B, int T, int Tp, cudaStream_t st)
+{
+    using scp::fa::BQ; using scp::fa::BKV; using scp::fa::fa_fwd_kernel;
+    CUtensorMap tq, tk, tv;
+    const uint64_t rows = (uint64_t)B * HEADS * T;
+    if (!scp::gemm::make_tmap_bf16(&tq, q, HD, rows, HD, BQ) || !scp::gemm::make_tmap_bf16(&tk, k, HD, rows, HD, BKV) ||
+        !scp::gemm::make_tmap_bf16(&tv, vt, Tp, (uint64_t)B * HEADS * HD, Tp, 64)) {
+        scp::set_last_error("tcgen05 attention: cuTensorMapEncodeTiled failed");
+        return -1;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scp::fa::SMEM_BYTES);
+        attr_done = true;
+    }
+    fa_fwd_kernel<<<dim3((T + BQ - 1) / BQ, B * HEADS), scp::fa::NTHREADS, scp::fa::SMEM_BYTES, st>>>(
+        tq, tk, tv, o, T, 0.125f * 1.4426950408889634f);
+    return 0;
+}
+
+// q,k: [B*6][T][64] bf16; vt: [B*6][64][Tp] bf16 with Tp = ceil(T/8)*8 and zero padding; o: [B][T][384] bf16
+extern "C" int scp_attention_tc5(const void *q, const void *k, const void *vt, void *o, int B, int T, void *stream)
+{
+    if (B <= 0 || T <= 0) { scp::set_last_error("scp_attention_tc5: bad shape"); return -1; }
+    const int Tp = (T + 7) / 8 * 8;
+    int rc = launch_fa((const bf16 *)q, (const bf16 *)k, (const bf16 *)vt, (bf16 *)o, B, T, Tp, (cudaStream_t)stream);
+    return rc ? rc : scp::check_launch("scp_attention_tc5");
+}
+
 extern "C" size_t scp_vit_workspace_bytes(int B, int H, int W)
 {
     if (B <= 0 || H <= 0 || W <= 0 || H % PATCH || W % PATCH) return 0;
     const size_t np = (size_t)(H / PATCH) * (W / PATCH), T = np + 1, M = (size_t)B * T;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
-    return al(M * D * 4) + al(M * D * 2) * 5 + al(M * MLP * 2) + al((size_t)B * np * KP * 2);
+    const size_t Tp = (T + 7) / 8 * 8;
+    return al(M * D * 4) + al(M * D * 2) * 4 + al((size_t)B * D * Tp * 2) + al(M * MLP * 2) + al((size_t)B * np * KP * 2);
 }
 
 extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float *feat, int B, int H, int W,
@@ -393,7 +461,9 @@ extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float
     bf16 *y = (bf16 *)p; p += al(M * D * 2);
     bf16 *qb = (bf16 *)p; p += al(M * D * 2);
     bf16 *kb = (bf16 *)p; p += al(M * D * 2);
-    bf16 *vb = (bf16 *)p; p += al(M * D * 2);
+    const int Tp = (T + 7) / 8 * 8;
+    bf16 *vb = (bf16 *)p; p += al((size_t)B * D * Tp * 2);   // V transposed per head: [B][6][64][Tp]
+    cudaMemsetAsync(vb, 0, (size_t)B * D * Tp * 2, st);     // pad columns t in [T, Tp) must be zero
     bf16 *ob = (bf16 *)p; p += al(M * D * 2);
     bf16 *hb = (bf16 *)p; p += al(M * MLP * 2);
     bf16 *a0 = (bf16 *)p;
@@ -407,14 +477,22 @@ extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float
         EpiPatch epi{ x, w->patch_b, w->pos, np, T };
         if ((rc = scp::gemm::launch(a0, KP, w->patch_w, KP, B * np, D, KP, epi, st))) return rc;
     }
+    const char *att_env = getenv("SCP_VIT_ATTENTION");
+    const bool use_tc5_attention = !(att_env && att_env[0] == 'm');
     const unsigned ln_grid = (unsigned)((M + 7) / 8);
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     for (int i = 0; i < n_blocks; i++) {
         const scp_vit_block &bw = w->blocks[i];
         layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, bw.ln1_w, bw.ln1_b, y, M);
-        EpiQKV eq{ qb, kb, vb, bw.qkv_b, T };
-        if ((rc = scp::gemm::launch(y, D, bw.qkv_w, D, (int)M, 3 * D, D, eq, st))) return rc;
-        attention_kernel<<<dim3((T + AQ - 1) / AQ, B * HEADS), 128, 0, st>>>(qb, kb, vb, ob, T, scale_log2e);
+        if (use_tc5_attention) {   // tcgen05 flash attention: V transposed per head
+            EpiQKV eq{ qb, kb, vb, bw.qkv_b, T, Tp };
+            if ((rc = scp::gemm::launch(y, D, bw.qkv_w, D, (int)M, 3 * D, D, eq, st))) return rc;
+            if ((rc = launch_fa(qb, kb, vb, ob, B, T, Tp, st))) return rc;
+        } else {                   // mma.sync variant (SCP_VIT_ATTENTION=mma)
+            EpiQKVPlain eq{ qb, kb, vb, bw.qkv_b, T };
+            if ((rc = scp::gemm::launch(y, D, bw.qkv_w, D, (int)M, 3 * D, D, eq, st))) return rc;
+            attention_kernel<<<dim3((T + AQ - 1) / AQ, B * HEADS), 128, 0, st>>>(qb, kb, vb, ob, T, scale_log2e);
+        }
         EpiResidual ep{ bw.proj_b };
         if ((rc = scp::gemm::launch(ob, D, bw.proj_w, D, (int)M, D, D, ep, st, x, D))) return rc;
         layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, bw.ln2_w, bw.ln2_b, y, M);

@@ -51,6 +51,25 @@ def test_attention(B, T):
     assert r < 1e-2    # P and the output are rounded to bf16 (2^-9 relative)
 
 
+@pytest.mark.parametrize('B,T', [(1, 128), (2, 65), (1, 1025), (3, 300)])
+def test_attention_tcgen05(B, T):
+    from self_corr_pose_b200 import _lib
+    g = torch.Generator().manual_seed(1)
+    q, k, v = (torch.randn(B * 6, T, 64, generator=g).to(torch.bfloat16).cuda() for _ in range(3))
+    Tp = (T + 7) // 8 * 8
+    vt = torch.zeros(B * 6, 64, Tp, dtype=torch.bfloat16, device='cuda')
+    vt[:, :, :T] = v.transpose(1, 2)
+    o = torch.empty(B, T, 384, dtype=torch.bfloat16, device='cuda')
+    rc = _lib.lib().scp_attention_tc5(_lib.ptr(q), _lib.ptr(k), _lib.ptr(vt), _lib.ptr(o), B, T, _lib.stream_ptr())
+    _lib.check(rc, 'scp_attention_tc5')
+    torch.cuda.synchronize()
+    attn = ((q.double() @ k.double().transpose(1, 2)) * 0.125).softmax(-1) @ v.double()
+    ref = attn.reshape(B, 6, T, 64).permute(0, 2, 1, 3).reshape(B, T, 384)
+    r = rel(o.float(), ref)
+    print('PARITY attention_tc5 B%d T%d rel=%.2e' % (B, T, r))
+    assert r < 1e-2
+
+
 @pytest.mark.parametrize('B,size', [(2, 64), (2, 256)])
 def test_dino_features_vs_oracle(B, size):
     from self_corr_pose_b200.model.module.network.dino import DINO
