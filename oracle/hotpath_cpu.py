@@ -24,11 +24,11 @@ from oracle import vit as ovit
 
 class _CpuSoftRasterize(Function):
     @staticmethod
-    def forward(ctx, face_vertices, textures, kw, use_ref, nthreads):
+    def forward(ctx, face_vertices, textures, kw, use_ref, nthreads, fma=False):
         fwd = osr.ref_forward if use_ref else osr.forward
-        extra = {} if use_ref else {'nthreads': nthreads}
+        extra = {} if use_ref else {'nthreads': nthreads, 'fma': fma}
         col, info, aggr = fwd(face_vertices.detach().numpy(), textures.detach().numpy(), **kw, **extra)
-        ctx.kw, ctx.use_ref, ctx.nthreads = kw, use_ref, nthreads
+        ctx.kw, ctx.use_ref, ctx.nthreads, ctx.fma = kw, use_ref, nthreads, fma
         ctx.save_for_backward(face_vertices.detach(), textures.detach())
         ctx.np_saved = (col, info, aggr)
         return torch.from_numpy(col)
@@ -38,13 +38,13 @@ class _CpuSoftRasterize(Function):
         fv, tex = ctx.saved_tensors
         col, info, aggr = ctx.np_saved
         bwd = osr.ref_backward if ctx.use_ref else osr.backward
-        extra = {} if ctx.use_ref else {'nthreads': ctx.nthreads}
+        extra = {} if ctx.use_ref else {'nthreads': ctx.nthreads, 'fma': ctx.fma}
         gf, gt = bwd(fv.numpy(), tex.numpy(), col, info, aggr, g.contiguous().numpy(), **ctx.kw, **extra)
-        return torch.from_numpy(gf).reshape(fv.shape), torch.from_numpy(gt).reshape(tex.shape), None, None, None
+        return torch.from_numpy(gf).reshape(fv.shape), torch.from_numpy(gt).reshape(tex.shape), None, None, None, None
 
 
 @contextlib.contextmanager
-def cpu_rasterizer(use_ref=False, nthreads=0):
+def cpu_rasterizer(use_ref=False, nthreads=0, fma=False):
     """Routes soft_renderer.functional.soft_rasterize to the CPU checker while the context is active
     (oracle harness only; the product never does this)."""
     from self_corr_pose_b200.soft_renderer import functional as srf
@@ -57,7 +57,7 @@ def cpu_rasterizer(use_ref=False, nthreads=0):
                   gamma_val=gamma_val, aggr_func_rgb=aggr_func_rgb, aggr_func_alpha=aggr_func_alpha,
                   texture_type=texture_type)
         return _CpuSoftRasterize.apply(face_vertices.float().contiguous(), textures.float().contiguous(), kw, use_ref,
-                                       nthreads)
+                                       nthreads, fma)
     saved = srf.soft_rasterize
     srf.soft_rasterize = soft_rasterize
     try:
@@ -76,7 +76,7 @@ def make_batch_cpu(opts, verts, faces, B, seed=0, nthreads=0):
         return synthetic.make_batch(opts, verts, faces, B, device='cpu', seed=seed, renderer=Renderer(opts, mesh))
 
 
-def forward(opts, mean_v, faces, data, enc, vit_sd, it=0, use_ref=False, nthreads=0, all_vit_blocks=False):
+def forward(opts, mean_v, faces, data, enc, vit_sd, it=0, use_ref=False, nthreads=0, all_vit_blocks=False, fma=False):
     """Reference-formulation forward of HotPath.forward on CPU tensors.  Returns (total, aux)."""
     from types import SimpleNamespace
     from self_corr_pose_b200.model.module.renderer import Renderer
@@ -94,7 +94,7 @@ def forward(opts, mean_v, faces, data, enc, vit_sd, it=0, use_ref=False, nthread
 
     pointcorr, match, imatch, _ = ocorr.match(img_feat, mesh_feat, mask, pred_v, hf, wf, opts.tau_img, opts.tau_mesh)
     tex = F.grid_sample(img, imatch.permute(0, 2, 1)[:, None], align_corners=False)[:, :, 0].permute(0, 2, 1)
-    with cpu_rasterizer(use_ref=use_ref, nthreads=nthreads):
+    with cpu_rasterizer(use_ref=use_ref, nthreads=nthreads, fma=fma):
         (mask_render, tex_render, depth_render, match_gt, imatch_gt, tex_mask, depth_mask, match_mask,
          depth_weight) = Renderer(opts, mesh).render_all(pred_v, fb, tex, foc_crop, pp_crop, rotation, translation)
     aux = {}

@@ -25,7 +25,7 @@ def run_pair(opts, B, mesh):
     data, enc = H.make_batch_cpu(opts, v, f, B, seed=3)
     sd = synthetic_state_dict(0)
     mean_v, faces = torch.from_numpy(v), torch.from_numpy(f)
-    total_o, aux_o = H.step(opts, mean_v, faces, data, enc, sd)
+    total_o, aux_o = H.step(opts, mean_v, faces, data, enc, sd, fma=True)   # nvcc's rounding model for SoftRas
     grads_o = [e.grad.clone() for e in enc]
 
     hot = HotPath(opts, mean_v, faces, device='cuda')
@@ -45,12 +45,10 @@ def test_step_parity_without_dino_term():
     print('PARITY hotpath(no dino) losses', {k: '%.6g/%.6g' % v for k, v in rep.items()}, 'grad rel', g)
     for k, (a, b) in rep.items():
         assert abs(a - b) <= 1e-3 * abs(b) + 1e-7, (k, a, b)
-    # SoftRas gradients are ill-conditioned in fp32 (see tests/test_softras_gpu.py): the CPU oracle here is the
-    # strict (no-FMA) build, so geometry gradients are held to 5e-2 norm-wise, feature gradients to 1e-3 + that
-    for n in ('img_feat', 'mesh_feat'):
-        assert g[n] < 2e-2, (n, g[n])
-    for n in ('pred_v', 'rotation', 'translation'):
-        assert g[n] < 1e-1, (n, g[n])
+    # against the FMA build of the SoftRas oracle every gradient is within a few 1e-3 norm-wise (the residual is
+    # the order of the atomic gradient accumulation and single-TF32 correspondence gradient products)
+    for n in g:
+        assert g[n] < 5e-3, (n, g[n])
 
 
 def test_step_parity_full():
