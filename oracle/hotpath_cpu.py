@@ -96,7 +96,8 @@ def forward(opts, mean_v, faces, data, enc, vit_sd, it=0, use_ref=False, nthread
     tex = F.grid_sample(img, imatch.permute(0, 2, 1)[:, None], align_corners=False)[:, :, 0].permute(0, 2, 1)
     with cpu_rasterizer(use_ref=use_ref, nthreads=nthreads, fma=fma):
         (mask_render, tex_render, depth_render, match_gt, imatch_gt, tex_mask, depth_mask, match_mask,
-         depth_weight) = Renderer(opts, mesh).render_all(pred_v, fb, tex, foc_crop, pp_crop, rotation, translation)
+         depth_weight) = Renderer(opts, mesh, reference_launches=True).render_all(pred_v, fb, tex, foc_crop, pp_crop, rotation,
+                                                                                  translation)
     aux = {}
     aux['mask_loss'] = wts.mask_wt * L.compute_mask_loss(img, mask, mask_render).mean(0)
     aux['texture_loss'] = wts.tex_wt * L.compute_texture_loss(img, mask, tex_render, tex_mask).mean(0)

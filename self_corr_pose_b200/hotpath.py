@@ -41,9 +41,9 @@ class HotPath:
     """data = (img, mask, depth, foc_crop, pp_crop); enc = (img_feat[B,C,P], mesh_feat[B,N,C], pred_v[B,N,3],
     rotation[B,3,3], translation[B,1,3]).  forward() -> (total_loss, aux dict with the reference's keys)."""
 
-    # kernels of this package launched by one forward+backward (see DESIGN.md): SoftRas 4x(pack+fwd) + 3x(pack+bwd),
-    # correspondence 2 fwd + 2 bwd, ViT 3 + 9*7 + 2
-    GPU_LAUNCHES = 8 + 6 + 4 + 68
+    # kernels of this package launched by one forward+backward (see DESIGN.md): SoftRas 3x(pack+fwd) + 2x(pack+bwd)
+    # (mask shares the depth traversal), correspondence 3 fwd + 2 bwd, ViT 3 + 9*7 + 2
+    GPU_LAUNCHES = 6 + 4 + 5 + 68
 
     def __init__(self, opts, mean_v, faces, device='cuda'):
         self.opts = opts

@@ -18,9 +18,12 @@ def _soft_renderer(img_size, sigma, gamma, rgb):
 
 class Renderer:
 
-    def __init__(self, opts, mesh):
+    def __init__(self, opts, mesh, reference_launches=False):
+        """reference_launches=True reproduces the reference's launch structure (separate mask render, NOCS backward):
+        used by the CPU reference-formulation harness; the product shares / skips them (identical results)."""
         self.opts = opts
         self.mesh = mesh
+        self.reference_launches = reference_launches
         size = opts.img_size
         self.renderer_mask = _soft_renderer(size, 1e-4, 1e-4, 'hard')
         self.renderer_depth = _soft_renderer(size, 1e-4, 1e-4, 'softmax')
@@ -38,8 +41,22 @@ class Renderer:
 
     def render_all(self, pred_v, faces, tex, foc_crop, pp_crop, rotation, translation, scale=None):
         texture_type = getattr(self.mesh, 'texture_type', 'vertex')
-        mask_render = render(self.renderer_mask, pred_v, faces, None, foc_crop, pp_crop, rotation, translation,
-                             render_mask=True, texture_type='vertex')[:, -1]
+        # The mask, depth and NOCS renders share sigma = 1e-4 and 'prod' alpha aggregation, and the alpha channel is
+        # accumulated before any RGB logic (soft_rasterize_cuda_kernel.cu:408-417): their alpha channels are the same
+        # tensor (note B).  One traversal (the depth render) therefore provides mask_render too;
+        # autograd sums the mask-loss and depth-loss gradients into a single backward launch.
+        depth_full = render(self.renderer_depth, pred_v, faces, None, foc_crop, pp_crop, rotation, translation,
+                            render_depth=True, texture_type='vertex')
+        if self.reference_launches:
+            mask_render = render(self.renderer_mask, pred_v, faces, None, foc_crop, pp_crop, rotation, translation,
+                                 render_mask=True, texture_type='vertex')[:, -1]
+        else:
+            mask_render = depth_full[:, 3]
+        depth_mask = depth_full[:, 3]
+        depth_render = depth_full[:, 2].clone()
+        if not self.opts.use_depth:
+            depth_render = depth_render.detach()
+
         if tex is not None:
             tex_render = render(self.renderer_softtex, pred_v, faces, tex, foc_crop, pp_crop, rotation,
                                 translation, texture_type=texture_type)
@@ -47,19 +64,13 @@ class Renderer:
         else:
             tex_mask = tex_render = None
 
-        depth_render = render(self.renderer_depth, pred_v, faces, None, foc_crop, pp_crop, rotation, translation,
-                              render_depth=True, texture_type='vertex')
-        if not self.opts.use_depth:
-            depth_render = depth_render.detach()
-        depth_mask = depth_render[:, 3]
-        depth_render = depth_render[:, 2].clone()
-
         # NOCS map: hard RGB with the canonical (detached) coordinates as vertex colours.  Its gradient w.r.t.
         # geometry is exactly zero (hard RGB has no xyz gradient, soft_rasterize_cuda_kernel.cu:602; the alpha
         # channel only feeds a boolean mask, loss_utils.py:318), so the pose is detached too and the backward
         # launch the reference performs for this render is skipped.
+        detach_pose = not self.reference_launches
         match_gt = render(self.renderer_hardtex, pred_v.detach(), faces, pred_v.detach(), foc_crop, pp_crop,
-                          rotation, translation, rotation_detach=True, translation_detach=True,
+                          rotation, translation, rotation_detach=detach_pose, translation_detach=detach_pose,
                           texture_type='vertex')
         match_mask, match_gt = match_gt[:, -1], match_gt[:, :3]
 
