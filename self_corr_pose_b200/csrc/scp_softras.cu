@@ -469,7 +469,7 @@ __device__ __forceinline__ void forward_pair(const Params &p, const float *__res
 }
 
 template <int RGB, bool FAST>
-__global__ void __launch_bounds__(NTHREADS) forward_kernel(Params p, const float4 *__restrict__ bbox,
+__global__ void __launch_bounds__(NTHREADS, 3) forward_kernel(Params p, const float4 *__restrict__ bbox,
                                                           const float *__restrict__ rec,
                                                           const int *__restrict__ img_bbox,
                                                           const float *__restrict__ textures,
@@ -691,7 +691,7 @@ __device__ __forceinline__ bool backward_pair(const Params &p, const float *__re
 }
 
 template <int RGB, bool FAST>
-__global__ void __launch_bounds__(NTHREADS) backward_kernel(Params p, const float4 *__restrict__ bbox,
+__global__ void __launch_bounds__(NTHREADS, 3) backward_kernel(Params p, const float4 *__restrict__ bbox,
                                                            const float *__restrict__ rec,
                                                            const int *__restrict__ img_bbox,
                                                            const float *__restrict__ textures,
