@@ -177,9 +177,11 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
         bytes_f = B * (72 * nf + 24 * is_ * is_)
         bytes_b = B * (144 * nf + 40 * is_ * is_)
         out.append(dict(kernel=name + '_fwd (pack+forward_kernel)', ms=t_f, bound='hbm', achieved=bytes_f / t_f / 1e6,
-                        peak=hbm, unit='GB/s', launches_per_step=1 if 'softtex' in name else 3))
+                        peak=hbm, unit='GB/s', launches_per_step=1 if 'softtex' in name else 3,
+                        ncu_name='softras::forward_kernel<1, 1> #0' if 'softtex' in name else ''))
         out.append(dict(kernel=name + '_bwd (pack+backward_kernel)', ms=t_b, bound='hbm', achieved=bytes_b / t_b / 1e6,
-                        peak=hbm, unit='GB/s', launches_per_step=1 if 'softtex' in name else 2))
+                        peak=hbm, unit='GB/s', launches_per_step=1 if 'softtex' in name else 2,
+                        ncu_name='softras::backward_kernel<1, 1> #0' if 'softtex' in name else ''))
     # --- correspondence
     from self_corr_pose_b200.ops.corr_match import corr_match
     import torch.nn.functional as F
@@ -196,7 +198,7 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
     bytes_f = B * (4 * (C * P + N * C + P + 3 * N) + 4 * (P * N // 4 + 2 * N + 3 * P))
     bytes_b = B * 4 * (2 * C * P + 2 * N * C + P * N // 4 + 6 * P + 7 * N)
     out.append(dict(kernel='corr_fwd_kernel(+colreduce)', ms=t_f, bound='hbm', achieved=bytes_f / t_f / 1e6, peak=hbm,
-                    unit='GB/s', launches_per_step=1))
+                    unit='GB/s', launches_per_step=1, ncu_name='corr::corr_fwd_kernel #0'))
     out.append(dict(kernel='corr_bwd_rows+cols', ms=t_b, bound='hbm', achieved=bytes_b / t_b / 1e6, peak=hbm,
                     unit='GB/s', launches_per_step=1))
     # --- ViT: whole extractor, the attention kernel and the QKV GEMM alone
@@ -210,7 +212,7 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
     st = _lib.stream_ptr(dev)
     t_a = timeit(lambda: L.scp_attention_bf16(_lib.ptr(q), _lib.ptr(q), _lib.ptr(q), _lib.ptr(o), B, T, st))
     out.append(dict(kernel='attention_kernel', ms=t_a, bound='tensor', achieved=4.0 * T * T * 64 * 6 * B / t_a / 1e9,
-                    peak=tf, unit='TFLOP/s', launches_per_step=9))
+                    peak=tf, unit='TFLOP/s', launches_per_step=9, ncu_name='fa::fa_fwd_kernel #0'))
     M = B * T
     A = torch.randn(M, 384, device=dev).to(torch.bfloat16)
     W = torch.randn(1152, 384, device=dev).to(torch.bfloat16)
@@ -222,8 +224,15 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
         k['frac'] = k['achieved'] / k['peak']
         k['step_ms'] = k['ms'] * k['launches_per_step']
     dom = max(out, key=lambda k: k['step_ms'] if 'vit_s8' not in k['kernel'] else 0)
+    # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture (profiles/)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+        traffic = tr.get(dom.get('ncu_name', ''), {}).get('dram_bytes')
+    except Exception:
+        pass
     roof = {'kernel': dom['kernel'], 'bound': dom['bound'], 'achieved': dom['achieved'], 'peak': dom['peak'],
-            'unit': dom['unit'], 'frac': dom['frac'], 'traffic': None, 'peak_source': which,
+            'unit': dom['unit'], 'frac': dom['frac'], 'traffic': traffic, 'peak_source': which,
             'ms_per_launch': dom['ms'], 'launches_per_step': dom['launches_per_step']}
     return roof, out
 
@@ -354,7 +363,7 @@ def main():
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': hot.GPU_LAUNCHES * args.steps,
         'clocks': sampler.summary() if sampler else None,
-        'roofline': roof, 'kernels': kernels, 'cpu_baseline': cpu, 'loss': float(loss),
+        'roofline': roof, 'kernels': kernels, 'cpu_baseline': cpu, 'loss': float(loss.detach()),
     }
     print(json.dumps(line))
     if world > 1:
