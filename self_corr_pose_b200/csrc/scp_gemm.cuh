@@ -8,6 +8,8 @@
 // Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue),
 // and a static round-robin tile schedule (tile = blockIdx.x + i * gridDim.x), one CTA per SM.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "scp_common.cuh"
 #include "scp_tc5.cuh"
 
@@ -26,9 +28,23 @@ constexpr int EPI_BYTES = EPI_WARPS * STG_FLOATS * 4;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
 constexpr int TMEM_COLS = ACC_STAGES * BN;          // 256
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
 struct Shape {
     int M, N, K;
 };
+
+// optional fourth epilogue mode (Epi::kTmaStoreBf16 == true): out[tile] = bf16(epi.apply(acc + bias[col])) computed in
+// registers (thread = row, 32 independent columns in flight), packed into a 32 x 64 bf16 box in TMA SWIZZLE_128B
+// layout and written with ONE cp.async.bulk.tensor store per warp and tile -- the SM issues no global stores
+template <class E, class = void>
+struct tma_store_mode { static constexpr bool value = false; };
+template <class E>
+struct tma_store_mode<E, decltype((void)E::kTmaStoreBf16)> { static constexpr bool value = E::kTmaStoreBf16; };
 
 // Epi: struct with
 //   static constexpr bool kStaged;
@@ -122,6 +138,35 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tc5::mbar_wait(tfull + acc, acc_phase);
             tc5::tc_fence_after();
             const int row0 = m_blk * BM + quarter * 32;
+            if constexpr (tma_store_mode<Epi>::value) {
+                uint8_t *box = epi_buf + (warp - 2) * TMA_TILE_BYTES;          // 32 rows x 128 B (64 bf16), SWIZZLE_128B
+                if (lane == 0) tc5::tma_store_wait_read();                      // previous bulk store has read the box
+                __syncwarp();
+#pragma unroll
+                for (int cc = 0; cc < BN / 2; cc += 32) {
+                    const int c0 = half * (BN / 2) + cc;
+                    float v[32];
+                    tc5::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, v);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(epi.bias + n_blk * BN + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {                               // 8 columns -> one 16-byte chunk
+                        const float4 ba = __ldg(b4 + 2 * j), bb = __ldg(b4 + 2 * j + 1);
+                        uint32_t w[4];
+                        w[0] = pack_bf16x2(epi.apply(v[8 * j + 0] + ba.x), epi.apply(v[8 * j + 1] + ba.y));
+                        w[1] = pack_bf16x2(epi.apply(v[8 * j + 2] + ba.z), epi.apply(v[8 * j + 3] + ba.w));
+                        w[2] = pack_bf16x2(epi.apply(v[8 * j + 4] + bb.x), epi.apply(v[8 * j + 5] + bb.y));
+                        w[3] = pack_bf16x2(epi.apply(v[8 * j + 6] + bb.z), epi.apply(v[8 * j + 7] + bb.w));
+                        const int chunk = (cc >> 3) + j;
+                        *reinterpret_cast<uint4 *>(box + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                tc5::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && row0 < s.M) {   // rows past M are clipped by the tensor map
+                    tc5::tma_store_2d(&tmap_c, box, n_blk * BN + half * (BN / 2), row0);
+                    tc5::tma_store_commit();
+                }
+            } else
 #pragma unroll 1
             for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                 float v[32];
@@ -165,8 +210,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (lane == 0) tc5::mbar_arrive(tempty + acc);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
-        if constexpr (Epi::kTmaReduceAdd) {
-            if (lane == 0) tc5::tma_store_wait_all();   // all reduce-adds of this warp have completed
+        if constexpr (Epi::kTmaReduceAdd || tma_store_mode<Epi>::value) {
+            if (lane == 0) tc5::tma_store_wait_all();   // all bulk stores / reduce-adds of this warp have completed
         }
     }
     tc5::tc_fence_before();
@@ -232,10 +277,10 @@ inline int num_sms()
 }
 
 // A[M,K] (pitch lda), W[N,K] (pitch ldw); N % 128 == 0, K % 64 == 0
-// c_out / ldc: fp32 output matrix of the kTmaReduceAdd epilogue (ignored otherwise)
+// c_out / ldc: fp32 output matrix of the kTmaReduceAdd epilogue / bf16 output of the kTmaStoreBf16 epilogue (ignored otherwise)
 template <class Epi>
 int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, const Epi &epi, cudaStream_t st,
-           float *c_out = nullptr, int ldc = 0)
+           void *c_out = nullptr, int ldc = 0)
 {
     if (M <= 0 || N % BN != 0 || K % BK != 0) {
         set_last_error("tcgen05 gemm: unsupported shape M=%d N=%d K=%d", M, N, K);
@@ -250,6 +295,12 @@ int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, 
     if constexpr (Epi::kTmaReduceAdd) {
         if (!c_out || !make_tmap_f32_box32(&tc, c_out, N, M, ldc)) {
             set_last_error("tcgen05 gemm: output tensor map failed");
+            return -1;
+        }
+    }
+    if constexpr (tma_store_mode<Epi>::value) {   // bf16 output [M][N], box = 64 columns x 32 rows
+        if (!c_out || !make_tmap_bf16(&tc, c_out, N, M, ldc, 32)) {
+            set_last_error("tcgen05 gemm: bf16 output tensor map failed");
             return -1;
         }
     }

@@ -18,6 +18,7 @@
 #include "scp_common.cuh"
 #include "scp_gemm.cuh"
 #include "scp_fa.cuh"
+#include "scp_fa2.cuh"
 
 namespace scp {
 namespace vit {
@@ -170,21 +171,14 @@ struct EpiResidual {  // x[tile] += acc + bias: fp32 residual stream updated by 
     __device__ void operator()(int, int, const float (&)[32]) const {}
 };
 
-struct EpiGelu {  // h[row][:] = gelu_erf(acc + bias)  bf16
-    static constexpr bool kStaged = true;
+struct EpiGelu {  // h[row][:] = gelu_erf(acc + bias)  bf16, through the register -> swizzled box -> TMA store epilogue
+    static constexpr bool kStaged = false;
     static constexpr bool kTmaReduceAdd = false;
     static constexpr bool kMixed = false;
-    bf16 *h; const float *bias; int ld;
-    __device__ __forceinline__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const
-    {
-        bf16 *p = h + (long)row0 * ld + col;
-        const float bb = __ldg(bias + col);
-#pragma unroll 4
-        for (int r = 0; r < nrows; r++) {
-            const float z = stg[r * 33 + lane] + bb;
-            p[(long)r * ld] = __float2bfloat16(0.5f * z * (1.f + erf_as(z * 0.70710678118654752f)));
-        }
-    }
+    static constexpr bool kTmaStoreBf16 = true;
+    const float *bias;
+    __device__ __forceinline__ float apply(float z) const { return 0.5f * z * (1.f + erf_as(z * 0.70710678118654752f)); }
+    __device__ void operator()(int, int, const float (&)[32]) const {}
 };
 
 struct EpiKeys {  // feat[b][col][t-1] = acc + bias for patch tokens (CLS dropped); (b, 384, hp, wp) fp32
@@ -403,23 +397,39 @@ extern "C" int scp_attention_bf16(const void *q, const void *k, const void *v, v
     return scp::check_launch("scp_attention_bf16");
 }
 
+// SCP_VIT_ATTENTION: unset / "2" = fa2 (S double-buffered, P and O in TMEM), "1" = fa (first tcgen05 version),
+// "m" = mma.sync variant (different V layout; only through scp_vit_s8_keys)
+static int attention_variant()
+{
+    const char *e = getenv("SCP_VIT_ATTENTION");
+    if (!e || !e[0]) return 2;
+    return e[0] == 'm' ? 0 : (e[0] == '1' ? 1 : 2);
+}
+
 static int launch_fa(const bf16 *q, const bf16 *k, const bf16 *vt, bf16 *o, int B, int T, int Tp, cudaStream_t st)
 {
-    using scp::fa::BQ; using scp::fa::BKV; using scp::fa::fa_fwd_kernel;
+    const bool v2 = attention_variant() != 1;
     CUtensorMap tq, tk, tv;
     const uint64_t rows = (uint64_t)B * HEADS * T;
-    if (!scp::gemm::make_tmap_bf16(&tq, q, HD, rows, HD, BQ) || !scp::gemm::make_tmap_bf16(&tk, k, HD, rows, HD, BKV) ||
+    const uint32_t bq = v2 ? scp::fa2::BQ : scp::fa::BQ, bkv = v2 ? scp::fa2::BKV : scp::fa::BKV;
+    if (!scp::gemm::make_tmap_bf16(&tq, q, HD, rows, HD, bq) || !scp::gemm::make_tmap_bf16(&tk, k, HD, rows, HD, bkv) ||
         !scp::gemm::make_tmap_bf16(&tv, vt, Tp, (uint64_t)B * HEADS * HD, Tp, 64)) {
         scp::set_last_error("tcgen05 attention: cuTensorMapEncodeTiled failed");
         return -1;
     }
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scp::fa::SMEM_BYTES);
+        cudaFuncSetAttribute(scp::fa::fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scp::fa::SMEM_BYTES);
+        cudaFuncSetAttribute(scp::fa2::fa2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scp::fa2::SMEM_BYTES);
         attr_done = true;
     }
-    fa_fwd_kernel<<<dim3((T + BQ - 1) / BQ, B * HEADS), scp::fa::NTHREADS, scp::fa::SMEM_BYTES, st>>>(
-        tq, tk, tv, o, T, 0.125f * 1.4426950408889634f);
+    const float scale_log2e = 0.125f * 1.4426950408889634f;
+    if (v2)
+        scp::fa2::fa2_fwd_kernel<<<dim3((T + bq - 1) / bq, B * HEADS), scp::fa2::NTHREADS, scp::fa2::SMEM_BYTES, st>>>(
+            tq, tk, tv, o, T, scale_log2e);
+    else
+        scp::fa::fa_fwd_kernel<<<dim3((T + bq - 1) / bq, B * HEADS), scp::fa::NTHREADS, scp::fa::SMEM_BYTES, st>>>(
+            tq, tk, tv, o, T, scale_log2e);
     return 0;
 }
 
@@ -477,8 +487,7 @@ extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float
         EpiPatch epi{ x, w->patch_b, w->pos, np, T };
         if ((rc = scp::gemm::launch(a0, KP, w->patch_w, KP, B * np, D, KP, epi, st))) return rc;
     }
-    const char *att_env = getenv("SCP_VIT_ATTENTION");
-    const bool use_tc5_attention = !(att_env && att_env[0] == 'm');
+    const bool use_tc5_attention = attention_variant() != 0;
     const unsigned ln_grid = (unsigned)((M + 7) / 8);
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     for (int i = 0; i < n_blocks; i++) {
@@ -496,8 +505,8 @@ extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float
         EpiResidual ep{ bw.proj_b };
         if ((rc = scp::gemm::launch(ob, D, bw.proj_w, D, (int)M, D, D, ep, st, x, D))) return rc;
         layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, bw.ln2_w, bw.ln2_b, y, M);
-        EpiGelu eg{ hb, bw.fc1_b, MLP };
-        if ((rc = scp::gemm::launch(y, D, bw.fc1_w, D, (int)M, MLP, D, eg, st))) return rc;
+        EpiGelu eg{ bw.fc1_b };
+        if ((rc = scp::gemm::launch(y, D, bw.fc1_w, D, (int)M, MLP, D, eg, st, hb, MLP))) return rc;
         EpiResidual e2{ bw.fc2_b };
         if ((rc = scp::gemm::launch(hb, MLP, bw.fc2_w, MLP, (int)M, D, MLP, e2, st, x, D))) return rc;
     }

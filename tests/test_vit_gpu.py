@@ -51,11 +51,21 @@ def test_attention(B, T):
     assert r < 1e-2    # P and the output are rounded to bf16 (2^-9 relative)
 
 
-@pytest.mark.parametrize('B,T', [(1, 128), (2, 65), (1, 1025), (3, 300)])
-def test_attention_tcgen05(B, T):
+@pytest.mark.parametrize('variant', ['2', '1'])
+@pytest.mark.parametrize('B,T,ramp', [(1, 128, 0.), (2, 65, 0.), (1, 1025, 0.), (3, 300, 0.), (1, 64, 0.), (2, 1025, 7.),
+                                      (1, 449, -7.)])
+def test_attention_tcgen05(B, T, ramp, variant, monkeypatch):
+    """variant 2 = scp_fa2.cuh (P and O in tensor memory, lazy rescale), 1 = scp_fa.cuh.  ramp != 0 scales the keys
+    along the sequence so the row maxima keep growing (ramp > 0: every tile triggers the accumulator rescale) or are
+    set by the first tile (ramp < 0), with logits far outside the 2^8 lazy window."""
     from self_corr_pose_b200 import _lib
+    monkeypatch.setenv('SCP_VIT_ATTENTION', variant)
     g = torch.Generator().manual_seed(1)
-    q, k, v = (torch.randn(B * 6, T, 64, generator=g).to(torch.bfloat16).cuda() for _ in range(3))
+    q, k, v = (torch.randn(B * 6, T, 64, generator=g) for _ in range(3))
+    if ramp:
+        s = torch.linspace(0, 1, T)[None, :, None]
+        k = k * (1 + abs(ramp) * (s if ramp > 0 else 1 - s))
+    q, k, v = (t.to(torch.bfloat16).cuda() for t in (q, k, v))
     Tp = (T + 7) // 8 * 8
     vt = torch.zeros(B * 6, 64, Tp, dtype=torch.bfloat16, device='cuda')
     vt[:, :, :T] = v.transpose(1, 2)
@@ -66,7 +76,8 @@ def test_attention_tcgen05(B, T):
     attn = ((q.double() @ k.double().transpose(1, 2)) * 0.125).softmax(-1) @ v.double()
     ref = attn.reshape(B, 6, T, 64).permute(0, 2, 1, 3).reshape(B, T, 384)
     r = rel(o.float(), ref)
-    print('PARITY attention_tc5 B%d T%d rel=%.2e' % (B, T, r))
+    print('PARITY attention_tc5 v%s B%d T%d ramp%g rel=%.2e' % (variant, B, T, ramp, r))
+    assert torch.isfinite(o.float()).all()
     assert r < 1e-2
 
 
