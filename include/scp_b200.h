@@ -17,6 +17,10 @@
  *       + two weighted sums), reached through torch ops in the reference.
  *   scp_colsoftmax_bmm_forward / _backward
  *       model/module/correspondence.py:105-110 (rotation-cycle similarity, column softmax, grid.bmm).
+ *   scp_image_losses_forward / scp_image_losses_backward
+ *       model/util/loss_utils.py:236-244 (compute_mask_loss), :246-252 (compute_texture_loss), :273-284
+ *       (compute_depth_loss), :317-320 (compute_match_loss) with the nearest upsampling of `match`
+ *       (model/module/correspondence.py:71), reached through torch ops in the reference.
  *   scp_vit_*  — see the ViT section below
  *       third-party/zsp/zsp/method/vision_transformer_flexible.py:85-101,116-132,214-262 and
  *       model/module/network/dino.py:102-109.
@@ -165,6 +169,30 @@ int scp_attention_bf16(const void *q, const void *k, const void *v, void *o, int
 /* Same result on the tcgen05 tensor cores (S and O tiles in TMEM, TMA-staged operands); v is passed TRANSPOSED:
  * vt[B*6][64][Tp] bf16, Tp = T rounded up to a multiple of 8, columns t >= T zero.  Used by scp_vit_s8_keys. */
 int scp_attention_tc5(const void *q, const void *k, const void *vt, void *o, int B, int T, void *stream);
+
+/* ---- image-space loss terms (silhouette pyramid, texture, depth, 3D match) ------------------------------- */
+/*
+ * A "map" is a device pointer to a (B, [3,] H, W) fp32 view whose planes are contiguous (channel stride H*W) and
+ * whose batch stride is given separately in floats -- so channels of the (B,4,H,W) SoftRas outputs are passed
+ * without a copy.  16-byte aligned, W % 16 == 0.  Input map order (maps[] / bstrides[], 11 entries):
+ *   0 img(3ch) 1 mask 2 depth 3 mask_render 4 tex_render(3ch) 5 tex_mask 6 depth_render 7 depth_mask
+ *   8 match_gt(3ch) 9 match_mask 10 match at full resolution (3ch; only read when hf == 0)
+ * match_lr[B][hf*wf][3]: the correspondence kernel's 3D match; upsampled (nearest, top-left rule) on the fly when hf > 0.
+ * losses[B][4] = per-image (mask, texture, depth, match) loss values, un-weighted, as the reference's compute_*
+ * functions return them.  workspace: scp_image_losses_workspace_bytes(B), written by forward, read by backward
+ * (batch-global depth scale sums and its gradient coupling).
+ */
+size_t scp_image_losses_workspace_bytes(int B);
+int scp_image_losses_forward(const void *const *maps, const long long *bstrides, const float *match_lr, int B, int H,
+                             int W, int hf, int wf, int use_depth, float *losses, void *workspace, void *stream);
+/*
+ * g_losses[B][4]: upstream gradient of every loss value.  Gradient maps (g_maps[] / g_bstrides[], 5 entries, same view
+ * convention, every element written): 0 mask_render 1 tex_render(3ch) 2 tex_mask 3 depth_render 4 match at full
+ * resolution (3ch; hf == 0 only).  g_match_lr[B][hf*wf][3] (hf > 0) is zeroed and accumulated by the callee.
+ */
+int scp_image_losses_backward(const void *const *maps, const long long *bstrides, const float *match_lr, int B, int H,
+                              int W, int hf, int wf, int use_depth, const float *g_losses, const void *workspace,
+                              void *const *g_maps, const long long *g_bstrides, float *g_match_lr, void *stream);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,14 @@ _SIGNATURES.update({
     'scp_vit_s8_keys': ([ctypes.POINTER(VitWeights), _f, _f, _i, _i, _i, _i, _f, _sz, _f], _i),
 })
 
+_pp = ctypes.POINTER(ctypes.c_void_p)
+_pll = ctypes.POINTER(ctypes.c_longlong)
+_SIGNATURES.update({
+    'scp_image_losses_workspace_bytes': ([_i], _sz),
+    'scp_image_losses_forward': ([_pp, _pll, _f, _i, _i, _i, _i, _i, _i, _f, _f, _f], _i),
+    'scp_image_losses_backward': ([_pp, _pll, _f, _i, _i, _i, _i, _i, _i, _f, _f, _pp, _pll, _f, _f], _i),
+})
+
 _lib = None
 
 

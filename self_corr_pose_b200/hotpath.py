@@ -18,6 +18,7 @@ from .model.module.pretrained_corr import PretrainedCorrespondence
 from .model.module.renderer import Renderer
 from .model.module.weights import Weights
 from .model.util import loss_utils as L
+from .ops.image_losses import image_losses
 
 
 def default_opts(**over):
@@ -42,11 +43,12 @@ class HotPath:
     rotation[B,3,3], translation[B,1,3]).  forward() -> (total_loss, aux dict with the reference's keys)."""
 
     # kernels of this package launched by one forward+backward (see DESIGN.md): SoftRas 3x(pack+fwd) + 2x(pack+bwd)
-    # (mask shares the depth traversal), correspondence 3 fwd + 2 bwd, ViT 3 + 9*7 + 2
-    GPU_LAUNCHES = 6 + 4 + 5 + 68
+    # (mask shares the depth traversal), correspondence 3 fwd + 2 bwd, ViT 3 + 9*7 + 2, image losses 2 fwd + 1 bwd
+    GPU_LAUNCHES = 6 + 4 + 5 + 68 + 3
 
-    def __init__(self, opts, mean_v, faces, device='cuda'):
+    def __init__(self, opts, mean_v, faces, device='cuda', fused_losses=True):
         self.opts = opts
+        self.fused_losses = fused_losses
         self.device = device
         self.mesh = SimpleNamespace(mean_v=mean_v.to(device), faces=faces.to(device), texture_type='vertex')
         self.weights = Weights(opts)
@@ -65,20 +67,34 @@ class HotPath:
         faces = self.mesh.faces[None].repeat(bsz, 1, 1)
         mean_v = self.mesh.mean_v[None].repeat(bsz, 1, 1)
 
-        pointcorr, match, imatch, _ = self.corr_net.match(img_feat, mesh_feat, mask, pred_v, pooled=True)
+        fused = self.fused_losses and opts.img_size % 16 == 0
+        if fused:
+            pointcorr, match_lr, imatch = self.corr_net.match_lowres(img_feat, mesh_feat, mask, pred_v)
+        else:
+            pointcorr, match, imatch, _ = self.corr_net.match(img_feat, mesh_feat, mask, pred_v, pooled=True)
         # CanonicalMesh.get_texture (model/module/mesh.py:46-51): vertex colours sampled at the soft 2D matches
         tex = F.grid_sample(img, imatch.permute(0, 2, 1)[:, None], align_corners=False)[:, :, 0].permute(0, 2, 1)
 
-        (mask_render, tex_render, depth_render, match_gt, imatch_gt, tex_mask, depth_mask, match_mask,
-         depth_weight) = self.renderer.render_all(pred_v, faces, tex, foc_crop, pp_crop, rotation, translation)
-
         aux = {}
-        aux['mask_loss'] = wts.mask_wt * L.compute_mask_loss(img, mask, mask_render).mean(0)
-        aux['texture_loss'] = wts.tex_wt * L.compute_texture_loss(img, mask, tex_render, tex_mask).mean(0)
-        if opts.use_depth:
-            d_loss, _ = L.compute_depth_loss(depth, depth_render, depth_mask, mask)
-            aux['depth_loss'] = wts.depth_wt * d_loss.mean(0)
-        aux['match_loss'] = wts.match_wt * L.compute_match_loss(match, match_gt, match_mask, mask).mean(0)
+        if fused:   # shared screen-space geometry + the four image-space losses in one native forward / backward
+            r_depth, r_tex, r_nocs, imatch_gt, depth_weight = self.renderer.render_all_raw(
+                pred_v, faces, tex, foc_crop, pp_crop, rotation, translation)
+            l_mask, l_tex, l_depth, l_match = image_losses(r_depth, r_tex, match_lr, img, mask, depth, r_nocs,
+                                                           opts.corr_h, opts.corr_w, opts.use_depth)
+            aux['mask_loss'] = wts.mask_wt * l_mask.mean(0)
+            aux['texture_loss'] = wts.tex_wt * l_tex.mean(0)
+            if opts.use_depth:
+                aux['depth_loss'] = wts.depth_wt * l_depth.mean(0)
+            aux['match_loss'] = wts.match_wt * l_match.mean(0)
+        else:       # the reference's op-by-op statements (kept for parity tests of the fused path)
+            (mask_render, tex_render, depth_render, match_gt, imatch_gt, tex_mask, depth_mask, match_mask,
+             depth_weight) = self.renderer.render_all(pred_v, faces, tex, foc_crop, pp_crop, rotation, translation)
+            aux['mask_loss'] = wts.mask_wt * L.compute_mask_loss(img, mask, mask_render).mean(0)
+            aux['texture_loss'] = wts.tex_wt * L.compute_texture_loss(img, mask, tex_render, tex_mask).mean(0)
+            if opts.use_depth:
+                d_loss, _ = L.compute_depth_loss(depth, depth_render, depth_mask, mask)
+                aux['depth_loss'] = wts.depth_wt * d_loss.mean(0)
+            aux['match_loss'] = wts.match_wt * L.compute_match_loss(match, match_gt, match_mask, mask).mean(0)
         aux['imatch_loss'] = wts.imatch_wt * L.compute_imatch_loss(imatch, imatch_gt, depth_weight).mean(0)
         aux['triangle_loss'] = wts.triangle_wt * self.triangle_loss_fn(pred_v) * pred_v.shape[1] / 64.
         aux['pullfar_loss'] = wts.pullfar_wt * F.relu(1 - translation[:, :, -1]).mean()

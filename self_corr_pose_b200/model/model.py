@@ -14,6 +14,7 @@ from .module.correspondence import Correspondence
 from .module.pretrained_corr import PretrainedCorrespondence
 from .module.renderer import Renderer
 from .util import loss_utils as L
+from ..ops.image_losses import image_losses
 
 
 class MeshNet(nn.Module):
@@ -28,6 +29,7 @@ class MeshNet(nn.Module):
         self.pretrain_corr_net = PretrainedCorrespondence(opts, self.mesh, pretrained=True)
         self.renderer = Renderer(opts, self.mesh)
         self.iters = 0
+        self.fused_losses = True    # False: the reference's op-by-op loss statements (parity tests)
         self.triangle_loss_fn = L.LaplacianLoss(self.mesh.mean_v, self.mesh.faces, average=True)
 
     def forward(self, data):
@@ -39,32 +41,48 @@ class MeshNet(nn.Module):
         faces = self.mesh.faces[None].repeat(bsz, 1, 1)
 
         img_feat, mesh_feat, pred_v, rotation, translation, scale = self.encoder(img, mean_v, pp_crop, foc_crop)
-        pointcorr, match, imatch, match_conf = self.corr_net.match(img_feat, mesh_feat, mask, pred_v, pooled=opts.train)
+        fused = opts.train and self.fused_losses and opts.img_size % 16 == 0 and not opts.use_occ
+        if fused:
+            pointcorr, match_lr, imatch = self.corr_net.match_lowres(img_feat, mesh_feat, mask, pred_v)
+        else:
+            pointcorr, match, imatch, match_conf = self.corr_net.match(img_feat, mesh_feat, mask, pred_v,
+                                                                       pooled=opts.train)
         tex = self.mesh.get_texture(pred_v, faces, imatch, img)
         if not opts.train:
             return pred_v, faces, tex, imatch, match, match_conf, rotation, translation, scale, pointcorr
 
-        (mask_render, tex_render, depth_render, match_gt, imatch_gt, tex_mask, depth_mask, match_mask,
-         depth_weight) = self.renderer.render_all(pred_v, faces, tex, foc_crop, pp_crop, rotation, translation, scale)
-        if opts.use_occ:
-            raise NotImplementedError('use_occ is False in every shipped config')
         aux = {}
-        aux['mask_loss'] = wts.mask_wt * L.compute_mask_loss(img, mask, mask_render).mean(0)
+        if fused:   # shared screen-space geometry + the four image-space losses in one native forward / backward
+            r_depth, r_tex, r_nocs, imatch_gt, depth_weight = self.renderer.render_all_raw(
+                pred_v, faces, tex, foc_crop, pp_crop, rotation, translation)
+            l_mask, l_tex, l_depth, l_match = image_losses(r_depth, r_tex, match_lr, img, mask, depth, r_nocs,
+                                                           opts.corr_h, opts.corr_w, opts.use_depth)
+            aux['mask_loss'] = wts.mask_wt * l_mask.mean(0)
+            aux['match_loss'] = wts.match_wt * l_match.mean(0)
+            aux['texture_loss'] = wts.tex_wt * l_tex.mean(0)
+            if opts.use_depth:
+                aux['depth_loss'] = wts.depth_wt * l_depth.mean(0)
+        else:
+            (mask_render, tex_render, depth_render, match_gt, imatch_gt, tex_mask, depth_mask, match_mask,
+             depth_weight) = self.renderer.render_all(pred_v, faces, tex, foc_crop, pp_crop, rotation, translation, scale)
+            if opts.use_occ:
+                raise NotImplementedError('use_occ is False in every shipped config')
+            aux['mask_loss'] = wts.mask_wt * L.compute_mask_loss(img, mask, mask_render).mean(0)
+            aux['match_loss'] = wts.match_wt * L.compute_match_loss(match, match_gt, match_mask, mask).mean(0)
+            aux['texture_loss'] = wts.tex_wt * L.compute_texture_loss(img, mask, tex_render, tex_mask).mean(0)
+            if opts.use_depth:
+                d_loss, _ = L.compute_depth_loss(depth, depth_render, depth_mask, mask)
+                aux['depth_loss'] = wts.depth_wt * d_loss.mean(0)
         aux['triangle_loss'] = wts.triangle_wt * self.triangle_loss_fn(pred_v) * pred_v.shape[1] / 64.
         aux['deform_loss'] = wts.deform_wt * F.smooth_l1_loss(pred_v, mean_v, reduction='mean')
         aux['pullfar_loss'] = wts.pullfar_wt * F.relu(1 - translation[:, :, -1]).mean()
         aux['symmetry_loss'] = wts.symmetry_wt * self.mesh.compute_symmetry_loss(pred_v, faces)
-        aux['match_loss'] = wts.match_wt * L.compute_match_loss(match, match_gt, match_mask, mask).mean(0)
-        aux['texture_loss'] = wts.tex_wt * L.compute_texture_loss(img, mask, tex_render, tex_mask).mean(0)
         aux['imatch_loss'] = wts.imatch_wt * L.compute_imatch_loss(imatch, imatch_gt, depth_weight).mean(0)
         cyc = self.pretrain_corr_net.compute_cycle_loss(img, mask, depth_weight, pointcorr, pooled=True,
                                                         A=self.corr_net.pool_A)
         aux['cycle_loss_pretrain'] = cyc[0] * wts.cycle_loss_pt_wt
         rot_cyc = self.corr_net.compute_rotation_cycle_loss(img, mask, img_feat, self.encoder)
         aux['cycle_loss'] = rot_cyc[0] * wts.cycle_loss_wt
-        if opts.use_depth:
-            d_loss, _ = L.compute_depth_loss(depth, depth_render, depth_mask, mask)
-            aux['depth_loss'] = wts.depth_wt * d_loss.mean(0)
         total_loss = sum(aux.values())
         aux_output = {'total_loss': total_loss}
         aux_output.update(aux)

@@ -34,6 +34,17 @@ class Correspondence:
         self.meshgrid = make_meshgrid(self.hf, self.wf, device if device is not None else 'cuda')
         self.pool_A = None
 
+    def match_lowres(self, img_feat, mesh_feat, mask, pred_v):
+        """Training-step variant of `match` for the fused image losses: returns (pooled pointcorr (B,P/4,N),
+        match at the correspondence resolution (B,P,3) -- the loss kernel applies the nearest upsampling of :71 on
+        the fly --, imatch (B,2,N)); sets `pool_A` like `match(pooled=True)`."""
+        bsz = mask.shape[0]
+        mask_down = F.interpolate(mask[:, None], (self.hf, self.wf), mode='nearest').reshape(bsz, -1) * 1.0
+        _, pc_pool, match, imatch, A_pool = corr_match(img_feat, mesh_feat, mask_down, pred_v.detach(), self.meshgrid,
+                                                       self.tau_img, self.hf, self.wf, want_full=False, want_pool=True)
+        self.pool_A = A_pool
+        return pc_pool, match, imatch
+
     def match(self, img_feat, mesh_feat, mask, pred_v, pooled=False):
         """Returns (pointcorr, match, imatch, match_conf).  `pooled=True` (used by MeshNet.forward in
         training, where the only consumer is the pre-training cycle loss) returns the 2x2-averaged

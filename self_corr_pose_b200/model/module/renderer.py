@@ -7,7 +7,8 @@ import torch
 import torch.nn.functional as F
 
 from ... import soft_renderer as sr
-from ..util.loss_utils import render, pinhole_cam
+from ...soft_renderer import functional as srf
+from ..util.loss_utils import render, pinhole_cam, project_to_screen
 
 
 def _soft_renderer(img_size, sigma, gamma, rgb):
@@ -38,6 +39,44 @@ class Renderer:
         faces = self.mesh.faces[None].repeat(bsz, 1, 1)
         return render(self.renderer_depth, mean_v, faces, None, foc_crop, pp_crop, rotation, translation,
                       rotation_detach=True, translation_detach=True, render_depth=True)
+
+    def _rasterize(self, renderer, face_vertices, face_textures):
+        r = renderer.rasterizer
+        return srf.soft_rasterize(face_vertices, face_textures, r.image_size, r.background_color, r.near, r.far,
+                                  r.fill_back, r.eps, r.sigma_val, r.dist_func, r.dist_eps, r.gamma_val,
+                                  r.aggr_func_rgb, r.aggr_func_alpha, 'vertex')
+
+    def _visibility(self, pred_v, depth_render, foc_crop, pp_crop, rotation, translation):
+        """imatch_gt = projected vertices (no y-flip), depth_weight = exp(-5 relu(z_v - z_render)) (renderer.py:64-71)."""
+        imatch_gt = pred_v.detach().bmm(rotation) + translation
+        imatch_depth = imatch_gt[:, :, 2].clone()
+        imatch_gt = pinhole_cam(imatch_gt, pp_crop, foc_crop)[:, :, :2].permute(0, 2, 1)  # b,2,n
+        imatch_depth_gt = F.grid_sample(depth_render[:, None], imatch_gt.permute(0, 2, 1)[:, None],
+                                        align_corners=False)[:, 0, 0]
+        depth_weight = (5 * -F.relu(imatch_depth - imatch_depth_gt)).exp().detach()
+        return imatch_gt, depth_weight
+
+    def render_all_raw(self, pred_v, faces, tex, foc_crop, pp_crop, rotation, translation):
+        """The renders of render_all as the raw (B,4,H,W) SoftRas outputs, for the fused image losses
+        (ops/image_losses.py): returns (r_depth, r_tex, r_nocs, imatch_gt, depth_weight) with
+            mask_render = depth_mask = r_depth[:, 3], depth_render = r_depth[:, 2],
+            tex_render = r_tex[:, :3], tex_mask = r_tex[:, 3], match_gt = r_nocs[:, :3], match_mask = r_nocs[:, 3].
+        The three renders see the same screen-space geometry (same vertices, pose and camera; the renderers differ
+        only in sigma / gamma / aggregation), so the projection, the look_at transform and the face gather are done
+        ONCE here instead of once per render (loss_utils.render + sr.Mesh per call in the reference, renderer.py:39-61);
+        the ambient light of intensity 1 multiplies every texture by exactly 1 and is skipped."""
+        if getattr(self.mesh, 'texture_type', 'vertex') != 'vertex' or tex is None:
+            raise NotImplementedError('render_all_raw: vertex textures only (every shipped config)')
+        sv = project_to_screen(pred_v, foc_crop, pp_crop, rotation, translation)
+        fv = srf.face_vertices(self.renderer_depth.transform.transformer(sv), faces)
+        # depth render: texture = screen-space vertices themselves (render(..., render_depth=True): tex = verts.clone())
+        r_depth = self._rasterize(self.renderer_depth, fv, srf.face_vertices(sv, faces))
+        r_tex = self._rasterize(self.renderer_softtex, fv, srf.face_vertices(tex, faces))
+        # NOCS map: hard RGB of the detached canonical coordinates; no useful gradient (see render_all)
+        r_nocs = self._rasterize(self.renderer_hardtex, fv.detach(), srf.face_vertices(pred_v.detach(), faces))
+        depth_render = r_depth[:, 2] if self.opts.use_depth else r_depth[:, 2].detach()
+        imatch_gt, depth_weight = self._visibility(pred_v, depth_render, foc_crop, pp_crop, rotation, translation)
+        return r_depth, r_tex, r_nocs, imatch_gt, depth_weight
 
     def render_all(self, pred_v, faces, tex, foc_crop, pp_crop, rotation, translation, scale=None):
         texture_type = getattr(self.mesh, 'texture_type', 'vertex')
@@ -75,11 +114,6 @@ class Renderer:
         match_mask, match_gt = match_gt[:, -1], match_gt[:, :3]
 
         # projected vertices (no y-flip), visibility weight from the rendered depth
-        imatch_gt = pred_v.detach().bmm(rotation) + translation
-        imatch_depth = imatch_gt[:, :, 2].clone()
-        imatch_gt = pinhole_cam(imatch_gt, pp_crop, foc_crop)[:, :, :2].permute(0, 2, 1)  # b,2,n
-        imatch_depth_gt = F.grid_sample(depth_render[:, None], imatch_gt.permute(0, 2, 1)[:, None],
-                                        align_corners=False)[:, 0, 0]
-        depth_weight = (5 * -F.relu(imatch_depth - imatch_depth_gt)).exp().detach()
+        imatch_gt, depth_weight = self._visibility(pred_v, depth_render, foc_crop, pp_crop, rotation, translation)
         return (mask_render, tex_render, depth_render, match_gt, imatch_gt, tex_mask, depth_mask, match_mask,
                 depth_weight)
