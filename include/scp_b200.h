@@ -84,6 +84,19 @@ int scp_softras_backward(const float *faces, const float *textures, const float 
 
 /* ---- dense 2D<->3D correspondence (Correspondence.match) --------------------------------- */
 
+/*
+ * Two renders in ONE traversal (model/module/renderer.py:49-61 of the reference launches them separately): the
+ * softmax-RGB render of textures_soft (depth render) and the hard z-buffer render of textures_hard (NOCS map) over the
+ * same faces with the same sigma / euclidean distance / 'prod' alpha -- their fragments and alpha channels are
+ * identical (soft_rasterize_cuda_kernel.cu:408-417).  Vertex textures [B,nf,3,3]; each output pair is prepared by the
+ * caller as for scp_softras_forward.  The *_soft outputs feed scp_softras_backward unchanged.
+ */
+int scp_softras_forward_dual(const float *faces, const float *textures_soft, const float *textures_hard,
+                             float *faces_info, float *aggrs_info_soft, float *soft_colors_soft,
+                             float *aggrs_info_hard, float *soft_colors_hard, int B, int nf, int image_size,
+                             float near_, float far_, float eps, float sigma_val, float dist_eps, float gamma_val,
+                             int double_side, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Scratch bytes of scp_corr_match_forward (per-row-block column partials). */
 size_t scp_corr_workspace_bytes(int B, int hf, int wf, int N);
 

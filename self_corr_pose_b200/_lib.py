@@ -25,6 +25,7 @@ _SIGNATURES = {
     'scp_softras_workspace_bytes': ([_i, _i], _sz),
     'scp_softras_forward': ([_f] * 5 + _SOFTRAS_SCALARS + [_f, _sz, _f], _i),
     'scp_softras_backward': ([_f] * 8 + _SOFTRAS_SCALARS + [_f, _sz, _f], _i),
+    'scp_softras_forward_dual': ([_f] * 8 + [_i, _i, _i, _fl, _fl, _fl, _fl, _fl, _fl, _i, _f, _sz, _f], _i),
     'scp_corr_workspace_bytes': ([_i, _i, _i, _i], _sz),
     'scp_corr_match_forward': ([_f] * 5 + [_fl, _i, _i, _i, _i, _i] + [_f] * 8 + [_f, _sz, _f], _i),
     'scp_corr_match_backward': ([_f] * 5 + [_fl, _i, _i, _i, _i, _i] + [_f] * 13 + [_f], _i),

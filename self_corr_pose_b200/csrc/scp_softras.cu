@@ -422,11 +422,18 @@ struct FwdState {
     float col[3];
     float alpha, sm_sum, sm_max, depth_min;
     int face_min;
+    float col2[3];   // RGB_DUAL: colour of the hard z-buffer pass (second texture set)
 };
+
+// third aggregation mode of the fused depth + NOCS traversal: softmax RGB of `textures` AND hard RGB of `textures2`
+// over the same fragments (the two renders share sigma, the distance function and the alpha aggregation; gamma is
+// unused by the hard mode, soft_rasterize_cuda_kernel.cu:428-435)
+constexpr int RGB_DUAL = 2;
 
 template <int RGB, bool FAST>
 __device__ __forceinline__ void forward_pair(const Params &p, const float *__restrict__ r, const Pixel &px,
-                                             const float *__restrict__ textures, int b, FwdState &s)
+                                             const float *__restrict__ textures, const float *__restrict__ textures2,
+                                             int b, FwdState &s)
 {
     float bx0, bx1, by0, by1;
     load_bbox(r, bx0, bx1, by0, by1);
@@ -446,13 +453,20 @@ __device__ __forceinline__ void forward_pair(const Params &p, const float *__res
     const float zp = clip_and_depth(f, fr.w, wc);
     if (zp < p.near_ || zp > p.far_) return;
 
-    if (RGB == SCP_RGB_HARD) {
+    if (RGB == SCP_RGB_HARD || RGB == RGB_DUAL) {
         if (zp < s.depth_min && inside_closed(fr.w) && (p.double_side || f.front != 0.f)) {
             s.depth_min = zp;
             s.face_min = f.idx;
-            sample_color<FAST>(p, f, wc, textures, b, s.col);
+            if (RGB == RGB_DUAL) {   // vertex colours of the second texture set, fetched only for z-buffer winners
+                const float *t2 = textures2 + ((size_t)b * p.nf + f.idx) * 9;
+#pragma unroll
+                for (int k = 0; k < 3; k++) s.col2[k] = wc[0] * __ldg(t2 + k) + wc[1] * __ldg(t2 + 3 + k) + wc[2] * __ldg(t2 + 6 + k);
+            } else {
+                sample_color<FAST>(p, f, wc, textures, b, s.col);
+            }
         }
-    } else if (f.front != 0.f || p.double_side) {
+    }
+    if ((RGB == SCP_RGB_SOFTMAX || RGB == RGB_DUAL) && (f.front != 0.f || p.double_side)) {
         const float zn = (p.far_ - zp) * p.inv_depth_range;
         float rescale = 1.f;
         if (zn > s.sm_max) {
@@ -474,7 +488,10 @@ __global__ void __launch_bounds__(NTHREADS, 3) forward_kernel(Params p, const fl
                                                           const int *__restrict__ img_bbox,
                                                           const float *__restrict__ textures,
                                                           float *__restrict__ aggrs_info,
-                                                          float *__restrict__ soft_colors)
+                                                          float *__restrict__ soft_colors,
+                                                          const float *__restrict__ textures2,
+                                                          float *__restrict__ aggrs_info2,
+                                                          float *__restrict__ soft_colors2)
 {
     __shared__ int s_list[LIST_CAP];
     __shared__ int s_cnt[SCAN * NWARPS];
@@ -522,7 +539,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) forward_kernel(Params p, const fl
                     const int j = __ffs(todo) - 1;
                     todo &= todo - 1;
                     const int fsel = __shfl_sync(0xffffffffu, fi, j);
-                    if (px.valid) forward_pair<RGB, FAST>(p, rec + ((size_t)b * p.nf + fsel) * REC, px, textures, b, s);
+                    if (px.valid) forward_pair<RGB, FAST>(p, rec + ((size_t)b * p.nf + fsel) * REC, px, textures, textures2, b, s);
                 }
             }
             if (base < p.nf) __syncthreads();  // the list is about to be rebuilt
@@ -535,6 +552,15 @@ __global__ void __launch_bounds__(NTHREADS, 3) forward_kernel(Params p, const fl
     else if (alpha_mode == SCP_ALPHA_SUM) a_out = s.alpha / p.nf;
     else a_out = s.alpha;
     soft_colors[((size_t)b * 4 + 3) * plane + px.pn] = a_out;
+    if (RGB == RGB_DUAL) {   // hard pass -> second output set (its colours keep the pre-filled background when no face hit)
+        soft_colors2[((size_t)b * 4 + 3) * plane + px.pn] = a_out;
+        if (s.face_min != -1) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) soft_colors2[((size_t)b * 4 + k) * plane + px.pn] = s.col2[k];
+        }
+        aggrs_info2[((size_t)b * 2 + 0) * plane + px.pn] = s.depth_min;
+        aggrs_info2[((size_t)b * 2 + 1) * plane + px.pn] = (float)s.face_min;
+    }
     if (RGB == SCP_RGB_HARD) {
         if (s.face_min != -1) {
 #pragma unroll
@@ -838,13 +864,46 @@ extern "C" int scp_softras_forward(const float *faces, const float *textures, fl
     const dim3 grid(p.tiles_x * p.tiles_x, B);
     const bool fast = func_id_dist == SCP_DIST_EUCLIDEAN && func_id_alpha == SCP_ALPHA_PROD;
     if (func_id_rgb == SCP_RGB_HARD) {
-        if (fast) forward_kernel<SCP_RGB_HARD, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors);
-        else forward_kernel<SCP_RGB_HARD, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors);
+        if (fast) forward_kernel<SCP_RGB_HARD, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors, nullptr, nullptr, nullptr);
+        else forward_kernel<SCP_RGB_HARD, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors, nullptr, nullptr, nullptr);
     } else {
-        if (fast) forward_kernel<SCP_RGB_SOFTMAX, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors);
-        else forward_kernel<SCP_RGB_SOFTMAX, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors);
+        if (fast) forward_kernel<SCP_RGB_SOFTMAX, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors, nullptr, nullptr, nullptr);
+        else forward_kernel<SCP_RGB_SOFTMAX, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors, nullptr, nullptr, nullptr);
     }
     return scp::check_launch("scp_softras_forward");
+}
+
+extern "C" int scp_softras_forward_dual(const float *faces, const float *textures_soft, const float *textures_hard,
+                                        float *faces_info, float *aggrs_info_soft, float *soft_colors_soft,
+                                        float *aggrs_info_hard, float *soft_colors_hard, int B, int nf, int image_size,
+                                        float near_, float far_, float eps, float sigma_val, float dist_eps,
+                                        float gamma_val, int double_side, void *workspace, size_t workspace_bytes,
+                                        void *stream)
+{
+    Params p;
+    if (!make_params(p, B, nf, 3, image_size, near_, far_, eps, sigma_val, SCP_DIST_EUCLIDEAN, dist_eps, gamma_val,
+                     SCP_RGB_SOFTMAX, SCP_ALPHA_PROD, SCP_TEX_VERTEX, double_side) ||
+        !textures_hard || !aggrs_info_hard || !soft_colors_hard) {
+        scp::set_last_error("scp_softras_forward_dual: unsupported arguments (B=%d nf=%d is=%d)", B, nf, image_size);
+        return -1;
+    }
+    if (!workspace || workspace_bytes < scp_softras_workspace_bytes(B, nf)) {
+        scp::set_last_error("scp_softras_forward_dual: workspace too small");
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float4 *bbox = (float4 *)workspace;
+    float *rec = (float *)((char *)workspace + bbox_bytes(B, nf));
+    int *img_bbox = (int *)((char *)rec + rec_bytes(B, nf));
+    const long nfaces = (long)B * nf;
+    cudaMemsetAsync(img_bbox, 0x7f, (size_t)B * 4 * sizeof(int), st);
+    pack_kernel<<<(unsigned)((nfaces + 255) / 256), 256, 0, st>>>(p, faces, textures_soft, faces_info, 1, bbox, rec,
+                                                                 img_bbox);
+    const dim3 grid(p.tiles_x * p.tiles_x, B);
+    forward_kernel<RGB_DUAL, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures_soft, aggrs_info_soft,
+                                                              soft_colors_soft, textures_hard, aggrs_info_hard,
+                                                              soft_colors_hard);
+    return scp::check_launch("scp_softras_forward_dual");
 }
 
 extern "C" int scp_softras_backward(const float *faces, const float *textures, const float *soft_colors,

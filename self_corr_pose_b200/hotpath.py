@@ -42,9 +42,9 @@ class HotPath:
     """data = (img, mask, depth, foc_crop, pp_crop); enc = (img_feat[B,C,P], mesh_feat[B,N,C], pred_v[B,N,3],
     rotation[B,3,3], translation[B,1,3]).  forward() -> (total_loss, aux dict with the reference's keys)."""
 
-    # kernels of this package launched by one forward+backward (see DESIGN.md): SoftRas 3x(pack+fwd) + 2x(pack+bwd)
-    # (mask shares the depth traversal), correspondence 3 fwd + 2 bwd, ViT 3 + 9*7 + 2, image losses 2 fwd + 1 bwd
-    GPU_LAUNCHES = 6 + 4 + 5 + 68 + 3
+    # kernels of this package launched by one forward+backward (see DESIGN.md): SoftRas 2x(pack+fwd) + 2x(pack+bwd)
+    # (mask, depth and NOCS share one traversal), correspondence 3 fwd + 2 bwd, ViT 3 + 9*7 + 2, image losses 2 fwd + 1 bwd
+    GPU_LAUNCHES = 4 + 4 + 5 + 68 + 3
 
     def __init__(self, opts, mean_v, faces, device='cuda', fused_losses=True):
         self.opts = opts

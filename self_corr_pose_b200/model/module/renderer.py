@@ -69,11 +69,22 @@ class Renderer:
             raise NotImplementedError('render_all_raw: vertex textures only (every shipped config)')
         sv = project_to_screen(pred_v, foc_crop, pp_crop, rotation, translation)
         fv = srf.face_vertices(self.renderer_depth.transform.transformer(sv), faces)
-        # depth render: texture = screen-space vertices themselves (render(..., render_depth=True): tex = verts.clone())
-        r_depth = self._rasterize(self.renderer_depth, fv, srf.face_vertices(sv, faces))
+        # depth render (texture = the screen-space vertices themselves: render(..., render_depth=True) sets
+        # tex = verts.clone()) and NOCS map (hard RGB of the detached canonical coordinates; no useful gradient, see
+        # render_all) in ONE traversal: same sigma, same alpha, gamma unused by the hard mode
+        rd, rn = self.renderer_depth.rasterizer, self.renderer_hardtex.rasterizer
+        same = all(getattr(rd, k) == getattr(rn, k) for k in ('image_size', 'near', 'far', 'fill_back', 'eps', 'sigma_val',
+                                                              'dist_func', 'dist_eps', 'aggr_func_alpha'))
+        if same and rd.dist_func == 'euclidean' and rd.aggr_func_alpha == 'prod' and rd.aggr_func_rgb == 'softmax' \
+                and rn.aggr_func_rgb == 'hard':
+            r_depth, r_nocs = srf.soft_rasterize_dual(fv, srf.face_vertices(sv, faces),
+                                                      srf.face_vertices(pred_v.detach(), faces), rd.image_size,
+                                                      rd.background_color, rn.background_color, rd.near, rd.far,
+                                                      rd.fill_back, rd.eps, rd.sigma_val, rd.dist_eps, rd.gamma_val)
+        else:
+            r_depth = self._rasterize(self.renderer_depth, fv, srf.face_vertices(sv, faces))
+            r_nocs = self._rasterize(self.renderer_hardtex, fv.detach(), srf.face_vertices(pred_v.detach(), faces))
         r_tex = self._rasterize(self.renderer_softtex, fv, srf.face_vertices(tex, faces))
-        # NOCS map: hard RGB of the detached canonical coordinates; no useful gradient (see render_all)
-        r_nocs = self._rasterize(self.renderer_hardtex, fv.detach(), srf.face_vertices(pred_v.detach(), faces))
         depth_render = r_depth[:, 2] if self.opts.use_depth else r_depth[:, 2].detach()
         imatch_gt, depth_weight = self._visibility(pred_v, depth_render, foc_crop, pp_crop, rotation, translation)
         return r_depth, r_tex, r_nocs, imatch_gt, depth_weight

@@ -90,6 +90,66 @@ class SoftRasterizeFunction(Function):
         return (grad_faces.reshape(ctx.in_shapes[0]), grad_textures.reshape(ctx.in_shapes[1])) + (None,) * 13
 
 
+class SoftRasterizeDualFunction(Function):
+    """Depth render (softmax RGB of `textures_soft`) and NOCS map (hard RGB of `textures_hard`) in one traversal
+    (scp_softras_forward_dual).  Returns (soft_colors_soft, soft_colors_hard); only the first is differentiable
+    (w.r.t. face_vertices and textures_soft, through scp_softras_backward) -- the hard render's useful gradient is
+    exactly zero on this path."""
+
+    @staticmethod
+    def forward(ctx, face_vertices, textures_soft, textures_hard, image_size, background_soft, background_hard, near,
+                far, fill_back, eps, sigma_val, dist_eps, gamma_val):
+        if not face_vertices.is_cuda:
+            raise TypeError('Rasterize module supports only cuda Tensors')
+        ctx.image_size = image_size
+        ctx.near, ctx.far, ctx.eps = float(near), float(far), float(eps)
+        ctx.sigma_val, ctx.gamma_val = float(sigma_val), float(gamma_val)
+        ctx.func_dist_type, ctx.func_rgb_type, ctx.func_alpha_type = FUNC_DIST['euclidean'], FUNC_RGB['softmax'], \
+            FUNC_ALPHA['prod']
+        ctx.dist_eps = math.log(1. / dist_eps - 1.)
+        ctx.texture_type, ctx.texture_size, ctx.fill_back = FUNC_TEX['vertex'], 3, fill_back
+        ctx.batch_size, ctx.num_faces = face_vertices.shape[:2]
+        B, nf = ctx.batch_size, ctx.num_faces
+        dev = face_vertices.device
+        ctx.in_shapes = (face_vertices.shape, textures_soft.shape)
+        face_vertices = face_vertices.detach().float().reshape(B, nf, 3, 3).contiguous()
+        textures_soft = textures_soft.detach().float().reshape(B, nf, 3, 3).contiguous()
+        textures_hard = textures_hard.detach().float().reshape(B, nf, 3, 3).contiguous()
+        faces_info = torch.zeros(B, nf, 27, dtype=torch.float32, device=dev)
+        outs = []
+        for bg in (background_soft, background_hard):
+            aggrs = torch.zeros(B, 2, image_size, image_size, dtype=torch.float32, device=dev)
+            cols = torch.ones(B, 4, image_size, image_size, dtype=torch.float32, device=dev)
+            for k in range(3):
+                if bg[k] != 1:
+                    cols[:, k] *= bg[k]
+            outs.append((aggrs, cols))
+        ws, ws_bytes = _workspace(B, nf, dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().scp_softras_forward_dual(
+                _lib.ptr(face_vertices), _lib.ptr(textures_soft), _lib.ptr(textures_hard), _lib.ptr(faces_info),
+                _lib.ptr(outs[0][0]), _lib.ptr(outs[0][1]), _lib.ptr(outs[1][0]), _lib.ptr(outs[1][1]), B, nf,
+                image_size, ctx.near, ctx.far, ctx.eps, ctx.sigma_val, ctx.dist_eps, ctx.gamma_val,
+                int(bool(fill_back)), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+        _lib.check(rc, 'scp_softras_forward_dual')
+        ctx.save_for_backward(face_vertices, textures_soft, outs[0][1], faces_info, outs[0][0])
+        ctx.mark_non_differentiable(outs[1][1])
+        return outs[0][1], outs[1][1]
+
+    @staticmethod
+    def backward(ctx, grad_soft_colors, _grad_hard):
+        grads = SoftRasterizeFunction.backward(ctx, grad_soft_colors)
+        return (grads[0], grads[1]) + (None,) * 11
+
+
+def soft_rasterize_dual(face_vertices, textures_soft, textures_hard, image_size=256, background_soft=(1, 1, 1),
+                        background_hard=(0, 0, 0), near=1, far=100, fill_back=True, eps=1e-3, sigma_val=1e-4,
+                        dist_eps=1e-4, gamma_val=1e-4):
+    return SoftRasterizeDualFunction.apply(face_vertices, textures_soft, textures_hard, image_size,
+                                           list(background_soft), list(background_hard), near, far, fill_back, eps,
+                                           sigma_val, dist_eps, gamma_val)
+
+
 def soft_rasterize(face_vertices, textures, image_size=256, background_color=[0, 0, 0], near=1, far=100,
                    fill_back=True, eps=1e-3, sigma_val=1e-5, dist_func='euclidean', dist_eps=1e-4,
                    gamma_val=1e-4, aggr_func_rgb='softmax', aggr_func_alpha='prod', texture_type='surface'):

@@ -151,3 +151,34 @@ def test_render_is_deterministic_forward():
     a = srf.soft_rasterize(fv.cuda(), tex.cuda(), **kw)
     b = srf.soft_rasterize(fv.cuda(), tex.cuda(), **kw)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('mesh,size,B', [('uv1280', 128, 3), ('ico642', 256, 2), ('laptop', 64, 2)])
+def test_dual_traversal_equals_two_renders(mesh, size, B):
+    """scp_softras_forward_dual (depth render + NOCS map in one traversal) against the two separate launches of the
+    same kernels: forward outputs identical (up to FMA contraction), gradient of the soft render equal up to atomic-order noise."""
+    fv, sv, f = _scenes.config0(mesh, B=B)
+    tex_soft = srf.face_vertices(sv, f).cuda()
+    tex_hard = srf.face_vertices(_scenes.vertex_colors(sv) - 0.5, f).cuda()
+    cfg_d, cfg_h = _scenes.RENDER_CONFIGS['depth'], _scenes.RENDER_CONFIGS['hardtex']
+    a = fv.cuda().requires_grad_(True)
+    ts = tex_soft.clone().requires_grad_(True)
+    r_soft = srf.soft_rasterize(a, ts, image_size=size, texture_type='vertex', **cfg_d)
+    r_hard = srf.soft_rasterize(a.detach(), tex_hard, image_size=size, texture_type='vertex', **cfg_h)
+    g = torch.randn(r_soft.shape, generator=torch.Generator().manual_seed(5)).cuda()
+    r_soft.backward(g)
+    a2 = fv.cuda().requires_grad_(True)
+    ts2 = tex_soft.clone().requires_grad_(True)
+    d_soft, d_hard = srf.soft_rasterize_dual(a2, ts2, tex_hard, image_size=size, sigma_val=cfg_d['sigma_val'],
+                                             gamma_val=cfg_d['gamma_val'], background_soft=cfg_d['background_color'],
+                                             background_hard=cfg_h['background_color'])
+    d_soft.backward(g)
+    torch.cuda.synchronize()
+    # same statements in both instantiations; only the compiler's FMA contraction choices may differ
+    assert torch.allclose(d_soft, r_soft, rtol=1e-5, atol=1e-6)
+    assert float((d_hard != r_hard).float().mean()) < 1e-4 and torch.equal(d_hard[:, 3], d_soft[:, 3])
+    assert not d_hard.requires_grad
+    for x, y, name in ((a2.grad, a.grad, 'faces'), (ts2.grad, ts.grad, 'textures')):
+        rel = float((x - y).norm() / y.norm().clamp_min(1e-30))
+        print('PARITY dual-vs-separate grad_%s %s %dpx rel=%.2e' % (name, mesh, size, rel))
+        assert rel < 1e-4
