@@ -15,8 +15,8 @@
  *   scp_corr_match_forward / scp_corr_match_backward
  *       model/module/correspondence.py:36-73 (Correspondence.match: bmm + mask + two softmaxes
  *       + two weighted sums), reached through torch ops in the reference.
- *   scp_colsoftmax_bmm_forward / _backward
- *       model/module/correspondence.py:105-110 (rotation-cycle similarity, column softmax, grid.bmm).
+ *       The rotation-cycle similarity of :105-110 (column softmax, grid.bmm) runs on the same two entry points with
+ *       the target pixels in the role of the vertices.
  *   scp_image_losses_forward / scp_image_losses_backward
  *       model/util/loss_utils.py:236-244 (compute_mask_loss), :246-252 (compute_texture_loss), :273-284
  *       (compute_depth_loss), :317-320 (compute_match_loss) with the nearest upsampling of `match`
@@ -82,8 +82,6 @@ int scp_softras_backward(const float *faces, const float *textures, const float 
                          int texture_sample_type, int double_side, void *workspace, size_t workspace_bytes,
                          void *stream);
 
-/* ---- dense 2D<->3D correspondence (Correspondence.match) --------------------------------- */
-
 /*
  * Two renders in ONE traversal (model/module/renderer.py:49-61 of the reference launches them separately): the
  * softmax-RGB render of textures_soft (depth render) and the hard z-buffer render of textures_hard (NOCS map) over the
@@ -97,7 +95,9 @@ int scp_softras_forward_dual(const float *faces, const float *textures_soft, con
                              float near_, float far_, float eps, float sigma_val, float dist_eps, float gamma_val,
                              int double_side, void *workspace, size_t workspace_bytes, void *stream);
 
-/* Scratch bytes of scp_corr_match_forward (per-row-block column partials). */
+/* ---- dense 2D<->3D correspondence (Correspondence.match) --------------------------------- */
+
+/* Scratch bytes of scp_corr_match_forward / _backward (foreground block lists, per-row-block column partials). */
 size_t scp_corr_workspace_bytes(int B, int hf, int wf, int N);
 
 /*
@@ -115,6 +115,8 @@ size_t scp_corr_workspace_bytes(int B, int hf, int wf, int N);
  *                                        POOLED similarity times the pooled meshgrid = "grid.bmm(softmax(tau*
  *                                        pointcorr_src, dim=1))" of pretrained_corr.py:125,131-136, per image
  * Supported shapes: C == 64, wf in {8,16,32,64}, hf*wf a multiple of 128 with 128/wf even.
+ * Background pixels (mask_down == 0) are not traversed: the kernels walk a per-image list of the 2x2 pixel blocks that
+ * contain foreground; the constant outputs of the other blocks (uniform row softmax, -1e5 rows) are filled directly.
  */
 int scp_corr_match_forward(const float *img_feat, const float *mesh_feat, const float *mask_down,
                            const float *pred_v, const float *meshgrid, float tau, int B, int hf, int wf, int N,
@@ -126,14 +128,15 @@ int scp_corr_match_forward(const float *img_feat, const float *mesh_feat, const 
  * Backward of the above (autograd of correspondence.py:42-53 in the reference): gradients w.r.t.
  * img_feat and mesh_feat from g_match[B,hf*wf,3], g_imatch[B,2,N] and (optional, may be NULL)
  * g_pointcorr_pool / g_pointcorr_full / g_A_pool (with the saved A_pool, csum_pool).  The similarity tile is
- * recomputed, nothing P x N is read back.
+ * recomputed, nothing P x N is read back.  workspace: scp_corr_workspace_bytes (the foreground block list is rebuilt).
  */
 int scp_corr_match_backward(const float *img_feat, const float *mesh_feat, const float *mask_down,
                             const float *pred_v, const float *meshgrid, float tau, int B, int hf, int wf, int N,
                             int C, const float *match, const float *imatch, const float *rsum, const float *csum,
                             const float *g_match, const float *g_imatch, const float *g_pointcorr_pool,
                             const float *g_pointcorr_full, const float *A_pool, const float *csum_pool,
-                            const float *g_A_pool, float *g_img_feat, float *g_mesh_feat, void *stream);
+                            const float *g_A_pool, float *g_img_feat, float *g_mesh_feat, void *workspace,
+                            size_t workspace_bytes, void *stream);
 
 /* ---- frozen DINO ViT-S/8: layer-k key features ----------------------------------------------- */
 /* Replaces DINO.forward (model/module/network/dino.py:102-109) / VisionTransformer.get_specific_tokens

@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libscp_b200.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _f = ctypes.c_void_p   # device pointers travel as integers
 _i = ctypes.c_int
@@ -28,7 +28,7 @@ _SIGNATURES = {
     'scp_softras_forward_dual': ([_f] * 8 + [_i, _i, _i, _fl, _fl, _fl, _fl, _fl, _fl, _i, _f, _sz, _f], _i),
     'scp_corr_workspace_bytes': ([_i, _i, _i, _i], _sz),
     'scp_corr_match_forward': ([_f] * 5 + [_fl, _i, _i, _i, _i, _i] + [_f] * 8 + [_f, _sz, _f], _i),
-    'scp_corr_match_backward': ([_f] * 5 + [_fl, _i, _i, _i, _i, _i] + [_f] * 13 + [_f], _i),
+    'scp_corr_match_backward': ([_f] * 5 + [_fl, _i, _i, _i, _i, _i] + [_f] * 13 + [_f, _sz, _f], _i),
 }
 
 

@@ -16,6 +16,13 @@
 // written at most once (full, eval mode) or only as its 2x2 mean (training).  The backward
 // recomputes the S tile instead of reading saved softmaxes and runs the two gradient products on
 // the tensor cores as well.
+//
+// Background skipping: a background pixel contributes exactly nothing to the column softmax and its own
+// row outputs are constants (uniform row softmax -> match = mean vertex, pointcorr = -1e5, zero gradient).
+// A per-image pre-pass lists the 2x2 pixel blocks that contain at least one foreground pixel; the row
+// blocks of every kernel are built from that list (32 blocks = 128 rows per CTA), so the P x N work
+// shrinks to the silhouette's share of the map (the object mask covers ~40 % of a crop), and a fill
+// kernel writes the constants of the dropped blocks.
 #include "../../include/scp_b200.h"
 #include "scp_common.cuh"
 #include "scp_mma.cuh"
@@ -37,28 +44,32 @@ struct Geo {
     float tau;
 };
 
-// MMA row r (0..127) of row block `pblk` -> pixel index.  16-row MMA tiles are 8(x) x 2(y) patches:
-// rows q and q+8 of a tile are vertical neighbours, rows q and q^1 horizontal neighbours.
-__device__ __forceinline__ int row_pixel(const Geo &g, int pblk, int r, int &pool_idx)
+// Per-image list of kept 2x2 pixel blocks: blk[0] = count, blk[1..count] = pooled-pixel ids (ascending).
+// MMA row r (0..127) of row block `pblk` -> pixel index (-1 past the end of the list).  A 16-row MMA tile holds
+// four listed blocks: rows q and q^1 are horizontal neighbours, rows q and q+8 vertical neighbours of one block.
+constexpr int BLK_PER_CTA = BM / 4;
+__device__ __forceinline__ int row_pixel(const Geo &g, const int *__restrict__ blk, int pblk, int r, int &pool_idx)
 {
     const int j = r >> 4, q = r & 15;
-    const int tiles_per_pair = g.wf >> 3;
-    const int pair = j / tiles_per_pair, xt = j - pair * tiles_per_pair;
-    const int y = pblk * (BM / g.wf) + 2 * pair + (q >> 3);
-    const int x = 8 * xt + (q & 7);
-    pool_idx = (y >> 1) * (g.wf >> 1) + (x >> 1);
-    return y * g.wf + x;
+    const int li = pblk * BLK_PER_CTA + 4 * j + ((q & 7) >> 1);
+    if (li >= blk[0]) { pool_idx = -1; return -1; }
+    const int id = blk[1 + li], w2 = g.wf >> 1;
+    const int by = id / w2, bx = id - by * w2;
+    pool_idx = id;
+    return (2 * by + (q >> 3)) * g.wf + 2 * bx + (q & 1);
 }
+__device__ __forceinline__ int active_row_blocks(const int *__restrict__ blk) { return (blk[0] + BLK_PER_CTA - 1) / BLK_PER_CTA; }
 
 // ---- tile loaders --------------------------------------------------------------------------
-// As[c][r] <- img_feat[b][c][pixel(r)]: 32-byte runs (8 consecutive x), two cp.async each
-__device__ __forceinline__ void load_A(const Geo &g, float *As, const float *__restrict__ img_b, int pblk)
+// As[c][r] <- img_feat[b][c][pixel(r)]: rows 2i, 2i+1 are horizontally adjacent pixels (one 8-byte cp.async);
+// rows past the block list are zero-filled.  s_pix must be visible (barrier) before the call.
+__device__ __forceinline__ void load_A(const Geo &g, float *As, const float *__restrict__ img_b, const int *s_pix)
 {
-    for (int i = threadIdx.x; i < C * (BM / 4); i += NT) {
-        const int c = i / (BM / 4), r4 = (i - c * (BM / 4)) * 4;
-        int pool;
-        const int p = row_pixel(g, pblk, r4, pool);
-        cp_async16(As + c * AS + r4, img_b + (size_t)c * g.P + p);
+    for (int i = threadIdx.x; i < C * (BM / 2); i += NT) {
+        const int c = i / (BM / 2), r2 = (i - c * (BM / 2)) * 2;
+        const int p = s_pix[r2];
+        if (p >= 0) cp_async8(As + c * AS + r2, img_b + (size_t)c * g.P + p);
+        else *reinterpret_cast<float2 *>(As + c * AS + r2) = make_float2(0.f, 0.f);
     }
 }
 
@@ -140,8 +151,8 @@ constexpr int F_BS = F_AS + C * AS;              // 2 buffers
 constexpr int F_VS = F_BS + 2 * BN * BS;         // 2 buffers of [BN][4]: x, y, z, valid
 constexpr int F_COL = F_VS + 2 * BN * 4;         // [2: full-res / pooled][4 wm][BN][4]
 constexpr int F_ROW = F_COL + 2 * 4 * BN * 4;    // [2 wn][BM][4]
-constexpr int F_INFO = F_ROW + 2 * BM * 4;       // mask[BM], gx[BM], gy[BM], pixel[BM] (int)
-constexpr int F_TOTAL = F_INFO + 4 * BM;
+constexpr int F_INFO = F_ROW + 2 * BM * 4;       // mask[BM], gx[BM], gy[BM], pixel[BM] (int), pooled pixel[BM] (int)
+constexpr int F_TOTAL = F_INFO + 5 * BM;
 
 __device__ __forceinline__ void load_V(const Geo &g, float *Vs, const float *__restrict__ v_b, int n0)
 {
@@ -158,33 +169,36 @@ corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__rest
                 const float *__restrict__ mask_down, const float *__restrict__ pred_v,
                 const float *__restrict__ meshgrid, float *__restrict__ pc_full, float *__restrict__ pc_pool,
                 float *__restrict__ match, float *__restrict__ rsum, float *__restrict__ colpart,
-                float *__restrict__ colpart_pool)
+                float *__restrict__ colpart_pool, const int *__restrict__ blocks)
 {
     extern __shared__ __align__(16) float sm[];
     float *As = sm + F_AS, *Bs = sm + F_BS, *Vs = sm + F_VS, *s_col = sm + F_COL, *s_row = sm + F_ROW;
     float *s_mask = sm + F_INFO, *s_gx = s_mask + BM, *s_gy = s_gx + BM;
-    int *s_pix = reinterpret_cast<int *>(s_gy + BM);
+    int *s_pix = reinterpret_cast<int *>(s_gy + BM), *s_pool = s_pix + BM;
 
     const int pblk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int *blk = blocks + (size_t)b * ((geo.P >> 2) + 1);
+    if (pblk >= active_row_blocks(blk)) return;   // row blocks past the foreground list have no work
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3, wm = warp & 3, wn = warp >> 2;
     const float *img_b = img_feat + (size_t)b * C * geo.P;
     const float *mesh_b = mesh_feat + (size_t)b * geo.N * C;
     const float *v_b = pred_v + (size_t)b * geo.N * 3;
     const float kexp = geo.tau * LOG2E;
 
-    load_A(geo, As, img_b, pblk);
+    if (tid < BM) {
+        int pool;
+        const int p = row_pixel(geo, blk, pblk, tid, pool);
+        s_pix[tid] = p;
+        s_pool[tid] = pool;
+        s_mask[tid] = p >= 0 ? mask_down[(size_t)b * geo.P + p] : 0.f;
+        s_gx[tid] = p >= 0 ? meshgrid[p] : 0.f;
+        s_gy[tid] = p >= 0 ? meshgrid[geo.P + p] : 0.f;
+    }
+    __syncthreads();
+    load_A(geo, As, img_b, s_pix);
     load_B(geo, Bs, mesh_b, 0);
     cp_async_commit();
     load_V(geo, Vs, v_b, 0);
-    if (tid < BM) {
-        int pool;
-        const int p = row_pixel(geo, pblk, tid, pool);
-        s_pix[tid] = p;
-        s_mask[tid] = mask_down[(size_t)b * geo.P + p];
-        s_gx[tid] = meshgrid[p];
-        s_gy[tid] = meshgrid[geo.P + p];
-    }
-    __syncthreads();
 
     // this thread's four rows: ri = 2*mi + h  ->  r = 32*wm + 16*mi + 8*h + g
     float rmask[4], rgx[4], rgy[4];
@@ -195,11 +209,7 @@ corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__rest
         rmask[ri] = s_mask[r]; rgx[ri] = s_gx[r]; rgy[ri] = s_gy[r]; rpix[ri] = s_pix[r];
     }
 #pragma unroll
-    for (int mi = 0; mi < 2; mi++) {
-        int pool;
-        row_pixel(geo, pblk, 32 * wm + 16 * mi + g, pool);
-        rpool[mi] = pool;
-    }
+    for (int mi = 0; mi < 2; mi++) rpool[mi] = s_pool[32 * wm + 16 * mi + g];
     // grid coordinates of the 2x2-pooled pixel of each row pair (bilinear 1/2 of the meshgrid = 2x2 mean)
     float pgx[2], pgy[2];
 #pragma unroll
@@ -254,13 +264,13 @@ corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__rest
                         cv[(2 * ni + j) * 3 + 0] += e;
                         cv[(2 * ni + j) * 3 + 1] += e * rgx[ri];
                         cv[(2 * ni + j) * 3 + 2] += e * rgy[ri];
-                        if (pc_full != nullptr && valid) pc_full[((size_t)b * geo.P + rpix[ri]) * geo.N + n] = s;
+                        if (pc_full != nullptr && valid && rpix[ri] >= 0) pc_full[((size_t)b * geo.P + rpix[ri]) * geo.N + n] = s;
                     }
                     if (pc_pool != nullptr) {
                         float q = sm2[0] + sm2[1];
                         q += __shfl_xor_sync(0xffffffffu, q, 4);   // horizontal neighbour (g ^ 1)
                         const float pv = 0.25f * q;
-                        if (valid && !(g & 1)) {
+                        if (valid && !(g & 1) && rpool[mi] >= 0) {
                             pc_pool[((size_t)b * (geo.P >> 2) + rpool[mi]) * geo.N + n] = pv;
                             if (want_pool_stats) {   // pooled rows containing background pixels underflow to 0
                                 const float ep = exp2f((pv - 1.f) * kexp);
@@ -313,7 +323,7 @@ corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__rest
         }
     }
     __syncthreads();
-    if (tid < BM) {
+    if (tid < BM && s_pix[tid] >= 0) {
         const float4 a = *reinterpret_cast<const float4 *>(s_row + tid * 4);
         const float4 c = *reinterpret_cast<const float4 *>(s_row + (BM + tid) * 4);
         const float l = a.x + c.x, inv = 1.f / l;
@@ -330,12 +340,13 @@ corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__rest
 // pooled grid, which has the same mean as the full one)
 __global__ void corr_colreduce_kernel(Geo geo, const float *__restrict__ colpart,
                                       const float *__restrict__ meshgrid, float *__restrict__ imatch,
-                                      float *__restrict__ csum)
+                                      float *__restrict__ csum, const int *__restrict__ blocks)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (n >= geo.N) return;
+    const int nact = active_row_blocks(blocks + (size_t)b * ((geo.P >> 2) + 1));
     float s = 0.f, gx = 0.f, gy = 0.f;
-    for (int k = 0; k < geo.npblk; k++) {
+    for (int k = 0; k < nact; k++) {
         const float4 q = *reinterpret_cast<const float4 *>(colpart + (((size_t)b * geo.npblk + k) * geo.N + n) * 4);
         s += q.x; gx += q.y; gy += q.z;
     }
@@ -364,6 +375,7 @@ struct BwdArgs {
     const float *g_match, *g_imatch, *g_pool, *g_full;
     const float *A_pool, *csum_pool, *g_A_pool;   // pooled column softmax (may be NULL)
     float *g_img_feat, *g_mesh_feat;
+    const int *blocks;   // per-image foreground block lists (see row_pixel)
 };
 constexpr int CPS = 12;   // floats per column-parameter record
 
@@ -373,16 +385,21 @@ __device__ __forceinline__ void load_rowparams(const Geo &geo, const BwdArgs &a,
     if (threadIdx.x < BM) {
         const int r = threadIdx.x;
         int pool;
-        const int p = row_pixel(geo, pblk, r, pool);
-        const size_t bp = (size_t)b * geo.P + p;
-        const float mk = a.mask_down[bp];
-        const float gx = a.meshgrid[p], gy = a.meshgrid[geo.P + p];
-        const float l = a.rsum[bp];
-        const float g0 = a.g_match[bp * 3], g1 = a.g_match[bp * 3 + 1], g2 = a.g_match[bp * 3 + 2];
-        const float dot = g0 * a.match[bp * 3] + g1 * a.match[bp * 3 + 1] + g2 * a.match[bp * 3 + 2];
+        const int p = row_pixel(geo, a.blocks + (size_t)b * ((geo.P >> 2) + 1), pblk, r, pool);
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;   // rows past the list: mask 0 -> dS = 0
+        if (p >= 0) {
+            const size_t bp = (size_t)b * geo.P + p;
+            const float mk = a.mask_down[bp];
+            const float gx = a.meshgrid[p], gy = a.meshgrid[geo.P + p];
+            const float l = a.rsum[bp];
+            const float g0 = a.g_match[bp * 3], g1 = a.g_match[bp * 3 + 1], g2 = a.g_match[bp * 3 + 2];
+            const float dot = g0 * a.match[bp * 3] + g1 * a.match[bp * 3 + 1] + g2 * a.match[bp * 3 + 2];
+            q0 = make_float4(mk, gx, gy, geo.tau / l);
+            q1 = make_float4(g0, g1, g2, dot);
+        }
         float4 *dst = reinterpret_cast<float4 *>(Rp + 8 * r);
-        dst[0] = make_float4(mk, gx, gy, geo.tau / l);
-        dst[1] = make_float4(g0, g1, g2, dot);
+        dst[0] = q0;
+        dst[1] = q1;
         s_pix[r] = p;
         s_pool[r] = pool;
     }
@@ -449,7 +466,7 @@ __device__ __forceinline__ void make_dS(const Geo &geo, const BwdArgs &a, int b,
                 const int n = n0 + cl;
                 // gradient through the pooled similarity: shared by the four pixels of the block
                 float dpool = 0.f;
-                if (a.g_pool != nullptr && valid) dpool = 0.25f * a.g_pool[((size_t)b * (geo.P >> 2) + pool) * geo.N + n];
+                if (a.g_pool != nullptr && valid && pool >= 0) dpool = 0.25f * a.g_pool[((size_t)b * (geo.P >> 2) + pool) * geo.N + n];
                 if (pooled_softmax) {
                     const float4 c2 = *reinterpret_cast<const float4 *>(Cp + CPS * cl + 8);
                     float q = (ra[0].x == 0.f ? -1e5f : acc[mi][ni][j]) + (ra[1].x == 0.f ? -1e5f : acc[mi][ni][2 + j]);
@@ -493,14 +510,16 @@ __global__ void __launch_bounds__(NT, 2) corr_bwd_rows_kernel(Geo geo, BwdArgs a
     int *s_pix = reinterpret_cast<int *>(sm + R_IX), *s_pool = s_pix + BM;
 
     const int pblk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    if (pblk >= active_row_blocks(a.blocks + (size_t)b * ((geo.P >> 2) + 1))) return;
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3, wm = warp & 3, wn = warp >> 2;
     const float *img_b = a.img_feat + (size_t)b * C * geo.P;
     const float *mesh_b = a.mesh_feat + (size_t)b * geo.N * C;
 
-    load_A(geo, As, img_b, pblk);
+    load_rowparams(geo, a, b, pblk, Rp, s_pix, s_pool);
+    __syncthreads();
+    load_A(geo, As, img_b, s_pix);
     load_B(geo, Bs, mesh_b, 0);
     cp_async_commit();
-    load_rowparams(geo, a, b, pblk, Rp, s_pix, s_pool);
     load_colparams(geo, a, b, 0, Cp);
 
     float out[2][4][4];  // g_img tile: rows = pixels (32 per warp), cols = channels (32 per warp)
@@ -552,6 +571,7 @@ __global__ void __launch_bounds__(NT, 2) corr_bwd_rows_kernel(Geo geo, BwdArgs a
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int pix = s_pix[32 * wm + 16 * mi + 8 * h + g];
+            if (pix < 0) continue;
 #pragma unroll
             for (int ci = 0; ci < 4; ci++)
 #pragma unroll
@@ -591,11 +611,13 @@ __global__ void __launch_bounds__(NT, 2) corr_bwd_cols_kernel(Geo geo, BwdArgs a
 #pragma unroll
         for (int k = 0; k < 4; k++) out[ci][k] = 0.f;
 
-    for (int pblk = 0; pblk < geo.npblk; pblk++) {
+    const int nact = active_row_blocks(a.blocks + (size_t)b * ((geo.P >> 2) + 1));
+    for (int pblk = 0; pblk < nact; pblk++) {
         __syncthreads();  // previous iteration finished reading As / Ds / Rp
-        load_A(geo, As, img_b, pblk);
-        cp_async_commit();
         load_rowparams(geo, a, b, pblk, Rp, s_pix, s_pool);
+        __syncthreads();
+        load_A(geo, As, img_b, s_pix);
+        cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
         float acc[2][4][4];
@@ -632,6 +654,92 @@ __global__ void __launch_bounds__(NT, 2) corr_bwd_cols_kernel(Geo geo, BwdArgs a
     }
 }
 
+// ---- foreground block list + constants of the dropped blocks ----------------------------------
+// one CTA per image: ordered compaction of the 2x2 blocks with at least one foreground pixel; mean vertex
+__global__ void __launch_bounds__(NT) corr_blocklist_kernel(Geo geo, const float *__restrict__ mask_down,
+                                                            const float *__restrict__ pred_v, int *__restrict__ blocks,
+                                                            float *__restrict__ vmean)
+{
+    __shared__ int s_cnt[NT / 32];
+    __shared__ float s_red[3 * (NT / 32)];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nblk = geo.P >> 2, w2 = geo.wf >> 1;
+    const float *m = mask_down + (size_t)b * geo.P;
+    int *blk = blocks + (size_t)b * (nblk + 1);
+    int base = 0;
+    for (int i0 = 0; i0 < nblk; i0 += NT) {
+        const int id = i0 + tid;
+        bool keep = false;
+        if (id < nblk) {
+            const int by = id / w2, bx = id - by * w2, p = 2 * by * geo.wf + 2 * bx;
+            keep = m[p] != 0.f || m[p + 1] != 0.f || m[p + geo.wf] != 0.f || m[p + geo.wf + 1] != 0.f;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++) {
+            if (w == warp) off = total;
+            total += s_cnt[w];
+        }
+        if (keep) blk[1 + base + off + __popc(bal & ((1u << lane) - 1u))] = id;
+        base += total;
+        __syncthreads();
+    }
+    if (tid == 0) blk[0] = base;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int n = tid; n < geo.N; n += NT) {
+        const float *v = pred_v + ((size_t)b * geo.N + n) * 3;
+        sx += v[0]; sy += v[1]; sz += v[2];
+    }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    if (lane == 0) { s_red[warp] = sx; s_red[NT / 32 + warp] = sy; s_red[2 * (NT / 32) + warp] = sz; }
+    __syncthreads();
+    if (tid < 3) {
+        float t = 0.f;
+        for (int w = 0; w < NT / 32; w++) t += s_red[tid * (NT / 32) + w];
+        vmean[b * 4 + tid] = t / (float)geo.N;
+    }
+}
+
+// one warp per 2x2 block that is NOT on the list: uniform row softmax -> match = mean vertex, rsum = N;
+// pointcorr rows (pooled / full) = -1e5 exactly (correspondence.py:44,48)
+__global__ void __launch_bounds__(NT) corr_fill_kernel(Geo geo, const float *__restrict__ mask_down,
+                                                       const float *__restrict__ vmean, float *__restrict__ pc_full,
+                                                       float *__restrict__ pc_pool, float *__restrict__ match,
+                                                       float *__restrict__ rsum)
+{
+    const int b = blockIdx.y, lane = threadIdx.x & 31, id = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    const int nblk = geo.P >> 2, w2 = geo.wf >> 1;
+    if (id >= nblk) return;
+    const float *m = mask_down + (size_t)b * geo.P;
+    const int by = id / w2, bx = id - by * w2, p0 = 2 * by * geo.wf + 2 * bx;
+    if (m[p0] != 0.f || m[p0 + 1] != 0.f || m[p0 + geo.wf] != 0.f || m[p0 + geo.wf + 1] != 0.f) return;
+    if (pc_pool != nullptr) {
+        float *row = pc_pool + ((size_t)b * nblk + id) * geo.N;
+        for (int n = lane; n < geo.N; n += 32) row[n] = -1e5f;
+    }
+    const int px[4] = { p0, p0 + 1, p0 + geo.wf, p0 + geo.wf + 1 };
+    if (pc_full != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float *row = pc_full + ((size_t)b * geo.P + px[k]) * geo.N;
+            for (int n = lane; n < geo.N; n += 32) row[n] = -1e5f;
+        }
+    }
+    if (lane < 4) {
+        const size_t bp = (size_t)b * geo.P + px[lane];
+        match[bp * 3 + 0] = vmean[b * 4 + 0];
+        match[bp * 3 + 1] = vmean[b * 4 + 1];
+        match[bp * 3 + 2] = vmean[b * 4 + 2];
+        rsum[bp] = (float)geo.N;
+    }
+}
+
+static size_t blocks_bytes(int B, int P) { return ((size_t)B * ((P >> 2) + 1) * sizeof(int) + 255) / 256 * 256; }
+static size_t vmean_bytes(int B) { return ((size_t)B * 4 * sizeof(float) + 255) / 256 * 256; }
+
 static bool make_geo(Geo &g, int B, int hf, int wf, int N, int Cc, float tau)
 {
     if (B <= 0 || B > 65535 || N <= 0 || Cc != C) return false;
@@ -651,7 +759,8 @@ using namespace scp::corr;
 extern "C" size_t scp_corr_workspace_bytes(int B, int hf, int wf, int N)
 {
     if (B <= 0 || hf <= 0 || wf <= 0 || N <= 0) return 0;
-    return 2 * (size_t)B * ((size_t)hf * wf / BM) * N * 4 * sizeof(float);   // full-res + pooled column partials
+    // foreground block lists, mean vertices, full-res + pooled column partials
+    return blocks_bytes(B, hf * wf) + vmean_bytes(B) + 2 * (size_t)B * ((size_t)hf * wf / BM) * N * 4 * sizeof(float);
 }
 
 extern "C" int scp_corr_match_forward(const float *img_feat, const float *mesh_feat, const float *mask_down,
@@ -677,13 +786,19 @@ extern "C" int scp_corr_match_forward(const float *img_feat, const float *mesh_f
         scp::set_last_error("scp_corr_match_forward: A_pool needs pointcorr_pool and csum_pool");
         return -1;
     }
-    float *part = (float *)workspace;
+    int *blocks = (int *)workspace;
+    float *vmean = (float *)((char *)workspace + blocks_bytes(B, geo.P));
+    float *part = (float *)((char *)vmean + vmean_bytes(B));
     float *part_pool = A_pool != nullptr ? part + (size_t)B * geo.npblk * N * 4 : nullptr;
+    corr_blocklist_kernel<<<B, NT, 0, st>>>(geo, mask_down, pred_v, blocks, vmean);
+    corr_fill_kernel<<<dim3(((geo.P >> 2) + NT / 32 - 1) / (NT / 32), B), NT, 0, st>>>(geo, mask_down, vmean, pointcorr_full,
+                                                                                 pointcorr_pool, match, rsum);
     corr_fwd_kernel<<<dim3(geo.npblk, B), NT, smem, st>>>(geo, img_feat, mesh_feat, mask_down, pred_v, meshgrid,
-                                                         pointcorr_full, pointcorr_pool, match, rsum, part, part_pool);
-    corr_colreduce_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(geo, part, meshgrid, imatch, csum);
+                                                         pointcorr_full, pointcorr_pool, match, rsum, part, part_pool,
+                                                         blocks);
+    corr_colreduce_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(geo, part, meshgrid, imatch, csum, blocks);
     if (A_pool != nullptr)
-        corr_colreduce_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(geo, part_pool, meshgrid, A_pool, csum_pool);
+        corr_colreduce_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(geo, part_pool, meshgrid, A_pool, csum_pool, blocks);
     return scp::check_launch("scp_corr_match_forward");
 }
 
@@ -693,11 +808,16 @@ extern "C" int scp_corr_match_backward(const float *img_feat, const float *mesh_
                                        const float *csum, const float *g_match, const float *g_imatch,
                                        const float *g_pointcorr_pool, const float *g_pointcorr_full,
                                        const float *A_pool, const float *csum_pool, const float *g_A_pool,
-                                       float *g_img_feat, float *g_mesh_feat, void *stream)
+                                       float *g_img_feat, float *g_mesh_feat, void *workspace, size_t workspace_bytes,
+                                       void *stream)
 {
     Geo geo;
     if (!make_geo(geo, B, hf, wf, N, Cc, tau)) {
         scp::set_last_error("scp_corr_match_backward: unsupported shape");
+        return -1;
+    }
+    if (!workspace || workspace_bytes < blocks_bytes(B, geo.P) + vmean_bytes(B)) {
+        scp::set_last_error("scp_corr_match_backward: workspace too small");
         return -1;
     }
     BwdArgs a;
@@ -707,6 +827,10 @@ extern "C" int scp_corr_match_backward(const float *img_feat, const float *mesh_
     a.A_pool = A_pool; a.csum_pool = csum_pool; a.g_A_pool = (A_pool && csum_pool) ? g_A_pool : nullptr;
     a.g_img_feat = g_img_feat; a.g_mesh_feat = g_mesh_feat;
     cudaStream_t st = (cudaStream_t)stream;
+    int *blocks = (int *)workspace;   // rebuilt here: the backward keeps no state besides the saved tensors
+    corr_blocklist_kernel<<<B, NT, 0, st>>>(geo, mask_down, pred_v, blocks, (float *)((char *)workspace + blocks_bytes(B, geo.P)));
+    a.blocks = blocks;
+    cudaMemsetAsync(g_img_feat, 0, (size_t)B * C * geo.P * sizeof(float), st);   // background pixels: zero gradient
     const size_t smem_r = R_TOTAL * sizeof(float), smem_v = V_TOTAL * sizeof(float);
     cudaFuncSetAttribute(corr_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
     cudaFuncSetAttribute(corr_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);

@@ -66,12 +66,15 @@ class CorrMatchFunction(Function):
         g_imatch = prep(g_imatch, None) if g_imatch is not None else torch.zeros_like(imatch)
         g_img = torch.empty_like(img_feat)
         g_mesh = torch.empty_like(mesh_feat)
+        ws_bytes = _lib.lib().scp_corr_workspace_bytes(B, hf, wf, N)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = _lib.lib().scp_corr_match_backward(
                 _lib.ptr(img_feat), _lib.ptr(mesh_feat), _lib.ptr(mask_down), _lib.ptr(pred_v), _lib.ptr(meshgrid),
                 tau, B, hf, wf, N, C, _lib.ptr(match), _lib.ptr(imatch), _lib.ptr(rsum), _lib.ptr(csum),
                 _lib.ptr(g_match), _lib.ptr(g_imatch), _lib.ptr(g_pool), _lib.ptr(g_full), _lib.ptr(A_pool),
-                _lib.ptr(csum_pool), _lib.ptr(g_A), _lib.ptr(g_img), _lib.ptr(g_mesh), _lib.stream_ptr(dev))
+                _lib.ptr(csum_pool), _lib.ptr(g_A), _lib.ptr(g_img), _lib.ptr(g_mesh), _lib.ptr(ws), ws_bytes,
+                _lib.stream_ptr(dev))
         _lib.check(rc, 'scp_corr_match_backward')
         return g_img, g_mesh, None, None, None, None, None, None, None, None
 
