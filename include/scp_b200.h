@@ -17,6 +17,10 @@
  *       + two weighted sums), reached through torch ops in the reference.
  *       The rotation-cycle similarity of :105-110 (column softmax, grid.bmm) runs on the same two entry points with
  *       the target pixels in the role of the vertices.
+ *   scp_project_faces_forward / scp_project_faces_backward
+ *       model/util/loss_utils.py:38-61 (pinhole_cam, render: camera transform, fp64-promoted projection, y flip,
+ *       depth texture), third-party/softras/soft_renderer/transform.py:29-49 + functional/look_at.py:6-62 +
+ *       orthogonal.py:4-16 (fixed look_at camera of the model) and functional/face_vertices.py:4-22.
  *   scp_image_losses_forward / scp_image_losses_backward
  *       model/util/loss_utils.py:236-244 (compute_mask_loss), :246-252 (compute_texture_loss), :273-284
  *       (compute_depth_loss), :317-320 (compute_match_loss) with the nearest upsampling of `match`
@@ -185,6 +189,28 @@ int scp_attention_bf16(const void *q, const void *k, const void *v, void *o, int
 /* Same result on the tcgen05 tensor cores (S and O tiles in TMEM, TMA-staged operands); v is passed TRANSPOSED:
  * vt[B*6][64][Tp] bf16, Tp = T rounded up to a multiple of 8, columns t >= T zero.  Used by scp_vit_s8_keys. */
 int scp_attention_tc5(const void *q, const void *k, const void *vt, void *o, int B, int T, void *stream);
+
+/* ---- screen-space geometry shared by the renders of a step ---------------------------------------------- */
+/*
+ * screen_v[B,N,3] = (x', y', z): c = pred_v . rotation + translation (row vectors), x' = pp_x + c_x f_x / z,
+ * y' = -(pp_y + c_y f_y / z) with the fp64 intrinsics foc[B,2], pp[B,2] (evaluated in fp64, rounded to fp32), z = c_z.
+ * Optional (faces[nf,3] int32 given): face_vertices[B,nf,3,3] = screen_v gathered per face corner with z + z_offset
+ * (the model's look_at camera at (0,0,-z_offset) with the identity rotation, orthographic scale 1) and
+ * face_textures[B,nf,3,3] = screen_v gathered (the depth render's texture = the screen-space vertices themselves).
+ */
+int scp_project_faces_forward(const float *pred_v, const float *rotation, const float *translation, const double *foc,
+                              const double *pp, const int *faces, int B, int N, int nf, float z_offset,
+                              float *screen_v, float *face_vertices, float *face_textures, void *stream);
+/*
+ * Gradients w.r.t. pred_v[B,N,3] (may be NULL), rotation[B,3,3], translation[B,3] given any of g_screen_v,
+ * g_face_vertices, g_face_textures (NULL = zero).  csr_offsets[N+1] / csr_corners[3*nf]: for every vertex the
+ * face corners (face*3 + corner) that reference it, ascending -- the face gradients are gathered per vertex in a
+ * fixed order (no atomics on the vertex gradients).
+ */
+int scp_project_faces_backward(const float *pred_v, const float *rotation, const float *translation, const double *foc,
+                               const double *pp, const int *csr_offsets, const int *csr_corners, int B, int N, int nf,
+                               const float *g_screen_v, const float *g_face_vertices, const float *g_face_textures,
+                               float *g_pred_v, float *g_rotation, float *g_translation, void *stream);
 
 /* ---- image-space loss terms (silhouette pyramid, texture, depth, 3D match) ------------------------------- */
 /*

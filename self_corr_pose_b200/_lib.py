@@ -59,6 +59,11 @@ _SIGNATURES.update({
     'scp_image_losses_backward': ([_pp, _pll, _f, _i, _i, _i, _i, _i, _i, _f, _f, _pp, _pll, _f, _f], _i),
 })
 
+_SIGNATURES.update({
+    'scp_project_faces_forward': ([_f] * 6 + [_i, _i, _i, _fl] + [_f] * 4, _i),
+    'scp_project_faces_backward': ([_f] * 7 + [_i, _i, _i] + [_f] * 7, _i),
+})
+
 _lib = None
 
 

@@ -1,0 +1,175 @@
+// Screen-space geometry of one training step, fused: camera transform + pinhole projection (fp64 intrinsics) +
+// y-flip + look_at/orthographic offset + per-face gathers, forward and backward.
+//
+// Replaces, per render, the torch op chain of the reference's model/util/loss_utils.py:38-61 (pinhole_cam, render:
+// verts.bmm(rotation) + translation, in-place fp64-promoted projection, y flip, tex = verts.clone()),
+// third-party/softras/soft_renderer/transform.py:29-49 + functional/look_at.py:6-62 + orthogonal.py:4-16 (for the
+// model's fixed camera: eye (0,0,-(1/tan 30deg + 1)), at 0, up y -> identity rotation, z offset) and
+// functional/face_vertices.py:4-22 (two gathers), plus their autograd (bmm backward, fp64 element-wise chain,
+// index_add scatter).  The three renders of a step share this geometry, so it runs once.
+//
+// HBM-bound and tiny (B*N vertices, B*nf faces): one thread per vertex / face; the backward gathers the face
+// gradients of every vertex through a vertex -> face-corner adjacency (CSR, built once per mesh) -- no atomics on
+// the vertex gradients, deterministic summation order.
+#include "../../include/scp_b200.h"
+#include "scp_common.cuh"
+
+namespace scp {
+namespace geom {
+
+constexpr int NT = 256;
+
+struct Cam {
+    const float *v, *R, *t;      // [B,N,3], [B,3,3], [B,3]
+    const double *foc, *pp;      // [B,2] fp64 NDC intrinsics (data/dataset_wild6d.py:174-177)
+    int B, N, nf;
+    float z_off;                 // look_at: vertices - eye, eye = (0, 0, -z_off)
+};
+
+// camera-space point c = v R + t (row vector times matrix, as verts.bmm(rotation)), then
+// x' = pp_x + c_x f_x / z, y' = -(pp_y + c_y f_y / z) evaluated in fp64 and rounded to fp32 (loss_utils.py:40-46, :57)
+__device__ __forceinline__ void project(const Cam &a, int b, int n, float (&c)[3], float (&s)[3])
+{
+    const float *v = a.v + ((size_t)b * a.N + n) * 3, *R = a.R + (size_t)b * 9, *t = a.t + (size_t)b * 3;
+#pragma unroll
+    for (int j = 0; j < 3; j++) c[j] = fmaf(v[2], R[6 + j], fmaf(v[1], R[3 + j], v[0] * R[j])) + t[j];
+    const double z = (double)c[2];
+    s[0] = (float)(a.pp[b * 2 + 0] + (double)c[0] * a.foc[b * 2 + 0] / z);
+    s[1] = -(float)(a.pp[b * 2 + 1] + (double)c[1] * a.foc[b * 2 + 1] / z);
+    s[2] = c[2];
+}
+
+// index space: [0, B*N) vertices -> sv; [B*N, B*N + B*nf) faces -> face_vertices / face_textures
+__global__ void __launch_bounds__(NT) project_faces_kernel(Cam a, const int *__restrict__ faces, float *__restrict__ sv,
+                                                           float *__restrict__ fv, float *__restrict__ ft)
+{
+    const long i = (long)blockIdx.x * NT + threadIdx.x;
+    const long nv = (long)a.B * a.N, nfa = (long)a.B * a.nf;
+    float c[3], s[3];
+    if (i < nv) {
+        const int b = (int)(i / a.N), n = (int)(i - (long)b * a.N);
+        project(a, b, n, c, s);
+        float *o = sv + i * 3;
+        o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+    } else if (i < nv + nfa && fv != nullptr) {
+        const long fi = i - nv;
+        const int b = (int)(fi / a.nf), f = (int)(fi - (long)b * a.nf);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            project(a, b, faces[f * 3 + k], c, s);
+            float *o = fv + fi * 9 + k * 3;
+            o[0] = s[0]; o[1] = s[1]; o[2] = s[2] + a.z_off;
+            if (ft != nullptr) {
+                float *q = ft + fi * 9 + k * 3;
+                q[0] = s[0]; q[1] = s[1]; q[2] = s[2];
+            }
+        }
+    }
+}
+
+// one thread per vertex: total screen-space gradient = g_sv + sum over incident face corners of (g_fv + g_ft),
+// chained through the projection (fp64, like autograd of the promoted expression) and the camera transform
+__global__ void __launch_bounds__(NT) project_faces_bwd_kernel(Cam a, const int *__restrict__ csr_off,
+                                                               const int *__restrict__ csr_idx,
+                                                               const float *__restrict__ g_sv,
+                                                               const float *__restrict__ g_fv,
+                                                               const float *__restrict__ g_ft, float *__restrict__ g_v,
+                                                               float *__restrict__ g_R, float *__restrict__ g_t)
+{
+    __shared__ float red[12 * (NT / 32)];
+    const int b = blockIdx.y, n = blockIdx.x * NT + threadIdx.x;
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) acc[k] = 0.f;
+    if (n < a.N) {
+        float g[3] = { 0.f, 0.f, 0.f };
+        if (g_sv != nullptr) {
+            const float *p = g_sv + ((size_t)b * a.N + n) * 3;
+            g[0] = p[0]; g[1] = p[1]; g[2] = p[2];
+        }
+        if (csr_off != nullptr) {
+            for (int e = csr_off[n]; e < csr_off[n + 1]; e++) {
+                const size_t o = ((size_t)b * a.nf * 3 + csr_idx[e]) * 3;   // csr_idx = face * 3 + corner
+                if (g_fv != nullptr) { g[0] += g_fv[o]; g[1] += g_fv[o + 1]; g[2] += g_fv[o + 2]; }
+                if (g_ft != nullptr) { g[0] += g_ft[o]; g[1] += g_ft[o + 1]; g[2] += g_ft[o + 2]; }
+            }
+        }
+        float c[3], s[3];
+        project(a, b, n, c, s);
+        const double z = (double)c[2], fx = a.foc[b * 2 + 0], fy = a.foc[b * 2 + 1];
+        float gc[3];
+        gc[0] = (float)((double)g[0] * fx / z);
+        gc[1] = (float)(-(double)g[1] * fy / z);
+        gc[2] = (float)((double)g[2] - (double)g[0] * (double)c[0] * fx / (z * z) + (double)g[1] * (double)c[1] * fy / (z * z));
+        const float *v = a.v + ((size_t)b * a.N + n) * 3, *R = a.R + (size_t)b * 9;
+        if (g_v != nullptr) {
+            float *o = g_v + ((size_t)b * a.N + n) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; k++) o[k] = gc[0] * R[3 * k] + gc[1] * R[3 * k + 1] + gc[2] * R[3 * k + 2];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) acc[3 * k + j] = v[k] * gc[j];
+#pragma unroll
+        for (int j = 0; j < 3; j++) acc[9 + j] = gc[j];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        const float w = warp_sum(acc[k]);
+        if (lane == 0) red[k * (NT / 32) + warp] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++) t += red[threadIdx.x * (NT / 32) + w];
+        if (threadIdx.x < 9) atomicAdd(g_R + (size_t)b * 9 + threadIdx.x, t);
+        else atomicAdd(g_t + (size_t)b * 3 + (threadIdx.x - 9), t);
+    }
+}
+
+}  // namespace geom
+}  // namespace scp
+
+using namespace scp::geom;
+
+extern "C" int scp_project_faces_forward(const float *pred_v, const float *rotation, const float *translation,
+                                         const double *foc, const double *pp, const int *faces, int B, int N, int nf,
+                                         float z_offset, float *screen_v, float *face_vertices, float *face_textures,
+                                         void *stream)
+{
+    if (B <= 0 || N <= 0 || nf < 0 || !pred_v || !rotation || !translation || !foc || !pp || !screen_v ||
+        (face_vertices && (!faces || nf <= 0))) {
+        scp::set_last_error("scp_project_faces_forward: bad arguments (B=%d N=%d nf=%d)", B, N, nf);
+        return -1;
+    }
+    Cam a{ pred_v, rotation, translation, foc, pp, B, N, nf, z_offset };
+    const long total = (long)B * N + (face_vertices ? (long)B * nf : 0);
+    project_faces_kernel<<<(unsigned)((total + NT - 1) / NT), NT, 0, (cudaStream_t)stream>>>(a, faces, screen_v, face_vertices,
+                                                                                            face_textures);
+    return scp::check_launch("scp_project_faces_forward");
+}
+
+extern "C" int scp_project_faces_backward(const float *pred_v, const float *rotation, const float *translation,
+                                          const double *foc, const double *pp, const int *csr_offsets,
+                                          const int *csr_corners, int B, int N, int nf, const float *g_screen_v,
+                                          const float *g_face_vertices, const float *g_face_textures, float *g_pred_v,
+                                          float *g_rotation, float *g_translation, void *stream)
+{
+    if (B <= 0 || B > 65535 || N <= 0 || !pred_v || !rotation || !translation || !foc || !pp || !g_rotation ||
+        !g_translation || ((g_face_vertices || g_face_textures) && (!csr_offsets || !csr_corners))) {
+        scp::set_last_error("scp_project_faces_backward: bad arguments (B=%d N=%d nf=%d)", B, N, nf);
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(g_rotation, 0, (size_t)B * 9 * sizeof(float), st);
+    cudaMemsetAsync(g_translation, 0, (size_t)B * 3 * sizeof(float), st);
+    Cam a{ pred_v, rotation, translation, foc, pp, B, N, nf, 0.f };
+    const bool faces_used = g_face_vertices || g_face_textures;
+    project_faces_bwd_kernel<<<dim3((N + NT - 1) / NT, B), NT, 0, st>>>(a, faces_used ? csr_offsets : nullptr, csr_corners,
+                                                                       g_screen_v, g_face_vertices, g_face_textures,
+                                                                       g_pred_v, g_rotation, g_translation);
+    return scp::check_launch("scp_project_faces_backward");
+}

@@ -8,6 +8,7 @@ import torch.nn.functional as F
 
 from ... import soft_renderer as sr
 from ...soft_renderer import functional as srf
+from ...ops.project_faces import project_faces, FaceTopology, LOOK_AT_Z
 from ..util.loss_utils import render, pinhole_cam, project_to_screen
 
 
@@ -32,6 +33,23 @@ class Renderer:
         self.renderer_hardtex = _soft_renderer(size, 1e-4, 1e-3, 'hard')
         self.renderer_depth.rasterizer.background_color = [1, 1, 1]
         self.renderer_softtex.rasterizer.background_color = [1, 1, 1]
+        self._topo = None
+
+    def _topology(self, num_verts):
+        if self._topo is None or self._topo.N != num_verts or self._topo.faces.device != self.mesh.faces.device:
+            self._topo = FaceTopology(self.mesh.faces, num_verts)
+        return self._topo
+
+    def _fixed_camera(self):
+        """True when every renderer uses the model's camera (look_at from (0,0,-(1/tan30+1)), orthographic, scale 1),
+        for which look_at is the identity rotation plus a z offset -- the case the fused geometry kernel implements."""
+        for r in (self.renderer_depth, self.renderer_softtex, self.renderer_hardtex):
+            tr = r.transform.transformer
+            eye = getattr(tr, '_eye', None)
+            if r.transform.camera_mode != 'look_at' or tr.perspective or tr.viewing_scale != 1.0 or \
+                    not isinstance(eye, (list, tuple)) or list(eye) != [0, 0, -LOOK_AT_Z]:
+                return False
+        return True
 
     def render_mean_mesh(self, foc_crop, pp_crop, rotation, translation):
         bsz = rotation.shape[0]
@@ -67,26 +85,35 @@ class Renderer:
         the ambient light of intensity 1 multiplies every texture by exactly 1 and is skipped."""
         if getattr(self.mesh, 'texture_type', 'vertex') != 'vertex' or tex is None:
             raise NotImplementedError('render_all_raw: vertex textures only (every shipped config)')
-        sv = project_to_screen(pred_v, foc_crop, pp_crop, rotation, translation)
-        fv = srf.face_vertices(self.renderer_depth.transform.transformer(sv), faces)
-        # depth render (texture = the screen-space vertices themselves: render(..., render_depth=True) sets
-        # tex = verts.clone()) and NOCS map (hard RGB of the detached canonical coordinates; no useful gradient, see
-        # render_all) in ONE traversal: same sigma, same alpha, gamma unused by the hard mode
+        if self._fixed_camera():   # native: projection + look_at offset + both face gathers, one launch (csrc/scp_geom.cu)
+            sv, fv, ft_depth = project_faces(pred_v, rotation, translation, foc_crop, pp_crop,
+                                             self._topology(pred_v.shape[1]))
+        else:
+            sv = project_to_screen(pred_v, foc_crop, pp_crop, rotation, translation)
+            fv = srf.face_vertices(self.renderer_depth.transform.transformer(sv), faces)
+            ft_depth = srf.face_vertices(sv, faces)
         rd, rn = self.renderer_depth.rasterizer, self.renderer_hardtex.rasterizer
         same = all(getattr(rd, k) == getattr(rn, k) for k in ('image_size', 'near', 'far', 'fill_back', 'eps', 'sigma_val',
                                                               'dist_func', 'dist_eps', 'aggr_func_alpha'))
         if same and rd.dist_func == 'euclidean' and rd.aggr_func_alpha == 'prod' and rd.aggr_func_rgb == 'softmax' \
                 and rn.aggr_func_rgb == 'hard':
-            r_depth, r_nocs = srf.soft_rasterize_dual(fv, srf.face_vertices(sv, faces),
+            r_depth, r_nocs = srf.soft_rasterize_dual(fv, ft_depth,
                                                       srf.face_vertices(pred_v.detach(), faces), rd.image_size,
                                                       rd.background_color, rn.background_color, rd.near, rd.far,
                                                       rd.fill_back, rd.eps, rd.sigma_val, rd.dist_eps, rd.gamma_val)
         else:
-            r_depth = self._rasterize(self.renderer_depth, fv, srf.face_vertices(sv, faces))
+            r_depth = self._rasterize(self.renderer_depth, fv, ft_depth)
             r_nocs = self._rasterize(self.renderer_hardtex, fv.detach(), srf.face_vertices(pred_v.detach(), faces))
         r_tex = self._rasterize(self.renderer_softtex, fv, srf.face_vertices(tex, faces))
         depth_render = r_depth[:, 2] if self.opts.use_depth else r_depth[:, 2].detach()
-        imatch_gt, depth_weight = self._visibility(pred_v, depth_render, foc_crop, pp_crop, rotation, translation)
+        if self._fixed_camera():   # same projection, gradient to the pose only (pred_v detached, renderer.py:64)
+            sv_d = project_faces(pred_v.detach(), rotation, translation, foc_crop, pp_crop)[0]
+            imatch_gt = torch.stack((sv_d[:, :, 0], -sv_d[:, :, 1]), dim=1)     # b,2,n (no y flip)
+            imatch_depth_gt = F.grid_sample(depth_render[:, None], imatch_gt.permute(0, 2, 1)[:, None],
+                                            align_corners=False)[:, 0, 0]
+            depth_weight = (5 * -F.relu(sv_d[:, :, 2] - imatch_depth_gt)).exp().detach()
+        else:
+            imatch_gt, depth_weight = self._visibility(pred_v, depth_render, foc_crop, pp_crop, rotation, translation)
         return r_depth, r_tex, r_nocs, imatch_gt, depth_weight
 
     def render_all(self, pred_v, faces, tex, foc_crop, pp_crop, rotation, translation, scale=None):
