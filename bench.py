@@ -35,6 +35,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-breakdown', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--no-overlap', action='store_true', help='run the DINO ViT on the main stream (no side-stream overlap)')
     return ap.parse_args()
 
 
@@ -264,7 +265,7 @@ def main():
     opts = default_opts(img_size=256, corr_h=64, corr_w=64, batch_size=B // 4, repeat=4)
     v, f = load_mesh(args.mesh)
     mean_v, faces = torch.from_numpy(v), torch.from_numpy(f)
-    hot = HotPath(opts, mean_v, faces, device=dev)
+    hot = HotPath(opts, mean_v, faces, device=dev, overlap_vit=not args.no_overlap)
     data, enc = synthetic.make_batch(opts, v, f, B, device=dev, seed=rank, renderer=Renderer(opts, hot.mesh))
     from self_corr_pose_b200.dist import FlatGradReducer
     # the one parameter shared across the batch on this path: the canonical mesh (pred_v = mean_v + deformation)

@@ -17,6 +17,9 @@
  *       + two weighted sums), reached through torch ops in the reference.
  *       The rotation-cycle similarity of :105-110 (column softmax, grid.bmm) runs on the same two entry points with
  *       the target pixels in the role of the vertices.
+ *   scp_cycle_rows_forward / scp_cycle_rows_backward
+ *       model/module/pretrained_corr.py:120-139 (PretrainedCorrespondence.compute_cycle_loss after the DINO matching:
+ *       gated softmaxes, corr = Pm . Pi^T column-normalised, match = grid . corr gathered at the top-k pixels, loss).
  *   scp_project_faces_forward / scp_project_faces_backward
  *       model/util/loss_utils.py:38-61 (pinhole_cam, render: camera transform, fp64-promoted projection, y flip,
  *       depth texture), third-party/softras/soft_renderer/transform.py:29-49 + functional/look_at.py:6-62 +
@@ -189,6 +192,26 @@ int scp_attention_bf16(const void *q, const void *k, const void *v, void *o, int
 /* Same result on the tcgen05 tensor cores (S and O tiles in TMEM, TMA-staged operands); v is passed TRANSPOSED:
  * vt[B*6][64][Tp] bf16, Tp = T rounded up to a multiple of 8, columns t >= T zero.  Used by scp_vit_s8_keys. */
 int scp_attention_tc5(const void *q, const void *k, const void *vt, void *o, int B, int T, void *stream);
+
+/* ---- pre-training cycle loss: the k gathered target rows of every image pair ------------------------------ */
+/*
+ * pointcorr_pool[B,P4,N] (2x2-pooled similarity), A_pool[B,2,N] (= pooled grid . softmax over pixels, from
+ * scp_corr_match_forward), depth_weight[B,N]; pairs p = 0..NP-1: images src_idx[p], tgt_idx[p] (int64), gathered target
+ * rows rows[NP,k] (int64, pooled-pixel ids), pts_src[NP,2,k], mask_k[NP,k].  Outputs: pair_loss[p] = sum_j
+ * |match_j - pts_src_j|_2 mask_j and match[NP,2,k] with
+ *   match_j = sum_n A[src,:,n] w_n Pi_j[n] / (sum_n w_n Pi_j[n] + 1e-5), Pi_j = softmax_n(tau * pointcorr_pool[tgt, rows_j, :]),
+ *   w_n = [depth_weight[src,n] >= 0.5] [depth_weight[tgt,n] >= 0.5].
+ * (the reference's loss is sum_p pair_loss[p] / (NP * k), pretrained_corr.py:139)
+ */
+int scp_cycle_rows_forward(const float *pointcorr_pool, const float *A_pool, const float *depth_weight,
+                           const long long *src_idx, const long long *tgt_idx, const long long *rows,
+                           const float *pts_src, const float *mask_k, float tau, int B, int P4, int N, int NP, int k,
+                           float *pair_loss, float *match, void *stream);
+/* g_pointcorr_pool[B,P4,N] and g_A_pool[B,2,N] are zeroed and accumulated by the callee (forward recomputed). */
+int scp_cycle_rows_backward(const float *pointcorr_pool, const float *A_pool, const float *depth_weight,
+                            const long long *src_idx, const long long *tgt_idx, const long long *rows,
+                            const float *pts_src, const float *mask_k, float tau, int B, int P4, int N, int NP, int k,
+                            const float *g_pair_loss, float *g_pointcorr_pool, float *g_A_pool, void *stream);
 
 /* ---- screen-space geometry shared by the renders of a step ---------------------------------------------- */
 /*

@@ -64,6 +64,11 @@ _SIGNATURES.update({
     'scp_project_faces_backward': ([_f] * 7 + [_i, _i, _i] + [_f] * 7, _i),
 })
 
+_SIGNATURES.update({
+    'scp_cycle_rows_forward': ([_f] * 8 + [_fl, _i, _i, _i, _i, _i] + [_f] * 3, _i),
+    'scp_cycle_rows_backward': ([_f] * 8 + [_fl, _i, _i, _i, _i, _i] + [_f] * 4, _i),
+})
+
 _lib = None
 
 

@@ -44,12 +44,15 @@ class HotPath:
 
     # kernels of this package launched by one forward+backward: SoftRas 2x(pack+fwd) + 2x(pack+bwd)
     # (mask, depth and NOCS share one traversal), correspondence 5 fwd + 3 bwd (block list, fill, main, 2 column
-    # reductions / block list, rows, columns), ViT 3 + 9*7 + 2, image losses 2 fwd + 1 bwd, geometry 2 fwd + 2 bwd
-    GPU_LAUNCHES = 4 + 4 + 8 + 68 + 3 + 4
+    # reductions / block list, rows, columns), ViT 3 + 9*7 + 2, image losses 2 fwd + 1 bwd, geometry 2 fwd + 2 bwd,
+    # pre-training cycle rows 1 fwd + 1 bwd
+    GPU_LAUNCHES = 4 + 4 + 8 + 68 + 3 + 4 + 2
 
-    def __init__(self, opts, mean_v, faces, device='cuda', fused_losses=True):
+    def __init__(self, opts, mean_v, faces, device='cuda', fused_losses=True, overlap_vit=True):
         self.opts = opts
         self.fused_losses = fused_losses
+        self.overlap_vit = overlap_vit
+        self._side = None
         self.device = device
         self.mesh = SimpleNamespace(mean_v=mean_v.to(device), faces=faces.to(device), texture_type='vertex')
         self.weights = Weights(opts)
@@ -67,6 +70,19 @@ class HotPath:
         bsz = img.shape[0]
         faces = self.mesh.faces[None].repeat(bsz, 1, 1)
         mean_v = self.mesh.mean_v[None].repeat(bsz, 1, 1)
+
+        # frozen DINO features depend on the images only: issue the ViT on a side stream so that its tensor-core
+        # GEMMs overlap the ALU-bound SoftRas / correspondence kernels of the main stream (captured as a parallel
+        # branch of the CUDA graph); joined just before the pre-training cycle loss
+        feat = None
+        if self.overlap_vit and img.is_cuda:
+            main = torch.cuda.current_stream(img.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(img.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side), torch.no_grad():
+                feat = self.pretrain_corr_net.net(img)
+            feat.record_stream(main)
 
         fused = self.fused_losses and opts.img_size % 16 == 0
         if fused:
@@ -100,8 +116,10 @@ class HotPath:
         aux['triangle_loss'] = wts.triangle_wt * self.triangle_loss_fn(pred_v) * pred_v.shape[1] / 64.
         aux['pullfar_loss'] = wts.pullfar_wt * F.relu(1 - translation[:, :, -1]).mean()
         aux['deform_loss'] = wts.deform_wt * F.smooth_l1_loss(pred_v, mean_v, reduction='mean')
+        if feat is not None:
+            torch.cuda.current_stream(img.device).wait_stream(self._side)
         cyc = self.pretrain_corr_net.compute_cycle_loss(img, mask, depth_weight, pointcorr, pooled=True,
-                                                        A=self.corr_net.pool_A)
+                                                        A=self.corr_net.pool_A, feat=feat)
         aux['cycle_loss_pretrain'] = cyc[0] * wts.cycle_loss_pt_wt
         total = sum(aux.values())
         aux['total_loss'] = total

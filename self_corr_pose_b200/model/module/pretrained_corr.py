@@ -15,6 +15,7 @@ import torch.nn.functional as F
 
 from .network.dino import DINO
 from .correspondence import make_meshgrid
+from ...ops.cycle_rows import cycle_rows
 from ..util.loss_utils import divide_by_frame, divide_by_instance, divide_by_both
 
 
@@ -81,7 +82,7 @@ class PretrainedCorrespondence(nn.Module):
             bsz = src_img.shape[0]
             return self._match_from_feats(feat[:bsz], feat[bsz:], src_mask, tgt_mask, grid)
 
-    def compute_cycle_loss(self, img, mask, depth_weight, pointcorr, pooled=False, feat=None, A=None):
+    def compute_cycle_loss(self, img, mask, depth_weight, pointcorr, pooled=False, feat=None, A=None, fused=True):
         opts = self.opts
         num_verts = pointcorr.shape[-1]
         bs, rep = opts.batch_size, opts.repeat
@@ -110,15 +111,21 @@ class PretrainedCorrespondence(nn.Module):
         if A is None:
             Pm = torch.softmax(self.tau_mesh * pointcorr, dim=1)                # B, h2*w2, N
             A = torch.matmul(grid_flat[None], Pm)                               # B, 2, N
-        A_src = A.index_select(0, src_idx) * (dw_src[:, None] >= 0.5)
-        s_src = (dw_src >= 0.5).to(pointcorr.dtype)                             # = column sums of the gated Pm
-        # target rows needed: only the k gathered pixels of every pair, straight from the per-image tensor
-        # (index_select on the flattened rows: its backward is an atomic index_add, not a sorting index_put)
-        flat_rows = (tgt_idx[:, None] * pointcorr.shape[1] + indices_tgt).reshape(-1)
-        rows = pointcorr.reshape(-1, num_verts).index_select(0, flat_rows).reshape(bsz, -1, num_verts)   # 2B, k, N
-        Pi = torch.softmax(self.tau_img * rows, dim=2) * (dw_tgt[:, None] >= 0.5)
-        num = torch.matmul(A_src, Pi.permute(0, 2, 1))                          # 2B, 2, k
-        den = torch.matmul(s_src[:, None], Pi.permute(0, 2, 1)) + 1e-5          # 2B, 1, k
-        match = num / den
-        cycle_loss = ((match - pts_src).norm(2, 1) * mask_k).mean()
+        if fused and pointcorr.is_cuda and self.tau_img == self.tau_mesh:
+            # native: gathered rows, gated softmaxes, both products, normalisation, distance (csrc/scp_cycle.cu)
+            pair_loss, match = cycle_rows(pointcorr.contiguous(), A, depth_weight, src_idx, tgt_idx, indices_tgt, pts_src,
+                                          mask_k, self.tau_img)
+            cycle_loss = pair_loss.sum() / (bsz * indices_tgt.shape[1])
+        else:
+            A_src = A.index_select(0, src_idx) * (dw_src[:, None] >= 0.5)
+            s_src = (dw_src >= 0.5).to(pointcorr.dtype)                         # = column sums of the gated Pm
+            # target rows needed: only the k gathered pixels of every pair, straight from the per-image tensor
+            # (index_select on the flattened rows: its backward is an atomic index_add, not a sorting index_put)
+            flat_rows = (tgt_idx[:, None] * pointcorr.shape[1] + indices_tgt).reshape(-1)
+            rows = pointcorr.reshape(-1, num_verts).index_select(0, flat_rows).reshape(bsz, -1, num_verts)  # 2B, k, N
+            Pi = torch.softmax(self.tau_img * rows, dim=2) * (dw_tgt[:, None] >= 0.5)
+            num = torch.matmul(A_src, Pi.permute(0, 2, 1))                      # 2B, 2, k
+            den = torch.matmul(s_src[:, None], Pi.permute(0, 2, 1)) + 1e-5      # 2B, 1, k
+            match = num / den
+            cycle_loss = ((match - pts_src).norm(2, 1) * mask_k).mean()
         return cycle_loss, pts_src, pts_tgt, match, mask_k, img.index_select(0, src_idx), img.index_select(0, tgt_idx)

@@ -79,3 +79,44 @@ def test_hotpath_step_fused_equals_op_by_op():
         rel = float((a - b).norm() / b.norm().clamp_min(1e-30))
         print('PARITY fused-vs-op-by-op grad %s rel=%.2e' % (name, rel))
         assert rel < 2e-3   # SoftRas backward accumulates with atomics in both runs (order noise)
+
+
+@pytest.mark.parametrize('B,P4,N,k', [(4, 256, 642, 50), (6, 1024, 1280, 200)])
+def test_cycle_rows_match_reference_statements(B, P4, N, k):
+    """ops/cycle_rows.py (csrc/scp_cycle.cu) against the op-by-op statements of pretrained_corr.py:120-139."""
+    from self_corr_pose_b200.ops.cycle_rows import cycle_rows
+    g = torch.Generator().manual_seed(B + k)
+    NP = 2 * B
+    pc = (torch.rand(B, P4, N, generator=g) * 2 - 1)
+    pc[:, ::7] -= 25000.          # rows of partially masked pooled blocks
+    A = torch.rand(B, 2, N, generator=g) * 2 - 1
+    dw = torch.rand(B, N, generator=g)
+    src_idx = torch.arange(NP) % B
+    tgt_idx = (torch.arange(NP) + 1 + (torch.arange(NP) // B)) % B
+    rows = torch.stack([torch.randperm(P4, generator=g)[:k] for _ in range(NP)])
+    pts = torch.rand(NP, 2, k, generator=g) * 2 - 1
+    mask_k = (torch.rand(NP, k, generator=g) > 0.3).float()
+    w = torch.rand(NP, generator=g) + 0.5
+    pc, A, dw, src_idx, tgt_idx, rows, pts, mask_k, w = (t.cuda() for t in (pc, A, dw, src_idx, tgt_idx, rows, pts, mask_k, w))
+    tau = 10.0
+
+    pc_r, A_r = pc.double().requires_grad_(True), A.double().requires_grad_(True)
+    dw_src, dw_tgt = dw.index_select(0, src_idx), dw.index_select(0, tgt_idx)
+    A_src = A_r.index_select(0, src_idx) * (dw_src[:, None] >= 0.5)
+    s_src = (dw_src >= 0.5).double()
+    flat = (tgt_idx[:, None] * P4 + rows).reshape(-1)
+    r = pc_r.reshape(-1, N).index_select(0, flat).reshape(NP, k, N)
+    Pi = torch.softmax(tau * r, dim=2) * (dw_tgt[:, None] >= 0.5)
+    match_r = torch.matmul(A_src, Pi.permute(0, 2, 1)) / (torch.matmul(s_src[:, None], Pi.permute(0, 2, 1)) + 1e-5)
+    pair_r = ((match_r - pts.double()).norm(2, 1) * mask_k.double()).sum(1)
+    (pair_r * w.double()).sum().backward()
+
+    pc_g, A_g = pc.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    pair, match = cycle_rows(pc_g, A_g, dw, src_idx, tgt_idx, rows, pts, mask_k, tau)
+    (pair * w).sum().backward()
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    res = dict(pair_loss=rel(pair, pair_r), match=rel(match, match_r), g_pc=rel(pc_g.grad, pc_r.grad), g_A=rel(A_g.grad, A_r.grad))
+    print('PARITY cycle_rows B%d P4 %d N%d k%d ' % (B, P4, N, k) + ' '.join('%s=%.2e' % kv for kv in res.items()))
+    for name, v in res.items():
+        assert v < 1e-4, (name, v)
