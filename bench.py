@@ -143,17 +143,38 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
     hbm, tf = peaks.get('hbm_gbs', 6650.0), peaks.get('bf16_tflops', 1590.0)
     which = 'measured' if peaks else 'fallback'
 
-    def timeit(fn, n=5):
-        for _ in range(2):
+    def timeit(fn, n=7):
+        """Device time of one call of `fn`: the call is captured into a CUDA graph (no host launch overhead, same as the
+        graph-replayed step) and replayed n times between CUDA events; median of 3 such measurements."""
+        for _ in range(3):
             fn()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
+        graph = None
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                keep = fn()   # noqa: F841 -- keeps the captured outputs alive
+            run = graph.replay
+        except Exception:   # noqa: BLE001
+            graph, run = None, fn
+        ts = []
+        for _ in range(3):
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / n)
+        del graph
+        return sorted(ts)[1]
 
     out = []
     img, mask, depth, foc, pp = data
@@ -167,22 +188,28 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
         sv = torch.stack((sv[..., 0], sv[..., 1], sv[..., 2] + 2.7320508), -1)
         fv = srf.face_vertices(sv, hot.mesh.faces[None].repeat(B, 1, 1)).contiguous()
         tex = srf.face_vertices(torch.rand_like(sv), hot.mesh.faces[None].repeat(B, 1, 1)).contiguous()
-    for name, sigma, gamma, rgb in (('softras_softtex', 1e-3, 1e-2, 'softmax'), ('softras_mask', 1e-4, 1e-4, 'hard')):
-        kw = dict(image_size=is_, background_color=[1, 1, 1], sigma_val=sigma, gamma_val=gamma, aggr_func_rgb=rgb,
-                  texture_type='vertex')
+    bytes_f = B * (72 * nf + 24 * is_ * is_)
+    bytes_b = B * (144 * nf + 40 * is_ * is_)
+    for name in ('softras_softtex', 'softras_depth+nocs'):
         fvg = fv.clone().requires_grad_(True)
-        t_f = timeit(lambda: srf.soft_rasterize(fvg, tex, **kw))
-        o = srf.soft_rasterize(fvg, tex, **kw)
+        if name == 'softras_softtex':
+            kw = dict(image_size=is_, background_color=[1, 1, 1], sigma_val=1e-3, gamma_val=1e-2, aggr_func_rgb='softmax',
+                      texture_type='vertex')
+            run = lambda: srf.soft_rasterize(fvg, tex, **kw)
+            bf = bytes_f
+        else:   # depth render + NOCS map in one traversal (two output sets)
+            run = lambda: srf.soft_rasterize_dual(fvg, tex, tex, image_size=is_, sigma_val=1e-4, gamma_val=1e-4)[0]
+            bf = bytes_f + B * (36 * nf + 24 * is_ * is_)
+        t_f = timeit(run)
+        o = run()
         g = torch.randn_like(o)
         t_b = timeit(lambda: torch.autograd.grad(o, fvg, g, retain_graph=True))
-        bytes_f = B * (72 * nf + 24 * is_ * is_)
-        bytes_b = B * (144 * nf + 40 * is_ * is_)
-        out.append(dict(kernel=name + '_fwd (pack+forward_kernel)', ms=t_f, bound='hbm', achieved=bytes_f / t_f / 1e6,
-                        peak=hbm, unit='GB/s', launches_per_step=1 if 'softtex' in name else 3,
-                        ncu_name='softras::forward_kernel<1, 1> #0' if 'softtex' in name else ''))
-        out.append(dict(kernel=name + '_bwd (pack+backward_kernel)', ms=t_b, bound='hbm', achieved=bytes_b / t_b / 1e6,
-                        peak=hbm, unit='GB/s', launches_per_step=1 if 'softtex' in name else 2,
-                        ncu_name='softras::backward_kernel<1, 1> #0' if 'softtex' in name else ''))
+        out.append(dict(kernel=name + '_fwd (pack+forward_kernel)', ms=t_f, bound='hbm', achieved=bf / t_f / 1e6,
+                        peak=hbm, unit='GB/s', launches_per_step=1,
+                        ncu_name='softras::forward_kernel<1, 1> #0' if 'softtex' in name else 'softras::forward_kernel<2, 1> #0'))
+        out.append(dict(kernel=name.replace('+nocs', '') + '_bwd (pack+backward_kernel)', ms=t_b, bound='hbm',
+                        achieved=bytes_b / t_b / 1e6, peak=hbm, unit='GB/s', launches_per_step=1,
+                        ncu_name='softras::backward_kernel<1, 1> #%d' % (0 if 'softtex' in name else 1)))
     # --- correspondence
     from self_corr_pose_b200.ops.corr_match import corr_match
     import torch.nn.functional as F
@@ -204,7 +231,7 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
                     unit='GB/s', launches_per_step=1))
     # --- ViT: whole extractor, the attention kernel and the QKV GEMM alone
     net = hot.pretrain_corr_net.net
-    t_v = timeit(lambda: net(img), n=3)
+    t_v = timeit(lambda: net(img), n=5)
     out.append(dict(kernel='vit_s8_keys (68 launches)', ms=t_v, bound='tensor', achieved=47.62e9 * B / t_v / 1e9,
                     peak=tf, unit='TFLOP/s', launches_per_step=1))
     T = (is_ // 8) ** 2 + 1
@@ -322,11 +349,41 @@ def main():
     h2d = sum(t.numel() * t.element_size() for t in host)
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
+    # double-buffered upload: the H2D copy of step i+1's batch (copy stream) overlaps the compute of step i; every
+    # timed step performs one full upload from pinned memory and one loss read-back
+    copy_stream = torch.cuda.Stream(dev)
+    staging = [tuple(torch.empty_like(t) for t in data) for _ in range(2)]
+    uploaded = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    state = {'i': 0}
+
+    def upload(slot):
+        copy_stream.wait_event(consumed[slot])          # the step that read this slot has copied it out
+        with torch.cuda.stream(copy_stream):
+            for dst, src in zip(staging[slot], host):
+                dst.copy_(src, non_blocking=True)
+            uploaded[slot].record(copy_stream)
+
+    for ev in consumed:
+        ev.record(torch.cuda.current_stream(dev))
+    upload(0)
+
     def e2e_step():
-        d = tuple(t.to(dev, non_blocking=True) for t in host)
-        total = step(d)
+        slot = state['i'] & 1
+        state['i'] += 1
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(uploaded[slot])
+        if graphed is not None:
+            graphed.load(data=staging[slot])            # device-to-device into the graph's static buffers
+            consumed[slot].record(main)
+            upload(slot ^ 1)
+            total = step(data)
+        else:
+            upload(slot ^ 1)
+            total = step(staging[slot])
+            consumed[slot].record(main)
         loss_host.copy_(total.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()
         return float(loss_host)
     for _ in range(2):
         e2e_step()

@@ -23,6 +23,8 @@
 // blocks of every kernel are built from that list (32 blocks = 128 rows per CTA), so the P x N work
 // shrinks to the silhouette's share of the map (the object mask covers ~40 % of a crop), and a fill
 // kernel writes the constants of the dropped blocks.
+#include <stdlib.h>
+
 #include "../../include/scp_b200.h"
 #include "scp_common.cuh"
 #include "scp_mma.cuh"
@@ -503,6 +505,7 @@ constexpr int R_CP = R_RP + BM * 8;          // 2 buffers [BN][8]
 constexpr int R_IX = R_CP + 2 * BN * CPS;    // pix[BM], pool[BM] (int)
 constexpr int R_TOTAL = R_IX + 2 * BM;
 
+template <bool FUSE_COLS>
 __global__ void __launch_bounds__(NT, 2) corr_bwd_rows_kernel(Geo geo, BwdArgs a)
 {
     extern __shared__ __align__(16) float sm[];
@@ -563,6 +566,43 @@ __global__ void __launch_bounds__(NT, 2) corr_bwd_rows_kernel(Geo geo, BwdArgs a
             for (int mi = 0; mi < 2; mi++)
 #pragma unroll
                 for (int ci = 0; ci < 4; ci++) mma_tf32(out[mi][ci], af[mi], bf[ci]);
+        }
+        if (FUSE_COLS) {
+            // the same dS tile also yields this row block's share of g_mesh_feat[n][c] = sum_p dS[p][n] img_feat[c][p]
+            // (A[row = n][k = p] = Ds[k][row], B[k = p][col = c] = As[col][k]); reduced over the row blocks with global
+            // float reductions into the zero-filled gradient -- the separate vertex-block kernel (a second recompute of
+            // S and dS for every tile) is not launched
+            float gm[4][4];
+#pragma unroll
+            for (int ci = 0; ci < 4; ci++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) gm[ci][k] = 0.f;
+#pragma unroll 4
+            for (int k0 = 0; k0 < BM; k0 += 8) {
+                uint32_t af[4], bf[4][2];
+                const float *p = Ds + (k0 + t) * DS + 16 * wm + g;
+                af[0] = f2tf32(p[0]); af[1] = f2tf32(p[8]);
+                af[2] = f2tf32(p[4 * DS]); af[3] = f2tf32(p[4 * DS + 8]);
+#pragma unroll
+                for (int ci = 0; ci < 4; ci++) {
+                    const float *q = As + (32 * wn + 8 * ci + g) * AS + k0 + t;
+                    bf[ci][0] = f2tf32(q[0]); bf[ci][1] = f2tf32(q[4]);
+                }
+#pragma unroll
+                for (int ci = 0; ci < 4; ci++) mma_tf32(gm[ci], af, bf[ci]);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int n = n0 + 16 * wm + 8 * h + g;
+                if (n < geo.N) {
+#pragma unroll
+                    for (int ci = 0; ci < 4; ci++) {
+                        float *dst = a.g_mesh_feat + ((size_t)b * geo.N + n) * C + 32 * wn + 8 * ci + 2 * t;
+                        atomicAdd(dst, gm[ci][2 * h]);
+                        atomicAdd(dst + 1, gm[ci][2 * h + 1]);
+                    }
+                }
+            }
         }
     }
     // g_img_feat[b][c][pixel(r)]
@@ -832,9 +872,17 @@ extern "C" int scp_corr_match_backward(const float *img_feat, const float *mesh_
     a.blocks = blocks;
     cudaMemsetAsync(g_img_feat, 0, (size_t)B * C * geo.P * sizeof(float), st);   // background pixels: zero gradient
     const size_t smem_r = R_TOTAL * sizeof(float), smem_v = V_TOTAL * sizeof(float);
-    cudaFuncSetAttribute(corr_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
-    cudaFuncSetAttribute(corr_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
-    corr_bwd_rows_kernel<<<dim3(geo.npblk, B), NT, smem_r, st>>>(geo, a);
-    corr_bwd_cols_kernel<<<dim3(geo.ntile, B), NT, smem_v, st>>>(geo, a);
+    // SCP_CORR_BWD=split: separate vertex-block kernel (deterministic summation order) instead of the fused reductions
+    const char *mode = getenv("SCP_CORR_BWD");
+    if (mode && mode[0] == 's') {
+        cudaFuncSetAttribute(corr_bwd_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+        cudaFuncSetAttribute(corr_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
+        corr_bwd_rows_kernel<false><<<dim3(geo.npblk, B), NT, smem_r, st>>>(geo, a);
+        corr_bwd_cols_kernel<<<dim3(geo.ntile, B), NT, smem_v, st>>>(geo, a);
+    } else {
+        cudaFuncSetAttribute(corr_bwd_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+        cudaMemsetAsync(g_mesh_feat, 0, (size_t)B * N * C * sizeof(float), st);
+        corr_bwd_rows_kernel<true><<<dim3(geo.npblk, B), NT, smem_r, st>>>(geo, a);
+    }
     return scp::check_launch("scp_corr_match_backward");
 }

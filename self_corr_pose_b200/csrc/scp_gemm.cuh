@@ -2,9 +2,13 @@
 // accumulate in TMEM), with a functor epilogue that receives 32 consecutive columns of one row.
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, 128-byte swizzled K-major tiles, mbarrier expect_tx)
-//   warp 1      : TMEM allocator + MMA issuer (one elected lane: tcgen05.mma cta_group::1, M=128, N=128, K=16)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane: tcgen05.mma cta_group::1, M=128, N=128, K=16;
+//                 a CTA tile is 256 x 128 = two M=128 accumulators sharing every B (weight) tile)
 //   warps 2..9  : epilogue (tcgen05.ld 32x32b.x32 -> registers -> smem transpose -> functor -> global);
-//                 warp w owns TMEM lanes 32*(w%4).. and the column half (w-2)/4 of the 128-wide tile
+//                 warp w owns TMEM lanes 32*(w%4).. of the M half (w-2)/4 of the tile
+// Tile shape: operand traffic per MAC is (BM + BN) / (BM * BN); at 128 x 128 the 148 SMs ask the L2 for ~120 B/clk
+// each at full tensor rate against a measured chip-wide L2 cap of ~43 B/clk/SM, i.e. the GEMM is L2-bound at ~35 %
+// of the tensor peak.  256 x 128 (A: 32 KiB, B: 16 KiB per 64-deep k block) lowers the demand by 25 % per MAC.
 // Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue),
 // and a static round-robin tile schedule (tile = blockIdx.x + i * gridDim.x), one CTA per SM.
 #pragma once
@@ -16,17 +20,19 @@
 namespace scp {
 namespace gemm {
 
-constexpr int BM = 128, BN = 128, BK = 64;          // BK * sizeof(bf16) = 128 B = one swizzle atom row
-constexpr int STAGES = 5;
+constexpr int BM = 256, BN = 128, BK = 64;          // BK * sizeof(bf16) = 128 B = one swizzle atom row
+constexpr int MH = BM / 128;                          // M = 128 accumulators per tile
+constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int EPI_WARPS = 8;                          // two warps per TMEM lane quarter, 64 columns each
 constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
-constexpr int STAGE_BYTES = (BM + BN) * BK * 2;     // 32 KiB
+constexpr int STAGE_BYTES = (BM + BN) * BK * 2;     // 48 KiB
 constexpr int STG_FLOATS = 32 * 33;                   // per-epilogue-warp transpose buffer (padded) ...
 constexpr int TMA_TILE_BYTES = 32 * 32 * 4;           // ... or a 32x32 fp32 box in TMA SWIZZLE_128B layout (same region)
 constexpr int EPI_BYTES = EPI_WARPS * STG_FLOATS * 4;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
-constexpr int TMEM_COLS = ACC_STAGES * BN;          // 256
+constexpr int ACC_COLS = MH * BN;                    // TMEM columns of one accumulator stage: [M half][BN]
+constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;    // 512
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 {
@@ -36,6 +42,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 
 struct Shape {
     int M, N, K;
+    int a_box_rows;   // rows of the A tensor-map box (BM; 128 for a matrix of at most 128 rows)
 };
 
 // optional fourth epilogue mode (Epi::kTmaStoreBf16 == true): out[tile] = bf16(epi.apply(acc + bias[col])) computed in
@@ -95,7 +102,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int kb = 0; kb < nkb; kb++) {
                     tc5::mbar_wait(empty + stage, phase ^ 1);
                     uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + BM * BK * 2;
-                    tc5::mbar_expect_tx(full + stage, STAGE_BYTES);
+                    tc5::mbar_expect_tx(full + stage, (s.a_box_rows + BN) * BK * 2);
                     tc5::tma_load_2d(sa, &tmap_a, full + stage, kb * BK, m_blk * BM);
                     tc5::tma_load_2d(sb, &tmap_w, full + stage, kb * BK, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -105,21 +112,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = tc5::umma_idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = tc5::umma_idesc_bf16(128, BN);
             int stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 tc5::mbar_wait(tempty + acc, acc_phase ^ 1);       // epilogue has drained this accumulator
                 tc5::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 for (int kb = 0; kb < nkb; kb++) {
                     tc5::mbar_wait(full + stage, phase);           // TMA bytes have landed
                     tc5::tc_fence_after();
                     const uint32_t sa = tc5::smem_u32(smem + stage * STAGE_BYTES), sb = sa + BM * BK * 2;
 #pragma unroll
-                    for (int k = 0; k < BK / 16; k++) {
-                        // advance 16 elements (32 B) along K inside the 128-byte swizzle atom
-                        tc5::umma_bf16(d_tmem, tc5::umma_desc_sw128(sa + k * 32), tc5::umma_desc_sw128(sb + k * 32), idesc,
-                                       (kb | k) != 0);
+                    for (int mh = 0; mh < MH; mh++) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++) {
+                            // advance 16 elements (32 B) along K inside the 128-byte swizzle atom
+                            tc5::umma_bf16(d_tmem + mh * BN, tc5::umma_desc_sw128(sa + mh * (128 * BK * 2) + k * 32),
+                                           tc5::umma_desc_sw128(sb + k * 32), idesc, (kb | k) != 0);
+                        }
                     }
                     tc5::umma_commit(empty + stage);               // frees the smem slot when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -129,24 +139,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else {
-        // ===== epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        // ===== epilogue warps: TMEM lane quarter = warp % 4, M half of the tile = (warp - 2) / 4 =====
         const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t t_acc = ((uint32_t)(quarter * 32) << 16) + half * BN;
         float *stg = stage_buf + (warp - 2) * STG_FLOATS;
         int acc = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
             tc5::mbar_wait(tfull + acc, acc_phase);
             tc5::tc_fence_after();
-            const int row0 = m_blk * BM + quarter * 32;
+            const int row0 = m_blk * BM + half * 128 + quarter * 32;
             if constexpr (tma_store_mode<Epi>::value) {
-                uint8_t *box = epi_buf + (warp - 2) * TMA_TILE_BYTES;          // 32 rows x 128 B (64 bf16), SWIZZLE_128B
+              uint8_t *box = epi_buf + (warp - 2) * TMA_TILE_BYTES;            // 32 rows x 128 B (64 bf16), SWIZZLE_128B
+#pragma unroll 1
+              for (int cg = 0; cg < BN; cg += 64) {
                 if (lane == 0) tc5::tma_store_wait_read();                      // previous bulk store has read the box
                 __syncwarp();
 #pragma unroll
-                for (int cc = 0; cc < BN / 2; cc += 32) {
-                    const int c0 = half * (BN / 2) + cc;
+                for (int cc = 0; cc < 64; cc += 32) {
+                    const int c0 = cg + cc;
                     float v[32];
-                    tc5::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, v);
+                    tc5::tmem_ld32(tmem_base + t_acc + acc * ACC_COLS + c0, v);
                     const float4 *b4 = reinterpret_cast<const float4 *>(epi.bias + n_blk * BN + c0);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {                               // 8 columns -> one 16-byte chunk
@@ -163,14 +176,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tc5::fence_proxy_async();
                 __syncwarp();
                 if (lane == 0 && row0 < s.M) {   // rows past M are clipped by the tensor map
-                    tc5::tma_store_2d(&tmap_c, box, n_blk * BN + half * (BN / 2), row0);
+                    tc5::tma_store_2d(&tmap_c, box, n_blk * BN + cg, row0);
                     tc5::tma_store_commit();
                 }
+              }
             } else
 #pragma unroll 1
-            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+            for (int c0 = 0; c0 < BN; c0 += 32) {
                 float v[32];
-                tc5::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, v);
+                tc5::tmem_ld32(tmem_base + t_acc + acc * ACC_COLS + c0, v);
                 if constexpr (Epi::kTmaReduceAdd) {
                     uint8_t *box = epi_buf + (warp - 2) * TMA_TILE_BYTES;      // 32 rows x 128 B, SWIZZLE_128B
                     if (lane == 0) tc5::tma_store_wait_read();                  // previous bulk store has read the box
@@ -287,8 +301,16 @@ int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, 
         return -1;
     }
     CUtensorMap ta, tw;
-    if (!make_tmap_bf16(&ta, A, K, M, lda) || !make_tmap_bf16(&tw, W, K, N, ldw)) {
-        set_last_error("tcgen05 gemm: cuTensorMapEncodeTiled failed");
+    int a_box = BM;
+    if (!make_tmap_bf16(&ta, A, K, M, lda, BM)) {
+        a_box = 128;   // a matrix of at most 128 rows: only the first M = 128 accumulator holds stored rows
+        if (M > 128 || !make_tmap_bf16(&ta, A, K, M, lda, 128)) {
+            set_last_error("tcgen05 gemm: cuTensorMapEncodeTiled failed (A)");
+            return -1;
+        }
+    }
+    if (!make_tmap_bf16(&tw, W, K, N, ldw, BN)) {
+        set_last_error("tcgen05 gemm: cuTensorMapEncodeTiled failed (W)");
         return -1;
     }
     CUtensorMap tc = ta;
@@ -311,7 +333,7 @@ int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, 
     }
     const int ntiles = ((M + BM - 1) / BM) * (N / BN);
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
-    Shape s{ M, N, K };
+    Shape s{ M, N, K, a_box };
     gemm_bf16_tn_kernel<Epi><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tw, tc, s, epi);
     return 0;
 }

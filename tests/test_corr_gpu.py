@@ -58,9 +58,13 @@ def oracle_fwd_bwd(img_feat, mesh_feat, mask, pred_v, hf, wf, w_match, w_imatch,
     return pc.detach(), pool.detach(), match3d.detach(), imatch.detach(), A.detach(), img_feat.grad, mesh_feat.grad
 
 
-@pytest.mark.parametrize('B,hf,wf,N', [(2, 16, 16, 70), (2, 32, 32, 1280), (2, 64, 64, 995), (1, 64, 64, 64)])
-def test_corr_match_forward_backward(B, hf, wf, N):
+@pytest.mark.parametrize('B,hf,wf,N,bwd', [(2, 16, 16, 70, 'fused'), (2, 32, 32, 1280, 'fused'), (2, 64, 64, 995, 'fused'),
+                                           (1, 64, 64, 64, 'fused'), (2, 32, 32, 1280, 'split'), (2, 64, 64, 995, 'split')])
+def test_corr_match_forward_backward(B, hf, wf, N, bwd, monkeypatch):
+    """bwd = 'fused': the row-block kernel also reduces g_mesh_feat (global float reductions); 'split': separate
+    vertex-block kernel (SCP_CORR_BWD=split)."""
     from self_corr_pose_b200.ops.corr_match import corr_match
+    monkeypatch.setenv('SCP_CORR_BWD', bwd)
     from self_corr_pose_b200.model.module.correspondence import make_meshgrid
     img_feat, mesh_feat, mask, pred_v = make_inputs(B, hf, wf, N)
     g = torch.Generator().manual_seed(1)
