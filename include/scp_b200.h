@@ -235,6 +235,12 @@ int scp_project_faces_backward(const float *pred_v, const float *rotation, const
                                const float *g_screen_v, const float *g_face_vertices, const float *g_face_textures,
                                float *g_pred_v, float *g_rotation, float *g_translation, void *stream);
 
+/* out[B,N,3] = S . in[B,N,3] per batch element, S an N x N sparse matrix in CSR form (row_offsets[N+1], cols, vals):
+ * the graph-Laplacian product of the smoothness loss (model/util/loss_utils.py:63-97: torch.matmul with the dense
+ * N x N buffer); the backward is the same call with the CSR of the transpose. */
+int scp_spmm3(const int *row_offsets, const int *cols, const float *vals, const float *in, float *out, int B, int N,
+              void *stream);
+
 /* ---- image-space loss terms (silhouette pyramid, texture, depth, 3D match) ------------------------------- */
 /*
  * A "map" is a device pointer to a (B, [3,] H, W) fp32 view whose planes are contiguous (channel stride H*W) and

@@ -60,6 +60,7 @@ _SIGNATURES.update({
 })
 
 _SIGNATURES.update({
+    'scp_spmm3': ([_f] * 5 + [_i, _i, _f], _i),
     'scp_project_faces_forward': ([_f] * 6 + [_i, _i, _i, _fl] + [_f] * 4, _i),
     'scp_project_faces_backward': ([_f] * 7 + [_i, _i, _i] + [_f] * 7, _i),
 })

@@ -173,3 +173,41 @@ extern "C" int scp_project_faces_backward(const float *pred_v, const float *rota
                                                                        g_pred_v, g_rotation, g_translation);
     return scp::check_launch("scp_project_faces_backward");
 }
+
+// ---- sparse (CSR) matrix times per-vertex 3-vectors: out[b][n][:] = sum_e val[e] * in[b][col[e]][:] ---------------
+// The graph Laplacian of the smoothness loss (model/util/loss_utils.py:63-97 of the reference) has ~7 non-zeros per
+// row; the reference multiplies by the dense N x N buffer (a 1280 x 1280 SGEMM forward and backward).
+namespace scp {
+namespace geom {
+__global__ void __launch_bounds__(NT) spmm3_kernel(const int *__restrict__ row_off, const int *__restrict__ col,
+                                                   const float *__restrict__ val, const float *__restrict__ in,
+                                                   float *__restrict__ out, int B, int N)
+{
+    const long i = (long)blockIdx.x * NT + threadIdx.x;
+    if (i >= (long)B * N) return;
+    const int b = (int)(i / N), n = (int)(i - (long)b * N);
+    const float *src = in + (size_t)b * N * 3;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int e = row_off[n]; e < row_off[n + 1]; e++) {
+        const float w = val[e];
+        const float *p = src + (size_t)col[e] * 3;
+        a0 = fmaf(w, p[0], a0); a1 = fmaf(w, p[1], a1); a2 = fmaf(w, p[2], a2);
+    }
+    float *o = out + i * 3;
+    o[0] = a0; o[1] = a1; o[2] = a2;
+}
+}  // namespace geom
+}  // namespace scp
+
+extern "C" int scp_spmm3(const int *row_offsets, const int *cols, const float *vals, const float *in, float *out, int B,
+                         int N, void *stream)
+{
+    if (!row_offsets || !cols || !vals || !in || !out || B <= 0 || N <= 0) {
+        scp::set_last_error("scp_spmm3: bad arguments (B=%d N=%d)", B, N);
+        return -1;
+    }
+    const long total = (long)B * N;
+    scp::geom::spmm3_kernel<<<(unsigned)((total + NT - 1) / NT), NT, 0, (cudaStream_t)stream>>>(row_offsets, cols, vals, in,
+                                                                                                 out, B, N);
+    return scp::check_launch("scp_spmm3");
+}

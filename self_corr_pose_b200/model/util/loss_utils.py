@@ -65,11 +65,48 @@ class LaplacianLoss(nn.Module):
         nz = deg != 0
         lap[nz] /= deg[nz, None]
         self.register_buffer('laplacian', torch.from_numpy(lap))
+        # CSR of the Laplacian and of its transpose (~7 non-zeros per row) for the native sparse product on CUDA
+        for name, m in (('csr', lap), ('csr_t', lap.T)):
+            rows, cols = np.nonzero(m)
+            off = np.zeros(self.nv + 1, np.int32)
+            np.cumsum(np.bincount(rows, minlength=self.nv), out=off[1:])
+            self.register_buffer(name + '_off', torch.from_numpy(off), persistent=False)
+            self.register_buffer(name + '_col', torch.from_numpy(cols.astype(np.int32)), persistent=False)
+            self.register_buffer(name + '_val', torch.from_numpy(m[rows, cols].astype(np.float32)), persistent=False)
 
     def forward(self, x):
-        y = torch.matmul(self.laplacian, x).pow(2)
+        if x.is_cuda and x.dim() == 3 and x.dtype == torch.float32:
+            y = _LaplacianProduct.apply(x, self).pow(2)
+        else:
+            y = torch.matmul(self.laplacian, x).pow(2)
         y = y.sum(tuple(range(1, y.dim())))
         return y.sum() / x.size(0) if self.average else y
+
+
+class _LaplacianProduct(torch.autograd.Function):
+    """y = L x with the sparse Laplacian (csrc/scp_geom.cu: scp_spmm3); backward = L^T g."""
+
+    @staticmethod
+    def _spmm(mod, t, transpose):
+        from ... import _lib
+        pre = 'csr_t' if transpose else 'csr'
+        off, col, val = (getattr(mod, pre + s) for s in ('_off', '_col', '_val'))
+        t = t.contiguous()
+        out = torch.empty_like(t)
+        with torch.cuda.device(t.device):
+            rc = _lib.lib().scp_spmm3(_lib.ptr(off), _lib.ptr(col), _lib.ptr(val), _lib.ptr(t), _lib.ptr(out), t.shape[0],
+                                      t.shape[1], _lib.stream_ptr(t.device))
+        _lib.check(rc, 'scp_spmm3')
+        return out
+
+    @staticmethod
+    def forward(ctx, x, mod):
+        ctx.mod = mod
+        return _LaplacianProduct._spmm(mod, x.detach(), False)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _LaplacianProduct._spmm(ctx.mod, g, True), None
 
 
 def compute_mask_loss(img, mask, mask_pred):

@@ -50,3 +50,23 @@ def test_project_faces_matches_op_chain(B, mesh):
     # projection only (imatch_gt path): no faces, pred_v detached
     sv2 = project_faces(pv0, leaves[1], leaves[2], foc, pp)[0]
     assert torch.equal(sv2, sv.detach())
+
+
+def test_laplacian_loss_sparse_equals_dense():
+    """LaplacianLoss on CUDA (sparse product, scp_spmm3) against the reference's dense-buffer matmul
+    (loss_utils.py:63-97), value and gradient."""
+    from self_corr_pose_b200.model.util.loss_utils import LaplacianLoss
+    v, f = synthetic.uv_sphere()
+    mod = LaplacianLoss(torch.from_numpy(v), torch.from_numpy(f), average=True)
+    g = torch.Generator().manual_seed(0)
+    x = torch.from_numpy(v)[None] + 0.05 * torch.randn(5, v.shape[0], 3, generator=g)
+    x_ref = x.clone().double().requires_grad_(True)
+    ref = (torch.matmul(mod.laplacian.double(), x_ref).pow(2).sum((1, 2))).sum() / x.shape[0]
+    ref.backward()
+    mod = mod.cuda()
+    x_d = x.cuda().requires_grad_(True)
+    out = mod(x_d)
+    out.backward()
+    rel = lambda a, b: float((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm().clamp_min(1e-30))
+    print('PARITY laplacian value rel=%.2e grad rel=%.2e' % (rel(out, ref), rel(x_d.grad, x_ref.grad)))
+    assert rel(out, ref) < 1e-5 and rel(x_d.grad, x_ref.grad) < 1e-5
