@@ -180,8 +180,17 @@ size_t scp_vit_workspace_bytes(int B, int H, int W);
  * feat[B][384][H/8][W/8] (fp32) = keys of block `n_blocks` (0-based; the reference uses 9) without the CLS
  * token, channel = head*64 + d, after running blocks 0..n_blocks-1 on img[B][3][H][W] (fp32, raw [0,1] RGB).
  */
-int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float *feat, int B, int H, int W, int n_blocks,
-                    void *workspace, size_t workspace_bytes, void *stream);
+int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float *feat, void *feat_tokens, int B, int H, int W,
+                    int n_blocks, void *workspace, size_t workspace_bytes, void *stream);
+/* feat_tokens (may be NULL): the same features token-major in bf16, [B][(H/8)*(W/8)][384] -- the operand layout of
+ * scp_dino_argmatch.
+ *
+ * Arg-max matching of DINO features (model/module/pretrained_corr.py:85-89) without materialising the similarity:
+ * for pair p and pixel r of image a_idx[p], best[p][r] encodes max over the pixels c of image w_idx[p] with
+ * w_mask[p][c] > 0 of <tokens[a_idx[p]][r], tokens[w_idx[p]][c]> as (order-preserving similarity bits << 32 |
+ * 0xffffffff - c); 0 = no unmasked column.  np = pixels per image, a multiple of 256; best is zeroed by the callee. */
+int scp_dino_argmatch(const void *tokens, const long long *a_idx, const long long *w_idx, const float *w_mask, int B,
+                      int np, int NP, unsigned long long *best, void *stream);
 
 /* Building blocks of the above, exported for unit tests and reuse:
  *   C[M][N] (fp32) = A[M][K] (bf16) * W[N][K]^T (bf16) + bias[N] (may be NULL); N % 128 == 0, K % 64 == 0.

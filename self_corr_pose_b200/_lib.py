@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libscp_b200.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _f = ctypes.c_void_p   # device pointers travel as integers
 _i = ctypes.c_int
@@ -48,7 +48,8 @@ _SIGNATURES.update({
     'scp_attention_bf16': ([_f, _f, _f, _f, _i, _i, _f], _i),
     'scp_attention_tc5': ([_f, _f, _f, _f, _i, _i, _f], _i),
     'scp_vit_workspace_bytes': ([_i, _i, _i], _sz),
-    'scp_vit_s8_keys': ([ctypes.POINTER(VitWeights), _f, _f, _i, _i, _i, _i, _f, _sz, _f], _i),
+    'scp_vit_s8_keys': ([ctypes.POINTER(VitWeights), _f, _f, _f, _i, _i, _i, _i, _f, _sz, _f], _i),
+    'scp_dino_argmatch': ([_f, _f, _f, _f, _i, _i, _i, _f, _f], _i),
 })
 
 _pp = ctypes.POINTER(ctypes.c_void_p)

@@ -43,6 +43,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 struct Shape {
     int M, N, K;
     int a_box_rows;   // rows of the A tensor-map box (BM; 128 for a matrix of at most 128 rows)
+    // batched mode (a_idx != nullptr): the M axis is NB stacked problems of rows_per_batch rows; problem p multiplies
+    // rows [a_idx[p] * rows_per_batch, +rows_per_batch) of A with rows [w_idx[p] * N, +N) of W (N = s.N columns)
+    const long long *a_idx, *w_idx;
+    int rows_per_batch;
 };
 
 // optional fourth epilogue mode (Epi::kTmaStoreBf16 == true): out[tile] = bf16(epi.apply(acc + bias[col])) computed in
@@ -99,12 +103,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;   // n fastest: A tile reused from L2
+                int a_row = m_blk * BM, w_row = n_blk * BN;
+                if (s.a_idx != nullptr) {
+                    const int tpb = s.rows_per_batch / BM, p = m_blk / tpb;
+                    a_row = (int)s.a_idx[p] * s.rows_per_batch + (m_blk - p * tpb) * BM;
+                    w_row += (int)s.w_idx[p] * s.N;
+                }
                 for (int kb = 0; kb < nkb; kb++) {
                     tc5::mbar_wait(empty + stage, phase ^ 1);
                     uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + BM * BK * 2;
                     tc5::mbar_expect_tx(full + stage, (s.a_box_rows + BN) * BK * 2);
-                    tc5::tma_load_2d(sa, &tmap_a, full + stage, kb * BK, m_blk * BM);
-                    tc5::tma_load_2d(sb, &tmap_w, full + stage, kb * BK, n_blk * BN);
+                    tc5::tma_load_2d(sa, &tmap_a, full + stage, kb * BK, a_row);
+                    tc5::tma_load_2d(sb, &tmap_w, full + stage, kb * BK, w_row);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -294,22 +304,29 @@ inline int num_sms()
 // c_out / ldc: fp32 output matrix of the kTmaReduceAdd epilogue / bf16 output of the kTmaStoreBf16 epilogue (ignored otherwise)
 template <class Epi>
 int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, const Epi &epi, cudaStream_t st,
-           void *c_out = nullptr, int ldc = 0)
+           void *c_out = nullptr, int ldc = 0, const long long *a_idx = nullptr, const long long *w_idx = nullptr,
+           int rows_per_batch = 0, long a_rows_total = 0, long w_rows_total = 0)
 {
+    // batched mode: M = NB * rows_per_batch virtual rows; A has a_rows_total rows, W has w_rows_total rows
+    const bool batched = a_idx != nullptr;
+    if (batched && (rows_per_batch % BM != 0 || M % rows_per_batch != 0 || !w_idx)) {
+        set_last_error("tcgen05 gemm: batched mode needs rows_per_batch %% %d == 0", BM);
+        return -1;
+    }
     if (M <= 0 || N % BN != 0 || K % BK != 0) {
         set_last_error("tcgen05 gemm: unsupported shape M=%d N=%d K=%d", M, N, K);
         return -1;
     }
     CUtensorMap ta, tw;
     int a_box = BM;
-    if (!make_tmap_bf16(&ta, A, K, M, lda, BM)) {
+    if (!make_tmap_bf16(&ta, A, K, batched ? a_rows_total : M, lda, BM)) {
         a_box = 128;   // a matrix of at most 128 rows: only the first M = 128 accumulator holds stored rows
         if (M > 128 || !make_tmap_bf16(&ta, A, K, M, lda, 128)) {
             set_last_error("tcgen05 gemm: cuTensorMapEncodeTiled failed (A)");
             return -1;
         }
     }
-    if (!make_tmap_bf16(&tw, W, K, N, ldw, BN)) {
+    if (!make_tmap_bf16(&tw, W, K, batched ? w_rows_total : N, ldw, BN)) {
         set_last_error("tcgen05 gemm: cuTensorMapEncodeTiled failed (W)");
         return -1;
     }
@@ -333,7 +350,7 @@ int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, 
     }
     const int ntiles = ((M + BM - 1) / BM) * (N / BN);
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
-    Shape s{ M, N, K, a_box };
+    Shape s{ M, N, K, a_box, a_idx, w_idx, rows_per_batch };
     gemm_bf16_tn_kernel<Epi><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tw, tc, s, epi);
     return 0;
 }

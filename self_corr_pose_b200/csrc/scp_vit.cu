@@ -186,13 +186,55 @@ struct EpiKeys {  // feat[b][col][t-1] = acc + bias for patch tokens (CLS droppe
     static constexpr bool kTmaReduceAdd = false;
     static constexpr bool kMixed = false;
     float *feat; const float *bias; int T;
+    bf16 *tokens;   // optional second copy, token-major bf16 [b][t-1][384]: the K-major operand of the arg-match GEMM
     __device__ void operator()(int row, int col0, const float (&a)[32]) const
     {
         const int b = row / T, t = row - b * T;
         if (t == 0) return;
         float *dst = feat + ((long)b * D + col0) * (T - 1) + (t - 1);
+        float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; i++) dst[(long)i * (T - 1)] = a[i] + bias[col0 + i];
+        for (int i = 0; i < 32; i++) v[i] = a[i] + bias[col0 + i];
+#pragma unroll
+        for (int i = 0; i < 32; i++) dst[(long)i * (T - 1)] = v[i];
+        if (tokens != nullptr) {
+            uint4 *q = reinterpret_cast<uint4 *>(tokens + ((long)b * (T - 1) + (t - 1)) * D + col0);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                q[i] = make_uint4(scp::gemm::pack_bf16x2(v[8 * i], v[8 * i + 1]), scp::gemm::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                  scp::gemm::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), scp::gemm::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+        }
+    }
+};
+
+// arg-max of the masked feature similarity (model/module/pretrained_corr.py:85-89): best[row] = max over the unmasked
+// columns of (ordered similarity bits << 32 | ~column) -- larger similarity wins, the lower column wins ties
+struct EpiArgmax {
+    static constexpr bool kStaged = false;
+    static constexpr bool kTmaReduceAdd = false;
+    static constexpr bool kMixed = false;
+    unsigned long long *best; const float *col_mask; int rows_per_batch, ncols;
+    __device__ void operator()(int row, int col0, const float (&a)[32]) const
+    {
+        const int p = row / rows_per_batch;
+        const float4 *cm = reinterpret_cast<const float4 *>(col_mask + (long)p * ncols + col0);
+        float bv = 0.f;
+        int bi = -1;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 m = __ldg(cm + i);
+            const float mk[4] = { m.x, m.y, m.z, m.w };
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float x = a[4 * i + j];
+                if (mk[j] > 0.f && (bi < 0 || x > bv)) { bv = x; bi = col0 + 4 * i + j; }
+            }
+        }
+        if (bi >= 0) {
+            const uint32_t u = __float_as_uint(bv);
+            const uint32_t key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // order-preserving float -> uint
+            atomicMax(best + row, ((unsigned long long)key << 32) | (uint32_t)(0xffffffffu - (uint32_t)bi));
+        }
     }
 };
 
@@ -451,8 +493,8 @@ extern "C" size_t scp_vit_workspace_bytes(int B, int H, int W)
     return al(M * D * 4) + al(M * D * 2) * 4 + al((size_t)B * D * Tp * 2) + al(M * MLP * 2) + al((size_t)B * np * KP * 2);
 }
 
-extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float *feat, int B, int H, int W,
-                               int n_blocks, void *workspace, size_t workspace_bytes, void *stream)
+extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float *feat, void *feat_tokens, int B, int H,
+                               int W, int n_blocks, void *workspace, size_t workspace_bytes, void *stream)
 {
     if (!w || B <= 0 || H % PATCH || W % PATCH || n_blocks < 0 || n_blocks >= SCP_VIT_MAX_BLOCKS) {
         scp::set_last_error("scp_vit_s8_keys: bad arguments (B=%d H=%d W=%d n_blocks=%d)", B, H, W, n_blocks);
@@ -514,8 +556,27 @@ extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float
     {
         const scp_vit_block &bw = w->blocks[n_blocks];
         layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, bw.ln1_w, bw.ln1_b, y, M);
-        EpiKeys ek{ feat, bw.qkv_b + D, T };
+        EpiKeys ek{ feat, bw.qkv_b + D, T, (bf16 *)feat_tokens };
         if ((rc = scp::gemm::launch(y, D, (const bf16 *)bw.qkv_w + (size_t)D * D, D, (int)M, D, D, ek, st))) return rc;
     }
     return scp::check_launch("scp_vit_s8_keys");
+}
+
+// fw/bw arg-max matching of DINO features without the (pairs, np, np) similarity tensor: for pair p and every pixel r
+// of image a_idx[p]: best[p][r] = arg-max over the pixels c of image w_idx[p] with w_mask[p][c] > 0 of
+// <tokens[a_idx[p]][r], tokens[w_idx[p]][c]> (bf16 operands, fp32 accumulation on the tcgen05 GEMM).
+extern "C" int scp_dino_argmatch(const void *tokens, const long long *a_idx, const long long *w_idx, const float *w_mask,
+                                 int B, int np, int NP, unsigned long long *best, void *stream)
+{
+    if (!tokens || !a_idx || !w_idx || !w_mask || !best || B <= 0 || NP <= 0 || np <= 0 || np % scp::gemm::BM != 0) {
+        scp::set_last_error("scp_dino_argmatch: bad arguments (B=%d np=%d NP=%d; np must be a multiple of %d)", B, np, NP,
+                            scp::gemm::BM);
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(best, 0, (size_t)NP * np * sizeof(unsigned long long), st);
+    EpiArgmax epi{ best, w_mask, np, np };
+    int rc = scp::gemm::launch(tokens, D, tokens, D, NP * np, np, D, epi, st, nullptr, 0, a_idx, w_idx, np, (long)B * np,
+                               (long)B * np);
+    return rc ? rc : scp::check_launch("scp_dino_argmatch");
 }

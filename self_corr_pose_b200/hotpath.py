@@ -81,8 +81,10 @@ class HotPath:
                 self._side = torch.cuda.Stream(img.device)
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side), torch.no_grad():
-                feat = self.pretrain_corr_net.net(img)
-            feat.record_stream(main)
+                want_tokens = (opts.img_size // 8) ** 2 % 256 == 0
+                feat = self.pretrain_corr_net.net(img, tokens=want_tokens)
+            for t in (feat if isinstance(feat, tuple) else (feat,)):
+                t.record_stream(main)
 
         fused = self.fused_losses and opts.img_size % 16 == 0
         if fused:

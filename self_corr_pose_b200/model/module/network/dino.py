@@ -109,8 +109,10 @@ class DINO(nn.Module):
         return self._packed[key]
 
     @torch.no_grad()
-    def forward(self, img, layer=None):
-        """img (b,3,H,W) raw [0,1] RGB -> layer-9 key features (b, 384, H/8, W/8); frozen, no autograd."""
+    def forward(self, img, layer=None, tokens=False):
+        """img (b,3,H,W) raw [0,1] RGB -> layer-9 key features (b, 384, H/8, W/8); frozen, no autograd.
+        tokens=True additionally returns the same features token-major in bf16, (b, H/8*W/8, 384): the operand of the
+        native arg-max matching (PretrainedCorrespondence)."""
         if not img.is_cuda:
             raise TypeError('DINO supports only CUDA tensors (no CPU path)')
         layer = self.feat_layer if layer is None else layer
@@ -122,8 +124,9 @@ class DINO(nn.Module):
         L = _lib.lib()
         ws_bytes = L.scp_vit_workspace_bytes(B, H, W)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        tok = torch.empty(B, (H // 8) * (W // 8), VW.EMBED, dtype=torch.bfloat16, device=dev) if tokens else None
         with torch.cuda.device(dev):
-            rc = L.scp_vit_s8_keys(ctypes.byref(w), _lib.ptr(img), _lib.ptr(feat), B, H, W, layer, _lib.ptr(ws),
-                                   ws_bytes, _lib.stream_ptr(dev))
+            rc = L.scp_vit_s8_keys(ctypes.byref(w), _lib.ptr(img), _lib.ptr(feat), _lib.ptr(tok), B, H, W, layer,
+                                   _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
         _lib.check(rc, 'scp_vit_s8_keys')
-        return feat
+        return (feat, tok) if tokens else feat

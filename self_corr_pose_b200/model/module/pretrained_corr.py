@@ -40,29 +40,52 @@ class PretrainedCorrespondence(nn.Module):
         except KeyError:
             raise ValueError(opts.divide_fn)
 
-    def _match_from_feats(self, src_feat, tgt_feat, src_mask, tgt_mask, grid):
-        bsz = src_feat.shape[0]
-        src_feat = src_feat.reshape(*src_feat.shape[:2], -1)
-        tgt_feat = tgt_feat.reshape(*tgt_feat.shape[:2], -1)
+    def _argmatch_tokens(self, tokens, src_idx, tgt_idx, src_mask_down, tgt_mask_down):
+        """max_fw / max_bw of :88-89 through the native arg-max GEMM (csrc/scp_vit.cu: scp_dino_argmatch) on the
+        token-major bf16 features of the UNIQUE images: the (pairs, hw, hw) similarity is never written."""
+        from ... import _lib
+        NP, npix = src_mask_down.shape
+        dev = tokens.device
+        L = _lib.lib()
+        out = []
+        for a_idx, w_idx, w_mask, a_mask in ((src_idx, tgt_idx, tgt_mask_down, src_mask_down),
+                                             (tgt_idx, src_idx, src_mask_down, tgt_mask_down)):
+            best = torch.empty(NP, npix, dtype=torch.int64, device=dev)
+            w_mask = w_mask.float().contiguous()
+            with torch.cuda.device(dev):
+                rc = L.scp_dino_argmatch(_lib.ptr(tokens), _lib.ptr(a_idx.contiguous()), _lib.ptr(w_idx.contiguous()),
+                                         _lib.ptr(w_mask), tokens.shape[0], npix, NP, _lib.ptr(best), _lib.stream_ptr(dev))
+            _lib.check(rc, 'scp_dino_argmatch')
+            idx = 0xffffffff - (best & 0xffffffff)
+            out.append(torch.where(best == 0, torch.zeros_like(idx), idx) * (a_mask > 0))
+        return out[0], out[1]     # max_fw (per source pixel), max_bw (per target pixel)
+
+    def _match_from_feats(self, src_feat, tgt_feat, src_mask, tgt_mask, grid, argmax=None):
+        bsz = src_mask.shape[0]
         fs = self.feat_size
         src_mask_down = F.interpolate(src_mask[:, None], (fs, fs), mode='nearest').reshape(bsz, -1) * 1.0
         tgt_mask_down = F.interpolate(tgt_mask[:, None], (fs, fs), mode='nearest').reshape(bsz, -1) * 1.0
-        # arg-max of the masked similarity in both directions (pretrained_corr.py:85-89) without materialising the
-        # mask product: background entries are exactly -1e5 in the reference, so (a) an unmasked row/column never
-        # picks a masked partner -> a large negative bias on masked partners gives the same arg-max, folded into
-        # the GEMM as two extra channels; (b) a fully masked row/column is constant -> first index (0).
-        neg = -1e5
-        ones = torch.ones_like(src_mask_down)[:, None]
-        a = torch.cat([src_feat, ones, (neg * (src_mask_down == 0))[:, None]], dim=1)           # b, C+2, hw(src)
-        b = torch.cat([tgt_feat, (neg * (tgt_mask_down == 0))[:, None], ones], dim=1)           # b, C+2, hw(tgt)
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True      # tensor-core GEMM; the features are bf16-accurate already
-        try:
-            pointcorr = a.permute(0, 2, 1).bmm(b)                                              # b, hw(src), hw(tgt)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
-        max_bw = pointcorr.max(1).indices * (tgt_mask_down > 0)      # per target pixel: best source pixel
-        max_fw = pointcorr.max(2).indices * (src_mask_down > 0)      # per source pixel: best target pixel
+        if argmax is not None:
+            max_fw, max_bw = argmax(src_mask_down, tgt_mask_down)
+        else:
+            src_feat = src_feat.reshape(*src_feat.shape[:2], -1)
+            tgt_feat = tgt_feat.reshape(*tgt_feat.shape[:2], -1)
+            # arg-max of the masked similarity in both directions (pretrained_corr.py:85-89) without materialising the
+            # mask product: background entries are exactly -1e5 in the reference, so (a) an unmasked row/column never
+            # picks a masked partner -> a large negative bias on masked partners gives the same arg-max, folded into
+            # the GEMM as two extra channels; (b) a fully masked row/column is constant -> first index (0).
+            neg = -1e5
+            ones = torch.ones_like(src_mask_down)[:, None]
+            a = torch.cat([src_feat, ones, (neg * (src_mask_down == 0))[:, None]], dim=1)           # b, C+2, hw(src)
+            b = torch.cat([tgt_feat, (neg * (tgt_mask_down == 0))[:, None], ones], dim=1)           # b, C+2, hw(tgt)
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True      # tensor-core GEMM; the features are bf16-accurate already
+            try:
+                pointcorr = a.permute(0, 2, 1).bmm(b)                                              # b, hw(src), hw(tgt)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+            max_bw = pointcorr.max(1).indices * (tgt_mask_down > 0)      # per target pixel: best source pixel
+            max_fw = pointcorr.max(2).indices * (src_mask_down > 0)      # per source pixel: best target pixel
         max_cy = torch.gather(max_fw, -1, max_bw)
         grid = grid.reshape(bsz, 2, -1)
         match = torch.gather(grid, -1, max_bw[:, None].expand(-1, 2, -1))
@@ -97,11 +120,23 @@ class PretrainedCorrespondence(nn.Module):
         grid_flat = grid.reshape(2, -1)                                         # 2, h2*w2 (same for every pair)
 
         with torch.no_grad():   # DINO once per unique image, then paired
-            if feat is None:
-                feat = self.net(img)
-            pts_src, pts_tgt, indices_src, indices_tgt, mask_k = self._match_from_feats(
-                feat.index_select(0, src_idx), feat.index_select(0, tgt_idx), mask_src, mask_tgt,
-                grid.expand(bsz, -1, -1, -1))
+            tokens = None
+            if isinstance(feat, tuple):
+                feat, tokens = feat
+            elif feat is None:
+                npix = (self.img_size // 8) ** 2
+                if img.is_cuda and npix % 256 == 0:
+                    feat, tokens = self.net(img, tokens=True)
+                else:
+                    feat = self.net(img)
+            if tokens is not None:   # native arg-max GEMM on the unique images' token-major features
+                pts_src, pts_tgt, indices_src, indices_tgt, mask_k = self._match_from_feats(
+                    None, None, mask_src, mask_tgt, grid.expand(bsz, -1, -1, -1),
+                    argmax=lambda ms, mt: self._argmatch_tokens(tokens, src_idx, tgt_idx, ms, mt))
+            else:
+                pts_src, pts_tgt, indices_src, indices_tgt, mask_k = self._match_from_feats(
+                    feat.index_select(0, src_idx), feat.index_select(0, tgt_idx), mask_src, mask_tgt,
+                    grid.expand(bsz, -1, -1, -1))
 
         if not pooled:  # bilinear 1/2 with align_corners=False == exact 2x2 mean
             pointcorr = F.avg_pool2d(pointcorr.permute(0, 2, 1).reshape(B, num_verts, self.hf, self.wf), 2) \

@@ -102,3 +102,34 @@ def test_dino_features_vs_oracle(B, size):
     print('PARITY dino B%d %dpx feat_rel=%.3e argmax_agree=%.4f' % (B, size, r, agree))
     assert r < 2e-2        # bf16 operands through 9 blocks
     assert agree >= 0.95
+
+
+@pytest.mark.parametrize('B,npix', [(3, 256), (4, 1024)])
+def test_dino_argmatch_vs_masked_similarity(B, npix):
+    """scp_dino_argmatch (batched tcgen05 GEMM with an arg-max epilogue) against the reference statements
+    (pretrained_corr.py:85-89: masked similarity, max over both axes) evaluated in fp64 on the same bf16 tokens."""
+    from types import SimpleNamespace
+    from self_corr_pose_b200.model.module.pretrained_corr import PretrainedCorrespondence
+    g = torch.Generator().manual_seed(npix)
+    tokens = torch.randn(B, npix, 384, generator=g).to(torch.bfloat16).cuda()
+    NP = 2 * B
+    src_idx = (torch.arange(NP) % B).cuda()
+    tgt_idx = ((torch.arange(NP) + 1 + torch.arange(NP) // B) % B).cuda()
+    ms = (torch.rand(NP, npix, generator=g) > 0.5).float().cuda()
+    mt = (torch.rand(NP, npix, generator=g) > 0.5).float().cuda()
+    ms[0] = 0          # a pair whose source is entirely background
+    mt[1] = 0
+    max_fw, max_bw = PretrainedCorrespondence._argmatch_tokens(SimpleNamespace(), tokens, src_idx, tgt_idx, ms, mt)
+    t = tokens.double()
+    S = torch.einsum('pic,pjc->pij', t[src_idx], t[tgt_idx])
+    S = S * ms[:, :, None] * mt[:, None, :] + (-1e5) * (1 - ms[:, :, None] * mt[:, None, :])
+    ref_bw = S.max(1).indices * (mt > 0)
+    ref_fw = S.max(2).indices * (ms > 0)
+    # rows / columns that are entirely -1e5 have no defined arg-max in the reference (any index of a constant row):
+    # compare where an unmasked partner exists, and require index 0 elsewhere (what the product defines)
+    has_t, has_s = (mt.sum(1, keepdim=True) > 0), (ms.sum(1, keepdim=True) > 0)
+    ok_fw = torch.where((ms > 0) & has_t, max_fw == ref_fw, max_fw == 0)
+    ok_bw = torch.where((mt > 0) & has_s, max_bw == ref_bw, max_bw == 0)
+    agree = float(ok_fw.float().mean()), float(ok_bw.float().mean())
+    print('PARITY dino_argmatch B%d np%d agree fw=%.5f bw=%.5f' % (B, npix, *agree))
+    assert min(agree) >= 0.9995

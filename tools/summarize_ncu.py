@@ -10,11 +10,6 @@ import sys
 
 src, dst_md, dst_json = sys.argv[1:4]
 note = sys.argv[4] if len(sys.argv) > 4 else ''
-rows = list(csv.reader(open(src)))
-hdr = rows[0]
-# second row holds the units
-units = rows[1]
-col = {h: i for i, h in enumerate(hdr)}
 KEEP = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__registers_per_thread',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'smsp__thread_inst_executed_per_inst_executed.ratio',
@@ -31,35 +26,39 @@ scale = {'Mbyte': 1e6, 'Kbyte': 1e3, 'Gbyte': 1e9, 'byte': 1.0}
 tscale = {'ms': 1e3, 'us': 1.0, 'ns': 1e-3, 's': 1e6, 'msecond': 1e3, 'usecond': 1.0, 'nsecond': 1e-3, 'second': 1e6}
 seen = {}
 out, traffic = [], {}
-for r in rows[2:]:
-    name = re.sub(r'\(.*', '', r[col['Kernel Name']])
-    name = name.replace('void ', '').replace('scp::', '')
-    if not re.search(r'softras::|corr::|gemm::|vit::|fa2?::|loss::|geom::', name):
-        continue
-    k = seen.get(name, 0)
-    seen[name] = k + 1
-    if k >= 2:
-        continue
-    key = '%s #%d' % (name, k)
-    out.append('## `%s`\n\n| metric | value |\n|---|---|' % key)
-    rd = wr = us = 0.0
-    for m in KEEP:
-        if m not in col:
+for part in src.split(','):            # several captures of the same step (different -k filters)
+    rows = list(csv.reader(open(part)))
+    hdr, units = rows[0], rows[1]      # second row holds the units
+    col = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        name = re.sub(r'\(.*', '', r[col['Kernel Name']])
+        name = name.replace('void ', '').replace('scp::', '')
+        if not re.search(r'softras::|corr::|gemm::|vit::|fa2?::|loss::|geom::|cycle::', name):
             continue
-        val, unit = r[col[m]], units[col[m]]
-        out.append('| %s | %s %s |' % (m, val, unit))
-        try:
-            x = float(val.replace(',', ''))
-        except ValueError:
+        k = seen.get(name, 0)
+        seen[name] = k + 1
+        if k >= 2:
             continue
-        if m == 'dram__bytes_read.sum':
-            rd = x * scale.get(unit, 1.0)
-        elif m == 'dram__bytes_write.sum':
-            wr = x * scale.get(unit, 1.0)
-        elif m == 'gpu__time_duration.sum':
-            us = x * tscale.get(unit, 1.0)
-    out.append('')
-    traffic[key] = {'dram_bytes': rd + wr, 'us': us}
+        key = '%s #%d' % (name, k)
+        out.append('## `%s`\n\n| metric | value |\n|---|---|' % key)
+        rd = wr = us = 0.0
+        for m in KEEP:
+            if m not in col:
+                continue
+            val, unit = r[col[m]], units[col[m]]
+            out.append('| %s | %s %s |' % (m, val, unit))
+            try:
+                x = float(val.replace(',', ''))
+            except ValueError:
+                continue
+            if m == 'dram__bytes_read.sum':
+                rd = x * scale.get(unit, 1.0)
+            elif m == 'dram__bytes_write.sum':
+                wr = x * scale.get(unit, 1.0)
+            elif m == 'gpu__time_duration.sum':
+                us = x * tscale.get(unit, 1.0)
+        out.append('')
+        traffic[key] = {'dram_bytes': rd + wr, 'us': us}
 open(dst_md, 'w').write('# `ncu --set full --clock-control none` of the hot kernels (one step, B = 64, 1xB200)\n\n%s\n\n' % note +
                         '\n'.join(out) + '\n')
 json.dump(traffic, open(dst_json, 'w'), indent=1)
