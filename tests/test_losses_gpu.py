@@ -120,3 +120,35 @@ def test_cycle_rows_match_reference_statements(B, P4, N, k):
     print('PARITY cycle_rows B%d P4 %d N%d k%d ' % (B, P4, N, k) + ' '.join('%s=%.2e' % kv for kv in res.items()))
     for name, v in res.items():
         assert v < 1e-4, (name, v)
+
+
+def test_fused_kernels_match_reference_golden():
+    """Fused image losses and fused geometry on the golden inputs of tests/golden/make_loss_golden.py: outputs of the
+    REFERENCE's own loss_utils functions (values and autograd gradients)."""
+    import os
+    import numpy as np
+    from self_corr_pose_b200.ops.image_losses import image_losses
+    from self_corr_pose_b200.ops.project_faces import project_faces
+    from self_corr_pose_b200.model.util.loss_utils import LaplacianLoss
+    G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'loss_golden.npz'))
+    T = lambda k: torch.from_numpy(np.asarray(G[k])).cuda()
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    rd, rt, ml = (T(k).clone().requires_grad_(True) for k in ('r_depth', 'r_tex', 'match_lr'))
+    hf = int(round(ml.shape[1] ** 0.5))
+    out = torch.stack(image_losses(rd, rt, ml, T('img'), T('mask'), T('depth'), T('r_nocs'), hf, hf, True), 1)
+    (out * T('w')).sum().backward()
+    res = dict(losses=rel(out, T('losses')), g_r_depth=rel(rd.grad, T('g_r_depth')), g_r_tex=rel(rt.grad, T('g_r_tex')),
+               g_match_lr=rel(ml.grad, T('g_match_lr')))
+    leaves = [T(k).clone().requires_grad_(True) for k in ('c_verts', 'c_rot', 'c_trans')]
+    sv = project_faces(leaves[0], leaves[1], leaves[2], T('c_foc'), T('c_pp'))[0]
+    (sv * T('c_w')).sum().backward()
+    res.update(screen=rel(sv, T('c_screen')), g_verts=rel(leaves[0].grad, T('c_g_verts')),
+               g_rot=rel(leaves[1].grad, T('c_g_rot')), g_trans=rel(leaves[2].grad, T('c_g_trans')))
+    lap = LaplacianLoss(T('lap_v').cpu(), T('lap_f').cpu(), average=True).cuda()
+    x = T('lap_x').clone().requires_grad_(True)
+    ll = lap(x)
+    ll.backward()
+    res.update(lap=rel(ll, T('lap_loss')), lap_g=rel(x.grad, T('lap_g')))
+    print('PARITY fused kernels vs reference golden ' + ' '.join('%s=%.2e' % kv for kv in res.items()))
+    for k, v in res.items():
+        assert v < 1e-5, (k, v)
