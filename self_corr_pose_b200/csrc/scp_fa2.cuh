@@ -42,7 +42,8 @@ __device__ __forceinline__ float ex2(float x)
 
 __global__ void __launch_bounds__(NTHREADS, 2)
 fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-               const __grid_constant__ CUtensorMap tmap_vt, __nv_bfloat16 *__restrict__ o, int T, float scale_log2e)
+               const __grid_constant__ CUtensorMap tmap_vt, __nv_bfloat16 *__restrict__ o, int T, float scale_log2e,
+               int token_major)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -54,6 +55,10 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.y, q0 = blockIdx.x * BQ;
+    // q / k operand layouts: head-major [B*6][T][64] (tmap rows = (b*6+h)*T + t, column 0), or token-major as the QKV
+    // GEMM writes them, one [B*T][768] matrix (tmap rows = b*T + t, columns h*64 for q and 384 + h*64 for k)
+    const int qk_row0 = token_major ? (bh / HEADS) * T : bh * T;
+    const int q_col = token_major ? (bh % HEADS) * HD : 0, k_col = token_major ? HEADS * HD + q_col : 0;
     const int nt = (T + BKV - 1) / BKV;
     const int rows_valid = T - q0;                                  // > 0 by the grid size
     const int n_active = min(4, (rows_valid + 31) >> 5);            // softmax warps that own a valid query row
@@ -78,12 +83,12 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {   // ===== TMA producer =====
             tc5::mbar_expect_tx(q_full, Q_BYTES);
-            tc5::tma_load_2d(sQ, &tmap_q, q_full, 0, bh * T + q0);
+            tc5::tma_load_2d(sQ, &tmap_q, q_full, q_col, qk_row0 + q0);
             for (int j = 0; j < nt; j++) {
                 const int ks = j % NK, vs = j % NV;
                 tc5::mbar_wait(k_empty + ks, ((j / NK) & 1) ^ 1);
                 tc5::mbar_expect_tx(k_full + ks, KT_BYTES);
-                tc5::tma_load_2d(sK + ks * KT_BYTES, &tmap_k, k_full + ks, 0, bh * T + j * BKV);
+                tc5::tma_load_2d(sK + ks * KT_BYTES, &tmap_k, k_full + ks, k_col, qk_row0 + j * BKV);
                 tc5::mbar_wait(v_empty + vs, ((j / NV) & 1) ^ 1);
                 tc5::mbar_expect_tx(v_full + vs, VT_BYTES);
                 tc5::tma_load_2d(sV + vs * VT_BYTES, &tmap_vt, v_full + vs, j * BKV, bh * HD);

@@ -163,6 +163,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               uint8_t *box = epi_buf + (warp - 2) * TMA_TILE_BYTES;            // 32 rows x 128 B (64 bf16), SWIZZLE_128B
 #pragma unroll 1
               for (int cg = 0; cg < BN; cg += 64) {
+                if constexpr (Epi::kMixed) {   // column ranges that are contiguous along the rows go through operator()
+                    if (epi.direct(n_blk * BN + cg)) {
+#pragma unroll 1
+                        for (int cc = 0; cc < 64; cc += 32) {
+                            float v[32];
+                            tc5::tmem_ld32(tmem_base + t_acc + acc * ACC_COLS + cg + cc, v);
+                            if (row0 + lane < s.M) epi(row0 + lane, n_blk * BN + cg + cc, v);
+                        }
+                        continue;
+                    }
+                }
                 if (lane == 0) tc5::tma_store_wait_read();                      // previous bulk store has read the box
                 __syncwarp();
 #pragma unroll
@@ -338,7 +349,8 @@ int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, 
         }
     }
     if constexpr (tma_store_mode<Epi>::value) {   // bf16 output [M][N], box = 64 columns x 32 rows
-        if (!c_out || !make_tmap_bf16(&tc, c_out, N, M, ldc, 32)) {
+        // (an epilogue with direct column ranges may store fewer than N columns through TMA: the matrix is ldc wide)
+        if (!c_out || !make_tmap_bf16(&tc, c_out, N < ldc ? N : ldc, M, ldc, 32)) {
             set_last_error("tcgen05 gemm: bf16 output tensor map failed");
             return -1;
         }

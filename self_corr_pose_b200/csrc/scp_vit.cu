@@ -144,6 +144,25 @@ struct EpiQKV {  // head-major split: q/k[b][h][t][64] bf16, and v TRANSPOSED vT
     }
 };
 
+struct EpiQKVTokens {  // q | k token-major bf16 in one [M][768] matrix (bias added; register -> swizzled box -> TMA store, no
+                       // per-image row arithmetic: GEMM rows ARE the token rows); v TRANSPOSED per head as in EpiQKV
+    static constexpr bool kStaged = false;
+    static constexpr bool kTmaReduceAdd = false;
+    static constexpr bool kMixed = true;
+    static constexpr bool kTmaStoreBf16 = true;
+    bf16 *vt; const float *bias; int T, Tp;
+    __device__ __forceinline__ float apply(float z) const { return z; }
+    __device__ __forceinline__ bool direct(int col0) const { return col0 >= 2 * D; }
+    __device__ __forceinline__ void operator()(int row, int col0, const float (&a)[32]) const
+    {
+        const int c = col0 - 2 * D, h = c >> 6, d0 = c & 63;
+        const int b = row / T, t = row - b * T;
+        bf16 *dst = vt + (((long)b * HEADS + h) * HD + d0) * Tp + t;
+#pragma unroll
+        for (int i = 0; i < 32; i++) dst[(long)i * Tp] = __float2bfloat16(a[i] + __ldg(bias + col0 + i));
+    }
+};
+
 struct EpiQKVPlain {  // q/k/v[b][h][t][64] bf16 (layout of the mma.sync attention variant)
     static constexpr bool kStaged = true;
     static constexpr bool kTmaReduceAdd = false;
@@ -448,13 +467,20 @@ static int attention_variant()
     return e[0] == 'm' ? 0 : (e[0] == '1' ? 1 : 2);
 }
 
-static int launch_fa(const bf16 *q, const bf16 *k, const bf16 *vt, bf16 *o, int B, int T, int Tp, cudaStream_t st)
+// token_major (fa2 only): q = k = the [B*T][768] q|k matrix of EpiQKVTokens
+static int launch_fa(const bf16 *q, const bf16 *k, const bf16 *vt, bf16 *o, int B, int T, int Tp, cudaStream_t st,
+                     bool token_major = false)
 {
     const bool v2 = attention_variant() != 1;
     CUtensorMap tq, tk, tv;
-    const uint64_t rows = (uint64_t)B * HEADS * T;
+    const uint64_t rows = token_major ? (uint64_t)B * T : (uint64_t)B * HEADS * T;
+    const uint64_t inner = token_major ? 2 * D : HD;
     const uint32_t bq = v2 ? scp::fa2::BQ : scp::fa::BQ, bkv = v2 ? scp::fa2::BKV : scp::fa::BKV;
-    if (!scp::gemm::make_tmap_bf16(&tq, q, HD, rows, HD, bq) || !scp::gemm::make_tmap_bf16(&tk, k, HD, rows, HD, bkv) ||
+    if (token_major && !v2) {
+        scp::set_last_error("tcgen05 attention: the token-major q|k layout needs variant 2");
+        return -1;
+    }
+    if (!scp::gemm::make_tmap_bf16(&tq, q, inner, rows, inner, bq) || !scp::gemm::make_tmap_bf16(&tk, k, inner, rows, inner, bkv) ||
         !scp::gemm::make_tmap_bf16(&tv, vt, Tp, (uint64_t)B * HEADS * HD, Tp, 64)) {
         scp::set_last_error("tcgen05 attention: cuTensorMapEncodeTiled failed");
         return -1;
@@ -468,7 +494,7 @@ static int launch_fa(const bf16 *q, const bf16 *k, const bf16 *vt, bf16 *o, int 
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     if (v2)
         scp::fa2::fa2_fwd_kernel<<<dim3((T + bq - 1) / bq, B * HEADS), scp::fa2::NTHREADS, scp::fa2::SMEM_BYTES, st>>>(
-            tq, tk, tv, o, T, scale_log2e);
+            tq, tk, tv, o, T, scale_log2e, token_major ? 1 : 0);
     else
         scp::fa::fa_fwd_kernel<<<dim3((T + bq - 1) / bq, B * HEADS), scp::fa::NTHREADS, scp::fa::SMEM_BYTES, st>>>(
             tq, tk, tv, o, T, scale_log2e);
@@ -535,7 +561,11 @@ extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float
     for (int i = 0; i < n_blocks; i++) {
         const scp_vit_block &bw = w->blocks[i];
         layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, bw.ln1_w, bw.ln1_b, y, M);
-        if (use_tc5_attention) {   // tcgen05 flash attention: V transposed per head
+        if (attention_variant() == 2) {   // fa2: q | k token-major in one matrix (qb and kb are adjacent), V^T per head
+            EpiQKVTokens eq{ vb, bw.qkv_b, T, Tp };
+            if ((rc = scp::gemm::launch(y, D, bw.qkv_w, D, (int)M, 3 * D, D, eq, st, qb, 2 * D))) return rc;
+            if ((rc = launch_fa(qb, qb, vb, ob, B, T, Tp, st, true))) return rc;
+        } else if (use_tc5_attention) {   // first tcgen05 version: head-major q, k; V transposed per head
             EpiQKV eq{ qb, kb, vb, bw.qkv_b, T, Tp };
             if ((rc = scp::gemm::launch(y, D, bw.qkv_w, D, (int)M, 3 * D, D, eq, st))) return rc;
             if ((rc = launch_fa(qb, kb, vb, ob, B, T, Tp, st))) return rc;

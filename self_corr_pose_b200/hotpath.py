@@ -45,8 +45,8 @@ class HotPath:
     # kernels of this package launched by one forward+backward: SoftRas 2x(pack+fwd) + 2x(pack+bwd)
     # (mask, depth and NOCS share one traversal), correspondence 5 fwd + 3 bwd (block list, fill, main, 2 column
     # reductions / block list, rows, columns), ViT 3 + 9*7 + 2, image losses 2 fwd + 1 bwd, geometry 2 fwd + 2 bwd,
-    # pre-training cycle rows 1 fwd + 1 bwd
-    GPU_LAUNCHES = 4 + 4 + 8 + 68 + 3 + 4 + 2
+    # pre-training cycle rows 1 fwd + 1 bwd, DINO arg-match 2, sparse Laplacian 1 fwd + 1 bwd
+    GPU_LAUNCHES = 4 + 4 + 8 + 68 + 3 + 4 + 2 + 2 + 2
 
     def __init__(self, opts, mean_v, faces, device='cuda', fused_losses=True, overlap_vit=True):
         self.opts = opts
