@@ -286,6 +286,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep stdout to the one JSON line (NCCL_DEBUG=VERSION)
         dist.init_process_group('nccl', init_method='env://', device_id=dev)
     B = args.batch
     assert B % 4 == 0
