@@ -20,6 +20,15 @@ inline int check_launch(const char *what)
     return 0;
 }
 
+// 2^x on the MUFU pipe (ex2.approx.ftz: relative error 2^-22, results below 2^-126 flush to 0) -- one instruction
+// instead of exp2f's range-handling sequence; used where x <= 0 up to rounding (softmax numerators)
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll

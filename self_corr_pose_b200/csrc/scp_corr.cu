@@ -260,7 +260,7 @@ corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__rest
                         const bool masked = rmask[ri] == 0.f;
                         const float s = masked ? -1e5f : acc[mi][ni][2 * h + j];
                         sm2[h] = s;
-                        const float e = (valid && !masked) ? exp2f((s - 1.f) * kexp) : 0.f;
+                        const float e = (valid && !masked) ? ex2_approx((s - 1.f) * kexp) : 0.f;
                         const float er = valid ? (masked ? 1.f : e) : 0.f;  // background rows: uniform softmax
                         rl[ri] += er; rax[ri] += er * vq.x; ray[ri] += er * vq.y; raz[ri] += er * vq.z;
                         cv[(2 * ni + j) * 3 + 0] += e;
@@ -275,7 +275,7 @@ corr_fwd_kernel(Geo geo, const float *__restrict__ img_feat, const float *__rest
                         if (valid && !(g & 1) && rpool[mi] >= 0) {
                             pc_pool[((size_t)b * (geo.P >> 2) + rpool[mi]) * geo.N + n] = pv;
                             if (want_pool_stats) {   // pooled rows containing background pixels underflow to 0
-                                const float ep = exp2f((pv - 1.f) * kexp);
+                                const float ep = ex2_approx((pv - 1.f) * kexp);
                                 cvp[(2 * ni + j) * 3 + 0] += ep;
                                 cvp[(2 * ni + j) * 3 + 1] += ep * pgx[mi];
                                 cvp[(2 * ni + j) * 3 + 2] += ep * pgy[mi];
@@ -473,14 +473,14 @@ __device__ __forceinline__ void make_dS(const Geo &geo, const BwdArgs &a, int b,
                     const float4 c2 = *reinterpret_cast<const float4 *>(Cp + CPS * cl + 8);
                     float q = (ra[0].x == 0.f ? -1e5f : acc[mi][ni][j]) + (ra[1].x == 0.f ? -1e5f : acc[mi][ni][2 + j]);
                     q += __shfl_xor_sync(0xffffffffu, q, 4);
-                    const float ep = exp2f((0.25f * q - 1.f) * kexp);
+                    const float ep = ex2_approx((0.25f * q - 1.f) * kexp);
                     if (valid) dpool += 0.25f * ep * c2.x * (c2.y * pgx + c2.z * pgy - c2.w);
                 }
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     float d = 0.f;
                     if (ra[h].x != 0.f && valid) {
-                        const float e = exp2f((acc[mi][ni][2 * h + j] - 1.f) * kexp);
+                        const float e = ex2_approx((acc[mi][ni][2 * h + j] - 1.f) * kexp);
                         const float row_term = ra[h].w * (rb[h].x * c0.x + rb[h].y * c0.y + rb[h].z * c0.z - rb[h].w);
                         const float col_term = c0.w * (c1.x * ra[h].y + c1.y * ra[h].z - c1.z);
                         d = e * (row_term + col_term) + dpool;

@@ -45,7 +45,7 @@ __device__ __forceinline__ RowStats row_forward(const Args &a, const float *__re
     const float kk = a.tau * LOG2E;
     float S = 0.f, Sx = 0.f, Sy = 0.f, Sw = 0.f;
     for (int n = lane; n < a.N; n += 32) {
-        const float e = exp2f((__ldg(row + n) - r.m) * kk);
+        const float e = ex2_approx((__ldg(row + n) - r.m) * kk);
         S += e; Sx += e * sAx[n]; Sy += e * sAy[n]; Sw += e * sw[n];
     }
     r.S = warp_sum(S);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(NT) cycle_rows_bwd_kernel(Args a, const float 
         const float inv = 1.f / r.S;
         float *grow = g_pc + roff;
         for (int n = lane; n < a.N; n += 32) {
-            const float pi = exp2f((__ldg(row + n) - r.m) * kk) * inv;
+            const float pi = ex2_approx((__ldg(row + n) - r.m) * kk) * inv;
             const float w = sw[n];
             const float dpi = dnx * sAx[n] + dny * sAy[n] + dden * w;
             atomicAdd(grow + n, a.tau * pi * (dpi - dot));

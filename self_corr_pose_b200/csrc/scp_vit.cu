@@ -158,8 +158,15 @@ struct EpiQKVTokens {  // q | k token-major bf16 in one [M][768] matrix (bias ad
         const int c = col0 - 2 * D, h = c >> 6, d0 = c & 63;
         const int b = row / T, t = row - b * T;
         bf16 *dst = vt + (((long)b * HEADS + h) * HD + d0) * Tp + t;
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias + col0);
 #pragma unroll
-        for (int i = 0; i < 32; i++) dst[(long)i * Tp] = __float2bfloat16(a[i] + __ldg(bias + col0 + i));
+        for (int i = 0; i < 8; i++) {
+            const float4 bb = __ldg(b4 + i);
+            dst[(long)(4 * i) * Tp] = __float2bfloat16(a[4 * i] + bb.x);
+            dst[(long)(4 * i + 1) * Tp] = __float2bfloat16(a[4 * i + 1] + bb.y);
+            dst[(long)(4 * i + 2) * Tp] = __float2bfloat16(a[4 * i + 2] + bb.z);
+            dst[(long)(4 * i + 3) * Tp] = __float2bfloat16(a[4 * i + 3] + bb.w);
+        }
     }
 };
 
@@ -196,7 +203,21 @@ struct EpiGelu {  // h[row][:] = gelu_erf(acc + bias)  bf16, through the registe
     static constexpr bool kMixed = false;
     static constexpr bool kTmaStoreBf16 = true;
     const float *bias;
-    __device__ __forceinline__ float apply(float z) const { return 0.5f * z * (1.f + erf_as(z * 0.70710678118654752f)); }
+    // exact-erf GELU with erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7), folded so that the sign handling and
+    // the 0.5 (1 + erf) disappear:  0.5 z (1 + erf(z / sqrt 2)) = max(z, 0) - |z| * [0.5 P(t)] * exp(-z^2 / 2),
+    // t = 1 / (1 + p |z| / sqrt 2)  -- 14 instructions per element (2 on the MUFU pipe); the epilogue of this GEMM is
+    // issue-bound (ncu: 71 % issue slots with two epilogue warps per scheduler)
+    __device__ __forceinline__ float apply(float z) const
+    {
+        const float a = fabsf(z);
+        const float t = __fdividef(1.f, fmaf(0.3275911f * 0.70710678118654752f, a, 1.f));
+        const float hp = t * (0.5f * 0.254829592f + t * (0.5f * -0.284496736f + t * (0.5f * 1.421413741f +
+                         t * (0.5f * -1.453152027f + t * (0.5f * 1.061405429f)))));
+        const float w = z * 0.84932180028801904f;              // sqrt(log2(e) / 2): exp(-z^2/2) = 2^(-w^2)
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-w * w));
+        return fmaf(-a, hp * e, fmaxf(z, 0.f));
+    }
     __device__ void operator()(int, int, const float (&)[32]) const {}
 };
 
