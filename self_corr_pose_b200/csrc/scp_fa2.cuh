@@ -40,6 +40,25 @@ __device__ __forceinline__ float ex2(float x)
     return y;
 }
 
+// 2^x for x <= ~8 on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (relative error 7.7e-5, far below the bf16 rounding of P) and n added into the exponent field.
+// Measured and rejected for this kernel (SCP_FA2_POLY_EVERY = 4: 0.211 -> 0.224 ms per layer at B = 64): with two
+// softmax warps per scheduler the kernel is issue / latency bound, not bound by the 16 ex2 / clk / SM of the MUFU pipe,
+// so trading one MUFU op for nine ALU ops loses.  Kept behind the macro for wider softmax configurations.
+__device__ __forceinline__ float ex2_poly(float x)
+{
+    x = fmaxf(x, -126.f);
+    const float r = x + 12582912.f;                 // 1.5 * 2^23: n = round(x) lands in the low mantissa bits
+    const float f = x - (r - 12582912.f);
+    const float p = fmaf(fmaf(fmaf(0.05508868396282196f, f, 0.24260404706001282f), f, 0.6932762265205383f), f,
+                         0.9999289512634277f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
+#ifndef SCP_FA2_POLY_EVERY
+#define SCP_FA2_POLY_EVERY 0      // N > 0: every N-th element of a row takes the polynomial path
+#endif
+
 __global__ void __launch_bounds__(NTHREADS, 2)
 fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                const __grid_constant__ CUtensorMap tmap_vt, __nv_bfloat16 *__restrict__ o, int T, float scale_log2e,
@@ -179,7 +198,10 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
             for (int i = 0; i < BKV / 2; i++) {
-                const float p0 = ex2(fmaf(v[2 * i], scale_log2e, nm)), p1 = ex2(fmaf(v[2 * i + 1], scale_log2e, nm));
+                const float x0 = fmaf(v[2 * i], scale_log2e, nm), x1 = fmaf(v[2 * i + 1], scale_log2e, nm);
+                const float p0 = ex2(x0);
+                const float p1 = (SCP_FA2_POLY_EVERY > 0 && ((2 * i + 1) % SCP_FA2_POLY_EVERY) == SCP_FA2_POLY_EVERY - 1)
+                                     ? ex2_poly(x1) : ex2(x1);
                 rs0 += p0;
                 rs1 += p1;
                 __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);   // low half = even key
