@@ -10,6 +10,12 @@
 //   * query tiles with fewer than 128 valid rows (T = 1025: the last tile holds ONE token) only run the softmax
 //     warps that own a valid row.
 //
+// Measured and rejected variants (B = 64, per layer; the kernel stays at ~1000 cycles per 128 x 64 score tile per SM):
+//   * two softmax threads per row (8 softmax warps, partial maxima exchanged through smem): 0.211 -> 0.232 ms;
+//   * exp2 emulation on the FMA pipe for every 4th element: 0.211 -> 0.224 ms (below).
+// More softmax warps or fewer MUFU ops do not help: per tile the 32 KiB tcgen05.ld of S and the 8192 ex2 each cost
+// ~500 cycles of an SM and do not overlap.
+//
 //   TMEM columns (256 per CTA, two CTAs per SM):  S0 [0,64)  S1 [64,128)  P0 [128,160)  P1 [160,192)  O [192,256)
 //   warp 0 : TMA producer     warp 1 : TMEM allocator + MMA issuer     warps 2..5 : softmax (thread = query row)
 // Replaces the (b,6,1025,1025) attention materialisation of vision_transformer_flexible.py:90-94.
