@@ -13,6 +13,7 @@
 // each lane ending up with one total) and issues one global reduction per value per
 // (warp, face) instead of one per (pixel, face).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/scp_b200.h"
 #include "scp_common.cuh"
@@ -622,17 +623,13 @@ __device__ __forceinline__ float fold18(float (&v)[18], int lane, int &idx)
     return tot;
 }
 
+// gradient contribution of one (pixel, face) pair, ADDED into gv[0..8] (face coordinates) / gv[9..17] (vertex colours)
 template <int RGB, bool FAST>
-__device__ __forceinline__ bool backward_pair(const Params &p, const float *__restrict__ r, const Pixel &px,
-                                              const float *__restrict__ textures, int b, const float *g,
-                                              const float *out, float sm_sum, float sm_max, float *grad_textures,
-                                              float (&gv)[18])
+__device__ __forceinline__ bool backward_pair_loaded(const Params &p, const Face &f, const Pixel &px,
+                                                     const float *__restrict__ textures, int b, const float *g,
+                                                     const float *out, float sm_sum, float sm_max, float *grad_textures,
+                                                     float (&gv)[18])
 {
-    float bx0, bx1, by0, by1;
-    load_bbox(r, bx0, bx1, by0, by1);
-    if (px.xp > bx1 || px.xp < bx0 || px.yp > by1 || px.yp < by0) return false;
-    Face f;
-    load_face(r, f);
     Frag fr;
     if (!eval_frag<FAST>(p, f, px.xp, px.yp, fr)) return false;
     const int alpha_mode = FAST ? SCP_ALPHA_PROD : p.alpha_mode;
@@ -652,10 +649,10 @@ __device__ __forceinline__ bool backward_pair(const Params &p, const float *__re
 #pragma unroll
                 for (int v = 0; v < 3; v++)
 #pragma unroll
-                    for (int k = 0; k < 3; k++) gt[3 * v + k] = wc[v] * g[k];
+                    for (int k = 0; k < 3; k++) gt[3 * v + k] += wc[v] * g[k];
             } else if (p.T == 1) {
 #pragma unroll
-                for (int k = 0; k < 3; k++) gt[k] = g[k];
+                for (int k = 0; k < 3; k++) gt[k] += g[k];
             } else {
                 float *dst = grad_textures + ((size_t)b * p.nf + f.idx) * p.T * 3 + surface_texel(wc, p.R) * 3;
 #pragma unroll
@@ -674,10 +671,10 @@ __device__ __forceinline__ bool backward_pair(const Params &p, const float *__re
 #pragma unroll
             for (int v = 0; v < 3; v++)
 #pragma unroll
-                for (int k = 0; k < 3; k++) gt[3 * v + k] = s * (wc[v] * g[k]);
+                for (int k = 0; k < 3; k++) gt[3 * v + k] += s * (wc[v] * g[k]);
         } else if (p.T == 1) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) gt[k] = s * g[k];
+            for (int k = 0; k < 3; k++) gt[k] += s * g[k];
         } else {
             float *dst = grad_textures + ((size_t)b * p.nf + f.idx) * p.T * 3 + surface_texel(wc, p.R) * 3;
 #pragma unroll
@@ -687,15 +684,15 @@ __device__ __forceinline__ bool backward_pair(const Params &p, const float *__re
         Gxy += __fdividef(Q, fr.frag);
         const float Gz = Q * p.inv_gamma / (p.near_ - p.far_) * zp * zp;
 #pragma unroll
-        for (int v = 0; v < 3; v++) gv[3 * v + 2] = Gz * wc[v] * f.rz[v] * f.rz[v];
+        for (int v = 0; v < 3; v++) gv[3 * v + 2] += Gz * wc[v] * f.rz[v] * f.rz[v];
     }
     Gxy *= fr.frag * (1.f - fr.frag) * p.inv_sigma;  // sigmoid'
     if (dist_mode == SCP_DIST_EUCLIDEAN) {
 #pragma unroll
         for (int v = 0; v < 3; v++) {
             const float s2 = 2.f * fr.sign * Gxy * fr.c[v];
-            gv[3 * v + 0] = s2 * fr.dx;
-            gv[3 * v + 1] = s2 * fr.dy;
+            gv[3 * v + 0] += s2 * fr.dx;
+            gv[3 * v + 1] += s2 * fr.dy;
         }
     } else if (dist_mode == SCP_DIST_BARYCENTRIC) {
         // kernel.cu:161-175
@@ -709,11 +706,100 @@ __device__ __forceinline__ bool backward_pair(const Params &p, const float *__re
             for (int v = 0; v < 3; v++) {
                 const float acc = -iq * f.inv[3 * v + 0] * px.xp + -iq * f.inv[3 * v + 1] * px.yp +
                                   -iq * f.inv[3 * v + 2];
-                gv[3 * v + l] = acc * Gxy * sc;
+                gv[3 * v + l] += acc * Gxy * sc;
             }
         }
     }
     return true;
+}
+
+template <int RGB, bool FAST>
+__device__ __forceinline__ bool backward_pair(const Params &p, const float *__restrict__ r, const Pixel &px,
+                                              const float *__restrict__ textures, int b, const float *g,
+                                              const float *out, float sm_sum, float sm_max, float *grad_textures,
+                                              float (&gv)[18])
+{
+    float bx0, bx1, by0, by1;
+    load_bbox(r, bx0, bx1, by0, by1);
+    if (px.xp > bx1 || px.xp < bx0 || px.yp > by1 || px.yp < by0) return false;
+    Face f;
+    load_face(r, f);
+    return backward_pair_loaded<RGB, FAST>(p, f, px, textures, b, g, out, sm_sum, sm_max, grad_textures, gv);
+}
+
+// ---- backward, face-centric traversal ------------------------------------------------------------------------
+// One warp per (image, face): the packed record is loaded ONCE into registers, the warp walks the face's inflated
+// bounding box in 8x4 pixel blocks (one pixel per lane), accumulates the 18 gradients in registers across ALL blocks and
+// reduces them across the warp once at the end -- no per-(warp, face) record loads / butterfly / global reductions as in
+// the tile-centric kernel (41 % of its instructions, profiles/r1_softras_backward_source_page.csv.gz), no atomics on
+// grad_faces / grad_textures at all (one warp owns a face), deterministic summation order.  The per-pixel operands
+// (incoming gradient, colours, aggregates: 10 floats) are re-read per block through L1.
+constexpr int FACE_WARPS = 8;
+template <int RGB, bool FAST>
+__global__ void __launch_bounds__(FACE_WARPS * 32) backward_face_kernel(Params p, const float4 *__restrict__ bbox,
+                                                                         const float *__restrict__ rec,
+                                                                         const float *__restrict__ textures,
+                                                                         const float *__restrict__ soft_colors,
+                                                                         const float *__restrict__ aggrs_info,
+                                                                         const float *__restrict__ grad_soft_colors,
+                                                                         float *grad_faces, float *grad_textures)
+{
+    const int lane = threadIdx.x & 31;
+    const long fg = (long)blockIdx.x * FACE_WARPS + (threadIdx.x >> 5);     // flat (image, face) index
+    if (fg >= (long)p.B * p.nf) return;
+    const int b = (int)(fg / p.nf);
+    const float4 bb = __ldg(bbox + fg);
+    // pixel range whose centres can lie inside the inflated bbox (one pixel of slack; backward_pair re-tests exactly):
+    // xp = (2 px + 1 - is) / is,  yp = (is - 1 - 2 py) / is  (row 0 = top)
+    const float is = (float)p.is;
+    const int ix0 = max(0, (int)floorf((bb.x * is + is - 1.f) * 0.5f) - 1);
+    const int ix1 = min(p.is - 1, (int)ceilf((bb.y * is + is - 1.f) * 0.5f) + 1);
+    const int iy0 = max(0, (int)floorf((is - 1.f - bb.w * is) * 0.5f) - 1);
+    const int iy1 = min(p.is - 1, (int)ceilf((is - 1.f - bb.z * is) * 0.5f) + 1);
+    if (ix0 > ix1 || iy0 > iy1) return;
+    Face f;
+    load_face(rec + fg * REC, f);
+    const int ntex = p.T * 3 <= 9 ? p.T * 3 : 0;
+    const size_t plane = (size_t)p.is * p.is;
+    const float *gsc = grad_soft_colors + (size_t)b * 4 * plane, *sc = soft_colors + (size_t)b * 4 * plane;
+    const float *ag = aggrs_info + (size_t)b * 2 * plane;
+    float gv[18];
+#pragma unroll
+    for (int k = 0; k < 18; k++) gv[k] = 0.f;
+    bool any = false;
+    for (int y0 = iy0; y0 <= iy1; y0 += 4) {
+        for (int x0 = ix0; x0 <= ix1; x0 += 8) {
+            Pixel px;
+            px.px = x0 + (lane & 7);
+            px.py = y0 + (lane >> 3);
+            px.valid = px.px <= ix1 && px.py <= iy1;
+            px.pn = px.py * p.is + px.px;
+            px.xp = centre_x(px.px, p.is);
+            px.yp = centre_y(px.py, p.is);
+            const bool in_box = px.valid && !(px.xp > bb.y || px.xp < bb.x || px.yp > bb.w || px.yp < bb.z);
+            float g[4] = { 0.f, 0.f, 0.f, 0.f };
+            if (in_box) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) g[k] = __ldg(gsc + k * plane + px.pn);
+            }
+            const bool lane_grad = in_box && (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f || g[3] != 0.f);
+            if (!__any_sync(0xffffffffu, lane_grad)) continue;
+            if (lane_grad) {
+                float out[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) out[k] = __ldg(sc + k * plane + px.pn);
+                const float sm_sum = __ldg(ag + px.pn), sm_max = __ldg(ag + plane + px.pn);
+                any |= backward_pair_loaded<RGB, FAST>(p, f, px, textures, b, g, out, sm_sum, sm_max, grad_textures, gv);
+            }
+        }
+    }
+    if (!__any_sync(0xffffffffu, any)) return;
+    int idx;
+    const float tot = fold18(gv, lane, idx);
+    if (tot != 0.f) {    // single writer per face: plain read-modify-write into the caller's zero-filled buffers
+        if (idx < 9) grad_faces[fg * 9 + idx] += tot;
+        else if (idx - 9 < ntex) grad_textures[fg * ntex + (idx - 9)] += tot;
+    }
 }
 
 template <int RGB, bool FAST>
@@ -932,14 +1018,33 @@ extern "C" int scp_softras_backward(const float *faces, const float *textures, c
     cudaMemsetAsync(img_bbox, 0x7f, (size_t)B * 4 * sizeof(int), st);
     pack_kernel<<<(unsigned)((nfaces + 255) / 256), 256, 0, st>>>(p, faces, textures, const_cast<float *>(faces_info),
                                                                  0, bbox, rec, img_bbox);
-    const dim3 grid(p.tiles_x * p.tiles_x, B);
     const bool fast = func_id_dist == SCP_DIST_EUCLIDEAN && func_id_alpha == SCP_ALPHA_PROD;
-    if (func_id_rgb == SCP_RGB_HARD) {
-        if (fast) backward_kernel<SCP_RGB_HARD, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
-        else backward_kernel<SCP_RGB_HARD, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+    // Traversal: face-centric (one warp per face, record and gradient accumulators in registers, no atomics) for the
+    // softmax-RGB renders -- the two backward launches of a training step; tile-centric (same traversal as the forward,
+    // gradients reduced with global float reductions) for hard RGB, whose geometry gradient is the ill-conditioned alpha
+    // term alone: there the two instantiations differ by the compiler's FMA contraction choices at
+    // the 1e-2 level, and the tile kernel is the one pinned to the oracle.  SCP_SOFTRAS_BWD=tile / face forces one.
+    const char *mode = getenv("SCP_SOFTRAS_BWD");
+    const bool use_tile = mode && mode[0] == 't' ? true : (mode && mode[0] == 'f' ? false : func_id_rgb == SCP_RGB_HARD);
+    if (use_tile) {
+        const dim3 grid(p.tiles_x * p.tiles_x, B);
+        if (func_id_rgb == SCP_RGB_HARD) {
+            if (fast) backward_kernel<SCP_RGB_HARD, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+            else backward_kernel<SCP_RGB_HARD, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+        } else {
+            if (fast) backward_kernel<SCP_RGB_SOFTMAX, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+            else backward_kernel<SCP_RGB_SOFTMAX, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+        }
     } else {
-        if (fast) backward_kernel<SCP_RGB_SOFTMAX, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
-        else backward_kernel<SCP_RGB_SOFTMAX, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+        const unsigned grid = (unsigned)((nfaces + FACE_WARPS - 1) / FACE_WARPS);
+        const int nt = FACE_WARPS * 32;
+        if (func_id_rgb == SCP_RGB_HARD) {
+            if (fast) backward_face_kernel<SCP_RGB_HARD, true><<<grid, nt, 0, st>>>(p, bbox, rec, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+            else backward_face_kernel<SCP_RGB_HARD, false><<<grid, nt, 0, st>>>(p, bbox, rec, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+        } else {
+            if (fast) backward_face_kernel<SCP_RGB_SOFTMAX, true><<<grid, nt, 0, st>>>(p, bbox, rec, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+            else backward_face_kernel<SCP_RGB_SOFTMAX, false><<<grid, nt, 0, st>>>(p, bbox, rec, textures, soft_colors, aggrs_info, grad_soft_colors, grad_faces, grad_textures);
+        }
     }
     return scp::check_launch("scp_softras_backward");
 }
