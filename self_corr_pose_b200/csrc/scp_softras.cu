@@ -734,7 +734,7 @@ __device__ __forceinline__ bool backward_pair(const Params &p, const float *__re
 // the tile-centric kernel (41 % of its instructions, profiles/r1_softras_backward_source_page.csv.gz), no atomics on
 // grad_faces / grad_textures at all (one warp owns a face), deterministic summation order.  The per-pixel operands
 // (incoming gradient, colours, aggregates: 10 floats) are re-read per block through L1.
-constexpr int FACE_WARPS = 8;
+constexpr int FACE_WARPS = 2;    // small CTAs: a warp that finishes its face early frees its slot (face sizes vary)
 template <int RGB, bool FAST>
 __global__ void __launch_bounds__(FACE_WARPS * 32) backward_face_kernel(Params p, const float4 *__restrict__ bbox,
                                                                          const float *__restrict__ rec,
