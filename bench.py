@@ -207,9 +207,9 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
         out.append(dict(kernel=name + '_fwd (pack+forward_kernel)', ms=t_f, bound='hbm', achieved=bf / t_f / 1e6,
                         peak=hbm, unit='GB/s', launches_per_step=1,
                         ncu_name='softras::forward_kernel<1, 1> #0' if 'softtex' in name else 'softras::forward_kernel<2, 1> #0'))
-        out.append(dict(kernel=name.replace('+nocs', '') + '_bwd (pack+backward_kernel)', ms=t_b, bound='hbm',
+        out.append(dict(kernel=name.replace('+nocs', '') + '_bwd (pack+backward_face_kernel)', ms=t_b, bound='hbm',
                         achieved=bytes_b / t_b / 1e6, peak=hbm, unit='GB/s', launches_per_step=1,
-                        ncu_name='softras::backward_kernel<1, 1> #%d' % (0 if 'softtex' in name else 1)))
+                        ncu_name='softras::backward_face_kernel<1, 1> #%d' % (0 if 'softtex' in name else 1)))
     # --- correspondence
     from self_corr_pose_b200.ops.corr_match import corr_match
     import torch.nn.functional as F

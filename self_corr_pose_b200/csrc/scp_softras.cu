@@ -731,12 +731,12 @@ __device__ __forceinline__ bool backward_pair(const Params &p, const float *__re
 // One warp per (image, face): the packed record is loaded ONCE into registers, the warp walks the face's inflated
 // bounding box in 8x4 pixel blocks (one pixel per lane), accumulates the 18 gradients in registers across ALL blocks and
 // reduces them across the warp once at the end -- no per-(warp, face) record loads / butterfly / global reductions as in
-// the tile-centric kernel (41 % of its instructions, profiles/r1_softras_backward_source_page.csv.gz), no atomics on
+// the tile-centric kernel (41 % of its instructions, profiles/r1_softras_backward_tile_source_page.csv.gz), no atomics on
 // grad_faces / grad_textures at all (one warp owns a face), deterministic summation order.  The per-pixel operands
 // (incoming gradient, colours, aggregates: 10 floats) are re-read per block through L1.
 constexpr int FACE_WARPS = 2;    // small CTAs: a warp that finishes its face early frees its slot (face sizes vary)
 template <int RGB, bool FAST>
-__global__ void __launch_bounds__(FACE_WARPS * 32) backward_face_kernel(Params p, const float4 *__restrict__ bbox,
+__global__ void __launch_bounds__(FACE_WARPS * 32, 8) backward_face_kernel(Params p, const float4 *__restrict__ bbox,
                                                                          const float *__restrict__ rec,
                                                                          const float *__restrict__ textures,
                                                                          const float *__restrict__ soft_colors,
@@ -777,20 +777,19 @@ __global__ void __launch_bounds__(FACE_WARPS * 32) backward_face_kernel(Params p
             px.xp = centre_x(px.px, p.is);
             px.yp = centre_y(px.py, p.is);
             const bool in_box = px.valid && !(px.xp > bb.y || px.xp < bb.x || px.yp > bb.w || px.yp < bb.z);
-            float g[4] = { 0.f, 0.f, 0.f, 0.f };
+            // all ten per-pixel operands are requested at once (one memory latency per block instead of two)
+            float g[4] = { 0.f, 0.f, 0.f, 0.f }, out[4] = { 0.f, 0.f, 0.f, 0.f }, sm_sum = 1.f, sm_max = 0.f;
             if (in_box) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) g[k] = __ldg(gsc + k * plane + px.pn);
-            }
-            const bool lane_grad = in_box && (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f || g[3] != 0.f);
-            if (!__any_sync(0xffffffffu, lane_grad)) continue;
-            if (lane_grad) {
-                float out[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) out[k] = __ldg(sc + k * plane + px.pn);
-                const float sm_sum = __ldg(ag + px.pn), sm_max = __ldg(ag + plane + px.pn);
-                any |= backward_pair_loaded<RGB, FAST>(p, f, px, textures, b, g, out, sm_sum, sm_max, grad_textures, gv);
+                sm_sum = __ldg(ag + px.pn);
+                sm_max = __ldg(ag + plane + px.pn);
             }
+            const bool lane_grad = in_box && (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f || g[3] != 0.f);
+            if (lane_grad)
+                any |= backward_pair_loaded<RGB, FAST>(p, f, px, textures, b, g, out, sm_sum, sm_max, grad_textures, gv);
         }
     }
     if (!__any_sync(0xffffffffu, any)) return;

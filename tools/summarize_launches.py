@@ -2,7 +2,7 @@
 
     python tools/summarize_launches.py gpurun_out/launches.csv.gz profiles/rN_bench_launch_summary.md "<note>"
 
-The step count is recovered from the soft-texture SoftRas backward kernel (launched twice per step)."""
+The step count is recovered from the attention kernel (nine launches per step)."""
 import collections
 import csv
 import gzip
@@ -21,9 +21,9 @@ for r in rows[1:]:
     name = re.sub(r'\(.*', '', r[ki])[:110]
     agg[name][0] += 1
     agg[name][1] += float(r[vi].replace(',', '')) * scale[r[ui]]
-steps = max(v[0] for k, v in agg.items() if 'softras::backward_kernel<1, 1>' in k) // 2
+steps = max(v[0] for k, v in agg.items() if 'fa2::fa2_fwd_kernel' in k or 'fa::fa_fwd_kernel' in k) // 9
 total = sum(v[1] for v in agg.values()) / steps
-mine = sum(v[1] for k, v in agg.items() if re.search(r'softras::|corr::|gemm::|vit::|fa::|loss::', k)) / steps
+mine = sum(v[1] for k, v in agg.items() if re.search(r'softras::|corr::|gemm::|vit::|fa2?::|loss::|geom::|cycle::', k)) / steps
 with open(dst, 'w') as f:
     f.write('# ncu launch list of `bench.py`, aggregated per step\n\n%s\n\n' % note)
     f.write('%d launches over %d steps (warm-up, timed and end-to-end steps all run under the profiler); times are '
