@@ -19,6 +19,13 @@ from ...ops.cycle_rows import cycle_rows
 from ..util.loss_utils import divide_by_frame, divide_by_instance, divide_by_both
 
 
+def decode_argmax(best):
+    """scp_dino_argmatch packs (order-preserving similarity bits << 32 | 0xffffffff - column) into 64 bits (stored in an
+    int64 tensor); 0 = no unmasked column -> index 0 (a constant row of the reference's masked similarity)."""
+    idx = 0xffffffff - (best & 0xffffffff)
+    return torch.where(best == 0, torch.zeros_like(idx), idx)
+
+
 class PretrainedCorrespondence(nn.Module):
 
     def __init__(self, opts, mesh=None, pretrained=True, device=None):
@@ -56,8 +63,7 @@ class PretrainedCorrespondence(nn.Module):
                 rc = L.scp_dino_argmatch(_lib.ptr(tokens), _lib.ptr(a_idx.contiguous()), _lib.ptr(w_idx.contiguous()),
                                          _lib.ptr(w_mask), tokens.shape[0], npix, NP, _lib.ptr(best), _lib.stream_ptr(dev))
             _lib.check(rc, 'scp_dino_argmatch')
-            idx = 0xffffffff - (best & 0xffffffff)
-            out.append(torch.where(best == 0, torch.zeros_like(idx), idx) * (a_mask > 0))
+            out.append(decode_argmax(best) * (a_mask > 0))
         return out[0], out[1]     # max_fw (per source pixel), max_bw (per target pixel)
 
     def _match_from_feats(self, src_feat, tgt_feat, src_mask, tgt_mask, grid, argmax=None):

@@ -128,3 +128,64 @@ def test_flat_gradient_allreduce_gloo_world2():
         torch.testing.assert_close(out[r][0], exp0)
         torch.testing.assert_close(out[r][1], exp1)
         torch.testing.assert_close(out[r][2], torch.zeros(2))
+
+
+def test_face_topology_csr():
+    """vertex -> face-corner adjacency of ops/project_faces.py: every corner listed exactly once under its vertex,
+    corners of a vertex in ascending order (the fixed summation order of the geometry backward)."""
+    from self_corr_pose_b200 import synthetic
+    from self_corr_pose_b200.ops.project_faces import FaceTopology
+    v, f = synthetic.icosphere(2)
+    topo = FaceTopology(torch.from_numpy(f), v.shape[0])
+    off, idx, faces = topo.csr_off.long(), topo.csr_idx.long(), topo.faces.long()
+    assert off[0] == 0 and off[-1] == faces.numel() and sorted(idx.tolist()) == list(range(faces.numel()))
+    flat = faces.reshape(-1)
+    for n in range(v.shape[0]):
+        seg = idx[off[n]:off[n + 1]]
+        assert (flat[seg] == n).all() and (seg[1:] > seg[:-1]).all()
+
+
+def test_laplacian_csr_equals_dense_buffer():
+    from self_corr_pose_b200 import synthetic
+    from self_corr_pose_b200.model.util.loss_utils import LaplacianLoss
+    v, f = synthetic.icosphere(1)
+    lap = LaplacianLoss(torch.from_numpy(v), torch.from_numpy(f), average=True)
+    for pre, dense in (('csr', lap.laplacian), ('csr_t', lap.laplacian.t())):
+        off, col, val = (getattr(lap, pre + s) for s in ('_off', '_col', '_val'))
+        rebuilt = torch.zeros_like(dense)
+        for n in range(dense.shape[0]):
+            rebuilt[n, col[off[n]:off[n + 1]].long()] = val[off[n]:off[n + 1]]
+        assert torch.equal(rebuilt, dense.contiguous())
+    assert 'csr_off' not in lap.state_dict()          # derived buffers stay out of checkpoints
+
+
+def test_argmax_decode():
+    from self_corr_pose_b200.model.module.pretrained_corr import decode_argmax
+
+    def pack(x, col):   # what the arg-max epilogue writes (csrc/scp_vit.cu: EpiArgmax)
+        u = int(np.float32(x).view(np.uint32))
+        key = (~u & 0xffffffff) if u & 0x80000000 else (u | 0x80000000)
+        v = (key << 32) | (0xffffffff - col)
+        return v - (1 << 64) if v >= (1 << 63) else v      # stored in an int64 tensor
+
+    cands = [(-3.5, 7), (2.25, 900), (2.25, 12), (-0.0, 3), (1e-30, 5)]
+    best = max(cands, key=lambda c: (np.float32(c[0]), -c[1]))
+    packed = [pack(*c) for c in cands]
+    as_u64 = lambda v: v + (1 << 64) if v < 0 else v
+    assert max(packed, key=as_u64) == pack(*best)          # larger similarity wins, lower column wins ties
+    t = torch.tensor([pack(2.25, 12), 0, pack(-7.0, 1023)], dtype=torch.int64)
+    assert decode_argmax(t).tolist() == [12, 0, 1023]
+
+
+def test_new_ops_fail_loudly_on_cpu_tensors():
+    from self_corr_pose_b200.ops.image_losses import image_losses
+    from self_corr_pose_b200.ops.project_faces import project_faces
+    from self_corr_pose_b200.ops.cycle_rows import cycle_rows
+    z = torch.zeros
+    with pytest.raises(TypeError):
+        image_losses(z(1, 4, 16, 16), z(1, 4, 16, 16), z(1, 16, 3), z(1, 3, 16, 16), z(1, 16, 16), z(1, 16, 16),
+                     z(1, 4, 16, 16), 4, 4)
+    with pytest.raises(TypeError):
+        project_faces(z(1, 4, 3), z(1, 3, 3), z(1, 1, 3), z(1, 2).double(), z(1, 2).double())
+    with pytest.raises(TypeError):
+        cycle_rows(z(1, 4, 8), z(1, 2, 8), z(1, 8), z(2).long(), z(2).long(), z(2, 3).long(), z(2, 2, 3), z(2, 3), 10.)
