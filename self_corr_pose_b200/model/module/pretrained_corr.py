@@ -7,7 +7,12 @@ API of the reference's model/module/pretrained_corr.py (`PretrainedCorrespondenc
   * the (2B,1024,1024) `corr` matrix of :130-131 is never formed: only its k gathered columns are needed
     (note A):  match[:,j] = sum_n A[:,n] Pi[j,n] / (sum_n s[n] Pi[j,n] + 1e-5) with
     A = grid . Pm (2 x N) and s[n] = sum_p Pm[p,n] = [depth_weight_src[n] >= 0.5];
-  * `pointcorr` may arrive already 2x2-averaged (pooled=True) from the fused correspondence kernel.
+  * `pointcorr` may arrive already 2x2-averaged (pooled=True) from the fused correspondence kernel;
+  * on CUDA the fw / bw arg-max matching of :85-89 runs as a batched tcgen05 GEMM with an arg-max epilogue on the
+    token-major bf16 features of the unique images (`_argmatch_tokens`, scp_dino_argmatch) and the target-row part of
+    the loss as fused kernels (ops/cycle_rows.py); the op-by-op CUDA statements are kept below (`fused=False`, feature
+    maps whose size is not a multiple of 256 pixels) and serve as the parity reference in the tests.  There is no CPU
+    path: the ViT raises on CPU tensors.
 """
 import torch
 import torch.nn as nn
