@@ -13,8 +13,12 @@
 // Measured and rejected variants (B = 64, per layer; the kernel stays at ~1000 cycles per 128 x 64 score tile per SM):
 //   * two softmax threads per row (8 softmax warps, partial maxima exchanged through smem): 0.211 -> 0.232 ms;
 //   * exp2 emulation on the FMA pipe for every 4th element: 0.211 -> 0.224 ms (below).
-// More softmax warps or fewer MUFU ops do not help: per tile the 32 KiB tcgen05.ld of S and the 8192 ex2 each cost
-// ~500 cycles of an SM and do not overlap.
+//   * THREE S accumulators with P(j) written over the head of S(j) (S(j+3) issued right after PV(j)): 0.211 -> 0.202 ms
+//     but WRONG results once a buffer is reused (T = 1025 fails, T <= 128 passes) -- not kept; to be debugged with GPU
+//     time (suspect: the product that overwrites the aliased columns starts before PV(j) has read P(j)).
+// What the source page shows (profiles/r1_fa2_source_page.csv.gz): 68 % of the softmax warps' waits for the next S tile
+// spin (11.7 % of all stall samples): S(j+2) is only issued after PV(j), so the tensor pipe's latency is exposed once per
+// tile; a deeper S ring is the lever, more softmax warps or fewer MUFU ops are not.
 //
 //   TMEM columns (256 per CTA, two CTAs per SM):  S0 [0,64)  S1 [64,128)  P0 [128,160)  P1 [160,192)  O [192,256)
 //   warp 0 : TMA producer     warp 1 : TMEM allocator + MMA issuer     warps 2..5 : softmax (thread = query row)
