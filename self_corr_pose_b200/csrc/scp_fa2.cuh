@@ -65,6 +65,13 @@ __device__ __forceinline__ float ex2_poly(float x)
     return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
 }
 
+// Next-round candidate, NOT validated on a GPU yet (default off): a separate "S consumed" barrier, arrived by the softmax
+// warps right after their tcgen05.ld of S(j), lets the MMA warp issue Q K(j+2)^T during the softmax of tile j instead of
+// after it (P and S do not alias, so only the read of S(j) has to be over) -- addresses the s_full starvation above.
+#ifndef SCP_FA2_EARLY_QK
+#define SCP_FA2_EARLY_QK 0
+#endif
+
 #ifndef SCP_FA2_POLY_EVERY
 #define SCP_FA2_POLY_EVERY 0      // N > 0: every N-th element of a row takes the polynomial path
 #endif
@@ -79,8 +86,8 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint8_t *sQ = smem, *sK = sQ + Q_BYTES, *sV = sK + NK * KT_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sV + NV * VT_BYTES);
     uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = k_full + NK, *v_full = k_empty + NK, *v_empty = v_full + NV,
-             *s_full = v_empty + NV, *p_full = s_full + 2, *pv_done = p_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pv_done + 1);
+             *s_full = v_empty + NV, *p_full = s_full + 2, *pv_done = p_full + 2, *s_free = pv_done + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(s_free + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.y, q0 = blockIdx.x * BQ;
@@ -101,6 +108,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         for (int i = 0; i < NV; i++) { tc5::mbar_init(v_full + i, 1); tc5::mbar_init(v_empty + i, 1); }
         for (int i = 0; i < 2; i++) { tc5::mbar_init(s_full + i, 1); tc5::mbar_init(p_full + i, n_active); }
         tc5::mbar_init(pv_done, 1);
+        for (int i = 0; i < 2; i++) tc5::mbar_init(s_free + i, n_active);
         tc5::mbar_fence_init();
     }
     if (warp == 1) tc5::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -147,6 +155,13 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             if (nt > 1) issue_qk(1);
             for (int j = 0; j < nt; j++) {
                 const int buf = j & 1, vs = j % NV;
+#if SCP_FA2_EARLY_QK
+                if (j + 2 < nt) {                                // S(j) has been read: its buffer can take S(j+2) now
+                    tc5::mbar_wait(s_free + buf, (j >> 1) & 1);
+                    tc5::tc_fence_after();
+                    issue_qk(j + 2);
+                }
+#endif
                 tc5::mbar_wait(p_full + buf, (j >> 1) & 1);      // P(j) is in TMEM, S buffer `buf` is free again
                 tc5::mbar_wait(v_full + vs, (j / NV) & 1);
                 tc5::tc_fence_after();
@@ -157,7 +172,9 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                                       tc5::umma_desc_sw128(aV + k * 32), idesc_pv, (j | k) != 0);
                 tc5::umma_commit(v_empty + vs);
                 tc5::umma_commit(pv_done);
+#if !SCP_FA2_EARLY_QK
                 if (j + 2 < nt) issue_qk(j + 2);
+#endif
             }
         }
     } else if ((warp & 3) < n_active) {
@@ -172,6 +189,11 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             tc5::tc_fence_after();
             float v[BKV];
             tc5::tmem_ld64(tmem_base + t_lane + COL_S + buf * BKV, v);
+#if SCP_FA2_EARLY_QK
+            tc5::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc5::mbar_arrive(s_free + buf);
+#endif
             const int nvalid = T - j * BKV;
             if (nvalid < BKV) {                                  // last tile: keys past the sequence
 #pragma unroll
