@@ -232,7 +232,8 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             for (int i = 0; i < BKV / 2; i++) {
                 const float x0 = fmaf(v[2 * i], scale_log2e, nm), x1 = fmaf(v[2 * i + 1], scale_log2e, nm);
                 const float p0 = ex2(x0);
-                const float p1 = (SCP_FA2_POLY_EVERY > 0 && ((2 * i + 1) % SCP_FA2_POLY_EVERY) == SCP_FA2_POLY_EVERY - 1)
+                constexpr int every = SCP_FA2_POLY_EVERY > 0 ? SCP_FA2_POLY_EVERY : 1;
+                const float p1 = (SCP_FA2_POLY_EVERY > 0 && ((2 * i + 1) % every) == every - 1)
                                      ? ex2_poly(x1) : ex2(x1);
                 rs0 += p0;
                 rs1 += p1;
