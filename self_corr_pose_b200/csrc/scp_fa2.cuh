@@ -86,8 +86,13 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint8_t *sQ = smem, *sK = sQ + Q_BYTES, *sV = sK + NK * KT_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sV + NV * VT_BYTES);
     uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = k_full + NK, *v_full = k_empty + NK, *v_empty = v_full + NV,
-             *s_full = v_empty + NV, *p_full = s_full + 2, *pv_done = p_full + 2, *s_free = pv_done + 1;
+             *s_full = v_empty + NV, *p_full = s_full + 2, *pv_done = p_full + 2;
+#if SCP_FA2_EARLY_QK
+    uint64_t *s_free = pv_done + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(s_free + 2);
+#else
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pv_done + 1);
+#endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.y, q0 = blockIdx.x * BQ;
@@ -108,7 +113,9 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         for (int i = 0; i < NV; i++) { tc5::mbar_init(v_full + i, 1); tc5::mbar_init(v_empty + i, 1); }
         for (int i = 0; i < 2; i++) { tc5::mbar_init(s_full + i, 1); tc5::mbar_init(p_full + i, n_active); }
         tc5::mbar_init(pv_done, 1);
+#if SCP_FA2_EARLY_QK
         for (int i = 0; i < 2; i++) tc5::mbar_init(s_free + i, n_active);
+#endif
         tc5::mbar_fence_init();
     }
     if (warp == 1) tc5::tmem_alloc(tmem_slot, TMEM_COLS);
