@@ -256,15 +256,23 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
         k['frac'] = k['achieved'] / k['peak']
         k['step_ms'] = k['ms'] * k['launches_per_step']
     dom = max(out, key=lambda k: k['step_ms'] if 'vit_s8' not in k['kernel'] else 0)
-    # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture (profiles/)
-    traffic = None
+    # DRAM bytes of one launch of that kernel -- and, because these kernels are issue / tensor bound rather than HBM
+    # bound, its issue-slot and tensor-pipe utilisation -- from the committed `ncu --set full` capture (profiles/)
+    traffic, ncu = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
-        traffic = tr.get(dom.get('ncu_name', ''), {}).get('dram_bytes')
+        for k in out:
+            rec = tr.get(k.get('ncu_name', ''))
+            if rec:
+                k['ncu'] = {m: rec[m] for m in ('dram_bytes', 'issue_active_pct', 'tensor_pipe_pct', 'dram_throughput_pct')
+                            if m in rec}
+        rec = tr.get(dom.get('ncu_name', ''), {})
+        traffic = rec.get('dram_bytes')
+        ncu = {m: rec[m] for m in ('issue_active_pct', 'tensor_pipe_pct', 'dram_throughput_pct') if m in rec} or None
     except Exception:
         pass
     roof = {'kernel': dom['kernel'], 'bound': dom['bound'], 'achieved': dom['achieved'], 'peak': dom['peak'],
-            'unit': dom['unit'], 'frac': dom['frac'], 'traffic': traffic, 'peak_source': which,
+            'unit': dom['unit'], 'frac': dom['frac'], 'traffic': traffic, 'ncu': ncu, 'peak_source': which,
             'ms_per_launch': dom['ms'], 'launches_per_step': dom['launches_per_step']}
     return roof, out
 

@@ -42,6 +42,7 @@ for part in src.split(','):            # several captures of the same step (diff
         key = '%s #%d' % (name, k)
         out.append('## `%s`\n\n| metric | value |\n|---|---|' % key)
         rd = wr = us = 0.0
+        extra = {}
         for m in KEEP:
             if m not in col:
                 continue
@@ -57,8 +58,14 @@ for part in src.split(','):            # several captures of the same step (diff
                 wr = x * scale.get(unit, 1.0)
             elif m == 'gpu__time_duration.sum':
                 us = x * tscale.get(unit, 1.0)
+            elif m == 'smsp__issue_active.avg.pct_of_peak_sustained_active':
+                extra['issue_active_pct'] = x
+            elif m == 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active':
+                extra['tensor_pipe_pct'] = x
+            elif m == 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed':
+                extra['dram_throughput_pct'] = x
         out.append('')
-        traffic[key] = {'dram_bytes': rd + wr, 'us': us}
+        traffic[key] = dict({'dram_bytes': rd + wr, 'us': us}, **extra)
 open(dst_md, 'w').write('# `ncu --set full --clock-control none` of the hot kernels (one step, B = 64, 1xB200)\n\n%s\n\n' % note +
                         '\n'.join(out) + '\n')
 json.dump(traffic, open(dst_json, 'w'), indent=1)
