@@ -75,3 +75,58 @@ def test_optimizer_groups_and_lr_trace_match_reference(capsys):
         assert [g['lr'] for g in a.optimizer.param_groups] == [g['lr'] for g in b.optimizer.param_groups]
     for p, q in zip(m1.parameters(), m2.parameters()):
         assert torch.equal(p, q)
+
+
+def _reference_trainer_methods():
+    """batch_reshape / collect_grad of the reference's Trainer, compiled from its source without importing the module
+    (which pulls in the dataset, TensorBoard and the CUDA-only model)."""
+    import ast
+    import textwrap
+    src = open(os.path.join(REF, 'model', 'trainer.py')).read()
+    tree = ast.parse(src)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'Trainer')
+    ns = {'torch': torch}
+    for fn in cls.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in ('batch_reshape', 'collect_grad'):
+            exec(compile(ast.Module(body=[fn], type_ignores=[]), 'reference_trainer', 'exec'), ns)
+    return ns['batch_reshape'], ns['collect_grad']
+
+
+def test_trainer_batch_reshape_and_collect_grad_match_reference(monkeypatch, capsys):
+    from self_corr_pose_b200.model.trainer import Trainer
+    ref_reshape, ref_collect = _reference_trainer_methods()
+    monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
+    opts = _opts()
+    g = torch.Generator().manual_seed(3)
+    B = 4
+    batch = {'img': torch.rand(B, 3, 16, 16, generator=g).double(), 'mask': (torch.rand(B, 1, 16, 16, generator=g) > 0.5).float(),
+             'depth': torch.rand(B, 1, 16, 16, generator=g), 'center': torch.zeros(B, 2, dtype=torch.int64),
+             'length': torch.full((B, 2), 256, dtype=torch.int64), 'idx': torch.arange(B)[:, None],
+             'foc': torch.rand(B, 2, generator=g).double() * 500, 'pp': torch.rand(B, 2, generator=g).double() * 256,
+             'foc_crop': torch.rand(B, 2, generator=g).double() * 500, 'pp_crop': torch.rand(B, 2, generator=g).double() * 256}
+    t = Trainer(opts)
+    t.device = torch.device('cpu')
+    got = t.batch_reshape(batch)
+    want = ref_reshape(SimpleNamespace(opts=opts), batch)
+    assert len(got) == len(want) == 12
+    for a, b in zip(got, want):
+        if a is None or b is None:
+            assert a is None and b is None
+        else:
+            assert a.dtype == b.dtype and torch.equal(a, b)
+    # gradient clipping: mean_v to norm 1, pose predictor to 0.1, everything else untouched
+    torch.manual_seed(1)
+    m1, m2 = _Toy(), _Toy()
+    m2.load_state_dict(m1.state_dict())
+    for m in (m1, m2):
+        for i, p in enumerate(q for q in m.parameters() if q.requires_grad):
+            p.grad = torch.full_like(p, 0.5 + i)
+    t.model, t.optim = m1, SimpleNamespace(zero_grad=lambda: None)
+    ra = t.collect_grad()
+    rb = ref_collect(SimpleNamespace(model=m2, optim=SimpleNamespace(zero_grad=lambda: None)))
+    capsys.readouterr()
+    for a, b in zip(ra, rb):
+        assert float(a) == pytest.approx(float(b), rel=1e-6)
+    for (n, p), (_, q) in zip(m1.named_parameters(), m2.named_parameters()):
+        if p.grad is not None:
+            assert torch.allclose(p.grad, q.grad, rtol=1e-6, atol=0), n
