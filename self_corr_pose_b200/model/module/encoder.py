@@ -1,11 +1,19 @@
-"""Encoder: image -> (image code, per-pixel features), mesh -> per-vertex features, pose and shape heads.
-API and statements of the reference's model/module/encoder.py:13-52 (host code, PyTorch)."""
+"""Trainable encoder of the model: ResNet-18 image branch (global code + per-pixel correspondence features), mesh
+branch (per-vertex features), shape and pose heads.
+
+Host code in PyTorch / cuDNN (the next component after the hot path), behaviour of the reference's
+model/module/encoder.py:13-52 -- pinned to it by tests/test_reference_encoder_cpu.py (same parameter names, same RNG
+consumption, same outputs).  Submodule names are part of the contract: checkpoints and the optimiser's name-keyed
+parameter groups (model/module/optimizers.py) depend on them.
+"""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
-import torchvision
+from torchvision import transforms
 
-from .network.encoder_nets import ResNetEncoder, ResNetDecoder, MeshEncoder, PosePredictor, ShapePredictor
+from .network import encoder_nets as nets
+
+_IMAGENET_MEAN, _IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 
 
 class Encoder(nn.Module):
@@ -13,30 +21,42 @@ class Encoder(nn.Module):
     def __init__(self, opts):
         super().__init__()
         self.opts = opts
-        self.resnet_transform = torchvision.transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
-        self.random_jitter = torchvision.transforms.ColorJitter(0.2, 0.2, 0.2, 0.05)
-        self.backbone = ResNetEncoder()
-        self.featnet = ResNetDecoder(is_proj=True, out_channel=opts.n_corr_feat, downsample=opts.img_size // opts.corr_h)
-        self.featnet_mesh = MeshEncoder(opts.n_corr_feat)
-        self.shape_code_predictor = nn.Linear(512, opts.codedim)
-        self.shape_predictor = ShapePredictor(opts)
-        self.pose_predictor = PosePredictor(opts, 512)
+        C = opts.n_corr_feat
+        for name, module in (
+                ('backbone', nets.ResNetEncoder()),
+                ('featnet', nets.ResNetDecoder(is_proj=True, out_channel=C, downsample=opts.img_size // opts.corr_h)),
+                ('featnet_mesh', nets.MeshEncoder(C)),
+                ('shape_code_predictor', nn.Linear(512, opts.codedim)),
+                ('shape_predictor', nets.ShapePredictor(opts)),
+                ('pose_predictor', nets.PosePredictor(opts, 512))):
+            self.add_module(name, module)
+        # photometric jitter is applied in evaluation mode as well (appendix A.7 of SURVEY.md), then ImageNet statistics
+        self.random_jitter = transforms.ColorJitter(0.2, 0.2, 0.2, 0.05)
+        self.resnet_transform = transforms.Normalize(mean=list(_IMAGENET_MEAN), std=list(_IMAGENET_STD))
 
     def encode_img(self, img):
-        bsz = img.shape[0]
-        x = self.resnet_transform(self.random_jitter(img))       # jitter runs in eval too (encoder.py:31)
-        c2, c3, c4, c5 = self.backbone(x)
-        img_code = c5.mean((2, 3))
-        img_feat = self.featnet(c2, c3, c4, c5).reshape(bsz, self.opts.n_corr_feat, -1)
-        return img_code, F.normalize(img_feat, 2, 1)
+        """(b,3,H,W) in [0,1] -> (global code (b,512), unit-norm pixel features (b,C,h*w))."""
+        pyramid = self.backbone(self.resnet_transform(self.random_jitter(img)))
+        code = pyramid[-1].mean(dim=(2, 3))
+        feat = self.featnet(*pyramid).flatten(2)
+        return code, F.normalize(feat, p=2, dim=1)
+
+    def _shape(self, code, mean_v):
+        return self.shape_predictor(mean_v, self.shape_code_predictor(code))
+
+    @staticmethod
+    def _recentre(translation, pp_crop, foc_crop):
+        """Principal-point shift of the xy translation with the depth detached.  The reference does this in place on an
+        fp32 tensor with fp64 intrinsics (encoder.py:49): the update is evaluated in fp64 and rounded back."""
+        z = translation[:, 2:]
+        xy = translation[:, :2] - (pp_crop / foc_crop) * z.detach()
+        return torch.cat((xy.to(translation.dtype), z), dim=1)
 
     def forward(self, img, mean_v, pp_crop, foc_crop):
-        img_code, img_feat = self.encode_img(img)
-        pred_v = self.shape_predictor(mean_v, self.shape_code_predictor(img_code))
-        mesh_feat = F.normalize(self.featnet_mesh(pred_v.detach()), 2, -1)
-        rotation, translation, scale = self.pose_predictor(img_code)
-        pred_v = pred_v * scale[:, None]
-        # principal-point shift with detached depth (encoder.py:49); out-of-place form of the reference's `-=`
-        shift = (pp_crop / foc_crop) * translation[:, 2:].detach()
-        translation = torch.cat(((translation[:, :2].to(shift.dtype) - shift).to(translation.dtype), translation[:, 2:]), dim=1)
-        return img_feat, mesh_feat, pred_v, rotation.reshape(-1, 3, 3), translation.reshape(-1, 1, 3), scale
+        code, img_feat = self.encode_img(img)
+        verts = self._shape(code, mean_v)
+        mesh_feat = F.normalize(self.featnet_mesh(verts.detach()), p=2, dim=-1)
+        rotation, translation, scale = self.pose_predictor(code)
+        translation = self._recentre(translation, pp_crop, foc_crop)
+        return (img_feat, mesh_feat, verts * scale[:, None], rotation.reshape(-1, 3, 3), translation.reshape(-1, 1, 3),
+                scale)

@@ -1,34 +1,47 @@
-"""Loss weights and their linear schedule (reference: model/module/weights.py:20-64)."""
-import numpy as np
+"""Loss weights of the training step and their schedule over the iterations.
+
+Behaviour of the reference's model/module/weights.py:20-64 (pinned by tests/test_reference_host_cpu.py): the
+regularisers and cycle terms decay linearly from their flag value to `decay_ratio` times it over `total_iters`, the two
+correspondence terms grow the other way round, everything else is constant."""
+import math
+
+_CONSTANT = ('mask_wt', 'depth_wt', 'tex_wt', 'pullfar_wt', 'deform_wt', 'camera_wt')
+# attribute -> (flag holding the base value, True = starts at the base value and decays to decay_ratio * base)
+_SCHEDULED = {
+    'triangle_wt': ('triangle_wt', True),
+    'symmetry_wt': ('symmetry_wt', True),
+    'cycle_loss_wt': ('cycle_loss_wt', True),
+    'cycle_loss_pt_wt': ('cycle_loss_pretrain_wt', True),
+    'match_wt': ('match_wt', False),
+    'imatch_wt': ('imatch_wt', False),
+}
 
 
 def reg_decay(curr_steps, max_steps, min_wt, max_wt, mode='linear'):
+    """Value at `curr_steps` of a ramp from max_wt (step 0) to min_wt (step max_steps), constant afterwards."""
     if curr_steps > max_steps:
         return min_wt
-    if mode == 'log':
-        return np.exp(curr_steps / float(max_steps) * (np.log(min_wt) - np.log(max_wt))) * max_wt
+    frac = curr_steps / float(max_steps)
     if mode == 'linear':
-        return curr_steps / float(max_steps) * (min_wt - max_wt) + max_wt
-    raise NotImplementedError
+        return frac * (min_wt - max_wt) + max_wt
+    if mode == 'log':
+        return math.exp(frac * (math.log(min_wt) - math.log(max_wt))) * max_wt
+    raise NotImplementedError(mode)
 
 
 class Weights:
-    _names = ('mask_wt', 'depth_wt', 'tex_wt', 'match_wt', 'imatch_wt', 'triangle_wt', 'pullfar_wt', 'deform_wt',
-              'symmetry_wt', 'camera_wt', 'cycle_loss_wt')
 
     def __init__(self, opts):
         self.opts = opts
         self.total_iters = opts.total_iters
-        for n in self._names:
-            setattr(self, n, getattr(opts, n))
-        self.cycle_loss_pt_wt = opts.cycle_loss_pretrain_wt
+        for name in _CONSTANT:
+            setattr(self, name, getattr(opts, name))
+        for name, (flag, _) in _SCHEDULED.items():
+            setattr(self, name, getattr(opts, flag))
 
     def schedule(self, it):
-        o, T = self.opts, self.total_iters
-        # decreasing regularisers / cycle terms, increasing correspondence terms
-        self.triangle_wt = reg_decay(it, T, o.decay_ratio * o.triangle_wt, o.triangle_wt)
-        self.symmetry_wt = reg_decay(it, T, o.decay_ratio * o.symmetry_wt, o.symmetry_wt)
-        self.cycle_loss_wt = reg_decay(it, T, o.decay_ratio * o.cycle_loss_wt, o.cycle_loss_wt)
-        self.cycle_loss_pt_wt = reg_decay(it, T, o.decay_ratio * o.cycle_loss_pretrain_wt, o.cycle_loss_pretrain_wt)
-        self.match_wt = reg_decay(it, T, o.match_wt, o.decay_ratio * o.match_wt)
-        self.imatch_wt = reg_decay(it, T, o.imatch_wt, o.decay_ratio * o.imatch_wt)
+        ratio = self.opts.decay_ratio
+        for name, (flag, decays) in _SCHEDULED.items():
+            base = getattr(self.opts, flag)
+            end_points = (ratio * base, base) if decays else (base, ratio * base)     # (value at the end, value at step 0)
+            setattr(self, name, reg_decay(it, self.total_iters, *end_points))

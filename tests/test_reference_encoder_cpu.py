@@ -95,3 +95,36 @@ def test_pose_and_shape_heads_match_reference(ref):
     rs.load_state_dict(s.state_dict())
     mv, code = torch.randn(2, 40, 3), torch.randn(2, 64)
     torch.testing.assert_close(s(mv, code), rs(mv.clone(), code.clone()), rtol=1e-5, atol=1e-6)
+
+
+def test_encoder_wrapper_matches_reference(ref):
+    """Encoder (model/module/encoder.py:13-52): same submodule / parameter names, same RNG consumption (ColorJitter),
+    same six outputs incl. the fp64-promoted principal-point shift of the translation."""
+    if ref.pose_predictor is None:
+        pytest.skip('reference heads not importable here: ' + getattr(ref, 'err', ''))
+    from types import SimpleNamespace
+    from model.module.encoder import Encoder as RefEncoder
+    from self_corr_pose_b200.model.module.encoder import Encoder
+    opts = SimpleNamespace(depth_offset=5., use_scale=False, symmetry_idx=1, rotation_offset=[0.2, 0, 0, 0, -0.2, 0.2],
+                           num_multipose_az=1, num_multipose_el=1, initial_quat_bias_deg=0, baseQuat_elevationBias=0,
+                           baseQuat_azimuthBias=0, codedim=64, no_deform=False, deform_ratio=1., n_corr_feat=64,
+                           img_size=64, corr_h=16, corr_w=16)
+    torch.manual_seed(4)
+    ours, theirs = Encoder(opts).eval(), RefEncoder(opts).eval()
+    assert set(ours.state_dict().keys()) == set(theirs.state_dict().keys())
+    theirs.load_state_dict(ours.state_dict())
+    g = torch.Generator().manual_seed(5)
+    B = 4    # not 3: the reference's Gram-Schmidt calls torch.cross without dim, which picks the batch axis when B == 3
+    img = torch.rand(B, 3, 64, 64, generator=g)
+    mean_v = torch.randn(B, 30, 3, generator=g) * 0.3
+    pp = (0.1 * (torch.rand(B, 2, generator=g) - 0.5)).double()
+    foc = (3.7 + 0.3 * torch.rand(B, 2, generator=g)).double()
+    outs = []
+    for enc in (ours, theirs):
+        torch.manual_seed(6)                 # ColorJitter draws its parameters from the global RNG, in eval too
+        with torch.no_grad():
+            outs.append(enc(img.clone(), mean_v.clone(), pp.clone(), foc.clone()))
+    names = ('img_feat', 'mesh_feat', 'pred_v', 'rotation', 'translation', 'scale')
+    for n, a, b in zip(names, *outs):
+        assert a.shape == b.shape and a.dtype == b.dtype, n
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6, msg=n)
