@@ -115,5 +115,14 @@ def ptr(t):
     return t.data_ptr()
 
 
+def expect_numel(op, **buffers):
+    """Raises unless every named (tensor, count) pair holds exactly the element count the kernel will index: the C-ABI
+    takes bare pointers, so a short buffer would be read or written out of bounds without any diagnostic."""
+    for name, (t, n) in buffers.items():
+        if t is not None and t.numel() != n:
+            raise ValueError('%s: `%s` has %d elements (shape %s), the kernel indexes %d'
+                             % (op, name, t.numel(), tuple(t.shape), n))
+
+
 def stream_ptr(device=None):
     return torch.cuda.current_stream(device).cuda_stream

@@ -9,6 +9,17 @@ from torch.autograd import Function
 from .. import _lib
 
 
+def check_shapes(img_feat, mesh_feat, mask_down, pred_v, meshgrid, hf, wf):
+    """(B, C, P, N) after checking every buffer against the element count the kernels index."""
+    B, C, P = img_feat.shape
+    N = mesh_feat.shape[1]
+    if P != hf * wf:
+        raise ValueError('corr_match: %d pixel features for a %d x %d feature map' % (P, hf, wf))
+    _lib.expect_numel('corr_match', mesh_feat=(mesh_feat, B * N * C), mask_down=(mask_down, B * P),
+                      pred_v=(pred_v, B * N * 3), meshgrid=(meshgrid, 2 * P))
+    return B, C, P, N
+
+
 class CorrMatchFunction(Function):
     """(img_feat[B,C,P], mesh_feat[B,N,C], mask_down[B,P], pred_v[B,N,3], meshgrid[2,P]) ->
     (pointcorr_full[B,P,N] | None, pointcorr_pool[B,P/4,N] | None, match[B,P,3], imatch[B,2,N],
@@ -17,8 +28,7 @@ class CorrMatchFunction(Function):
 
     @staticmethod
     def forward(ctx, img_feat, mesh_feat, mask_down, pred_v, meshgrid, tau, hf, wf, want_full, want_pool):
-        B, C, P = img_feat.shape
-        N = mesh_feat.shape[1]
+        B, C, P, N = check_shapes(img_feat, mesh_feat, mask_down, pred_v, meshgrid, hf, wf)
         dev = img_feat.device
         img_feat = img_feat.detach().float().contiguous()
         mesh_feat = mesh_feat.detach().float().contiguous()

@@ -8,6 +8,15 @@ from torch.autograd import Function
 from .. import _lib
 
 
+def check_shapes(pc, A, dw, src_idx, tgt_idx, rows, pts_src, mask_k):
+    """(B, P4, N, NP, k) after checking every buffer against the element count the kernels index."""
+    B, P4, N = pc.shape
+    NP, k = rows.shape
+    _lib.expect_numel('cycle_rows', A_pool=(A, B * 2 * N), depth_weight=(dw, B * N), src_idx=(src_idx, NP),
+                      tgt_idx=(tgt_idx, NP), pts_src=(pts_src, NP * 2 * k), mask_k=(mask_k, NP * k))
+    return B, P4, N, NP, k
+
+
 class CycleRowsFunction(Function):
     """(pointcorr_pool[B,P4,N], A_pool[B,2,N]; depth_weight[B,N], src_idx[NP], tgt_idx[NP], rows[NP,k] (int64),
     pts_src[NP,2,k], mask_k[NP,k], tau) -> (pair_loss[NP], match[NP,2,k])"""
@@ -16,8 +25,7 @@ class CycleRowsFunction(Function):
     def forward(ctx, pc, A, dw, src_idx, tgt_idx, rows, pts_src, mask_k, tau):
         if not pc.is_cuda:
             raise TypeError('cycle_rows supports only CUDA tensors (no CPU path)')
-        B, P4, N = pc.shape
-        NP, k = rows.shape
+        B, P4, N, NP, k = check_shapes(pc, A, dw, src_idx, tgt_idx, rows, pts_src, mask_k)
         dev = pc.device
         pc, A = pc.detach().float().contiguous(), A.detach().float().contiguous()
         dw = dw.detach().float().contiguous()

@@ -16,6 +16,20 @@ from .. import _lib
 _NIN, _NOUT = 11, 5
 
 
+def check_shapes(r_depth, r_tex, match_lr, img, mask, depth, r_nocs, hf, wf):
+    """(B, H, W) after checking every map and the match buffer against what the kernels index."""
+    B, ch, H, W = r_depth.shape
+    if ch != 4 or r_tex.shape != r_depth.shape or r_nocs.shape != r_depth.shape:
+        raise ValueError('image losses: renders must be three (B,4,H,W) maps, got %s %s %s'
+                         % (tuple(r_depth.shape), tuple(r_tex.shape), tuple(r_nocs.shape)))
+    _lib.expect_numel('image_losses', match_lr=(match_lr, B * hf * wf * 3), img=(img, B * 3 * H * W),
+                      mask=(mask, B * H * W), depth=(depth, B * H * W))
+    for name, t in (('img', img), ('mask', mask), ('depth', depth)):
+        if t is not None and (t.shape[0] != B or tuple(t.shape[-2:]) != (H, W)):
+            raise ValueError('image losses: `%s` of shape %s for (%d, ..., %d, %d) renders' % (name, tuple(t.shape), B, H, W))
+    return B, H, W
+
+
 def _view(t, channels, H, W):
     """(device pointer, batch stride) of a (B,[C,]H,W) view with contiguous planes."""
     if t is None:
@@ -42,7 +56,7 @@ class ImageLossFunction(Function):
 
     @staticmethod
     def forward(ctx, r_depth, r_tex, match_lr, img, mask, depth, r_nocs, hf, wf, use_depth):
-        B, _, H, W = r_depth.shape
+        B, H, W = check_shapes(r_depth, r_tex, match_lr, img, mask, depth if use_depth else None, r_nocs, hf, wf)
         dev = r_depth.device
         r_depth, r_tex, r_nocs = r_depth.detach(), r_tex.detach(), r_nocs.detach()
         match_lr = match_lr.detach().contiguous()

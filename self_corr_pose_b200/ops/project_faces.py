@@ -22,6 +22,8 @@ class FaceTopology:
         f = faces.detach().reshape(-1, 3).to(torch.int64)
         self.nf, self.N = f.shape[0], int(num_verts)
         flat = f.reshape(-1)
+        if flat.numel() and (int(flat.min()) < 0 or int(flat.max()) >= self.N):
+            raise ValueError('faces index vertices outside [0, %d)' % self.N)
         order = torch.sort(flat, stable=True).indices                    # corners grouped by vertex, ascending
         counts = torch.bincount(flat, minlength=self.N)
         off = torch.zeros(self.N + 1, dtype=torch.int64, device=f.device)
@@ -29,6 +31,16 @@ class FaceTopology:
         self.faces = f.to(torch.int32).contiguous()
         self.csr_off = off.to(torch.int32).contiguous()
         self.csr_idx = order.to(torch.int32).contiguous()
+
+
+def check_shapes(pred_v, rotation, translation, foc, pp, topo):
+    """(B, N) after checking every buffer against the element count the kernels index."""
+    B, N, _ = pred_v.shape
+    _lib.expect_numel('project_faces', pred_v=(pred_v, B * N * 3), rotation=(rotation, B * 9),
+                      translation=(translation, B * 3), foc=(foc, B * 2), pp=(pp, B * 2))
+    if topo is not None and topo.N != N:
+        raise ValueError('project_faces: topology built for %d vertices, got %d' % (topo.N, N))
+    return B, N
 
 
 class ProjectFacesFunction(Function):
@@ -39,7 +51,7 @@ class ProjectFacesFunction(Function):
     def forward(ctx, pred_v, rotation, translation, foc, pp, topo, z_offset):
         if not pred_v.is_cuda:
             raise TypeError('project_faces supports only CUDA tensors (no CPU path)')
-        B, N, _ = pred_v.shape
+        B, N = check_shapes(pred_v, rotation, translation, foc, pp, topo)
         dev = pred_v.device
         v = pred_v.detach().float().contiguous()
         R = rotation.detach().float().contiguous()

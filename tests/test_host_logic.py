@@ -189,3 +189,57 @@ def test_new_ops_fail_loudly_on_cpu_tensors():
         project_faces(z(1, 4, 3), z(1, 3, 3), z(1, 1, 3), z(1, 2).double(), z(1, 2).double())
     with pytest.raises(TypeError):
         cycle_rows(z(1, 4, 8), z(1, 2, 8), z(1, 8), z(2).long(), z(2).long(), z(2, 3).long(), z(2, 2, 3), z(2, 3), 10.)
+
+
+def test_buffer_size_validation():
+    """The C-ABI takes bare pointers: the wrappers refuse buffers whose element count differs from what the kernel
+    indexes, and a face list that points outside the vertex array."""
+    from self_corr_pose_b200 import _lib
+    from self_corr_pose_b200.ops.project_faces import FaceTopology
+    _lib.expect_numel('op', a=(torch.zeros(2, 3), 6), b=(None, 5), c=(torch.zeros(4, 1, 2), 8))
+    with pytest.raises(ValueError, match='`a` has 6 elements'):
+        _lib.expect_numel('op', a=(torch.zeros(2, 3), 8))
+    FaceTopology(torch.tensor([[0, 1, 2], [2, 1, 3]]), 4)
+    with pytest.raises(ValueError):
+        FaceTopology(torch.tensor([[0, 1, 4]]), 4)
+    with pytest.raises(ValueError):
+        FaceTopology(torch.tensor([[0, -1, 2]]), 4)
+
+
+def test_op_shape_checks_accept_the_step_shapes_and_reject_short_buffers():
+    """check_shapes of every fused op on the shapes the training step passes (hotpath.py / model.py call sites)."""
+    from self_corr_pose_b200.ops import corr_match, cycle_rows, image_losses, project_faces
+    z = torch.zeros
+    B, H, hf, N, C, nf = 4, 64, 16, 42, 64, 80
+    P = hf * hf
+    # correspondence: training-step call and the rotation-cycle call (target pixels in the role of vertices)
+    assert corr_match.check_shapes(z(B, C, P), z(B, N, C), z(B, P), z(B, N, 3), z(2, P), hf, hf) == (B, C, P, N)
+    assert corr_match.check_shapes(z(B, C, P // 4), z(B, P // 4, C), z(B, P // 4), z(B, P // 4, 3), z(2, P // 4),
+                                   hf // 2, hf // 2) == (B, C, P // 4, P // 4)
+    with pytest.raises(ValueError):
+        corr_match.check_shapes(z(B, C, P), z(B, N, C), z(B, P), z(B, N, 3), z(2, P), hf, hf // 2)
+    with pytest.raises(ValueError):
+        corr_match.check_shapes(z(B, C, P), z(B, N, C), z(B, P // 4), z(B, N, 3), z(2, P), hf, hf)
+    # image losses: raw renders + (B,3,H,W) image, (B,H,W) mask / depth, low-resolution match
+    args = lambda **kw: dict(dict(r_depth=z(B, 4, H, H), r_tex=z(B, 4, H, H), match_lr=z(B, P, 3), img=z(B, 3, H, H),
+                                  mask=z(B, H, H), depth=z(B, H, H), r_nocs=z(B, 4, H, H), hf=hf, wf=hf), **kw)
+    assert image_losses.check_shapes(**args()) == (B, H, H)
+    assert image_losses.check_shapes(**args(depth=None)) == (B, H, H)
+    for bad in (dict(mask=z(B, H, H // 2)), dict(match_lr=z(B, P // 4, 3)), dict(r_tex=z(B, 3, H, H)),
+                dict(img=z(B, 1, H, H)), dict(depth=z(B - 1, H, H))):
+        with pytest.raises(ValueError):
+            image_losses.check_shapes(**args(**bad))
+    # geometry
+    topo = project_faces.FaceTopology(torch.randint(0, N, (nf, 3)), N)
+    good = (z(B, N, 3), z(B, 3, 3), z(B, 1, 3), z(B, 2).double(), z(B, 2).double())
+    assert project_faces.check_shapes(*good, topo) == (B, N) and project_faces.check_shapes(*good, None) == (B, N)
+    with pytest.raises(ValueError):
+        project_faces.check_shapes(z(B, N + 1, 3), *good[1:], topo)
+    with pytest.raises(ValueError):
+        project_faces.check_shapes(good[0], z(B, 3), *good[2:], None)
+    # cycle rows: 2B pairs of k gathered rows
+    NP, k = 2 * B, 7
+    good = (z(B, P // 4, N), z(B, 2, N), z(B, N), z(NP).long(), z(NP).long(), z(NP, k).long(), z(NP, 2, k), z(NP, k))
+    assert cycle_rows.check_shapes(*good) == (B, P // 4, N, NP, k)
+    with pytest.raises(ValueError):
+        cycle_rows.check_shapes(*good[:6], z(NP, k), z(NP, k))
