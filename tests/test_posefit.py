@@ -1,0 +1,106 @@
+"""Inference pose fit: batched RANSAC + Umeyama and `PoseFitter.pose_fitting` against outputs of
+the REFERENCE (model/util/umeyama.py, model/tester.py:324-427) recorded in tests/golden/posefit_golden.npz by
+tests/golden/make_posefit_golden.py -- results and the number of random integers consumed from the global generator."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'posefit_golden.npz')
+
+
+@pytest.fixture(scope='module')
+def gold():
+    g = np.load(GOLD)
+    return lambda k: torch.from_numpy(g[k])
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def test_single_fit_matches_reference_outputs_and_rng_consumption(gold):
+    from self_corr_pose_b200.model.util import umeyama as U
+    for i in range(int(gold('fit_cases'))):
+        torch.manual_seed(100 + i)
+        scales, rot, trans, transform = U.estimateSimilarityTransform(gold('fit%d_src' % i), gold('fit%d_tgt' % i))
+        assert torch.equal(torch.randint(0, 1 << 30, (4,)), gold('fit%d_next_draw' % i)), i    # same generator state
+        for got, name in ((scales, 'scales'), (rot, 'rotation'), (trans, 'translation'), (transform, 'transform')):
+            want = gold('fit%d_%s' % (i, name))
+            assert got.shape == want.shape and _rel(got, want) < 1e-5, (i, name)
+
+
+def test_batched_fit_equals_consecutive_reference_calls(gold):
+    """All cases in ONE padded batch, seeded once: image b must see the random integers the b-th consecutive reference
+    call would draw, including after the two cases whose loop ends in its first round."""
+    from self_corr_pose_b200.model.util import umeyama as U
+    n_case = int(gold('fit_cases'))
+    probs = [(gold('fit%d_src' % i), gold('fit%d_tgt' % i)) for i in range(n_case)]
+    probs.insert(2, (torch.zeros(0, 3), torch.zeros(0, 3)))              # an image without correspondences draws nothing
+    counts = [p[0].shape[0] for p in probs]
+    S, T = torch.zeros(len(probs), max(counts), 3), torch.zeros(len(probs), max(counts), 3)
+    for b, (s, t) in enumerate(probs):
+        S[b, :counts[b]], T[b, :counts[b]] = s, t
+    torch.manual_seed(77)
+    want = [U.estimateSimilarityTransform(s, t) if s.shape[0] else None for s, t in probs]
+    state = torch.get_rng_state()
+    torch.manual_seed(77)
+    scale, rot, trans, ok = U.fit_similarity_batch(S, T, counts)
+    assert torch.equal(torch.get_rng_state(), state)
+    assert ok == [w is not None for w in want]
+    for b, w in enumerate(want):
+        if w is not None:
+            assert _rel(scale[b], w[0][0]) < 1e-5 and _rel(rot[b], w[1]) < 1e-5 and _rel(trans[b], w[2][0]) < 1e-5, b
+    # a small residual-table budget (several slabs of rounds) changes nothing
+    torch.manual_seed(77)
+    scale2, rot2, trans2, ok2 = U.fit_similarity_batch(S, T, counts, max_table_bytes=1 << 20)
+    assert ok2 == ok and torch.allclose(scale2, scale, rtol=1e-6) and torch.allclose(rot2, rot, atol=1e-6)
+
+
+def test_sequential_rules_of_the_ransac_loop():
+    from self_corr_pose_b200.model.util.umeyama import _sequential_choice
+    inf, nan = float('inf'), float('nan')
+    r = torch.tensor([[5., 3., 3., 0.5, 0.1, 9.],       # stop threshold 1: round 3 ends the loop, round 4 is never run
+                      [5., nan, 2., 2., 7., 4.],        # strict '<': the first of two equal residuals wins
+                      [nan, 2e10, inf, nan, 1e10, nan], # nothing below the 1e10 start value: no transform
+                      [4., 3., 2., 1.5, 9., 9.]])       # a NaN covariance in round 2 raises in the reference
+    bad = torch.zeros(4, 6, dtype=torch.bool)
+    bad[3, 2] = True
+    best, last, found = _sequential_choice(r, torch.tensor([1., 1., 1., 1.]), bad)
+    assert best[:2].tolist() == [3, 2] and last.tolist() == [3, 5, 5, 2] and found.tolist() == [True, True, False, False]
+
+
+def _pose_inputs(gold, dev):
+    size = int(gold('pose_size'))
+    opts = SimpleNamespace(img_size=size, base_rot=gold('pose_base_rot').tolist())
+    T = lambda k: gold('pose_' + k).to(dev)
+    B = T('mask').shape[0]
+    batch = (torch.zeros(B, 3, size, size, device=dev), T('mask'), T('depth'), None, None, None, None, T('foc'), None,
+             T('pp'), None, None)
+    pred = (T('pred_v'), None, None, None, T('match'), T('conf'))
+    return opts, batch, pred
+
+
+def _check_pose(gold, dev, tol):
+    from self_corr_pose_b200.model.pose_fit import PoseFitter
+    opts, batch, pred = _pose_inputs(gold, dev)
+    torch.manual_seed(9)
+    out = PoseFitter(opts, device=dev).pose_fitting(batch, pred)
+    assert torch.equal(torch.randint(0, 1 << 30, (4,)), gold('pose_next_draw'))
+    for got, name in zip(out, ('bbox', 'verts', 'rotation', 'translation')):
+        want = gold('pose_' + name)
+        assert got.shape == want.shape and _rel(got.cpu(), want) < tol, name
+    # images 3 and 4 have no / too few usable pixels: default pose (identity before the base rotation, 0.5 m ahead)
+    assert torch.allclose(out[3][3].cpu(), torch.tensor([[0., 0., 0.5]]))
+
+
+def test_pose_fitting_matches_reference_tester(gold):
+    _check_pose(gold, 'cpu', 1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason='added after the round\'s GPU budget was spent: first run on a B200 pending')
+def test_pose_fitting_on_gpu_matches_reference_tester(gold):
+    _check_pose(gold, 'cuda', 1e-4)
