@@ -60,20 +60,28 @@ class Correspondence:
         # source-side factor of the pre-training cycle loss (PretrainedCorrespondence.compute_cycle_loss(A=...))
         self.pool_A = A_pool
 
-        if opts.train:
-            match_conf = None
-        else:  # forward-backward consistency confidence, evaluation only (correspondence.py:57-69)
-            with torch.no_grad():
-                near = (match[:, None] - pred_v[:, :, None]).norm(2, -1).argmin(1).view(bsz, -1)  # b,h*w
-                ipred = torch.gather(imatch.permute(0, 2, 1), 1, near[:, :, None].expand(-1, -1, 2))
-                fberr = (self.meshgrid.permute(1, 0)[None] - ipred).norm(2, -1).view(bsz, 1, self.hf, self.wf)
-                match_conf = (-5 * fberr).exp()
-            match_conf = F.interpolate(match_conf, (h, w), mode='bilinear', align_corners=False).detach()
-            conf_mean = min(match_conf[mask[:, None] > 0].mean().item(), 0.5)
-            match_conf[match_conf < conf_mean] = 0
+        match_conf = None if opts.train else self.match_confidence(match, imatch, pred_v, mask)
 
         match = F.interpolate(match.reshape(bsz, self.hf, self.wf, 3).permute(0, 3, 1, 2), (h, w), mode='nearest')
         return pointcorr, match, imatch, match_conf
+
+    def match_confidence(self, match, imatch, pred_v, mask):
+        """Forward-backward consistency confidence of the dense matches, evaluation only (correspondence.py:57-69).
+        match (B,P,3): soft 3D match of every correspondence-map pixel; imatch (B,2,N): soft 2D match of every vertex.
+        A pixel is confident when the 2D match of the vertex nearest to its 3D match falls back onto the pixel:
+        conf = exp(-5 |pixel - imatch[nearest vertex]|), upsampled bilinearly to the mask's size; values under
+        min(mean over the foreground, 0.5) are zeroed.  Plain torch; the nearest-vertex search runs on a (B,N,P)
+        distance table instead of the reference's (B,N,P,3) difference tensor."""
+        bsz, h, w = mask.shape
+        with torch.no_grad():
+            near = torch.cdist(pred_v, match, compute_mode='donot_use_mm_for_euclid_dist').argmin(1)          # B, P
+            back = torch.gather(imatch.permute(0, 2, 1), 1, near[:, :, None].expand(-1, -1, 2))           # B, P, 2
+            fberr = (self.meshgrid.permute(1, 0)[None] - back).norm(2, -1).view(bsz, 1, self.hf, self.wf)
+            conf = (-5 * fberr).exp()
+        conf = F.interpolate(conf, (h, w), mode='bilinear', align_corners=False).detach()
+        floor = min(conf[mask[:, None] > 0].mean().item(), 0.5)
+        conf[conf < floor] = 0
+        return conf
 
     def compute_rotation_cycle_loss(self, src_img, src_mask, src_img_feat, encoder):
         bsz = src_img.shape[0]

@@ -104,3 +104,21 @@ def test_pose_fitting_matches_reference_tester(gold):
 @pytest.mark.xfail(strict=False, reason='added after the round\'s GPU budget was spent: first run on a B200 pending')
 def test_pose_fitting_on_gpu_matches_reference_tester(gold):
     _check_pose(gold, 'cuda', 1e-4)
+
+
+def test_eval_match_confidence_matches_reference():
+    """Correspondence.match_confidence (evaluation-mode output consumed by the pose fit) against the confidence map the
+    reference's Correspondence.match produced in evaluation mode (tests/golden/make_matchconf_golden.py)."""
+    from self_corr_pose_b200.model.module.correspondence import Correspondence, make_meshgrid
+    g = np.load(os.path.join(os.path.dirname(GOLD), 'matchconf_golden.npz'))
+    T = lambda k: torch.from_numpy(g[k])
+    hf = 16
+    corr = Correspondence.__new__(Correspondence)          # no device state needed for this method
+    corr.hf = corr.wf = hf
+    corr.meshgrid = make_meshgrid(hf, hf, 'cpu')
+    match_up = T('match')                                  # nearest upsampling 16 -> 64: every 4th pixel is the source
+    match_lr = match_up[:, :, ::4, ::4].permute(0, 2, 3, 1).reshape(match_up.shape[0], hf * hf, 3)
+    conf = corr.match_confidence(match_lr, T('imatch'), T('pred_v'), T('mask'))
+    want = T('match_conf')
+    assert conf.shape == want.shape and torch.equal(conf == 0, want == 0)
+    assert _rel(conf, want) < 1e-5
