@@ -122,3 +122,54 @@ def test_eval_match_confidence_matches_reference():
     want = T('match_conf')
     assert conf.shape == want.shape and torch.equal(conf == 0, want == 0)
     assert _rel(conf, want) < 1e-5
+
+
+def test_oracle_fit_pinned_to_reference(gold):
+    """oracle/posefit.py (the reference's sequential formulation, used for timing and large-size checks on the GPU box)
+    against the recorded reference outputs."""
+    from oracle import posefit as O
+    for i in range(int(gold('fit_cases'))):
+        torch.manual_seed(100 + i)
+        s, R, t = O.fit(gold('fit%d_src' % i), gold('fit%d_tgt' % i))
+        assert torch.equal(torch.randint(0, 1 << 30, (4,)), gold('fit%d_next_draw' % i)), i
+        assert _rel(s, gold('fit%d_scales' % i)[0]) < 1e-5 and _rel(R, gold('fit%d_rotation' % i)) < 1e-5
+        assert _rel(t, gold('fit%d_translation' % i)[0]) < 1e-5
+
+
+def test_oracle_pose_fitting_pinned_to_reference(gold):
+    from oracle import posefit as O
+    T = lambda k: gold('pose_' + k)
+    torch.manual_seed(9)
+    out = O.pose_fitting(T('mask'), T('depth'), T('match'), T('conf'), T('foc'), T('pp'), T('pred_v'), T('base_rot'),
+                         int(T('size')))
+    assert torch.equal(torch.randint(0, 1 << 30, (4,)), T('next_draw'))
+    for got, name in zip(out, ('bbox', 'verts', 'rotation', 'translation')):
+        assert _rel(got, T(name)) < 1e-5, name
+
+
+def test_batched_pose_fit_equals_oracle_on_a_larger_batch():
+    """Random 64 x 64 evaluation batch (thousands of correspondences per image, beyond the golden's size)."""
+    from oracle import posefit as O
+    from self_corr_pose_b200.model.pose_fit import PoseFitter
+    size, B, N = 64, 4, 200
+    g = torch.Generator().manual_seed(4)
+    foc = (3.5 + 0.3 * torch.rand(B, 2, generator=g)).double()
+    pp = (0.05 * torch.randn(B, 2, generator=g)).double()
+    match = torch.rand(B, 3, size, size, generator=g) - 0.5
+    A = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))[0]
+    cam = 300 * torch.einsum('bchw,bcd->bdhw', match, A) + torch.tensor([0., 0., 900.])[None, :, None, None]
+    depth = (cam[:, 2] + 3 * torch.randn(B, size, size, generator=g)) * (torch.rand(B, size, size, generator=g) > 0.1)
+    mask = (torch.rand(B, size, size, generator=g) > 0.3).float()
+    conf = torch.rand(B, 1, size, size, generator=g)
+    pred_v = torch.rand(B, N, 3, generator=g) - 0.5
+    base = torch.eye(3).reshape(-1)
+    torch.manual_seed(1)
+    want = O.pose_fitting(mask, depth, match, conf, foc, pp, pred_v, base, size)
+    state = torch.get_rng_state()
+    torch.manual_seed(1)
+    fitter = PoseFitter(SimpleNamespace(img_size=size), device='cpu')
+    got = fitter.pose_fitting((None, mask, depth, None, None, None, None, foc, None, pp, None, None),
+                              (pred_v, None, None, None, match, conf))
+    assert torch.equal(torch.get_rng_state(), state)
+    for a, b in zip(got, want):
+        assert _rel(a, b) < 1e-5
