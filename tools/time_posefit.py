@@ -20,6 +20,7 @@ ap.add_argument('--size', type=int, default=256)
 ap.add_argument('--verts', type=int, default=1280)
 ap.add_argument('--oracle-images', type=int, default=4)
 ap.add_argument('--repeat', type=int, default=5)
+ap.add_argument('--device', default='cuda')
 a = ap.parse_args()
 
 B, size, N = a.batch, a.size, a.verts
@@ -37,18 +38,20 @@ conf[conf < 0.4] = 0
 pred_v = torch.rand(B, N, 3, generator=g) - 0.5
 opts = SimpleNamespace(img_size=size)
 
-dev = 'cuda'
+dev = a.device
 to = lambda t: t.to(dev)
 batch = (None, to(mask), to(depth), None, None, None, None, to(foc), None, to(pp), None, None)
 pred = (to(pred_v), None, None, None, to(match), to(conf))
 fitter = PoseFitter(opts, device=dev)
 torch.manual_seed(1)
 got = fitter.pose_fitting(batch, pred)
-torch.cuda.synchronize()
+if dev != 'cpu':
+    torch.cuda.synchronize()
 t0 = time.perf_counter()
 for _ in range(a.repeat):
     fitter.pose_fitting(batch, pred)
-torch.cuda.synchronize()
+if dev != 'cpu':
+    torch.cuda.synchronize()
 t_gpu = (time.perf_counter() - t0) / a.repeat
 
 k = min(a.oracle_images, B)
@@ -59,6 +62,6 @@ t_cpu = (time.perf_counter() - t0) / k
 err = max(float((x[:k].cpu() - y).abs().max() / y.abs().max()) for x, y in zip(got, want))
 n = int(((depth > 0)[:, None] * mask[:, None] * conf > 0).sum()) // B
 print('pose fit: %d images of %dx%d, ~%d correspondences each' % (B, size, size, n))
-print('  batched, cuda:0          %8.2f ms / batch   %8.3f ms / image' % (1e3 * t_gpu, 1e3 * t_gpu / B))
+print('  batched, ' + dev + '            %8.2f ms / batch   %8.3f ms / image' % (1e3 * t_gpu, 1e3 * t_gpu / B))
 print('  reference formulation, host %6.2f ms / image  (%d images, %d threads)' % (1e3 * t_cpu, k, torch.get_num_threads()))
 print('  max relative difference on the first %d images: %.2e' % (k, err))
