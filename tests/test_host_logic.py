@@ -243,3 +243,22 @@ def test_op_shape_checks_accept_the_step_shapes_and_reject_short_buffers():
     assert cycle_rows.check_shapes(*good) == (B, P // 4, N, NP, k)
     with pytest.raises(ValueError):
         cycle_rows.check_shapes(*good[:6], z(NP, k), z(NP, k))
+
+
+def test_every_entry_point_rejects_null_arguments_with_a_message():
+    """Error behaviour of the C ABI: bad arguments return non-zero BEFORE any CUDA call and leave a text for
+    scp_last_error() -- checked for every compute entry point with all-null / all-zero arguments (no GPU involved)."""
+    from self_corr_pose_b200 import _lib
+    L = _lib.lib()
+    checked = 0
+    for name, (argtypes, restype) in _lib._SIGNATURES.items():
+        if restype is not ctypes.c_int or not argtypes:
+            continue
+        args = [0 if t in (ctypes.c_int, ctypes.c_size_t) else 0.0 if t is ctypes.c_float else None for t in argtypes]
+        assert getattr(L, name)(*args) != 0, name
+        msg = L.scp_last_error().decode()
+        assert name.replace('scp_', '').split('_')[0] in msg or 'gemm' in msg, (name, msg)
+        with pytest.raises(_lib.ScpNativeError, match='failed'):
+            _lib.check(-1, name)
+        checked += 1
+    assert checked >= 17
