@@ -10,6 +10,10 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libscp_b200.so')
+# kernel experiments only (build.py --variant): SCP_LIB_VARIANT=NAME loads libscp_b200.NAME.so instead
+_VARIANT = os.environ.get('SCP_LIB_VARIANT', '')
+if _VARIANT:
+    LIB_PATH = os.path.join(_HERE, 'libscp_b200.%s.so' % _VARIANT)
 ABI_VERSION = 4
 
 _f = ctypes.c_void_p   # device pointers travel as integers

@@ -1,9 +1,15 @@
 """Builds the C-ABI shared library `libscp_b200.so` (hand-written sm_100a CUDA) in-tree.
 
     python -m self_corr_pose_b200.build [--force]
+    python -m self_corr_pose_b200.build --variant NAME -DMACRO=1 [-DMACRO2=...]     # kernel experiments only
 
 nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels to the GPU box
 with the gpurun snapshot.
+
+A VARIANT is the same library compiled with extra -D macros (the compile-time switches documented in the kernel
+headers, e.g. SCP_FA2_EARLY_QK) into `libscp_b200.NAME.so`, loaded instead of the product library when the
+environment variable SCP_LIB_VARIANT=NAME is set (`_lib.py`) -- for A/B runs of a candidate kernel on the GPU box
+(`tools/ab_variants.py`); nothing in the product, the tests or bench.py sets that variable.
 """
 import os
 import subprocess
@@ -35,11 +41,15 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _compile(src, force):
-    obj = os.path.join(CSRC, 'build', os.path.basename(src)[:-3] + '.o')
+def lib_path(variant=None):
+    return LIB if not variant else os.path.join(HERE, 'libscp_b200.%s.so' % variant)
+
+
+def _compile(src, force, variant=None, defines=()):
+    obj = os.path.join(CSRC, 'build', variant or '', os.path.basename(src)[:-3] + '.o')
     os.makedirs(os.path.dirname(obj), exist_ok=True)
     if force or _stale(obj, [src] + _deps()):
-        cmd = [NVCC] + ARCH + FLAGS + ['-c', src, '-o', obj]
+        cmd = [NVCC] + ARCH + FLAGS + list(defines) + ['-c', src, '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + '.log', 'w') as f:
             f.write(' '.join(cmd) + '\n' + r.stdout + r.stderr)
@@ -48,20 +58,26 @@ def _compile(src, force):
     return obj
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
     srcs = sources()
+    out = lib_path(variant)
+    force = force or bool(variant)          # a variant's macros are not tracked by the staleness check
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, force), srcs))
-    if force or _stale(LIB, objs):
-        cmd = [NVCC] + ARCH + ['-shared', '-o', LIB] + objs
+        objs = list(ex.map(lambda s: _compile(s, force, variant, defines), srcs))
+    if force or _stale(out, objs):
+        cmd = [NVCC] + ARCH + ['-shared', '-o', out] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
     if verbose:
         for o in objs:
             print(open(o + '.log').read())
-    return LIB
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    variant = sys.argv[sys.argv.index('--variant') + 1] if '--variant' in sys.argv else None
+    defines = [a for a in sys.argv[1:] if a.startswith('-D')]
+    if defines and not variant:
+        sys.exit('-D macros build a variant: pass --variant NAME (the product library takes no macros)')
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, variant=variant, defines=defines))
