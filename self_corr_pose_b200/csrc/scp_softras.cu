@@ -29,6 +29,19 @@ constexpr int NWARPS = NTHREADS / 32;
 constexpr int SCAN = 4;         // faces tested per thread per culling round
 constexpr int LIST_CAP = 2048;  // tile face list capacity (indices) per phase
 
+// Occupancy tunables (compile-time, for A/B variant builds: python -m self_corr_pose_b200.build --variant NAME -D...;
+// the defaults are the measured round-1 choice): resident CTAs per SM the register allocator must allow for the
+// tile-centric kernels (3 -> 85 registers at 256 threads) and for the face-centric backward (8 x 2 warps at 128).
+#ifndef SCP_SOFTRAS_TILE_CTAS
+#define SCP_SOFTRAS_TILE_CTAS 3
+#endif
+#ifndef SCP_SOFTRAS_FACE_WARPS
+#define SCP_SOFTRAS_FACE_WARPS 2
+#endif
+#ifndef SCP_SOFTRAS_FACE_CTAS
+#define SCP_SOFTRAS_FACE_CTAS 8
+#endif
+
 struct Params {
     int B, nf, T, R, is, tiles_x;
     float near_, far_, eps, sigma, gamma, threshold, margin;
@@ -484,7 +497,7 @@ __device__ __forceinline__ void forward_pair(const Params &p, const float *__res
 }
 
 template <int RGB, bool FAST>
-__global__ void __launch_bounds__(NTHREADS, 3) forward_kernel(Params p, const float4 *__restrict__ bbox,
+__global__ void __launch_bounds__(NTHREADS, SCP_SOFTRAS_TILE_CTAS) forward_kernel(Params p, const float4 *__restrict__ bbox,
                                                           const float *__restrict__ rec,
                                                           const int *__restrict__ img_bbox,
                                                           const float *__restrict__ textures,
@@ -734,9 +747,9 @@ __device__ __forceinline__ bool backward_pair(const Params &p, const float *__re
 // the tile-centric kernel (41 % of its instructions, profiles/r1_softras_backward_tile_source_page.csv.gz), no atomics on
 // grad_faces / grad_textures at all (one warp owns a face), deterministic summation order.  The per-pixel operands
 // (incoming gradient, colours, aggregates: 10 floats) are re-read per block through L1.
-constexpr int FACE_WARPS = 2;    // small CTAs: a warp that finishes its face early frees its slot (face sizes vary)
+constexpr int FACE_WARPS = SCP_SOFTRAS_FACE_WARPS;    // small CTAs: a warp that finishes its face early frees its slot (face sizes vary)
 template <int RGB, bool FAST>
-__global__ void __launch_bounds__(FACE_WARPS * 32, 8) backward_face_kernel(Params p, const float4 *__restrict__ bbox,
+__global__ void __launch_bounds__(FACE_WARPS * 32, SCP_SOFTRAS_FACE_CTAS) backward_face_kernel(Params p, const float4 *__restrict__ bbox,
                                                                          const float *__restrict__ rec,
                                                                          const float *__restrict__ textures,
                                                                          const float *__restrict__ soft_colors,
@@ -802,7 +815,7 @@ __global__ void __launch_bounds__(FACE_WARPS * 32, 8) backward_face_kernel(Param
 }
 
 template <int RGB, bool FAST>
-__global__ void __launch_bounds__(NTHREADS, 3) backward_kernel(Params p, const float4 *__restrict__ bbox,
+__global__ void __launch_bounds__(NTHREADS, SCP_SOFTRAS_TILE_CTAS) backward_kernel(Params p, const float4 *__restrict__ bbox,
                                                            const float *__restrict__ rec,
                                                            const int *__restrict__ img_bbox,
                                                            const float *__restrict__ textures,
