@@ -41,6 +41,11 @@ constexpr int LIST_CAP = 2048;  // tile face list capacity (indices) per phase
 #ifndef SCP_SOFTRAS_FACE_CTAS
 #define SCP_SOFTRAS_FACE_CTAS 8
 #endif
+// Next-round candidate, NOT validated on a GPU yet (default off): the face-centric backward keeps its face record
+// (48 floats) in shared memory instead of registers, so that SCP_SOFTRAS_FACE_CTAS can rise above 8 without spilling.
+#ifndef SCP_SOFTRAS_FACE_SMEM
+#define SCP_SOFTRAS_FACE_SMEM 0
+#endif
 
 struct Params {
     int B, nf, T, R, is, tiles_x;
@@ -770,8 +775,15 @@ __global__ void __launch_bounds__(FACE_WARPS * 32, SCP_SOFTRAS_FACE_CTAS) backwa
     const int iy0 = max(0, (int)floorf((is - 1.f - bb.w * is) * 0.5f) - 1);
     const int iy1 = min(p.is - 1, (int)ceilf((is - 1.f - bb.z * is) * 0.5f) + 1);
     if (ix0 > ix1 || iy0 > iy1) return;
+#if SCP_SOFTRAS_FACE_SMEM
+    __shared__ Face s_face[FACE_WARPS];
+    Face &f = s_face[threadIdx.x >> 5];
+    if (lane == 0) load_face(rec + fg * REC, f);
+    __syncwarp();
+#else
     Face f;
     load_face(rec + fg * REC, f);
+#endif
     const int ntex = p.T * 3 <= 9 ? p.T * 3 : 0;
     const size_t plane = (size_t)p.is * p.is;
     const float *gsc = grad_soft_colors + (size_t)b * 4 * plane, *sc = soft_colors + (size_t)b * 4 * plane;
