@@ -46,6 +46,13 @@ constexpr int LIST_CAP = 2048;  // tile face list capacity (indices) per phase
 #ifndef SCP_SOFTRAS_FACE_SMEM
 #define SCP_SOFTRAS_FACE_SMEM 0
 #endif
+// Next-round candidate, NOT validated on a GPU yet (default off): forward traversal with TWO pixels per lane (4 warps per
+// 16x16 tile, a warp owns an 8x8 block, lane = column + rows r and r+4): one record load per (warp, face) serves 64
+// pixels instead of 32 -- halves the L1 data-path traffic that bounds forward_kernel and gives
+// every lane two independent dependency chains.  Same per-pixel arithmetic and face order as forward_kernel.
+#ifndef SCP_SOFTRAS_FWD_2PX
+#define SCP_SOFTRAS_FWD_2PX 0
+#endif
 
 struct Params {
     int B, nf, T, R, is, tiles_x;
@@ -596,6 +603,223 @@ __global__ void __launch_bounds__(NTHREADS, SCP_SOFTRAS_TILE_CTAS) forward_kerne
     }
 }
 
+#if SCP_SOFTRAS_FWD_2PX
+// ---- forward, two pixels per lane (candidate, see SCP_SOFTRAS_FWD_2PX above) ------------------------------------------
+constexpr int NT2 = 128, NW2 = NT2 / 32, SCAN2 = SCAN * NTHREADS / NT2;     // same 1024 faces per culling round
+
+// cull_round for a CTA of NT2 threads (ascending face order preserved)
+__device__ __forceinline__ int cull_round2(const Params &p, const float4 *__restrict__ bbox, int b, int base,
+                                           float x_lo, float x_hi, float y_lo, float y_hi, int n0, int *s_list,
+                                           int *s_cnt)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned ballots[SCAN2];
+#pragma unroll
+    for (int k = 0; k < SCAN2; k++) {
+        const int fidx = base + k * NT2 + tid;
+        bool hit = false;
+        if (fidx < p.nf) {
+            const float4 bb = __ldg(bbox + (size_t)b * p.nf + fidx);
+            hit = !(x_lo > bb.y || x_hi < bb.x || y_lo > bb.w || y_hi < bb.z);
+        }
+        ballots[k] = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_cnt[k * NW2 + warp] = __popc(ballots[k]);
+    }
+    __syncthreads();
+    int total = 0, my_off[SCAN2];
+#pragma unroll
+    for (int k = 0; k < SCAN2; k++) {
+#pragma unroll
+        for (int w = 0; w < NW2; w++) {
+            if (w == warp) my_off[k] = total;
+            total += s_cnt[k * NW2 + w];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN2; k++) {
+        if (ballots[k] & (1u << lane))
+            s_list[n0 + my_off[k] + __popc(ballots[k] & ((1u << lane) - 1u))] = base + k * NT2 + tid;
+    }
+    __syncthreads();
+    return n0 + total;
+}
+
+// forward_pair without the loads: the per-(pixel, face) update of the aggregation state
+template <int RGB, bool FAST>
+__device__ __forceinline__ void forward_eval(const Params &p, const Face &f, float xp, float yp,
+                                             const float *__restrict__ textures, const float *__restrict__ textures2,
+                                             int b, FwdState &s)
+{
+    Frag fr;
+    if (!eval_frag<FAST>(p, f, xp, yp, fr)) return;
+    const int alpha_mode = FAST ? SCP_ALPHA_PROD : p.alpha_mode;
+    if (alpha_mode == SCP_ALPHA_PROD) s.alpha *= 1.f - fr.frag;
+    else if (alpha_mode == SCP_ALPHA_SUM) s.alpha += fr.frag;
+    else if (fr.frag > 0.5f) s.alpha = 1.f;
+
+    float wc[3];
+    const float zp = clip_and_depth(f, fr.w, wc);
+    if (zp < p.near_ || zp > p.far_) return;
+
+    if (RGB == SCP_RGB_HARD || RGB == RGB_DUAL) {
+        if (zp < s.depth_min && inside_closed(fr.w) && (p.double_side || f.front != 0.f)) {
+            s.depth_min = zp;
+            s.face_min = f.idx;
+            if (RGB == RGB_DUAL) {
+                const float *t2 = textures2 + ((size_t)b * p.nf + f.idx) * 9;
+#pragma unroll
+                for (int k = 0; k < 3; k++) s.col2[k] = wc[0] * __ldg(t2 + k) + wc[1] * __ldg(t2 + 3 + k) + wc[2] * __ldg(t2 + 6 + k);
+            } else {
+                sample_color<FAST>(p, f, wc, textures, b, s.col);
+            }
+        }
+    }
+    if ((RGB == SCP_RGB_SOFTMAX || RGB == RGB_DUAL) && (f.front != 0.f || p.double_side)) {
+        const float zn = (p.far_ - zp) * p.inv_depth_range;
+        float rescale = 1.f;
+        if (zn > s.sm_max) {
+            rescale = __expf((s.sm_max - zn) * p.inv_gamma);
+            s.sm_max = zn;
+        }
+        const float ez = __expf((zn - s.sm_max) * p.inv_gamma) * fr.frag;
+        s.sm_sum = rescale * s.sm_sum + ez;
+        float c[3];
+        sample_color<FAST>(p, f, wc, textures, b, c);
+#pragma unroll
+        for (int k = 0; k < 3; k++) s.col[k] = rescale * s.col[k] + ez * c[k];
+    }
+}
+
+template <int RGB>
+__device__ __forceinline__ void init_state(const Params &p, FwdState &s, int alpha_mode, bool valid,
+                                           const float *__restrict__ soft_colors, int b, size_t plane, int pn)
+{
+    s.col[0] = s.col[1] = s.col[2] = 0.f;
+    s.alpha = alpha_mode == SCP_ALPHA_PROD ? 1.f : 0.f;
+    s.sm_sum = __expf(p.eps * p.inv_gamma);
+    s.sm_max = p.eps;
+    s.depth_min = 10000000.f;
+    s.face_min = -1;
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float bg = soft_colors[((size_t)b * 4 + k) * plane + pn];
+            s.col[k] = RGB == SCP_RGB_HARD ? bg : bg * s.sm_sum;
+        }
+    }
+}
+
+// epilogue of forward_kernel for one pixel
+template <int RGB>
+__device__ __forceinline__ void store_pixel(const Params &p, const FwdState &s, int alpha_mode, int b, size_t plane, int pn,
+                                            float *__restrict__ aggrs_info, float *__restrict__ soft_colors,
+                                            float *__restrict__ aggrs_info2, float *__restrict__ soft_colors2)
+{
+    float a_out;
+    if (alpha_mode == SCP_ALPHA_PROD) a_out = 1.f - s.alpha;
+    else if (alpha_mode == SCP_ALPHA_SUM) a_out = s.alpha / p.nf;
+    else a_out = s.alpha;
+    soft_colors[((size_t)b * 4 + 3) * plane + pn] = a_out;
+    if (RGB == RGB_DUAL) {
+        soft_colors2[((size_t)b * 4 + 3) * plane + pn] = a_out;
+        if (s.face_min != -1) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) soft_colors2[((size_t)b * 4 + k) * plane + pn] = s.col2[k];
+        }
+        aggrs_info2[((size_t)b * 2 + 0) * plane + pn] = s.depth_min;
+        aggrs_info2[((size_t)b * 2 + 1) * plane + pn] = (float)s.face_min;
+    }
+    if (RGB == SCP_RGB_HARD) {
+        if (s.face_min != -1) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) soft_colors[((size_t)b * 4 + k) * plane + pn] = s.col[k];
+        }
+        aggrs_info[((size_t)b * 2 + 0) * plane + pn] = s.depth_min;
+        aggrs_info[((size_t)b * 2 + 1) * plane + pn] = (float)s.face_min;
+    } else {
+        const float rs = 1.f / s.sm_sum;
+#pragma unroll
+        for (int k = 0; k < 3; k++) soft_colors[((size_t)b * 4 + k) * plane + pn] = s.col[k] * rs;
+        aggrs_info[((size_t)b * 2 + 0) * plane + pn] = s.sm_sum;
+        aggrs_info[((size_t)b * 2 + 1) * plane + pn] = s.sm_max;
+    }
+}
+
+template <int RGB, bool FAST>
+__global__ void __launch_bounds__(NT2, 4) forward_kernel2(Params p, const float4 *__restrict__ bbox,
+                                                        const float *__restrict__ rec,
+                                                        const int *__restrict__ img_bbox,
+                                                        const float *__restrict__ textures,
+                                                        float *__restrict__ aggrs_info,
+                                                        float *__restrict__ soft_colors,
+                                                        const float *__restrict__ textures2,
+                                                        float *__restrict__ aggrs_info2,
+                                                        float *__restrict__ soft_colors2)
+{
+    __shared__ int s_list[LIST_CAP];
+    __shared__ int s_cnt[SCAN2 * NW2];
+
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t plane = (size_t)p.is * p.is;
+    const int alpha_mode = FAST ? SCP_ALPHA_PROD : p.alpha_mode;
+    // tile and the warp's 8x8 block; lane = column (lane & 7) and the two rows (lane >> 3) and (lane >> 3) + 4
+    const int tx0 = (blockIdx.x % p.tiles_x) * TILE, ty0 = (blockIdx.x / p.tiles_x) * TILE;
+    const int bx = tx0 + (warp & 1) * 8, by = ty0 + (warp >> 1) * 8;
+    const int pxx = bx + (lane & 7), pyA = by + (lane >> 3), pyB = pyA + 4;
+    const bool validA = pxx < p.is && pyA < p.is, validB = pxx < p.is && pyB < p.is;
+    const int pnA = pyA * p.is + pxx, pnB = pyB * p.is + pxx;
+    const float xp = centre_x(pxx, p.is), ypA = centre_y(pyA, p.is), ypB = centre_y(pyB, p.is);
+    const float wx_lo = centre_x(bx, p.is), wx_hi = centre_x(min(bx + 7, p.is - 1), p.is);
+    const float wy_hi = centre_y(by, p.is), wy_lo = centre_y(min(by + 7, p.is - 1), p.is);
+    const float x_lo = centre_x(tx0, p.is), x_hi = centre_x(min(tx0 + TILE - 1, p.is - 1), p.is);
+    const float y_hi = centre_y(ty0, p.is), y_lo = centre_y(min(ty0 + TILE - 1, p.is - 1), p.is);
+
+    FwdState sA, sB;
+    init_state<RGB>(p, sA, alpha_mode, validA, soft_colors, b, plane, pnA);
+    init_state<RGB>(p, sB, alpha_mode, validB, soft_colors, b, plane, pnB);
+
+    if (!tile_outside_mesh(img_bbox, b, x_lo, x_hi, y_lo, y_hi)) {
+        int base = 0;
+        while (base < p.nf) {
+            int n = 0;
+            while (base < p.nf && n + SCAN2 * NT2 <= LIST_CAP) {
+                n = cull_round2(p, bbox, b, base, x_lo, x_hi, y_lo, y_hi, n, s_list, s_cnt);
+                base += SCAN2 * NT2;
+            }
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int fi = i0 + lane < n ? s_list[i0 + lane] : -1;
+                bool hit = false;
+                if (fi >= 0) {
+                    const float4 bb = __ldg(bbox + (size_t)b * p.nf + fi);
+                    hit = !(wx_lo > bb.y || wx_hi < bb.x || wy_lo > bb.w || wy_hi < bb.z);
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, hit);
+                while (todo) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int fsel = __shfl_sync(0xffffffffu, fi, j);
+                    const float *r = rec + ((size_t)b * p.nf + fsel) * REC;
+                    float bx0, bx1, by0, by1;
+                    load_bbox(r, bx0, bx1, by0, by1);
+                    const bool in_x = !(xp > bx1 || xp < bx0);
+                    const bool inA = validA && in_x && !(ypA > by1 || ypA < by0);
+                    const bool inB = validB && in_x && !(ypB > by1 || ypB < by0);
+                    if (inA || inB) {
+                        Face f;
+                        load_face(r, f);
+                        if (inA) forward_eval<RGB, FAST>(p, f, xp, ypA, textures, textures2, b, sA);
+                        if (inB) forward_eval<RGB, FAST>(p, f, xp, ypB, textures, textures2, b, sB);
+                    }
+                }
+            }
+            if (base < p.nf) __syncthreads();  // the list is about to be rebuilt
+        }
+    }
+    if (validA) store_pixel<RGB>(p, sA, alpha_mode, b, plane, pnA, aggrs_info, soft_colors, aggrs_info2, soft_colors2);
+    if (validB) store_pixel<RGB>(p, sB, alpha_mode, b, plane, pnB, aggrs_info, soft_colors, aggrs_info2, soft_colors2);
+}
+#endif  // SCP_SOFTRAS_FWD_2PX
+
 // ---- backward -----------------------------------------------------------------------------
 // Folded butterfly: 18 per-lane values -> after 20 shuffles each lane holds the warp total of ONE
 // value (index returned in `idx`; lanes holding padding get idx >= 18 and a zero total).
@@ -974,10 +1198,18 @@ extern "C" int scp_softras_forward(const float *faces, const float *textures, fl
     const dim3 grid(p.tiles_x * p.tiles_x, B);
     const bool fast = func_id_dist == SCP_DIST_EUCLIDEAN && func_id_alpha == SCP_ALPHA_PROD;
     if (func_id_rgb == SCP_RGB_HARD) {
+#if SCP_SOFTRAS_FWD_2PX
+        if (fast) forward_kernel2<SCP_RGB_HARD, true><<<grid, NT2, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors, nullptr, nullptr, nullptr);
+#else
         if (fast) forward_kernel<SCP_RGB_HARD, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors, nullptr, nullptr, nullptr);
+#endif
         else forward_kernel<SCP_RGB_HARD, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors, nullptr, nullptr, nullptr);
     } else {
+#if SCP_SOFTRAS_FWD_2PX
+        if (fast) forward_kernel2<SCP_RGB_SOFTMAX, true><<<grid, NT2, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors, nullptr, nullptr, nullptr);
+#else
         if (fast) forward_kernel<SCP_RGB_SOFTMAX, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors, nullptr, nullptr, nullptr);
+#endif
         else forward_kernel<SCP_RGB_SOFTMAX, false><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures, aggrs_info, soft_colors, nullptr, nullptr, nullptr);
     }
     return scp::check_launch("scp_softras_forward");
@@ -1010,9 +1242,15 @@ extern "C" int scp_softras_forward_dual(const float *faces, const float *texture
     pack_kernel<<<(unsigned)((nfaces + 255) / 256), 256, 0, st>>>(p, faces, textures_soft, faces_info, 1, bbox, rec,
                                                                  img_bbox);
     const dim3 grid(p.tiles_x * p.tiles_x, B);
+#if SCP_SOFTRAS_FWD_2PX
+    forward_kernel2<RGB_DUAL, true><<<grid, NT2, 0, st>>>(p, bbox, rec, img_bbox, textures_soft, aggrs_info_soft,
+                                                          soft_colors_soft, textures_hard, aggrs_info_hard,
+                                                          soft_colors_hard);
+#else
     forward_kernel<RGB_DUAL, true><<<grid, NTHREADS, 0, st>>>(p, bbox, rec, img_bbox, textures_soft, aggrs_info_soft,
                                                               soft_colors_soft, textures_hard, aggrs_info_hard,
                                                               soft_colors_hard);
+#endif
     return scp::check_launch("scp_softras_forward_dual");
 }
 
