@@ -173,3 +173,34 @@ def test_batched_pose_fit_equals_oracle_on_a_larger_batch():
     assert torch.equal(torch.get_rng_state(), state)
     for a, b in zip(got, want):
         assert _rel(a, b) < 1e-5
+
+
+def test_sequential_choice_equals_a_literal_loop_on_random_tables():
+    """300 random residual tables (ties, NaN, inf, values over the 1e10 start, NaN-covariance rounds, stop thresholds that
+    fire early / late / never) against the reference loop written out literally (umeyama.py:102-112)."""
+    from self_corr_pose_b200.model.util.umeyama import _sequential_choice
+    g = torch.Generator().manual_seed(0)
+    H, n_tab = 12, 300
+    r = torch.rand(n_tab, H, generator=g).mul(8).round() / 2                     # coarse values: many exact ties
+    special = torch.rand(n_tab, H, generator=g)
+    r[special < 0.08] = float('nan')
+    r[(special >= 0.08) & (special < 0.12)] = float('inf')
+    r[(special >= 0.12) & (special < 0.16)] = 3e10
+    bad = torch.rand(n_tab, H, generator=g) < 0.03
+    stop = torch.rand(n_tab, generator=g).mul(4).round() / 2                     # 0 (never) .. 2
+    best, last, found = _sequential_choice(r, stop, bad)
+    for t in range(n_tab):
+        inc, inc_i, executed, raised = 1e10, None, H - 1, False
+        for i in range(H):
+            executed = i
+            if bad[t, i]:
+                raised = True
+                break
+            if float(r[t, i]) < inc:
+                inc, inc_i = float(r[t, i]), i
+            if inc < float(stop[t]):
+                break
+        assert int(last[t]) == executed, t
+        assert bool(found[t]) == (inc_i is not None and not raised), t
+        if inc_i is not None and not raised:
+            assert int(best[t]) == inc_i, t
