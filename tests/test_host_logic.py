@@ -262,3 +262,18 @@ def test_every_entry_point_rejects_null_arguments_with_a_message():
             _lib.check(-1, name)
         checked += 1
     assert checked >= 17
+
+
+def test_variant_library_is_opt_in_only():
+    """Kernel-experiment variants (build.py --variant, SCP_LIB_VARIANT) never shadow the product library: without the
+    variable the product path is loaded, with it a missing variant fails loudly instead of falling back."""
+    import subprocess
+    import sys
+    from self_corr_pose_b200 import _lib, build
+    assert os.path.basename(_lib.LIB_PATH) == 'libscp_b200.so' and build.lib_path() == _lib.LIB_PATH
+    assert os.path.basename(build.lib_path('x')) == 'libscp_b200.x.so'
+    code = ('from self_corr_pose_b200 import _lib\n'
+            'try:\n    _lib.lib()\nexcept _lib.ScpNativeError as e:\n    print("LOUD", e)\n')
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=ROOT,
+                       env=dict(os.environ, SCP_LIB_VARIANT='does_not_exist'))
+    assert 'LOUD' in r.stdout and 'libscp_b200.does_not_exist.so' in r.stdout, r.stdout + r.stderr
