@@ -2,8 +2,10 @@
 API of the reference's model/module/mesh.py:29-131 (`CanonicalMesh(opts)`: `mean_v`, `faces`, `symm_rots`,
 `get_texture`, `compute_symmetry_loss`).  trimesh / pytorch3d are not available offline: OBJ priors are read with a
 plain parser (the shipped priors are duplicate-free, so `trimesh.load_mesh(process=True)` returns the same arrays)
-and the symmetry regulariser's point sampling + 1-NN search are restated in torch (parity unpinned: the reference
-delegates them to pytorch3d 0.6.1, absent here)."""
+and the symmetry regulariser's point sampling + 1-NN search are restated in torch: the reference delegates them to
+pytorch3d 0.6.1, absent here -- the symmetry rotations and the one-way chamfer reduction are
+pinned to the reference's own model/util/{symmetry,chamfer}.py with a brute-force stand-in for pytorch3d's knn_points
+(tests/test_reference_host_cpu.py); the random surface sampling stays unpinned."""
 import os
 
 import numpy as np

@@ -130,3 +130,41 @@ def test_trainer_batch_reshape_and_collect_grad_match_reference(monkeypatch, cap
     for (n, p), (_, q) in zip(m1.named_parameters(), m2.named_parameters()):
         if p.grad is not None:
             assert torch.allclose(p.grad, q.grad, rtol=1e-6, atol=0), n
+
+
+def test_symmetry_regulariser_pieces_match_reference(monkeypatch):
+    """`get_symm_rots` against model/util/symmetry.py, and the one-way chamfer reduction of the symmetry loss against the
+    reference's model/util/chamfer.py::chamfer_distance_single_way.  That function delegates the nearest-neighbour search
+    to pytorch3d (absent offline): it is given a brute-force `knn_points` with pytorch3d's documented contract
+    (K nearest points of the second cloud, SQUARED distances) -- the reduction logic around it is the reference's own.
+    The surface sampling of the regulariser (pytorch3d.ops.sample_points_from_meshes, random) stays unpinned."""
+    import sys
+    import types
+    from collections import namedtuple
+    from self_corr_pose_b200.model.module import mesh as M
+    ref_symm = _load('model/util/symmetry.py', 'ref_symmetry')
+    for division in (1, 2, 17):
+        assert torch.equal(M.get_symm_rots(division), ref_symm.get_symm_rots(division))
+
+    KNN = namedtuple('KNN', 'dists idx knn')
+
+    def knn_points(p1, p2, lengths1=None, lengths2=None, K=1):
+        d = torch.cdist(p1.double(), p2.double()).pow(2)
+        dists, idx = d.topk(K, dim=2, largest=False)
+        return KNN(dists.to(p1.dtype), idx, None)
+
+    knn = types.ModuleType('pytorch3d.ops.knn')
+    knn.knn_points, knn.knn_gather = knn_points, None
+    pcl = types.ModuleType('pytorch3d.structures.pointclouds')
+    pcl.Pointclouds = type('Pointclouds', (), {})
+    for name, mod in (('pytorch3d', types.ModuleType('pytorch3d')), ('pytorch3d.ops', types.ModuleType('pytorch3d.ops')),
+                      ('pytorch3d.structures', types.ModuleType('pytorch3d.structures')), ('pytorch3d.ops.knn', knn),
+                      ('pytorch3d.structures.pointclouds', pcl)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    ref_chamfer = _load('model/util/chamfer.py', 'ref_chamfer')
+    g = torch.Generator().manual_seed(2)
+    x, y = torch.randn(5, 70, 3, generator=g), torch.randn(5, 400, 3, generator=g)
+    want = ref_chamfer.chamfer_distance_single_way(x, y)[0]
+    for chunk in (2, 16):
+        got = M.chamfer_single_way(x, y, chunk=chunk)
+        assert got.shape == want.shape and abs(float(got) - float(want)) < 1e-5 * float(want)
