@@ -22,6 +22,10 @@ class MeshNet(nn.Module):
     def __init__(self, opts):
         super().__init__()
         self.opts = opts
+        for flag in ('flatten_loss', 'depth_loss_chamfer', 'use_occ'):      # model.py:28,30: off in every shipped config
+            if getattr(opts, flag, False):
+                raise NotImplementedError('option `%s` of the reference is not implemented (it is off in every shipped '
+                                          'config and outside the accelerated path)' % flag)
         self.mesh = CanonicalMesh(opts)
         self.weights = Weights(opts)
         self.encoder = Encoder(opts)
@@ -83,6 +87,10 @@ class MeshNet(nn.Module):
         aux['cycle_loss_pretrain'] = cyc[0] * wts.cycle_loss_pt_wt
         rot_cyc = self.corr_net.compute_rotation_cycle_loss(img, mask, img_feat, self.encoder)
         aux['cycle_loss'] = rot_cyc[0] * wts.cycle_loss_wt
+        if getattr(opts, 'camera_loss', False):     # model.py:124-127: rotation against the next frame's of the same video
+            nxt = rotation.detach().clone().reshape(-1, opts.repeat, 3, 3)
+            nxt = torch.cat((nxt[:, 1:], nxt[:, :1]), dim=1).reshape(bsz, 3, 3)
+            aux['cam_loss'] = wts.camera_wt * L.compute_camera_loss(rotation, nxt).mean()
         total_loss = sum(aux.values())
         aux_output = {'total_loss': total_loss}
         aux_output.update(aux)

@@ -152,6 +152,14 @@ def compute_imatch_loss(imatch, imatch_gt, depth_weight):
     return ((imatch - imatch_gt).norm(2, 1) * depth_weight).mean(1)
 
 
+def compute_camera_loss(m1, m2):
+    """Geodesic angle between two batches of rotation matrices (loss_utils.py:228-234; flag `camera_loss`, off in every
+    shipped config)."""
+    m = torch.bmm(m1, m2.transpose(1, 2))
+    cos = (m.diagonal(dim1=1, dim2=2).sum(1) - 1) / 2
+    return torch.acos(F.hardtanh(cos, -1, 1))
+
+
 def divide_by_frame(x, batch_size, repeat):
     """(src, tgt) = (frame r, frame r+1 of the same video), wrap-around inside each video."""
     src = x.reshape(batch_size, repeat, *x.shape[1:])

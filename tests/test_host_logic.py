@@ -277,3 +277,14 @@ def test_variant_library_is_opt_in_only():
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=ROOT,
                        env=dict(os.environ, SCP_LIB_VARIANT='does_not_exist'))
     assert 'LOUD' in r.stdout and 'libscp_b200.does_not_exist.so' in r.stdout, r.stdout + r.stderr
+
+
+def test_unimplemented_reference_options_fail_loudly():
+    """Options of the reference's MeshNet that this package does not implement raise instead of being ignored."""
+    from self_corr_pose_b200.hotpath import default_opts
+    from self_corr_pose_b200.model.model import MeshNet
+    for flag in ('flatten_loss', 'depth_loss_chamfer', 'use_occ'):
+        opts = default_opts()
+        setattr(opts, flag, True)
+        with pytest.raises(NotImplementedError, match=flag):
+            MeshNet(opts)

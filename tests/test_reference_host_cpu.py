@@ -168,3 +168,24 @@ def test_symmetry_regulariser_pieces_match_reference(monkeypatch):
     for chunk in (2, 16):
         got = M.chamfer_single_way(x, y, chunk=chunk)
         assert got.shape == want.shape and abs(float(got) - float(want)) < 1e-5 * float(want)
+
+
+def test_camera_loss_matches_reference(monkeypatch):
+    """compute_camera_loss (optional term of MeshNet.forward, flag `camera_loss`) against the reference's function,
+    extracted from model/util/loss_utils.py without importing the module (it pulls in soft_renderer and pytorch3d)."""
+    import ast
+    from self_corr_pose_b200.model.util.loss_utils import compute_camera_loss
+    tree = ast.parse(open(os.path.join(REF, 'model', 'util', 'loss_utils.py')).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'compute_camera_loss')
+    ns = {'torch': torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), 'reference_loss_utils', 'exec'), ns)
+    g = torch.Generator().manual_seed(5)
+    q1, q2 = torch.linalg.qr(torch.randn(9, 3, 3, generator=g))[0], torch.linalg.qr(torch.randn(9, 3, 3, generator=g))[0]
+    q2[0] = q1[0]                                           # identical rotations: clamped cosine, angle 0
+    a = q1.clone().requires_grad_(True)
+    b = q1.clone().requires_grad_(True)
+    got, want = compute_camera_loss(a, q2), ns['compute_camera_loss'](b, q2)
+    assert torch.equal(got, want)
+    got[1:].sum().backward()
+    want[1:].sum().backward()
+    assert torch.allclose(a.grad, b.grad, rtol=1e-6, atol=1e-7)
