@@ -190,6 +190,17 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
         tex = srf.face_vertices(torch.rand_like(sv), hot.mesh.faces[None].repeat(B, 1, 1)).contiguous()
     bytes_f = B * (72 * nf + 24 * is_ * is_)
     bytes_b = B * (144 * nf + 40 * is_ * is_)
+    def candidate_pairs(sigma):
+        """SURVEY.md 8(d) secondary figure: (pixel, face) pairs inside the faces' inflated bounding boxes, summed over the
+        batch -- what a traversal has to evaluate (dense would be B * nf * is^2).  None if anything goes wrong."""
+        try:
+            m = (9.2102404 * sigma) ** 0.5                       # sqrt(ln(1/dist_eps - 1) * sigma), dist_eps = 1e-4
+            lo, hi = fv[..., :2].amin(2) - m, fv[..., :2].amax(2) + m           # B, nf, 2
+            ext = (hi.clamp(-1, 1) - lo.clamp(-1, 1)).clamp_min(0) * (is_ / 2)  # pixels
+            return float((ext[..., 0] * ext[..., 1]).double().sum())
+        except Exception:   # noqa: BLE001
+            return None
+
     for name in ('softras_softtex', 'softras_depth+nocs'):
         fvg = fv.clone().requires_grad_(True)
         if name == 'softras_softtex':
@@ -210,6 +221,11 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
         out.append(dict(kernel=name.replace('+nocs', '') + '_bwd (pack+backward_face_kernel)', ms=t_b, bound='hbm',
                         achieved=bytes_b / t_b / 1e6, peak=hbm, unit='GB/s', launches_per_step=1,
                         ncu_name='softras::backward_face_kernel<1, 1> #%d' % (0 if 'softtex' in name else 1)))
+        pairs = candidate_pairs(1e-3 if 'softtex' in name else 1e-4)
+        if pairs:
+            for k, t in ((out[-2], t_f), (out[-1], t_b)):
+                k['candidate_pairs'] = pairs
+                k['gpairs_per_s'] = pairs / t / 1e6
     # --- correspondence
     from self_corr_pose_b200.ops.corr_match import corr_match
     import torch.nn.functional as F
