@@ -46,6 +46,12 @@ constexpr int LIST_CAP = 2048;  // tile face list capacity (indices) per phase
 #ifndef SCP_SOFTRAS_FACE_SMEM
 #define SCP_SOFTRAS_FACE_SMEM 0
 #endif
+// Pixel block a warp of the face-centric backward covers per iteration: BW x (32 / BW) pixels (default 8 x 4).  16 x 2
+// wastes fewer lanes on the 14-pixel boxes of the sigma = 1e-4 renders and on the 30-pixel boxes of the soft-texture
+// render (87 / 94 % instead of 77 / 88 % of the lanes inside the box) and reads 64-byte row segments; candidate, untimed.
+#ifndef SCP_SOFTRAS_FACE_BW
+#define SCP_SOFTRAS_FACE_BW 8
+#endif
 // Next-round candidate, NOT validated on a GPU yet (default off): forward traversal with TWO pixels per lane (4 warps per
 // 16x16 tile, a warp owns an 8x8 block, lane = column + rows r and r+4): one record load per (warp, face) serves 64
 // pixels instead of 32 -- halves the L1 data-path traffic that bounds forward_kernel and gives
@@ -1016,11 +1022,13 @@ __global__ void __launch_bounds__(FACE_WARPS * 32, SCP_SOFTRAS_FACE_CTAS) backwa
 #pragma unroll
     for (int k = 0; k < 18; k++) gv[k] = 0.f;
     bool any = false;
-    for (int y0 = iy0; y0 <= iy1; y0 += 4) {
-        for (int x0 = ix0; x0 <= ix1; x0 += 8) {
+    constexpr int BW = SCP_SOFTRAS_FACE_BW, BH = 32 / BW;
+    static_assert(BW == 8 || BW == 16 || BW == 32, "block width");
+    for (int y0 = iy0; y0 <= iy1; y0 += BH) {
+        for (int x0 = ix0; x0 <= ix1; x0 += BW) {
             Pixel px;
-            px.px = x0 + (lane & 7);
-            px.py = y0 + (lane >> 3);
+            px.px = x0 + (lane % BW);
+            px.py = y0 + (lane / BW);
             px.valid = px.px <= ix1 && px.py <= iy1;
             px.pn = px.py * p.is + px.px;
             px.xp = centre_x(px.px, p.is);

@@ -18,4 +18,4 @@ def test_emulated_softras_kernels_and_candidates_match_the_oracle(capsys):
     rc = run_emu.main()
     out = capsys.readouterr().out
     assert rc == 0 and 'EMU CHECK PASSED' in out, out
-    assert all(name in out for name in ('default', 'fwd2px', 'facesmem'))
+    assert all(name in out for name in ('default', 'fwd2px', 'facesmem', 'face16x2'))
