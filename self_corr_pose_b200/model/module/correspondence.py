@@ -70,11 +70,15 @@ class Correspondence:
         match (B,P,3): soft 3D match of every correspondence-map pixel; imatch (B,2,N): soft 2D match of every vertex.
         A pixel is confident when the 2D match of the vertex nearest to its 3D match falls back onto the pixel:
         conf = exp(-5 |pixel - imatch[nearest vertex]|), upsampled bilinearly to the mask's size; values under
-        min(mean over the foreground, 0.5) are zeroed.  Plain torch; the nearest-vertex search runs on a (B,N,P)
-        distance table instead of the reference's (B,N,P,3) difference tensor."""
+        min(mean over the foreground, 0.5) are zeroed.  Plain torch; the nearest-vertex search accumulates a (B,N,P)
+        table of squared distances instead of the reference's (B,N,P,3) difference tensor."""
         bsz, h, w = mask.shape
         with torch.no_grad():
-            near = torch.cdist(pred_v, match, compute_mode='donot_use_mm_for_euclid_dist').argmin(1)          # B, P
+            d2 = None                                       # squared distances vertex <-> 3D match, one coordinate at a time
+            for k in range(3):
+                diff = pred_v[:, :, None, k] - match[:, None, :, k]                                       # B, N, P
+                d2 = diff * diff if d2 is None else d2 + diff * diff
+            near = d2.argmin(1)                                                                           # B, P
             back = torch.gather(imatch.permute(0, 2, 1), 1, near[:, :, None].expand(-1, -1, 2))           # B, P, 2
             fberr = (self.meshgrid.permute(1, 0)[None] - back).norm(2, -1).view(bsz, 1, self.hf, self.wf)
             conf = (-5 * fberr).exp()
