@@ -27,6 +27,13 @@ N_SAMPLE = 5        # :104
 _START_RESIDUAL = 1e10
 
 
+def _det3(m):
+    """Determinant of (..., 3, 3) matrices by cofactor expansion (only its sign is used; avoids batched LU launches)."""
+    return (m[..., 0, 0] * (m[..., 1, 1] * m[..., 2, 2] - m[..., 1, 2] * m[..., 2, 1])
+            - m[..., 0, 1] * (m[..., 1, 0] * m[..., 2, 2] - m[..., 1, 2] * m[..., 2, 0])
+            + m[..., 0, 2] * (m[..., 1, 0] * m[..., 2, 1] - m[..., 1, 1] * m[..., 2, 0]))
+
+
 def _closed_form(src, tgt, weight=None, strict=True):
     """src, tgt (..., n, 3) rows; weight (..., n) bool or None (all points) -> s (...), R (..., 3, 3), t (..., 3), bad (...).
     bad marks problems whose covariance holds a NaN: with `strict` that raises like the reference (:180-184), otherwise
@@ -52,7 +59,7 @@ def _closed_form(src, tgt, weight=None, strict=True):
     else:       # LAPACK / cuSOLVER refuse non-finite input: decompose a stand-in and blank the result below
         cov = torch.where(bad[..., None, None], torch.eye(3, device=src.device, dtype=src.dtype), cov)
     U, D, Vh = torch.linalg.svd(cov, full_matrices=True)
-    sign = torch.where(torch.linalg.det(U) * torch.linalg.det(Vh) < 0.0, -1.0, 1.0).to(src.dtype)
+    sign = torch.where(_det3(U) * _det3(Vh) < 0.0, -1.0, 1.0).to(src.dtype)
     D = torch.cat((D[..., :2], D[..., 2:] * sign[..., None]), -1)
     U = torch.cat((U[..., :, :2], U[..., :, 2:] * sign[..., None, None]), -1)
     R = (U @ Vh).transpose(-1, -2)
