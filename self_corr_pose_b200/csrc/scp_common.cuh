@@ -24,9 +24,13 @@ inline int check_launch(const char *what)
 // instead of exp2f's range-handling sequence; used where x <= 0 up to rounding (softmax numerators)
 __device__ __forceinline__ float ex2_approx(float x)
 {
+#ifdef SCP_HOST_EMU      // host emulation of the plain-CUDA kernels (tools/emu, tests only)
+    return exp2f(x);
+#else
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 
 __device__ __forceinline__ float warp_sum(float v)

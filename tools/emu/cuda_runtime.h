@@ -10,6 +10,7 @@
 #pragma once
 #include <math.h>
 #include <pthread.h>
+#include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -51,12 +52,13 @@ struct Cta {
     unsigned nthreads = 0;
     pthread_barrier_t block_bar;
     std::vector<pthread_barrier_t> warp_bar;
-    std::vector<uint32_t> warp_slot;      // 32 words per warp
+    std::vector<uint64_t> warp_slot;      // 32 slots per warp
+    std::vector<unsigned char> dyn_smem;  // `extern __shared__` storage
     int block_or = 0;
 };
 extern thread_local Cta *cta;
 extern std::mutex atomic_mutex;
-void launch(dim3 grid, dim3 block, const std::function<void()> &body);
+void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()> &body);
 }  // namespace scp_emu
 
 extern thread_local uint3 threadIdx, blockIdx;
@@ -76,22 +78,22 @@ static inline int __syncthreads_or(int pred)
 }
 static inline void scp_emu_warp_wait() { pthread_barrier_wait(&scp_emu::cta->warp_bar[threadIdx.x >> 5]); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { scp_emu_warp_wait(); }
-static inline uint32_t scp_emu_exchange(uint32_t mine, int src_lane)
+static inline uint64_t scp_emu_exchange(uint64_t mine, int src_lane)
 {
-    uint32_t *slot = scp_emu::cta->warp_slot.data() + (threadIdx.x >> 5) * 32;
+    uint64_t *slot = scp_emu::cta->warp_slot.data() + (threadIdx.x >> 5) * 32;
     slot[threadIdx.x & 31] = mine;
     scp_emu_warp_wait();
-    const uint32_t got = slot[src_lane & 31];
+    const uint64_t got = slot[src_lane & 31];
     scp_emu_warp_wait();
     return got;
 }
 static inline unsigned __ballot_sync(unsigned, int pred)
 {
-    uint32_t *slot = scp_emu::cta->warp_slot.data() + (threadIdx.x >> 5) * 32;
+    uint64_t *slot = scp_emu::cta->warp_slot.data() + (threadIdx.x >> 5) * 32;
     slot[threadIdx.x & 31] = pred ? 1u : 0u;
     scp_emu_warp_wait();
     unsigned m = 0;
-    for (int i = 0; i < 32; i++) m |= (slot[i] & 1u) << i;
+    for (int i = 0; i < 32; i++) m |= (unsigned)(slot[i] & 1u) << i;
     scp_emu_warp_wait();
     return m;
 }
@@ -100,12 +102,20 @@ static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pre
 static inline uint32_t scp_emu_bits(float v) { uint32_t u; memcpy(&u, &v, 4); return u; }
 static inline float scp_emu_float(uint32_t u) { float v; memcpy(&v, &u, 4); return v; }
 static inline int __shfl_sync(unsigned, int v, int src) { return (int)scp_emu_exchange((uint32_t)v, src); }
-static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return scp_emu_exchange(v, src); }
-static inline float __shfl_sync(unsigned, float v, int src) { return scp_emu_float(scp_emu_exchange(scp_emu_bits(v), src)); }
+static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return (unsigned)scp_emu_exchange(v, src); }
+static inline float __shfl_sync(unsigned, float v, int src) { return scp_emu_float((uint32_t)scp_emu_exchange(scp_emu_bits(v), src)); }
 static inline int __shfl_xor_sync(unsigned, int v, int m) { return (int)scp_emu_exchange((uint32_t)v, (threadIdx.x & 31) ^ m); }
 static inline float __shfl_xor_sync(unsigned, float v, int m)
 {
-    return scp_emu_float(scp_emu_exchange(scp_emu_bits(v), (threadIdx.x & 31) ^ m));
+    return scp_emu_float((uint32_t)scp_emu_exchange(scp_emu_bits(v), (threadIdx.x & 31) ^ m));
+}
+static inline double __shfl_xor_sync(unsigned, double v, int m)
+{
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    u = scp_emu_exchange(u, (threadIdx.x & 31) ^ m);
+    memcpy(&v, &u, 8);
+    return v;
 }
 
 // ---- memory / arithmetic intrinsics ----
@@ -130,6 +140,13 @@ static inline float atomicAdd(float *p, float v)
     *p = old + v;
     return old;
 }
+static inline double atomicAdd(double *p, double v)
+{
+    std::lock_guard<std::mutex> g(scp_emu::atomic_mutex);
+    const double old = *p;
+    *p = old + v;
+    return old;
+}
 static inline int atomicMin(int *p, int v)
 {
     std::lock_guard<std::mutex> g(scp_emu::atomic_mutex);
@@ -137,4 +154,6 @@ static inline int atomicMin(int *p, int v)
     if (v < old) *p = v;
     return old;
 }
-#define SCP_EMU_LAUNCH(grid, block, ...) scp_emu::launch(dim3(grid), dim3(block), [&]() { __VA_ARGS__; })
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+#define SCP_EMU_LAUNCH(grid, block, smem, ...) scp_emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { __VA_ARGS__; })

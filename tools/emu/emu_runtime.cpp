@@ -7,7 +7,7 @@ namespace scp_emu {
 thread_local Cta *cta = nullptr;
 std::mutex atomic_mutex;
 
-void launch(dim3 grid, dim3 block, const std::function<void()> &body)
+void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()> &body)
 {
     const unsigned nt = block.x * block.y * block.z, nw = (nt + 31) / 32;
     if (block.y != 1 || block.z != 1 || nt % 32 != 0) {
@@ -23,6 +23,7 @@ void launch(dim3 grid, dim3 block, const std::function<void()> &body)
                 c.warp_bar.resize(nw);
                 for (auto &b : c.warp_bar) pthread_barrier_init(&b, nullptr, 32);
                 c.warp_slot.assign(nw * 32, 0);
+                c.dyn_smem.assign(dyn_smem + 16, 0);
                 std::vector<std::thread> threads;
                 threads.reserve(nt);
                 for (unsigned t = 0; t < nt; t++)

@@ -1,0 +1,161 @@
+"""Functional check WITHOUT a GPU of the fused loss / geometry / cycle kernels: the shipped csrc/scp_loss.cu,
+scp_geom.cu and scp_cycle.cu compiled for the host (tools/emu/build_emu.py) and called through their C ABI with host
+pointers, against the reference's op-by-op statements evaluated in fp64 with torch autograd (the same references the
+-m gpu tests use).  Values and gradients.      python tools/emu/run_emu_ops.py"""
+import ctypes
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+import build_emu  # noqa: E402
+from self_corr_pose_b200 import _lib, synthetic  # noqa: E402
+from self_corr_pose_b200.model.util import loss_utils as L  # noqa: E402
+from self_corr_pose_b200.ops.project_faces import FaceTopology, LOOK_AT_Z  # noqa: E402
+from self_corr_pose_b200.soft_renderer import functional as srf  # noqa: E402
+
+
+def load(source, names):
+    lib = ctypes.CDLL(build_emu.build(source=source))
+    for n in names:
+        fn = getattr(lib, n)
+        fn.argtypes, fn.restype = _lib._SIGNATURES[n]
+    return lib
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def views(ts):
+    p = (ctypes.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])
+    s = (ctypes.c_longlong * len(ts))(*[0 if t is None else t.stride(0) for t in ts])
+    return p, s
+
+
+def check_image_losses(B=2, H=32, hf=8, seed=0):
+    lib = load('scp_loss', ('scp_image_losses_workspace_bytes', 'scp_image_losses_forward', 'scp_image_losses_backward'))
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=g)
+    r_depth = torch.cat([r(B, 2, H, H), 3 * r(B, 1, H, H), (r(B, 1, H, H) - 0.3).clamp(0, 1)], 1)
+    r_tex = r(B, 4, H, H)
+    r_nocs = torch.cat([r(B, 3, H, H) - 0.5, (r(B, 1, H, H) - 0.4).clamp(0, 1)], 1)
+    match_lr = r(B, hf * hf, 3) - 0.5
+    img, mask = r(B, 3, H, H), (r(B, H, H) > 0.4).float()
+    depth = 3 * r(B, H, H) * (r(B, H, H) > 0.2).float()
+    w = r(B, 4) + 0.5
+    # reference statements, fp64
+    lv = [t.clone().double().requires_grad_(True) for t in (r_depth, r_tex, match_lr)]
+    match = F.interpolate(lv[2].reshape(B, hf, hf, 3).permute(0, 3, 1, 2), (H, H), mode='nearest')
+    ref = torch.stack([L.compute_mask_loss(img.double(), mask.double(), lv[0][:, 3]),
+                       L.compute_texture_loss(img.double(), mask.double(), lv[1][:, :3], lv[1][:, 3]),
+                       L.compute_depth_loss(depth.double(), lv[0][:, 2], lv[0][:, 3], mask.double())[0],
+                       L.compute_match_loss(match, r_nocs[:, :3].double(), r_nocs[:, 3].double(), mask.double())], 1)
+    (ref * w.double()).sum().backward()
+    # emulated kernels
+    maps = [img, mask, depth, r_depth[:, 3], r_tex[:, :3], r_tex[:, 3], r_depth[:, 2], r_depth[:, 3], r_nocs[:, :3],
+            r_nocs[:, 3], None]
+    losses = torch.empty(B, 4)
+    ws = torch.zeros(lib.scp_image_losses_workspace_bytes(B), dtype=torch.uint8)
+    mp, ms = views(maps)
+    assert lib.scp_image_losses_forward(mp, ms, ptr(match_lr), B, H, H, hf, hf, 1, ptr(losses), ptr(ws), None) == 0
+    g_depth, g_tex, g_match = torch.zeros_like(r_depth), torch.empty_like(r_tex), torch.empty_like(match_lr)
+    gp, gs = views([g_depth[:, 3], g_tex[:, :3], g_tex[:, 3], g_depth[:, 2], None])
+    assert lib.scp_image_losses_backward(mp, ms, ptr(match_lr), B, H, H, hf, hf, 1, ptr(w), ptr(ws), gp, gs, ptr(g_match),
+                                         None) == 0
+    return dict(losses=rel(losses, ref), g_r_depth=rel(g_depth, lv[0].grad), g_r_tex=rel(g_tex, lv[1].grad),
+                g_match_lr=rel(g_match, lv[2].grad))
+
+
+def check_geometry(B=3, seed=1):
+    lib = load('scp_geom', ('scp_project_faces_forward', 'scp_project_faces_backward', 'scp_spmm3'))
+    g = torch.Generator().manual_seed(seed)
+    v, f = synthetic.icosphere(1)
+    N, nf = v.shape[0], f.shape[0]
+    pv = torch.from_numpy(v)[None] + 0.01 * torch.randn(B, N, 3, generator=g)
+    rot, trans = (t.contiguous() for t in synthetic.random_poses(B, g))
+    foc = (3.7 + 0.3 * torch.rand(B, 2, generator=g)).double()
+    pp = (0.1 * (torch.rand(B, 2, generator=g) - 0.5)).double()
+    faces = torch.from_numpy(f)
+    topo = FaceTopology(faces, N)
+    w_sv, w_fv, w_ft = (torch.randn(s, generator=g) for s in ((B, N, 3), (B, nf, 3, 3), (B, nf, 3, 3)))
+    lv = [t.clone().double().requires_grad_(True) for t in (pv, rot, trans)]
+    sv_r = L.project_to_screen(lv[0], foc, pp, lv[1], lv[2])
+    fb = faces[None].repeat(B, 1, 1)
+    fv_r = srf.face_vertices(sv_r + torch.tensor([0., 0., LOOK_AT_Z], dtype=torch.float64), fb)
+    ft_r = srf.face_vertices(sv_r, fb)
+    ((sv_r * w_sv).sum() + (fv_r * w_fv).sum() + (ft_r * w_ft).sum()).backward()
+    sv, fv, ft = torch.empty(B, N, 3), torch.empty(B, nf, 3, 3), torch.empty(B, nf, 3, 3)
+    t3 = trans.reshape(B, 3).contiguous()
+    assert lib.scp_project_faces_forward(ptr(pv), ptr(rot), ptr(t3), ptr(foc), ptr(pp), ptr(topo.faces), B, N, nf,
+                                         float(LOOK_AT_Z), ptr(sv), ptr(fv), ptr(ft), None) == 0
+    g_v, g_R, g_t = torch.empty(B, N, 3), torch.empty(B, 3, 3), torch.empty(B, 3)
+    assert lib.scp_project_faces_backward(ptr(pv), ptr(rot), ptr(t3), ptr(foc), ptr(pp), ptr(topo.csr_off),
+                                          ptr(topo.csr_idx), B, N, nf, ptr(w_sv), ptr(w_fv), ptr(w_ft), ptr(g_v), ptr(g_R),
+                                          ptr(g_t), None) == 0
+    out = dict(screen=rel(sv, sv_r), face_v=rel(fv, fv_r), face_t=rel(ft, ft_r), g_verts=rel(g_v, lv[0].grad),
+               g_rot=rel(g_R, lv[1].grad), g_trans=rel(g_t, lv[2].grad.reshape(B, 3)))
+    # sparse Laplacian product against the dense buffer of LaplacianLoss
+    lap = L.LaplacianLoss(torch.from_numpy(v), faces, average=True)
+    x, y = torch.randn(B, N, 3, generator=g), torch.empty(B, N, 3)
+    assert lib.scp_spmm3(ptr(lap.csr_off), ptr(lap.csr_col), ptr(lap.csr_val), ptr(x), ptr(y), B, N, None) == 0
+    out['laplacian'] = rel(y, torch.matmul(lap.laplacian.double(), x.double()))
+    return out
+
+
+def check_cycle_rows(B=4, P4=64, N=90, k=12, seed=2):
+    lib = load('scp_cycle', ('scp_cycle_rows_forward', 'scp_cycle_rows_backward'))
+    g = torch.Generator().manual_seed(seed)
+    NP, tau = 2 * B, 10.0
+    pc = torch.rand(B, P4, N, generator=g) * 2 - 1
+    pc[:, ::7] -= 25000.
+    A = torch.rand(B, 2, N, generator=g) * 2 - 1
+    dw = torch.rand(B, N, generator=g)
+    src_idx = torch.arange(NP) % B
+    tgt_idx = (torch.arange(NP) + 1 + (torch.arange(NP) // B)) % B
+    rows = torch.stack([torch.randperm(P4, generator=g)[:k] for _ in range(NP)])
+    pts = torch.rand(NP, 2, k, generator=g) * 2 - 1
+    mask_k = (torch.rand(NP, k, generator=g) > 0.3).float()
+    w = torch.rand(NP, generator=g) + 0.5
+    pc_r, A_r = pc.double().requires_grad_(True), A.double().requires_grad_(True)
+    dw_src, dw_tgt = dw.index_select(0, src_idx), dw.index_select(0, tgt_idx)
+    A_src = A_r.index_select(0, src_idx) * (dw_src[:, None] >= 0.5)
+    s_src = (dw_src >= 0.5).double()
+    flat = (tgt_idx[:, None] * P4 + rows).reshape(-1)
+    rr = pc_r.reshape(-1, N).index_select(0, flat).reshape(NP, k, N)
+    Pi = torch.softmax(tau * rr, dim=2) * (dw_tgt[:, None] >= 0.5)
+    match_r = torch.matmul(A_src, Pi.permute(0, 2, 1)) / (torch.matmul(s_src[:, None], Pi.permute(0, 2, 1)) + 1e-5)
+    pair_r = ((match_r - pts.double()).norm(2, 1) * mask_k.double()).sum(1)
+    (pair_r * w.double()).sum().backward()
+    pair, match = torch.empty(NP), torch.empty(NP, 2, k)
+    a = (ptr(pc), ptr(A), ptr(dw), ptr(src_idx), ptr(tgt_idx), ptr(rows), ptr(pts), ptr(mask_k), tau, B, P4, N, NP, k)
+    assert lib.scp_cycle_rows_forward(*a, ptr(pair), ptr(match), None) == 0
+    g_pc, g_A = torch.empty_like(pc), torch.empty_like(A)
+    assert lib.scp_cycle_rows_backward(*a, ptr(w), ptr(g_pc), ptr(g_A), None) == 0
+    return dict(pair_loss=rel(pair, pair_r), match=rel(match, match_r), g_pointcorr=rel(g_pc, pc_r.grad),
+                g_A=rel(g_A, A_r.grad))
+
+
+def main():
+    ok = True
+    for name, fn, tol in (('image losses', check_image_losses, 1e-5), ('geometry', check_geometry, 1e-5),
+                          ('cycle rows', check_cycle_rows, 1e-4)):
+        res = fn()
+        ok &= all(v <= tol for v in res.values())
+        print('%-13s %s' % (name, '  '.join('%s %.1e' % kv for kv in res.items())), flush=True)
+    print('EMU OPS CHECK', 'PASSED' if ok else 'FAILED')
+    return 0 if ok else 1
+
+
+if __name__ == '__main__':
+    sys.exit(main())
