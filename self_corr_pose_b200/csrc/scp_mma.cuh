@@ -8,6 +8,46 @@
 
 namespace scp {
 
+#ifdef SCP_HOST_EMU
+// Host emulation (tools/emu, tests only): the same six helpers in plain C++.  mma_tf32 is a warp collective there too:
+// every lane publishes its fragments, then computes its four outputs of D += A B with the layout documented below.
+__device__ __forceinline__ uint32_t f2tf32(float x)
+{
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    return (u + 0x1000u) & ~0x1fffu;      // cvt.rna: nearest, ties away from zero, 10 mantissa bits kept
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
+{
+    hi = f2tf32(x);
+    lo = f2tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    uint32_t (*frag)[8] = scp_emu_warp_fragments();
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int i = 0; i < 4; i++) frag[lane][i] = a[i];
+    frag[lane][4] = b[0];
+    frag[lane][5] = b[1];
+    __syncwarp();
+    for (int i = 0; i < 4; i++) {
+        const int row = g + (i >= 2 ? 8 : 0), col = 2 * t + (i & 1);
+        float acc = d[i];
+        for (int k = 0; k < 8; k++) {
+            const float av = __uint_as_float(frag[(row & 7) * 4 + (k & 3)][(row >= 8 ? 1 : 0) + (k >= 4 ? 2 : 0)]);
+            const float bv = __uint_as_float(frag[col * 4 + (k & 3)][4 + (k >= 4 ? 1 : 0)]);
+            acc += av * bv;
+        }
+        d[i] = acc;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) { memcpy(smem, gmem, 16); }
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) { memcpy(smem, gmem, 8); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ uint32_t f2tf32(float x)
 {
     uint32_t r;
@@ -45,5 +85,7 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+#endif  // SCP_HOST_EMU
 
 }  // namespace scp

@@ -22,9 +22,10 @@ def test_emulated_softras_kernels_and_candidates_match_the_oracle(capsys):
 
 
 @pytest.mark.skipif(shutil.which('g++') is None, reason='no host C++ compiler')
-def test_emulated_loss_geometry_and_cycle_kernels_match_reference_statements(capsys):
-    """csrc/scp_loss.cu, scp_geom.cu, scp_cycle.cu compiled for the host and called through the C ABI with host pointers:
-    values and gradients against the reference's op-by-op statements in fp64 (the references of the -m gpu tests)."""
+def test_emulated_loss_geometry_cycle_and_correspondence_kernels_match_reference_statements(capsys):
+    """csrc/scp_loss.cu, scp_geom.cu, scp_cycle.cu and scp_corr.cu (its mma.sync / cp.async helpers in their host
+    statement) compiled for the host and called through the C ABI with host pointers: values and gradients against the
+    reference's op-by-op statements in fp64 (the references of the -m gpu tests)."""
     sys.path.insert(0, os.path.join(ROOT, 'tools', 'emu'))
     import run_emu_ops
     rc = run_emu_ops.main()

@@ -28,15 +28,18 @@
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __grid_constant__
+#define __align__(n) alignas(n)
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
+struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{ x, y }; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{ x, y, z, w }; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{ x, y, z, w }; }
 
@@ -54,6 +57,7 @@ struct Cta {
     std::vector<pthread_barrier_t> warp_bar;
     std::vector<uint64_t> warp_slot;      // 32 slots per warp
     std::vector<unsigned char> dyn_smem;  // `extern __shared__` storage
+    std::vector<uint32_t> warp_frag;      // 32 x 8 words per warp: operand fragments of an emulated mma.sync
     int block_or = 0;
 };
 extern thread_local Cta *cta;
@@ -116,6 +120,11 @@ static inline double __shfl_xor_sync(unsigned, double v, int m)
     u = scp_emu_exchange(u, (threadIdx.x & 31) ^ m);
     memcpy(&v, &u, 8);
     return v;
+}
+
+static inline uint32_t (*scp_emu_warp_fragments())[8]
+{
+    return reinterpret_cast<uint32_t (*)[8]>(scp_emu::cta->warp_frag.data() + (threadIdx.x >> 5) * 256);
 }
 
 // ---- memory / arithmetic intrinsics ----

@@ -24,6 +24,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()> 
                 for (auto &b : c.warp_bar) pthread_barrier_init(&b, nullptr, 32);
                 c.warp_slot.assign(nw * 32, 0);
                 c.dyn_smem.assign(dyn_smem + 16, 0);
+                c.warp_frag.assign(nw * 256, 0);
                 std::vector<std::thread> threads;
                 threads.reserve(nt);
                 for (unsigned t = 0; t < nt; t++)

@@ -1,5 +1,5 @@
-"""Functional check WITHOUT a GPU of the fused loss / geometry / cycle kernels: the shipped csrc/scp_loss.cu,
-scp_geom.cu and scp_cycle.cu compiled for the host (tools/emu/build_emu.py) and called through their C ABI with host
+"""Functional check WITHOUT a GPU of the fused loss / geometry / cycle / correspondence kernels: the shipped
+csrc/scp_loss.cu, scp_geom.cu, scp_cycle.cu and scp_corr.cu compiled for the host (tools/emu/build_emu.py) and called through their C ABI with host
 pointers, against the reference's op-by-op statements evaluated in fp64 with torch autograd (the same references the
 -m gpu tests use).  Values and gradients.      python tools/emu/run_emu_ops.py"""
 import ctypes
@@ -146,10 +146,57 @@ def check_cycle_rows(B=4, P4=64, N=90, k=12, seed=2):
                 g_A=rel(g_A, A_r.grad))
 
 
+def check_correspondence(B=2, hf=16, wf=16, N=70, C=64, seed=0):
+    """scp_corr.cu (mma.sync replaced by its host statement in scp_mma.cuh): forward outputs and both feature gradients,
+    fused (row kernel reduces g_mesh_feat too) and split backward, against the reference formulation in fp64."""
+    from oracle import corr as ocorr
+    lib = load('scp_corr', ('scp_corr_workspace_bytes', 'scp_corr_match_forward', 'scp_corr_match_backward'))
+    g = torch.Generator().manual_seed(seed)
+    P = hf * wf
+    img_feat = F.normalize(torch.randn(B, C, P, generator=g), 2, 1)
+    mesh_feat = F.normalize(torch.relu(torch.randn(B, N, C, generator=g)), 2, -1)
+    H = 4 * hf
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, H), indexing='ij')
+    mask = torch.stack([(((xx - 0.1 * b) ** 2 + yy ** 2) < 0.6 ** 2).float() for b in range(B)])
+    pred_v = torch.randn(B, N, 3, generator=g)
+    w_match, w_imatch = torch.randn(B, P, 3, generator=g), torch.randn(B, 2, N, generator=g)
+    w_pool, w_A = torch.randn(B, P // 4, N, generator=g) * 0.01, torch.randn(B, 2, N, generator=g)
+    a64 = img_feat.double().requires_grad_(True)
+    m64 = mesh_feat.double().requires_grad_(True)
+    pc, _, imatch_r, match_r = ocorr.match(a64, m64, mask.double(), pred_v.double(), hf, wf)
+    pool_r = F.interpolate(pc.permute(0, 2, 1).reshape(B, N, hf, wf), (hf // 2, wf // 2), mode='bilinear') \
+        .reshape(B, N, -1).permute(0, 2, 1)
+    grid2 = F.interpolate(ocorr.meshgrid(hf, wf).reshape(1, 2, hf, wf), (hf // 2, wf // 2), mode='bilinear').reshape(2, -1)
+    A_r = torch.matmul(grid2.double()[None], torch.softmax(10.0 * pool_r, dim=1))
+    ((match_r * w_match).sum() + (imatch_r * w_imatch).sum() + (pool_r * w_pool).sum() + (A_r * w_A).sum()).backward()
+
+    mask_down = F.interpolate(mask[:, None], (hf, wf), mode='nearest').reshape(B, -1).contiguous()
+    grid = ocorr.meshgrid(hf, wf).contiguous()
+    f32 = lambda *sh: torch.empty(*sh)
+    pc_full, pc_pool, match, imatch = f32(B, P, N), f32(B, P // 4, N), f32(B, P, 3), f32(B, 2, N)
+    rsum, csum, A_pool, csum_pool = f32(B, P), f32(B, N), f32(B, 2, N), f32(B, N)
+    ws_n = lib.scp_corr_workspace_bytes(B, hf, wf, N)
+    ws = torch.zeros(max(ws_n, 16), dtype=torch.uint8)
+    common = (ptr(img_feat), ptr(mesh_feat), ptr(mask_down), ptr(pred_v), ptr(grid), 10.0, B, hf, wf, N, C)
+    assert lib.scp_corr_match_forward(*common, ptr(pc_full), ptr(pc_pool), ptr(match), ptr(imatch), ptr(rsum), ptr(csum),
+                                      ptr(A_pool), ptr(csum_pool), ptr(ws), ws_n, None) == 0
+    out = dict(pointcorr=rel(pc_full, pc), pool=rel(pc_pool, pool_r), match=rel(match, match_r), imatch=rel(imatch, imatch_r),
+               A_pool=rel(A_pool, A_r))
+    for mode in ('fused', 'split'):
+        os.environ['SCP_CORR_BWD'] = mode
+        g_img, g_mesh = f32(B, C, P), f32(B, N, C)
+        assert lib.scp_corr_match_backward(*common, ptr(match), ptr(imatch), ptr(rsum), ptr(csum), ptr(w_match),
+                                           ptr(w_imatch), ptr(w_pool), None, ptr(A_pool), ptr(csum_pool), ptr(w_A),
+                                           ptr(g_img), ptr(g_mesh), ptr(ws), ws_n, None) == 0
+        out['g_img_' + mode], out['g_mesh_' + mode] = rel(g_img, a64.grad), rel(g_mesh, m64.grad)
+    os.environ.pop('SCP_CORR_BWD', None)
+    return out
+
+
 def main():
     ok = True
     for name, fn, tol in (('image losses', check_image_losses, 1e-5), ('geometry', check_geometry, 1e-5),
-                          ('cycle rows', check_cycle_rows, 1e-4)):
+                          ('cycle rows', check_cycle_rows, 1e-4), ('correspondence', check_correspondence, 1e-3)):
         res = fn()
         ok &= all(v <= tol for v in res.values())
         print('%-13s %s' % (name, '  '.join('%s %.1e' % kv for kv in res.items())), flush=True)
