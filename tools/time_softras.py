@@ -32,4 +32,4 @@ for kind, cfg in _scenes.RENDER_CONFIGS.items():
         torch.cuda.synchronize()
         tf += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
     res[kind] = dict(fwd_ms=tf / n, bwd_ms=tb / n, fwd_us_per_img=1e3 * tf / n / B, bwd_us_per_img=1e3 * tb / n / B)
-print(json.dumps(dict(B=B, size=size, mesh=mesh, nf=int(fv.shape[1]), **res), indent=1))
+print(json.dumps(dict(B=B, size=size, mesh=mesh, nf=int(fv.shape[1]), **{k: {a: round(b, 3) for a, b in v.items() if a.endswith("_ms")} for k, v in res.items()})))
