@@ -148,25 +148,35 @@ int scp_corr_match_backward(const float *img_feat, const float *mesh_feat, const
 /* ---- frozen DINO ViT-S/8: layer-k key features ----------------------------------------------- */
 /* Replaces DINO.forward (model/module/network/dino.py:102-109) / VisionTransformer.get_specific_tokens
  * (third-party/zsp/zsp/method/vision_transformer_flexible.py:249-262): embed 384, 6 heads x 64, MLP 1536,
- * patch 8, LayerNorm eps 1e-6, exact GELU.  Linear weights are bf16 [out][in] (row-major, as nn.Linear
- * stores them), everything else fp32.  All pointers are device pointers. */
+ * patch 8, LayerNorm eps 1e-6, exact GELU.  All pointers are device pointers.
+ *
+ * Two precisions of the tensor-core products (`precision` argument):
+ *   SCP_VIT_X3   (default of the Python layer, the parity mode): fp32-class.  Every operand is carried as a pair of bf16
+ *                numbers hi = bf16(x), lo = bf16(x - hi) and every product as hi*hi + hi*lo + lo*hi with fp32
+ *                accumulation (~2^-16 relative): the reference's ViT is fp32 and its consumer is arg-max / top-k.
+ *                Linear weights are SPLIT bf16 [out][2*in] in the "i32" layout: groups of 32 input columns stored as
+ *                [32 hi | 32 lo].
+ *   SCP_VIT_BF16 (labelled fast mode): plain bf16 operands [out][in]; features 5e-3 off the fp32 reference.
+ * Everything else (biases, LayerNorm vectors, position embedding, residual stream, softmax) is fp32 in both modes. */
 #define SCP_VIT_MAX_BLOCKS 12
+#define SCP_VIT_BF16 0
+#define SCP_VIT_X3 1
 
 typedef struct scp_vit_block {
     const float *ln1_w, *ln1_b;     /* [384] */
-    const void *qkv_w;              /* bf16 [1152][384] */
+    const void *qkv_w;              /* bf16 [1152][384]  (X3: split [1152][768]) */
     const float *qkv_b;             /* [1152] */
-    const void *proj_w;             /* bf16 [384][384] */
+    const void *proj_w;             /* bf16 [384][384]   (X3: split [384][768]) */
     const float *proj_b;            /* [384] */
     const float *ln2_w, *ln2_b;     /* [384] */
-    const void *fc1_w;              /* bf16 [1536][384] */
+    const void *fc1_w;              /* bf16 [1536][384]  (X3: split [1536][768]) */
     const float *fc1_b;             /* [1536] */
-    const void *fc2_w;              /* bf16 [384][1536] */
+    const void *fc2_w;              /* bf16 [384][1536]  (X3: split [384][3072]) */
     const float *fc2_b;             /* [384] */
 } scp_vit_block;
 
 typedef struct scp_vit_weights {
-    const void *patch_w;            /* bf16 [384][192]: conv weight (384,3,8,8) flattened */
+    const void *patch_w;            /* bf16 [384][192]: conv weight (384,3,8,8) flattened  (X3: split [384][384]) */
     const float *patch_b;           /* [384] */
     const float *cls_pos0;          /* [384]  = cls_token + pos_embed[0] */
     const float *pos;               /* [np][384] patch position embeddings ALREADY resampled to the np = (H/8)*(W/8)
@@ -174,33 +184,39 @@ typedef struct scp_vit_weights {
     scp_vit_block blocks[SCP_VIT_MAX_BLOCKS];
 } scp_vit_weights;
 
-size_t scp_vit_workspace_bytes(int B, int H, int W);
+size_t scp_vit_workspace_bytes(int B, int H, int W, int precision);
 
 /*
  * feat[B][384][H/8][W/8] (fp32) = keys of block `n_blocks` (0-based; the reference uses 9) without the CLS
  * token, channel = head*64 + d, after running blocks 0..n_blocks-1 on img[B][3][H][W] (fp32, raw [0,1] RGB).
  */
 int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float *feat, void *feat_tokens, int B, int H, int W,
-                    int n_blocks, void *workspace, size_t workspace_bytes, void *stream);
-/* feat_tokens (may be NULL): the same features token-major in bf16, [B][(H/8)*(W/8)][384] -- the operand layout of
- * scp_dino_argmatch.
+                    int n_blocks, int precision, void *workspace, size_t workspace_bytes, void *stream);
+/* feat_tokens (may be NULL): the same features token-major, the operand layout of scp_dino_argmatch: bf16
+ * [B][(H/8)*(W/8)][384] (SCP_VIT_BF16) or split pairs [B][(H/8)*(W/8)][768] in the i32 layout (SCP_VIT_X3).
  *
  * Arg-max matching of DINO features (model/module/pretrained_corr.py:85-89) without materialising the similarity:
  * for pair p and pixel r of image a_idx[p], best[p][r] encodes max over the pixels c of image w_idx[p] with
  * w_mask[p][c] > 0 of <tokens[a_idx[p]][r], tokens[w_idx[p]][c]> as (order-preserving similarity bits << 32 |
  * 0xffffffff - c); 0 = no unmasked column.  np = pixels per image, a multiple of 256; best is zeroed by the callee. */
 int scp_dino_argmatch(const void *tokens, const long long *a_idx, const long long *w_idx, const float *w_mask, int B,
-                      int np, int NP, unsigned long long *best, void *stream);
+                      int np, int NP, int precision, unsigned long long *best, void *stream);
 
 /* Building blocks of the above, exported for unit tests and reuse:
  *   C[M][N] (fp32) = A[M][K] (bf16) * W[N][K]^T (bf16) + bias[N] (may be NULL); N % 128 == 0, K % 64 == 0.
  *   Persistent tcgen05/TMEM GEMM fed by TMA. */
 int scp_gemm_bf16_tn(const void *A, const void *W, const float *bias, float *C, int M, int N, int K, void *stream);
+/* The same GEMM at fp32-class precision: A [M][2K] and W [N][2K] are split bf16 pairs in the i32 layout; K % 32 == 0. */
+int scp_gemm_bf16x3_tn(const void *A, const void *W, const float *bias, float *C, int M, int N, int K, void *stream);
 /* o[B][T][384] = softmax(q k^T / 8) v per head; q,k,v bf16 [B*6][T][64] (vision_transformer_flexible.py:85-101). */
 int scp_attention_bf16(const void *q, const void *k, const void *v, void *o, int B, int T, void *stream);
 /* Same result on the tcgen05 tensor cores (S and O tiles in TMEM, TMA-staged operands); v is passed TRANSPOSED:
  * vt[B*6][64][Tp] bf16, Tp = T rounded up to a multiple of 8, columns t >= T zero.  Used by scp_vit_s8_keys. */
 int scp_attention_tc5(const void *q, const void *k, const void *vt, void *o, int B, int T, void *stream);
+/* fp32-class attention (split operands, P split by the softmax warps): qk = split q | k token-major [B*T][1536] (head h of
+ * q: physical columns [128h, 128h+128), of k: 768 + the same; i32 layout), vt = two planes [2][B*6*64][Tp] (hi, lo) with
+ * zero padding, o = split [B*T][768]. */
+int scp_attention_x3(const void *qk, const void *vt, void *o, int B, int T, void *stream);
 
 /* ---- pre-training cycle loss: the k gathered target rows of every image pair ------------------------------ */
 /*

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, 'libscp_b200.so')
 _VARIANT = os.environ.get('SCP_LIB_VARIANT', '')
 if _VARIANT:
     LIB_PATH = os.path.join(_HERE, 'libscp_b200.%s.so' % _VARIANT)
-ABI_VERSION = 4
+ABI_VERSION = 5
+VIT_BF16, VIT_X3 = 0, 1      # `precision` of the ViT entry points (include/scp_b200.h)
 
 _f = ctypes.c_void_p   # device pointers travel as integers
 _i = ctypes.c_int
@@ -51,9 +52,11 @@ _SIGNATURES.update({
     'scp_gemm_bf16_tn': ([_f, _f, _f, _f, _i, _i, _i, _f], _i),
     'scp_attention_bf16': ([_f, _f, _f, _f, _i, _i, _f], _i),
     'scp_attention_tc5': ([_f, _f, _f, _f, _i, _i, _f], _i),
-    'scp_vit_workspace_bytes': ([_i, _i, _i], _sz),
-    'scp_vit_s8_keys': ([ctypes.POINTER(VitWeights), _f, _f, _f, _i, _i, _i, _i, _f, _sz, _f], _i),
-    'scp_dino_argmatch': ([_f, _f, _f, _f, _i, _i, _i, _f, _f], _i),
+    'scp_gemm_bf16x3_tn': ([_f, _f, _f, _f, _i, _i, _i, _f], _i),
+    'scp_attention_x3': ([_f, _f, _f, _i, _i, _f], _i),
+    'scp_vit_workspace_bytes': ([_i, _i, _i, _i], _sz),
+    'scp_vit_s8_keys': ([ctypes.POINTER(VitWeights), _f, _f, _f, _i, _i, _i, _i, _i, _f, _sz, _f], _i),
+    'scp_dino_argmatch': ([_f, _f, _f, _f, _i, _i, _i, _i, _f, _f], _i),
 })
 
 _pp = ctypes.POINTER(ctypes.c_void_p)

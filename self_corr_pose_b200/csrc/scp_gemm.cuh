@@ -40,6 +40,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
+// ---- fp32-class precision on the bf16 tensor cores ("x3" mode, NT = 3) -----------------------------------------
+// A value x is carried as TWO bf16 numbers, hi = bf16(x) and lo = bf16(x - hi) (16 mantissa bits together), and a
+// product of two such operands as three tensor-core products:  a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi  (the dropped
+// a_lo*w_lo term and the residual beyond lo are ~2^-16 relative), accumulated in fp32 in TMEM.  This is the mode that
+// meets the 1e-3 / 99.9 % arg-max parity contract against the reference's fp32 ViT; plain bf16 (NT = 1) is 5e-3.
+//
+// Memory layout of a split operand ("i32" layout): row r of a logical [rows][K] matrix is 2K bf16 numbers, groups of
+// 32 logical columns stored as [32 hi | 32 lo] (128 bytes).  A 64-element (128-byte) TMA box row therefore holds both
+// halves of 32 logical k values: one smem stage carries everything its three products need, the GEMM main loop is
+// the plain one over 2K physical columns with six K=16 instructions per stage and accumulator instead of four, and an
+// epilogue's 32-column accumulator chunk maps to exactly one 128-byte box row of the split output.
+// Split a pair of fp32 values: returns the packed hi pair, writes the packed lo pair.
+__device__ __forceinline__ uint32_t split_bf16x2(float a, float b, uint32_t &lo_pair)
+{
+    const uint32_t h = pack_bf16x2(a, b);
+    lo_pair = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xffff0000u));
+    return h;
+}
+
 struct Shape {
     int M, N, K;
     int a_box_rows;   // rows of the A tensor-map box (BM; 128 for a matrix of at most 128 rows)
@@ -68,7 +87,7 @@ struct tma_store_mode<E, decltype((void)E::kTmaStoreBf16)> { static constexpr bo
 //   static constexpr bool kTmaReduceAdd (optional third mode, takes precedence): C[tile] += acc + bias[col] through
 //                     cp.reduce.async.bulk.tensor (.add, fp32) from a swizzled smem box -- the read-modify-write of
 //                     the residual stream happens at L2, the SM issues no loads; needs `const float *bias` member
-template <class Epi>
+template <class Epi, int NT = 1>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_c, Shape s, Epi epi)
@@ -134,11 +153,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t sa = tc5::smem_u32(smem + stage * STAGE_BYTES), sb = sa + BM * BK * 2;
 #pragma unroll
                     for (int mh = 0; mh < MH; mh++) {
+                        if constexpr (NT == 3) {
+                            // split operands: a 128-byte tile row = [32 hi | 32 lo] of 32 logical k values; per K=16
+                            // chunk c: hi*hi, hi*lo, lo*hi (byte offsets c*32 for hi, 64 + c*32 for lo)
 #pragma unroll
-                        for (int k = 0; k < BK / 16; k++) {
-                            // advance 16 elements (32 B) along K inside the 128-byte swizzle atom
-                            tc5::umma_bf16(d_tmem + mh * BN, tc5::umma_desc_sw128(sa + mh * (128 * BK * 2) + k * 32),
-                                           tc5::umma_desc_sw128(sb + k * 32), idesc, (kb | k) != 0);
+                            for (int c = 0; c < 2; c++) {
+                                const uint32_t ah = sa + mh * (128 * BK * 2) + c * 32, bh = sb + c * 32;
+                                tc5::umma_bf16(d_tmem + mh * BN, tc5::umma_desc_sw128(ah), tc5::umma_desc_sw128(bh), idesc,
+                                               (kb | c) != 0);
+                                tc5::umma_bf16(d_tmem + mh * BN, tc5::umma_desc_sw128(ah), tc5::umma_desc_sw128(bh + 64), idesc, 1);
+                                tc5::umma_bf16(d_tmem + mh * BN, tc5::umma_desc_sw128(ah + 64), tc5::umma_desc_sw128(bh), idesc, 1);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++) {
+                                // advance 16 elements (32 B) along K inside the 128-byte swizzle atom
+                                tc5::umma_bf16(d_tmem + mh * BN, tc5::umma_desc_sw128(sa + mh * (128 * BK * 2) + k * 32),
+                                               tc5::umma_desc_sw128(sb + k * 32), idesc, (kb | k) != 0);
+                            }
                         }
                     }
                     tc5::umma_commit(empty + stage);               // frees the smem slot when the MMAs retire
@@ -159,7 +191,41 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tc5::mbar_wait(tfull + acc, acc_phase);
             tc5::tc_fence_after();
             const int row0 = m_blk * BM + half * 128 + quarter * 32;
-            if constexpr (tma_store_mode<Epi>::value) {
+            if constexpr (tma_store_mode<Epi>::value && NT == 3) {
+              // split output: one 32-column accumulator chunk -> one box row [32 hi | 32 lo] (128 B); physical column 2c
+              uint8_t *box = epi_buf + (warp - 2) * TMA_TILE_BYTES;
+#pragma unroll 1
+              for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tc5::tmem_ld32(tmem_base + t_acc + acc * ACC_COLS + c0, v);
+                if constexpr (Epi::kMixed) {
+                    if (epi.direct(n_blk * BN + c0)) {
+                        if (row0 + lane < s.M) epi(row0 + lane, n_blk * BN + c0, v);
+                        continue;
+                    }
+                }
+                if (lane == 0) tc5::tma_store_wait_read();
+                __syncwarp();
+                const float4 *b4 = reinterpret_cast<const float4 *>(epi.bias + n_blk * BN + c0);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {                                   // 8 columns -> one 16-byte chunk hi + one lo
+                    const float4 ba = __ldg(b4 + 2 * j), bb = __ldg(b4 + 2 * j + 1);
+                    uint32_t h[4], l[4];
+                    h[0] = split_bf16x2(epi.apply(v[8 * j + 0] + ba.x), epi.apply(v[8 * j + 1] + ba.y), l[0]);
+                    h[1] = split_bf16x2(epi.apply(v[8 * j + 2] + ba.z), epi.apply(v[8 * j + 3] + ba.w), l[1]);
+                    h[2] = split_bf16x2(epi.apply(v[8 * j + 4] + bb.x), epi.apply(v[8 * j + 5] + bb.y), l[2]);
+                    h[3] = split_bf16x2(epi.apply(v[8 * j + 6] + bb.z), epi.apply(v[8 * j + 7] + bb.w), l[3]);
+                    *reinterpret_cast<uint4 *>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4 *>(box + lane * 128 + (((4 + j) ^ (lane & 7)) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+                tc5::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && row0 < s.M) {   // rows past M are clipped by the tensor map
+                    tc5::tma_store_2d(&tmap_c, box, 2 * (n_blk * BN + c0), row0);
+                    tc5::tma_store_commit();
+                }
+              }
+            } else if constexpr (tma_store_mode<Epi>::value) {
               uint8_t *box = epi_buf + (warp - 2) * TMA_TILE_BYTES;            // 32 rows x 128 B (64 bf16), SWIZZLE_128B
 #pragma unroll 1
               for (int cg = 0; cg < BN; cg += 64) {
@@ -313,7 +379,9 @@ inline int num_sms()
 
 // A[M,K] (pitch lda), W[N,K] (pitch ldw); N % 128 == 0, K % 64 == 0
 // c_out / ldc: fp32 output matrix of the kTmaReduceAdd epilogue / bf16 output of the kTmaStoreBf16 epilogue (ignored otherwise)
-template <class Epi>
+// NT = 3: A and W are split operands in the i32 layout (see above): K is the LOGICAL depth (K % 32 == 0), lda / ldw /
+// ldc are PHYSICAL pitches in bf16 elements (>= 2K); a bf16 output (kTmaStoreBf16) is written split as well.
+template <class Epi, int NT = 1>
 int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, const Epi &epi, cudaStream_t st,
            void *c_out = nullptr, int ldc = 0, const long long *a_idx = nullptr, const long long *w_idx = nullptr,
            int rows_per_batch = 0, long a_rows_total = 0, long w_rows_total = 0)
@@ -324,10 +392,11 @@ int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, 
         set_last_error("tcgen05 gemm: batched mode needs rows_per_batch %% %d == 0", BM);
         return -1;
     }
-    if (M <= 0 || N % BN != 0 || K % BK != 0) {
+    if (M <= 0 || N % BN != 0 || (NT == 3 ? K % 32 : K % BK) != 0) {
         set_last_error("tcgen05 gemm: unsupported shape M=%d N=%d K=%d", M, N, K);
         return -1;
     }
+    if (NT == 3) K *= 2;   // physical columns of the split operands
     CUtensorMap ta, tw;
     int a_box = BM;
     if (!make_tmap_bf16(&ta, A, K, batched ? a_rows_total : M, lda, BM)) {
@@ -350,20 +419,21 @@ int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, 
     }
     if constexpr (tma_store_mode<Epi>::value) {   // bf16 output [M][N], box = 64 columns x 32 rows
         // (an epilogue with direct column ranges may store fewer than N columns through TMA: the matrix is ldc wide)
-        if (!c_out || !make_tmap_bf16(&tc, c_out, N < ldc ? N : ldc, M, ldc, 32)) {
+        const int out_cols = NT == 3 ? 2 * N : N;
+        if (!c_out || !make_tmap_bf16(&tc, c_out, out_cols < ldc ? out_cols : ldc, M, ldc, 32)) {
             set_last_error("tcgen05 gemm: bf16 output tensor map failed");
             return -1;
         }
     }
     static bool attr_done = false;  // per template instantiation
     if (!attr_done) {
-        cudaFuncSetAttribute(gemm_bf16_tn_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_bf16_tn_kernel<Epi, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         attr_done = true;
     }
     const int ntiles = ((M + BM - 1) / BM) * (N / BN);
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
     Shape s{ M, N, K, a_box, a_idx, w_idx, rows_per_batch };
-    gemm_bf16_tn_kernel<Epi><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tw, tc, s, epi);
+    gemm_bf16_tn_kernel<Epi, NT><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tw, tc, s, epi);
     return 0;
 }
 

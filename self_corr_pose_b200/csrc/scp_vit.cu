@@ -19,6 +19,7 @@
 #include "scp_gemm.cuh"
 #include "scp_fa.cuh"
 #include "scp_fa2.cuh"
+#include "scp_fa3.cuh"
 
 namespace scp {
 namespace vit {
@@ -83,6 +84,68 @@ __global__ void layernorm_kernel(const float *__restrict__ x, const float *__res
         __align__(8) bf16 o[4] = { __float2bfloat16(v[i].x * rstd * ww.x + bb.x), __float2bfloat16(v[i].y * rstd * ww.y + bb.y),
                                   __float2bfloat16(v[i].z * rstd * ww.z + bb.z), __float2bfloat16(v[i].w * rstd * ww.w + bb.w) };
         *reinterpret_cast<uint2 *>(y + row * D + c) = *reinterpret_cast<const uint2 *>(o);
+    }
+}
+
+// ---- x3 (fp32-class) variants: outputs are SPLIT bf16 pairs in the i32 layout of scp_gemm.cuh -------------------
+// physical element index of logical column c (hi part; the lo part is 32 elements further)
+__device__ __forceinline__ int i32_col(int c) { return ((c >> 5) << 6) + (c & 31); }
+
+__global__ void im2col_x3_kernel(const float *__restrict__ img, bf16 *__restrict__ out, int B, int H, int W)
+{
+    const int pw = W / PATCH, ph = H / PATCH;
+    const long total = (long)B * ph * pw * 3 * PATCH;  // one thread per (patch, c, dy): 8 contiguous pixels
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int dy = i % PATCH;
+    const int c = (i / PATCH) % 3;
+    const long patch = i / (3 * PATCH);
+    const int px = patch % pw, py = (patch / pw) % ph, b = patch / ((long)pw * ph);
+    const float *src = img + (((long)b * 3 + c) * H + py * PATCH + dy) * W + px * PATCH;
+    const float4 a = *reinterpret_cast<const float4 *>(src), d = *reinterpret_cast<const float4 *>(src + 4);
+    uint32_t h[4], l[4];
+    h[0] = scp::gemm::split_bf16x2(a.x, a.y, l[0]);
+    h[1] = scp::gemm::split_bf16x2(a.z, a.w, l[1]);
+    h[2] = scp::gemm::split_bf16x2(d.x, d.y, l[2]);
+    h[3] = scp::gemm::split_bf16x2(d.z, d.w, l[3]);
+    bf16 *dst = out + patch * (2 * KP) + i32_col(c * PATCH * PATCH + dy * PATCH);
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(dst + 32) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// LayerNorm over D = 384 (eps 1e-6), one warp per token, fp32 in -> split bf16 pairs out (row pitch 2 D)
+__global__ void layernorm_x3_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
+                                    bf16 *__restrict__ y, long M)
+{
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + row * D);
+    float4 v[3];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        v[i] = xr[lane + 32 * i];
+        s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const float mean = warp_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-6f);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int c = 4 * (lane + 32 * i);
+        const float4 ww = *reinterpret_cast<const float4 *>(w + c), bb = *reinterpret_cast<const float4 *>(b + c);
+        uint32_t h[2], l[2];
+        h[0] = scp::gemm::split_bf16x2(v[i].x * rstd * ww.x + bb.x, v[i].y * rstd * ww.y + bb.y, l[0]);
+        h[1] = scp::gemm::split_bf16x2(v[i].z * rstd * ww.z + bb.z, v[i].w * rstd * ww.w + bb.w, l[1]);
+        bf16 *dst = y + row * (2 * D) + i32_col(c);
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(h[0], h[1]);
+        *reinterpret_cast<uint2 *>(dst + 32) = make_uint2(l[0], l[1]);
     }
 }
 
@@ -170,6 +233,35 @@ struct EpiQKVTokens {  // q | k token-major bf16 in one [M][768] matrix (bias ad
     }
 };
 
+struct EpiQKVTokens3 {  // x3 mode: q | k split pairs through the TMA-store epilogue into one [M][1536] matrix (i32 layout);
+                        // v TRANSPOSED per head as two planes vt[2][B*6*64][Tp] (hi, lo)
+    static constexpr bool kStaged = false;
+    static constexpr bool kTmaReduceAdd = false;
+    static constexpr bool kMixed = true;
+    static constexpr bool kTmaStoreBf16 = true;
+    bf16 *vt; const float *bias; int T, Tp; long plane;
+    __device__ __forceinline__ float apply(float z) const { return z; }
+    __device__ __forceinline__ bool direct(int col0) const { return col0 >= 2 * D; }
+    __device__ __forceinline__ void operator()(int row, int col0, const float (&a)[32]) const
+    {
+        const int c = col0 - 2 * D, h = c >> 6, d0 = c & 63;
+        const int b = row / T, t = row - b * T;
+        bf16 *dst = vt + (((long)b * HEADS + h) * HD + d0) * Tp + t;
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias + col0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 bb = __ldg(b4 + i);
+            const float z[4] = { a[4 * i] + bb.x, a[4 * i + 1] + bb.y, a[4 * i + 2] + bb.z, a[4 * i + 3] + bb.w };
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bf16 hi = __float2bfloat16(z[j]);
+                dst[(long)(4 * i + j) * Tp] = hi;
+                dst[plane + (long)(4 * i + j) * Tp] = __float2bfloat16(z[j] - __bfloat162float(hi));
+            }
+        }
+    }
+};
+
 struct EpiQKVPlain {  // q/k/v[b][h][t][64] bf16 (layout of the mma.sync attention variant)
     static constexpr bool kStaged = true;
     static constexpr bool kTmaReduceAdd = false;
@@ -227,6 +319,7 @@ struct EpiKeys {  // feat[b][col][t-1] = acc + bias for patch tokens (CLS droppe
     static constexpr bool kMixed = false;
     float *feat; const float *bias; int T;
     bf16 *tokens;   // optional second copy, token-major bf16 [b][t-1][384]: the K-major operand of the arg-match GEMM
+    int split;      // x3 mode: the token copy is written as split pairs, [b][t-1][768] in the i32 layout
     __device__ void operator()(int row, int col0, const float (&a)[32]) const
     {
         const int b = row / T, t = row - b * T;
@@ -237,7 +330,17 @@ struct EpiKeys {  // feat[b][col][t-1] = acc + bias for patch tokens (CLS droppe
         for (int i = 0; i < 32; i++) v[i] = a[i] + bias[col0 + i];
 #pragma unroll
         for (int i = 0; i < 32; i++) dst[(long)i * (T - 1)] = v[i];
-        if (tokens != nullptr) {
+        if (tokens != nullptr && split) {
+            uint4 *q = reinterpret_cast<uint4 *>(tokens + ((long)b * (T - 1) + (t - 1)) * (2 * D) + 2 * col0);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) h[e] = scp::gemm::split_bf16x2(v[8 * i + 2 * e], v[8 * i + 2 * e + 1], l[e]);
+                q[i] = make_uint4(h[0], h[1], h[2], h[3]);
+                q[4 + i] = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+        } else if (tokens != nullptr) {
             uint4 *q = reinterpret_cast<uint4 *>(tokens + ((long)b * (T - 1) + (t - 1)) * D + col0);
 #pragma unroll
             for (int i = 0; i < 4; i++)
@@ -531,58 +634,103 @@ extern "C" int scp_attention_tc5(const void *q, const void *k, const void *vt, v
     return rc ? rc : scp::check_launch("scp_attention_tc5");
 }
 
-extern "C" size_t scp_vit_workspace_bytes(int B, int H, int W)
+// q | k split token-major [B*T][1536] (i32 layout), vt planes [2][B*6*64][Tp], o split [B*T][768]
+static int launch_fa3(const bf16 *qk, const bf16 *vt, bf16 *o, int B, int T, int Tp, cudaStream_t st)
 {
-    if (B <= 0 || H <= 0 || W <= 0 || H % PATCH || W % PATCH) return 0;
-    const size_t np = (size_t)(H / PATCH) * (W / PATCH), T = np + 1, M = (size_t)B * T;
-    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
-    const size_t Tp = (T + 7) / 8 * 8;
-    return al(M * D * 4) + al(M * D * 2) * 4 + al((size_t)B * D * Tp * 2) + al(M * MLP * 2) + al((size_t)B * np * KP * 2);
+    CUtensorMap tq, tk, tv;
+    const uint64_t rows = (uint64_t)B * T, inner = 4 * D;
+    if (!scp::gemm::make_tmap_bf16(&tq, qk, inner, rows, inner, scp::fa3::BQ) ||
+        !scp::gemm::make_tmap_bf16(&tk, qk, inner, rows, inner, scp::fa3::BKV) ||
+        !scp::gemm::make_tmap_bf16(&tv, vt, Tp, (uint64_t)2 * B * HEADS * HD, Tp, 64)) {
+        scp::set_last_error("tcgen05 attention (x3): cuTensorMapEncodeTiled failed");
+        return -1;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(scp::fa3::fa3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scp::fa3::SMEM_BYTES);
+        attr_done = true;
+    }
+    const float scale_log2e = 0.125f * 1.4426950408889634f;
+    scp::fa3::fa3_fwd_kernel<<<dim3((T + scp::fa3::BQ - 1) / scp::fa3::BQ, B * HEADS), scp::fa3::NTHREADS,
+                               scp::fa3::SMEM_BYTES, st>>>(tq, tk, tv, o, T, scale_log2e, B * HEADS * HD);
+    return 0;
 }
 
-extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float *feat, void *feat_tokens, int B, int H,
-                               int W, int n_blocks, void *workspace, size_t workspace_bytes, void *stream)
+extern "C" int scp_attention_x3(const void *qk, const void *vt, void *o, int B, int T, void *stream)
 {
-    if (!w || B <= 0 || H % PATCH || W % PATCH || n_blocks < 0 || n_blocks >= SCP_VIT_MAX_BLOCKS) {
-        scp::set_last_error("scp_vit_s8_keys: bad arguments (B=%d H=%d W=%d n_blocks=%d)", B, H, W, n_blocks);
-        return -1;
-    }
-    if (!workspace || workspace_bytes < scp_vit_workspace_bytes(B, H, W)) {
-        scp::set_last_error("scp_vit_s8_keys: workspace too small");
-        return -1;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || T <= 0) { scp::set_last_error("scp_attention_x3: bad shape"); return -1; }
+    const int Tp = (T + 7) / 8 * 8;
+    int rc = launch_fa3((const bf16 *)qk, (const bf16 *)vt, (bf16 *)o, B, T, Tp, (cudaStream_t)stream);
+    return rc ? rc : scp::check_launch("scp_attention_x3");
+}
+
+extern "C" int scp_gemm_bf16x3_tn(const void *A, const void *W, const float *bias, float *C, int M, int N, int K,
+                                  void *stream)
+{
+    EpiPlain epi{ C, bias, N };
+    int rc = scp::gemm::launch<EpiPlain, 3>(A, 2 * K, W, 2 * K, M, N, K, epi, (cudaStream_t)stream);
+    return rc ? rc : scp::check_launch("scp_gemm_bf16x3_tn");
+}
+
+// bf16 element count multiplier of the activation buffers: split pairs in x3 mode
+static inline size_t prec_mul(int precision) { return precision == SCP_VIT_X3 ? 2 : 1; }
+
+extern "C" size_t scp_vit_workspace_bytes(int B, int H, int W, int precision)
+{
+    if (B <= 0 || H <= 0 || W <= 0 || H % PATCH || W % PATCH) return 0;
+    const size_t np = (size_t)(H / PATCH) * (W / PATCH), T = np + 1, M = (size_t)B * T, pm = prec_mul(precision);
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t Tp = (T + 7) / 8 * 8;
+    return al(M * D * 4) + al(M * D * 2 * pm) * 4 + al((size_t)B * D * Tp * 2 * pm) + al(M * MLP * 2 * pm) +
+           al((size_t)B * np * KP * 2 * pm);
+}
+
+template <int NT>
+static int vit_keys_impl(const scp_vit_weights *w, const float *img, float *feat, void *feat_tokens, int B, int H, int W,
+                         int n_blocks, void *workspace, cudaStream_t st)
+{
+    constexpr size_t pm = NT == 3 ? 2 : 1;
     const int np = (H / PATCH) * (W / PATCH), T = np + 1;
     const long M = (long)B * T;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     char *p = (char *)workspace;
     float *x = (float *)p; p += al(M * D * 4);
-    bf16 *y = (bf16 *)p; p += al(M * D * 2);
-    bf16 *qb = (bf16 *)p; p += al(M * D * 2);
-    bf16 *kb = (bf16 *)p; p += al(M * D * 2);
+    bf16 *y = (bf16 *)p; p += al(M * D * 2 * pm);
+    bf16 *qb = (bf16 *)p; p += al(M * D * 2 * pm);          // q | k: one [M][768 * pm] matrix spanning qb and kb
+    bf16 *kb = (bf16 *)p; p += al(M * D * 2 * pm);
     const int Tp = (T + 7) / 8 * 8;
-    bf16 *vb = (bf16 *)p; p += al((size_t)B * D * Tp * 2);   // V transposed per head: [B][6][64][Tp]
-    cudaMemsetAsync(vb, 0, (size_t)B * D * Tp * 2, st);     // pad columns t in [T, Tp) must be zero
-    bf16 *ob = (bf16 *)p; p += al(M * D * 2);
-    bf16 *hb = (bf16 *)p; p += al(M * MLP * 2);
+    bf16 *vb = (bf16 *)p; p += al((size_t)B * D * Tp * 2 * pm);   // V transposed per head: [B][6][64][Tp] (x3: hi plane, lo plane)
+    cudaMemsetAsync(vb, 0, (size_t)B * D * Tp * 2 * pm, st);     // pad columns t in [T, Tp) must be zero
+    bf16 *ob = (bf16 *)p; p += al(M * D * 2 * pm);
+    bf16 *hb = (bf16 *)p; p += al(M * MLP * 2 * pm);
     bf16 *a0 = (bf16 *)p;
+    constexpr int PD = (int)pm * D, PMLP = (int)pm * MLP, PKP = (int)pm * KP;   // physical row pitches
 
     int rc;
     // tokens
     {
         const long n = (long)B * np * 3 * PATCH;
-        im2col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img, a0, B, H, W);
+        if (NT == 3) im2col_x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img, a0, B, H, W);
+        else im2col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img, a0, B, H, W);
         cls_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(x, w->cls_pos0, B, T);
         EpiPatch epi{ x, w->patch_b, w->pos, np, T };
-        if ((rc = scp::gemm::launch(a0, KP, w->patch_w, KP, B * np, D, KP, epi, st))) return rc;
+        if ((rc = scp::gemm::launch<EpiPatch, NT>(a0, PKP, w->patch_w, PKP, B * np, D, KP, epi, st))) return rc;
     }
     const bool use_tc5_attention = attention_variant() != 0;
     const unsigned ln_grid = (unsigned)((M + 7) / 8);
     const float scale_log2e = 0.125f * 1.4426950408889634f;
+    auto layernorm = [&](const float *lw, const float *lb) {
+        if (NT == 3) layernorm_x3_kernel<<<ln_grid, 256, 0, st>>>(x, lw, lb, y, M);
+        else layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, lw, lb, y, M);
+    };
     for (int i = 0; i < n_blocks; i++) {
         const scp_vit_block &bw = w->blocks[i];
-        layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, bw.ln1_w, bw.ln1_b, y, M);
-        if (attention_variant() == 2) {   // fa2: q | k token-major in one matrix (qb and kb are adjacent), V^T per head
+        layernorm(bw.ln1_w, bw.ln1_b);
+        if constexpr (NT == 3) {          // split q | k token-major, split V^T planes, fa3
+            EpiQKVTokens3 eq{ vb, bw.qkv_b, T, Tp, (long)B * D * Tp };
+            if ((rc = scp::gemm::launch<EpiQKVTokens3, 3>(y, PD, bw.qkv_w, PD, (int)M, 3 * D, D, eq, st, qb, 4 * D))) return rc;
+            if ((rc = launch_fa3(qb, vb, ob, B, T, Tp, st))) return rc;
+        } else if (attention_variant() == 2) {   // fa2: q | k token-major in one matrix (qb and kb are adjacent), V^T per head
             EpiQKVTokens eq{ vb, bw.qkv_b, T, Tp };
             if ((rc = scp::gemm::launch(y, D, bw.qkv_w, D, (int)M, 3 * D, D, eq, st, qb, 2 * D))) return rc;
             if ((rc = launch_fa(qb, qb, vb, ob, B, T, Tp, st, true))) return rc;
@@ -596,38 +744,63 @@ extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float
             attention_kernel<<<dim3((T + AQ - 1) / AQ, B * HEADS), 128, 0, st>>>(qb, kb, vb, ob, T, scale_log2e);
         }
         EpiResidual ep{ bw.proj_b };
-        if ((rc = scp::gemm::launch(ob, D, bw.proj_w, D, (int)M, D, D, ep, st, x, D))) return rc;
-        layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, bw.ln2_w, bw.ln2_b, y, M);
+        if ((rc = scp::gemm::launch<EpiResidual, NT>(ob, PD, bw.proj_w, PD, (int)M, D, D, ep, st, x, D))) return rc;
+        layernorm(bw.ln2_w, bw.ln2_b);
         EpiGelu eg{ bw.fc1_b };
-        if ((rc = scp::gemm::launch(y, D, bw.fc1_w, D, (int)M, MLP, D, eg, st, hb, MLP))) return rc;
+        if ((rc = scp::gemm::launch<EpiGelu, NT>(y, PD, bw.fc1_w, PD, (int)M, MLP, D, eg, st, hb, PMLP))) return rc;
         EpiResidual e2{ bw.fc2_b };
-        if ((rc = scp::gemm::launch(hb, MLP, bw.fc2_w, MLP, (int)M, D, MLP, e2, st, x, D))) return rc;
+        if ((rc = scp::gemm::launch<EpiResidual, NT>(hb, PMLP, bw.fc2_w, PMLP, (int)M, D, MLP, e2, st, x, D))) return rc;
     }
     // key projection of block `n_blocks` (rows D..2D-1 of its qkv weight) on norm1(x)
     {
         const scp_vit_block &bw = w->blocks[n_blocks];
-        layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, bw.ln1_w, bw.ln1_b, y, M);
-        EpiKeys ek{ feat, bw.qkv_b + D, T, (bf16 *)feat_tokens };
-        if ((rc = scp::gemm::launch(y, D, (const bf16 *)bw.qkv_w + (size_t)D * D, D, (int)M, D, D, ek, st))) return rc;
+        layernorm(bw.ln1_w, bw.ln1_b);
+        EpiKeys ek{ feat, bw.qkv_b + D, T, (bf16 *)feat_tokens, NT == 3 };
+        if ((rc = scp::gemm::launch<EpiKeys, NT>(y, PD, (const bf16 *)bw.qkv_w + (size_t)D * PD, PD, (int)M, D, D, ek, st))) return rc;
     }
     return scp::check_launch("scp_vit_s8_keys");
 }
 
+extern "C" int scp_vit_s8_keys(const scp_vit_weights *w, const float *img, float *feat, void *feat_tokens, int B, int H,
+                               int W, int n_blocks, int precision, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!w || B <= 0 || H % PATCH || W % PATCH || n_blocks < 0 || n_blocks >= SCP_VIT_MAX_BLOCKS ||
+        (precision != SCP_VIT_BF16 && precision != SCP_VIT_X3)) {
+        scp::set_last_error("scp_vit_s8_keys: bad arguments (B=%d H=%d W=%d n_blocks=%d precision=%d)", B, H, W, n_blocks,
+                            precision);
+        return -1;
+    }
+    if (!workspace || workspace_bytes < scp_vit_workspace_bytes(B, H, W, precision)) {
+        scp::set_last_error("scp_vit_s8_keys: workspace too small");
+        return -1;
+    }
+    return precision == SCP_VIT_X3
+               ? vit_keys_impl<3>(w, img, feat, feat_tokens, B, H, W, n_blocks, workspace, (cudaStream_t)stream)
+               : vit_keys_impl<1>(w, img, feat, feat_tokens, B, H, W, n_blocks, workspace, (cudaStream_t)stream);
+}
+
 // fw/bw arg-max matching of DINO features without the (pairs, np, np) similarity tensor: for pair p and every pixel r
 // of image a_idx[p]: best[p][r] = arg-max over the pixels c of image w_idx[p] with w_mask[p][c] > 0 of
-// <tokens[a_idx[p]][r], tokens[w_idx[p]][c]> (bf16 operands, fp32 accumulation on the tcgen05 GEMM).
+// <tokens[a_idx[p]][r], tokens[w_idx[p]][c]> (fp32 accumulation on the tcgen05 GEMM; operands bf16, or split bf16 pairs =
+// fp32-class products with precision = SCP_VIT_X3, where tokens is [B][np][768] in the i32 layout).
 extern "C" int scp_dino_argmatch(const void *tokens, const long long *a_idx, const long long *w_idx, const float *w_mask,
-                                 int B, int np, int NP, unsigned long long *best, void *stream)
+                                 int B, int np, int NP, int precision, unsigned long long *best, void *stream)
 {
-    if (!tokens || !a_idx || !w_idx || !w_mask || !best || B <= 0 || NP <= 0 || np <= 0 || np % scp::gemm::BM != 0) {
-        scp::set_last_error("scp_dino_argmatch: bad arguments (B=%d np=%d NP=%d; np must be a multiple of %d)", B, np, NP,
-                            scp::gemm::BM);
+    if (!tokens || !a_idx || !w_idx || !w_mask || !best || B <= 0 || NP <= 0 || np <= 0 || np % scp::gemm::BM != 0 ||
+        (precision != SCP_VIT_BF16 && precision != SCP_VIT_X3)) {
+        scp::set_last_error("scp_dino_argmatch: bad arguments (B=%d np=%d NP=%d precision=%d; np must be a multiple of %d)",
+                            B, np, NP, precision, scp::gemm::BM);
         return -1;
     }
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(best, 0, (size_t)NP * np * sizeof(unsigned long long), st);
     EpiArgmax epi{ best, w_mask, np, np };
-    int rc = scp::gemm::launch(tokens, D, tokens, D, NP * np, np, D, epi, st, nullptr, 0, a_idx, w_idx, np, (long)B * np,
+    int rc;
+    if (precision == SCP_VIT_X3)
+        rc = scp::gemm::launch<EpiArgmax, 3>(tokens, 2 * D, tokens, 2 * D, NP * np, np, D, epi, st, nullptr, 0, a_idx, w_idx, np,
+                                             (long)B * np, (long)B * np);
+    else
+        rc = scp::gemm::launch(tokens, D, tokens, D, NP * np, np, D, epi, st, nullptr, 0, a_idx, w_idx, np, (long)B * np,
                                (long)B * np);
     return rc ? rc : scp::check_launch("scp_dino_argmatch");
 }

@@ -52,13 +52,37 @@ def resampled_pos_embed(pos_embed, w_patches, h_patches):
     return torch.cat((pos_embed[0, :1], patch), dim=0)
 
 
+def split_bf16_i32(t):
+    """fp32 [R, K] -> bf16 [R, 2K] split pairs in the "i32" layout of csrc/scp_gemm.cuh: hi = bf16(x), lo = bf16(x - hi),
+    groups of 32 columns stored as [32 hi | 32 lo] -- the operand format of the fp32-class (x3) tensor-core products."""
+    t = t.float()
+    R, K = t.shape
+    assert K % 32 == 0
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return torch.stack((hi.reshape(R, K // 32, 32), lo.reshape(R, K // 32, 32)), dim=2).reshape(R, 2 * K).contiguous()
+
+
+def merge_bf16_i32(t):
+    """Inverse of split_bf16_i32 up to the split's own rounding: bf16 [..., 2K] -> fp32 [..., K] = hi + lo."""
+    sh = t.shape
+    g = t.float().reshape(*sh[:-1], sh[-1] // 64, 2, 32)
+    return (g[..., 0, :] + g[..., 1, :]).reshape(*sh[:-1], sh[-1] // 2)
+
+
 class DINO(nn.Module):
+    """precision: 'x3' (default; fp32-class split-bf16 products, the mode that meets the parity contract against the
+    reference's fp32 ViT) or 'bf16' (labelled fast mode, features 5e-3 off); env SCP_VIT_PRECISION overrides the default."""
     feat_layer = 9
     patch_size = 8
     pretrain_path = 'pretrain/dino_deitsmall8_pretrain.pth'
 
-    def __init__(self, state_dict=None):
+    def __init__(self, state_dict=None, precision=None):
         super().__init__()
+        precision = precision or os.environ.get('SCP_VIT_PRECISION', 'x3')
+        if precision not in ('x3', 'bf16'):
+            raise ValueError("DINO precision must be 'x3' or 'bf16', got %r" % (precision,))
+        self.precision = precision
         if state_dict is None and os.path.exists(self.pretrain_path):
             state_dict = torch.load(self.pretrain_path, map_location='cpu')
         self.model = ViTSmall8Params(state_dict)
@@ -74,7 +98,8 @@ class DINO(nn.Module):
 
     def _pack(self, H, W, device):
         """bf16 GEMM weights, fp32 vectors and the resampled position embedding, as the C-ABI struct."""
-        key = (H, W, str(device))
+        key = (H, W, str(device), self.precision)
+        x3 = self.precision == 'x3'
         if key in self._packed:
             return self._packed[key]
         sd = {k: v.detach().to(device) for k, v in self.model.state_dict().items()}
@@ -86,7 +111,7 @@ class DINO(nn.Module):
             return t.data_ptr()
 
         def b16(t):
-            t = t.to(torch.bfloat16).contiguous()
+            t = split_bf16_i32(t) if x3 else t.to(torch.bfloat16).contiguous()
             keep.append(t)
             return t.data_ptr()
 
@@ -111,8 +136,8 @@ class DINO(nn.Module):
     @torch.no_grad()
     def forward(self, img, layer=None, tokens=False):
         """img (b,3,H,W) raw [0,1] RGB -> layer-9 key features (b, 384, H/8, W/8); frozen, no autograd.
-        tokens=True additionally returns the same features token-major in bf16, (b, H/8*W/8, 384): the operand of the
-        native arg-max matching (PretrainedCorrespondence)."""
+        tokens=True additionally returns the same features token-major in bf16, the operand of the native arg-max
+        matching (PretrainedCorrespondence): (b, H/8*W/8, 384), or split pairs (b, H/8*W/8, 768) in x3 precision."""
         if not img.is_cuda:
             raise TypeError('DINO supports only CUDA tensors (no CPU path)')
         layer = self.feat_layer if layer is None else layer
@@ -122,11 +147,13 @@ class DINO(nn.Module):
         img = img.detach().float().contiguous()
         feat = torch.empty(B, VW.EMBED, H // 8, W // 8, dtype=torch.float32, device=dev)
         L = _lib.lib()
-        ws_bytes = L.scp_vit_workspace_bytes(B, H, W)
+        prec = _lib.VIT_X3 if self.precision == 'x3' else _lib.VIT_BF16
+        ws_bytes = L.scp_vit_workspace_bytes(B, H, W, prec)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        tok = torch.empty(B, (H // 8) * (W // 8), VW.EMBED, dtype=torch.bfloat16, device=dev) if tokens else None
+        tok_w = VW.EMBED * (2 if prec == _lib.VIT_X3 else 1)
+        tok = torch.empty(B, (H // 8) * (W // 8), tok_w, dtype=torch.bfloat16, device=dev) if tokens else None
         with torch.cuda.device(dev):
-            rc = L.scp_vit_s8_keys(ctypes.byref(w), _lib.ptr(img), _lib.ptr(feat), _lib.ptr(tok), B, H, W, layer,
+            rc = L.scp_vit_s8_keys(ctypes.byref(w), _lib.ptr(img), _lib.ptr(feat), _lib.ptr(tok), B, H, W, layer, prec,
                                    _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
         _lib.check(rc, 'scp_vit_s8_keys')
         return (feat, tok) if tokens else feat

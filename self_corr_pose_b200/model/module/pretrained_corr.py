@@ -64,9 +64,12 @@ class PretrainedCorrespondence(nn.Module):
                                              (tgt_idx, src_idx, src_mask_down, tgt_mask_down)):
             best = torch.empty(NP, npix, dtype=torch.int64, device=dev)
             w_mask = w_mask.float().contiguous()
+            # token width 768 = split bf16 pairs of the fp32-class ViT mode (DINO precision 'x3'), 384 = plain bf16
+            prec = _lib.VIT_X3 if tokens.shape[-1] == 768 else _lib.VIT_BF16
             with torch.cuda.device(dev):
                 rc = L.scp_dino_argmatch(_lib.ptr(tokens), _lib.ptr(a_idx.contiguous()), _lib.ptr(w_idx.contiguous()),
-                                         _lib.ptr(w_mask), tokens.shape[0], npix, NP, _lib.ptr(best), _lib.stream_ptr(dev))
+                                         _lib.ptr(w_mask), tokens.shape[0], npix, NP, prec, _lib.ptr(best),
+                                         _lib.stream_ptr(dev))
             _lib.check(rc, 'scp_dino_argmatch')
             out.append(decode_argmax(best) * (a_mask > 0))
         return out[0], out[1]     # max_fw (per source pixel), max_bw (per target pixel)

@@ -24,13 +24,14 @@ def test_c_abi_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), 'libscp_b200.so does not export %s' % n
     lib.scp_abi_version.restype = ctypes.c_int
-    assert lib.scp_abi_version() == 4
+    assert lib.scp_abi_version() == 5
     # size queries are pure host code
     lib.scp_softras_workspace_bytes.restype = ctypes.c_size_t
     assert lib.scp_softras_workspace_bytes(2, 100) >= 2 * 100 * (16 + 192)
     lib.scp_vit_workspace_bytes.restype = ctypes.c_size_t
-    assert lib.scp_vit_workspace_bytes(1, 256, 256) > 1025 * 384 * 4
-    assert lib.scp_vit_workspace_bytes(1, 250, 256) == 0
+    assert lib.scp_vit_workspace_bytes(1, 256, 256, 0) > 1025 * 384 * 4
+    assert lib.scp_vit_workspace_bytes(1, 250, 256, 0) == 0
+    assert lib.scp_vit_workspace_bytes(1, 256, 256, 1) > lib.scp_vit_workspace_bytes(1, 256, 256, 0)   # split pairs
 
 
 def test_product_fails_loudly_without_cuda():

@@ -1,7 +1,10 @@
 """GPU parity of the ViT pieces: tcgen05 GEMM, flash attention, and the whole layer-9 key extractor against
-the CPU oracle (oracle/vit.py, pinned to the reference ViT).  Operands are bf16 on the tensor cores, so the
-features are compared norm-wise (tolerances stated per check) and at the consumer: the arg-max matches that
-PretrainedCorrespondence.match derives from them."""
+the CPU oracle (oracle/vit.py, pinned to the reference ViT).
+
+Two precisions (include/scp_b200.h): the DEFAULT, fp32-class "x3" mode (operands carried as split bf16 pairs, three
+tensor-core products per logical product) is held to the north-star contract -- features within 1e-3 relative of the
+fp32 reference and >= 99.9 % identical arg-max matches at the consumer (PretrainedCorrespondence.match); the labelled
+fast mode (plain bf16 operands) is checked at what bf16 allows (2e-2 / 95 %)."""
 import numpy as np
 import pytest
 import torch
@@ -81,37 +84,124 @@ def test_attention_tcgen05(B, T, ramp, variant, monkeypatch):
     assert r < 1e-2
 
 
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (300, 384, 192), (2050, 1152, 384), (1025, 384, 1536), (70, 128, 32)])
+def test_tcgen05_gemm_x3(M, N, K):
+    """fp32-class GEMM: fp32 operands split into bf16 (hi, lo) pairs, hi*hi + hi*lo + lo*hi on the tensor cores."""
+    from self_corr_pose_b200 import _lib
+    from self_corr_pose_b200.model.module.network.dino import split_bf16_i32
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g).cuda()
+    As, Ws = split_bf16_i32(A).cuda(), split_bf16_i32(W).cuda()
+    C = torch.empty(M, N, device='cuda')
+    rc = _lib.lib().scp_gemm_bf16x3_tn(_lib.ptr(As), _lib.ptr(Ws), _lib.ptr(bias), _lib.ptr(C), M, N, K, _lib.stream_ptr())
+    _lib.check(rc, 'scp_gemm_bf16x3_tn')
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() + bias.double().cpu()
+    r = rel(C, ref)
+    r_fp32 = rel(A @ W.t() + bias.cpu(), ref)
+    print('PARITY gemm_x3 %dx%dx%d rel=%.2e (torch fp32 matmul: %.2e)' % (M, N, K, r, r_fp32))
+    assert r < 2e-5    # three-term split: ~2^-16 per product, averaged over K
+
+
+def _split_heads_tokens(q, k, v, B, T):
+    """(B*6,T,64) fp32 q,k,v -> the x3 attention operands: split q|k token-major [B*T][1536], V^T planes [2][B*384][Tp]."""
+    from self_corr_pose_b200.model.module.network.dino import split_bf16_i32
+    tok = lambda t: t.reshape(B, 6, T, 64).permute(0, 2, 1, 3).reshape(B * T, 384)
+    qk = torch.cat((split_bf16_i32(tok(q)), split_bf16_i32(tok(k))), dim=1).contiguous()
+    Tp = (T + 7) // 8 * 8
+    vt = torch.zeros(2, B * 6 * 64, Tp, dtype=torch.bfloat16)
+    vT = v.transpose(1, 2).reshape(B * 6 * 64, T)
+    hi = vT.to(torch.bfloat16)
+    vt[0, :, :T] = hi
+    vt[1, :, :T] = (vT - hi.float()).to(torch.bfloat16)
+    return qk, vt
+
+
+@pytest.mark.parametrize('B,T,ramp', [(1, 128, 0.), (2, 65, 0.), (1, 1025, 0.), (3, 300, 0.), (1, 64, 0.), (2, 1025, 7.),
+                                      (1, 449, -7.), (1, 1025, 3.)])
+def test_attention_x3(B, T, ramp):
+    """scp_fa3.cuh: fp32-class flash attention (split q, k, v; P split by the softmax warps).  ramp as above; the peaked
+    cases (ramp != 0) are where bf16 P loses 2^-9 and the split keeps ~1e-5."""
+    from self_corr_pose_b200 import _lib
+    from self_corr_pose_b200.model.module.network.dino import merge_bf16_i32
+    g = torch.Generator().manual_seed(1)
+    q, k, v = (torch.randn(B * 6, T, 64, generator=g) for _ in range(3))
+    if ramp:
+        s = torch.linspace(0, 1, T)[None, :, None]
+        k = k * (1 + abs(ramp) * (s if ramp > 0 else 1 - s))
+    qk, vt = _split_heads_tokens(q, k, v, B, T)
+    qk, vt = qk.cuda(), vt.cuda()
+    o = torch.empty(B * T, 768, dtype=torch.bfloat16, device='cuda')
+    rc = _lib.lib().scp_attention_x3(_lib.ptr(qk), _lib.ptr(vt), _lib.ptr(o), B, T, _lib.stream_ptr())
+    _lib.check(rc, 'scp_attention_x3')
+    torch.cuda.synchronize()
+    attn = ((q.double() @ k.double().transpose(1, 2)) * 0.125).softmax(-1) @ v.double()
+    ref = attn.reshape(B, 6, T, 64).permute(0, 2, 1, 3).reshape(B * T, 384)
+    got = merge_bf16_i32(o.cpu())
+    r = rel(got, ref)
+    print('PARITY attention_x3 B%d T%d ramp%g rel=%.2e' % (B, T, ramp, r))
+    assert torch.isfinite(got).all()
+    assert r < 1e-4
+
+
+@pytest.mark.parametrize('precision,rtol,min_agree', [('x3', 1e-3, 0.999), ('bf16', 2e-2, 0.95)])
 @pytest.mark.parametrize('B,size', [(2, 64), (2, 256)])
-def test_dino_features_vs_oracle(B, size):
+def test_dino_features_vs_oracle(B, size, precision, rtol, min_agree):
+    """Contract (north star / SURVEY 8d cfg 1): features within 1e-3 relative of the reference's fp32 ViT and >= 99.9 %
+    identical arg-max matches -- met by the default x3 precision; the bf16 fast mode is checked at its own level."""
     from self_corr_pose_b200.model.module.network.dino import DINO
     sd = synthetic_state_dict(0)
-    net = DINO(sd).cuda()
+    net = DINO(sd, precision=precision).cuda()
     g = torch.Generator().manual_seed(2)
     img = torch.rand(B, 3, size, size, generator=g)
     feat = net(img.cuda()).cpu()
     ref = ovit.dino_features(sd, img)
     r = rel(feat, ref)
     # consumer-level check: mutual arg-max matches between the two images (pretrained_corr.py:85-89)
-    fs = size // 8
     def argmatch(f):
         s = f[0].reshape(384, -1).t() @ f[1].reshape(384, -1)
-        return s.max(0).indices, s.max(1).indices
-    bw, fw = argmatch(feat)
-    bw_o, fw_o = argmatch(ref)
+        return s.max(0).indices, s.max(1).indices, s.topk(min(8, s.shape[1]), dim=1).indices
+    bw, fw, tk = argmatch(feat.double())
+    bw_o, fw_o, tk_o = argmatch(ref.double())
     agree = float(((bw == bw_o).float().mean() + (fw == fw_o).float().mean()) / 2)
-    print('PARITY dino B%d %dpx feat_rel=%.3e argmax_agree=%.4f' % (B, size, r, agree))
-    assert r < 2e-2        # bf16 operands through 9 blocks
-    assert agree >= 0.95
+    agree_topk = float((tk == tk_o).float().mean())
+    print('PARITY dino[%s] B%d %dpx feat_rel=%.3e argmax_agree=%.5f top8_agree=%.5f' % (precision, B, size, r, agree, agree_topk))
+    assert r < rtol
+    assert agree >= min_agree
+    if precision == 'x3' and size >= 256:      # with 16 candidates per row (64 px) one flip is already 0.1 %
+        assert agree_topk >= 0.995
 
 
+def test_dino_tokens_x3_match_features():
+    """The token-major split copy (operand of the arg-max GEMM) carries the same values as the fp32 feature map."""
+    from self_corr_pose_b200.model.module.network.dino import DINO, merge_bf16_i32
+    net = DINO(synthetic_state_dict(0)).cuda()
+    img = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(4)).cuda()
+    feat, tok = net(img, tokens=True)
+    assert tok.shape == (2, 256, 768)
+    got = merge_bf16_i32(tok.cpu())                                   # (2, 256, 384)
+    ref = feat.reshape(2, 384, 256).permute(0, 2, 1).cpu()
+    assert rel(got, ref) < 2e-5
+
+
+@pytest.mark.parametrize('precision', ['x3', 'bf16'])
 @pytest.mark.parametrize('B,npix', [(3, 256), (4, 1024)])
-def test_dino_argmatch_vs_masked_similarity(B, npix):
+def test_dino_argmatch_vs_masked_similarity(B, npix, precision):
     """scp_dino_argmatch (batched tcgen05 GEMM with an arg-max epilogue) against the reference statements
     (pretrained_corr.py:85-89: masked similarity, max over both axes) evaluated in fp64 on the same bf16 tokens."""
     from types import SimpleNamespace
     from self_corr_pose_b200.model.module.pretrained_corr import PretrainedCorrespondence
     g = torch.Generator().manual_seed(npix)
-    tokens = torch.randn(B, npix, 384, generator=g).to(torch.bfloat16).cuda()
+    from self_corr_pose_b200.model.module.network.dino import split_bf16_i32, merge_bf16_i32
+    tokens = torch.randn(B, npix, 384, generator=g)
+    if precision == 'x3':      # fp32 features as split pairs; reference = fp64 on the values the pairs carry (16 bits)
+        tokens = split_bf16_i32(tokens.reshape(B * npix, 384)).reshape(B, npix, 768).cuda()
+        t = merge_bf16_i32(tokens).double()
+    else:
+        tokens = tokens.to(torch.bfloat16).cuda()
+        t = tokens.double()
     NP = 2 * B
     src_idx = (torch.arange(NP) % B).cuda()
     tgt_idx = ((torch.arange(NP) + 1 + torch.arange(NP) // B) % B).cuda()
@@ -120,7 +210,6 @@ def test_dino_argmatch_vs_masked_similarity(B, npix):
     ms[0] = 0          # a pair whose source is entirely background
     mt[1] = 0
     max_fw, max_bw = PretrainedCorrespondence._argmatch_tokens(SimpleNamespace(), tokens, src_idx, tgt_idx, ms, mt)
-    t = tokens.double()
     S = torch.einsum('pic,pjc->pij', t[src_idx], t[tgt_idx])
     S = S * ms[:, :, None] * mt[:, None, :] + (-1e5) * (1 - ms[:, :, None] * mt[:, None, :])
     ref_bw = S.max(1).indices * (mt > 0)
@@ -131,5 +220,5 @@ def test_dino_argmatch_vs_masked_similarity(B, npix):
     ok_fw = torch.where((ms > 0) & has_t, max_fw == ref_fw, max_fw == 0)
     ok_bw = torch.where((mt > 0) & has_s, max_bw == ref_bw, max_bw == 0)
     agree = float(ok_fw.float().mean()), float(ok_bw.float().mean())
-    print('PARITY dino_argmatch B%d np%d agree fw=%.5f bw=%.5f' % (B, npix, *agree))
+    print('PARITY dino_argmatch[%s] B%d np%d agree fw=%.5f bw=%.5f' % (precision, B, npix, *agree))
     assert min(agree) >= 0.9995
