@@ -20,6 +20,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+os.environ.setdefault('SCP_SYNTHETIC_WEIGHTS', '1')   # no checkpoints offline: synthetic weights, stated in `data`
 sys.path.insert(0, ROOT)
 
 

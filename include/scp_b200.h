@@ -218,6 +218,37 @@ int scp_attention_tc5(const void *q, const void *k, const void *vt, void *o, int
  * zero padding, o = split [B*T][768]. */
 int scp_attention_x3(const void *qk, const void *vt, void *o, int B, int T, void *stream);
 
+/* ---- symmetry regulariser: rotated surface samples + 1-nearest-neighbour ------------------ */
+/*
+ * CanonicalMesh.compute_symmetry_loss (model/module/mesh.py:53-62): mesh m = b*k + i has the vertices pred_v[b][N][3];
+ * its S surface samples are pts[m][s] = sum_c w[m][s][c] * pred_v[b][faces[face_idx[m][s]][c]] (the random face indices
+ * and barycentric weights are drawn by the caller, pytorch3d.ops.sample_points_from_meshes semantics), rotated
+ * y = pts . rots[i] (row vector times the 3x3 matrix, `sample_pts.bmm(symm_rots)`).  Outputs, as pytorch3d's
+ * knn_points(K=1) inside chamfer_distance_single_way (model/util/chamfer.py:152-156):
+ *   dist[m][n] = min_s |pred_v[b][n] - y[m][s]|^2,  nn_idx[m][n] = arg min (lowest s on ties).
+ * faces: int32 [nf][3]; face_idx: int64 [B*k][S]; w: [B*k][S][3]; rots: [k][3][3].
+ */
+int scp_symmetry_nn_forward(const float *pred_v, const int *faces, const long long *face_idx, const float *w,
+                            const float *rots, int B, int k, int N, int S, float *dist, int *nn_idx, void *stream);
+/* g_pred_v[B][N][3] (zeroed by the callee) = d(sum_mn g_dist[m][n] * dist[m][n]) / d(pred_v): through the vertex itself and
+ * through the three face vertices of its nearest sample (face index and weights are constants). */
+int scp_symmetry_nn_backward(const float *pred_v, const int *faces, const long long *face_idx, const float *w,
+                             const float *rots, const int *nn_idx, const float *g_dist, int B, int k, int N, int S,
+                             float *g_pred_v, void *stream);
+
+/* ---- encoder input: photometric jitter + normalisation ------------------------------------ */
+/*
+ * out = Normalize(mean, std)(ColorJitter(img)) of Encoder.encode_img (model/module/encoder.py:30-32), torchvision tensor
+ * semantics (one parameter set for the whole batch): img, out [B][3][HW] fp32 planar, values in [0,1] on input.
+ * order[4]: torchvision step ids in application order (0 brightness, 1 contrast, 2 saturation, 3 hue; -1 skips a step);
+ * ratios[6] = (ratio, 1 - ratio) of brightness, contrast, saturation AS ROUNDED BY THE CALLER (torchvision forms 1 - ratio
+ * in double precision); hue in [-0.5, 0.5]; mean/std [3] host arrays.  All of order/ratios/mean/std are HOST pointers
+ * (read during the call).  workspace: scp_color_jitter_workspace_bytes(B) device bytes (per-image grey sums, fp64).
+ */
+size_t scp_color_jitter_workspace_bytes(int B);
+int scp_color_jitter_normalize(const float *img, float *out, int B, int HW, const int *order, const float *ratios, float hue,
+                               const float *mean, const float *std, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- pre-training cycle loss: the k gathered target rows of every image pair ------------------------------ */
 /*
  * pointcorr_pool[B,P4,N] (2x2-pooled similarity), A_pool[B,2,N] (= pooled grid . softmax over pixels, from

@@ -78,6 +78,17 @@ _SIGNATURES.update({
     'scp_cycle_rows_backward': ([_f] * 8 + [_fl, _i, _i, _i, _i, _i] + [_f] * 4, _i),
 })
 
+_SIGNATURES.update({
+    'scp_symmetry_nn_forward': ([_f] * 5 + [_i, _i, _i, _i] + [_f, _f, _f], _i),
+    'scp_symmetry_nn_backward': ([_f] * 7 + [_i, _i, _i, _i] + [_f, _f], _i),
+})
+
+_SIGNATURES.update({
+    'scp_color_jitter_workspace_bytes': ([_i], _sz),
+    'scp_color_jitter_normalize': ([_f, _f, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_fl), _fl, ctypes.POINTER(_fl),
+                                    ctypes.POINTER(_fl), _f, _sz, _f], _i),
+})
+
 _lib = None
 
 

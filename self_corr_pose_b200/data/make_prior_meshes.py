@@ -1,4 +1,4 @@
-"""Generates tests/golden/prior_meshes.npz from the reference's category prior OBJ files
+"""Generates self_corr_pose_b200/data/prior_meshes.npz from the reference's category prior OBJ files
 (config/<cat>_wild6d/<cat>.obj) -- run once in the build container where /root/reference is mounted.
 The priors are benchmark INPUT DATA; they are parsed with a plain
 OBJ reader (the files are duplicate-/degenerate-free, so trimesh.load_mesh(process=True) as used by

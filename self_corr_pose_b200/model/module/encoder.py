@@ -12,6 +12,7 @@ import torch.nn.functional as F
 from torchvision import transforms
 
 from .network import encoder_nets as nets
+from ...ops.color_jitter import jitter_normalize
 
 _IMAGENET_MEAN, _IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 
@@ -36,7 +37,11 @@ class Encoder(nn.Module):
 
     def encode_img(self, img):
         """(b,3,H,W) in [0,1] -> (global code (b,512), unit-norm pixel features (b,C,h*w))."""
-        pyramid = self.backbone(self.resnet_transform(self.random_jitter(img)))
+        if img.is_cuda:     # one native pass instead of torchvision's ~70 launches (same random draws, ops/color_jitter.py)
+            x = jitter_normalize(img, self.random_jitter, _IMAGENET_MEAN, _IMAGENET_STD)
+        else:
+            x = self.resnet_transform(self.random_jitter(img))
+        pyramid = self.backbone(x)
         code = pyramid[-1].mean(dim=(2, 3))
         feat = self.featnet(*pyramid).flatten(2)
         return code, F.normalize(feat, p=2, dim=1)

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ... import synthetic
+from ... import _flags, synthetic
 
 
 def read_obj(path):
@@ -38,8 +38,10 @@ def get_symm_rots(division):
     return rots
 
 
-def sample_points_from_meshes(verts, faces, num_samples):
-    """Area-weighted uniform surface samples, (B, num_samples, 3) (pytorch3d.ops.sample_points_from_meshes semantics)."""
+def sample_faces_and_weights(verts, faces, num_samples):
+    """The random part of pytorch3d.ops.sample_points_from_meshes: area-weighted face draws (multinomial with replacement)
+    and uniform barycentric weights (w0, w1, w2) = (1 - sqrt(u), sqrt(u) (1 - v), sqrt(u) v).  verts (B,N,3),
+    faces (B,nf,3) -> face_idx (B,S) int64, w (B,S,3).  Consumes the device generator: multinomial, then one rand."""
     B = verts.shape[0]
     idx = faces.long()
     v0, v1, v2 = (torch.gather(verts, 1, idx[:, :, k:k + 1].expand(-1, -1, 3)) for k in range(3))
@@ -47,9 +49,20 @@ def sample_points_from_meshes(verts, faces, num_samples):
     face_idx = torch.multinomial(areas.detach().clamp_min(1e-12), num_samples, replacement=True)   # B, S
     u = torch.rand(B, num_samples, 2, device=verts.device)
     su = u[..., 0].sqrt()
-    w0, w1, w2 = 1 - su, su * (1 - u[..., 1]), su * u[..., 1]
-    pick = lambda t: torch.gather(t, 1, face_idx[:, :, None].expand(-1, -1, 3))
-    return w0[..., None] * pick(v0) + w1[..., None] * pick(v1) + w2[..., None] * pick(v2)
+    return face_idx, torch.stack((1 - su, su * (1 - u[..., 1]), su * u[..., 1]), dim=-1)
+
+
+def points_from_samples(verts, faces, face_idx, w):
+    """pts = w0 v0 + w1 v1 + w2 v2 of the drawn faces, (B,S,3); differentiable in verts."""
+    idx = faces.long()
+    corner = lambda k: torch.gather(verts, 1, torch.gather(idx[:, :, k], 1, face_idx)[:, :, None].expand(-1, -1, 3))
+    return w[..., 0:1] * corner(0) + w[..., 1:2] * corner(1) + w[..., 2:3] * corner(2)
+
+
+def sample_points_from_meshes(verts, faces, num_samples):
+    """Area-weighted uniform surface samples, (B, num_samples, 3) (pytorch3d.ops.sample_points_from_meshes semantics)."""
+    face_idx, w = sample_faces_and_weights(verts, faces, num_samples)
+    return points_from_samples(verts, faces, face_idx, w)
 
 
 def chamfer_single_way(x, y, chunk=16):
@@ -57,7 +70,9 @@ def chamfer_single_way(x, y, chunk=16):
     (model/util/chamfer.py chamfer_distance_single_way with the default mean reductions)."""
     total = x.new_zeros(())
     for s in range(0, x.shape[0], chunk):
-        d = torch.cdist(x[s:s + chunk], y[s:s + chunk]).pow(2).min(dim=2)[0]     # b, Nx
+        # exact differences like pytorch3d's knn_points (the default cdist goes through |x|^2 + |y|^2 - 2 x.y, whose
+        # cancellation error (~1e-7) reorders near-tied neighbours)
+        d = torch.cdist(x[s:s + chunk], y[s:s + chunk], compute_mode='donot_use_mm_for_euclid_dist').pow(2).min(dim=2)[0]     # b, Nx
         total = total + d.mean(1).sum()
     return total / x.shape[0]
 
@@ -77,6 +92,24 @@ class CanonicalMesh(nn.Module):
         return F.grid_sample(img, imatch.permute(0, 2, 1)[:, None], align_corners=False)[:, :, 0].permute(0, 2, 1)
 
     def compute_symmetry_loss(self, pred_v, faces, npts=10000):
+        """mesh.py:53-62 of the reference.  On the GPU the sample reconstruction, the rotation and the 1-NN search of the
+        one-way chamfer distance run as ONE native kernel (ops/symmetry_nn.py); the random draws are the same torch calls
+        in the same order as `compute_symmetry_loss_reference`, so both produce the same value for the same seed."""
+        if not pred_v.is_cuda:
+            return self.compute_symmetry_loss_reference(pred_v, faces, npts)
+        from ...ops.symmetry_nn import symmetry_nn
+        k, bsz = self.symm_rots.shape[0], pred_v.shape[0]
+        v = pred_v[:, None].repeat(1, k, 1, 1).reshape(k * bsz, self.num_verts, 3)
+        f = faces[:, None].repeat(1, k, 1, 1).reshape(k * bsz, self.num_faces, 3)
+        with torch.no_grad():
+            face_idx, w = sample_faces_and_weights(v, f, npts)
+        if getattr(self, '_faces_i32', None) is None or self._faces_i32.device != pred_v.device:
+            self._faces_i32 = self.faces.detach().to(pred_v.device, torch.int32).contiguous()
+        dist, _ = symmetry_nn(pred_v, self._faces_i32, face_idx, w, self.symm_rots)
+        return dist.mean(1).mean(0)
+
+    def compute_symmetry_loss_reference(self, pred_v, faces, npts=10000):
+        """The reference's statements op by op (parity reference of the fused kernel; CPU-capable)."""
         k, bsz = self.symm_rots.shape[0], pred_v.shape[0]
         v = pred_v[:, None].repeat(1, k, 1, 1).reshape(k * bsz, self.num_verts, 3)
         f = faces[:, None].repeat(1, k, 1, 1).reshape(k * bsz, self.num_faces, 3)
@@ -90,8 +123,11 @@ class CanonicalMesh(nn.Module):
     def _load_prior(self, path):
         if os.path.exists(path):
             return read_obj(path)
+        if not _flags.synthetic_weights_allowed():
+            raise FileNotFoundError('shape prior %s not found (set SCP_SYNTHETIC_WEIGHTS=1 to fall back to the packaged '
+                                    'copy of the category prior, tests / benchmarks only)' % path)
         cat = os.path.splitext(os.path.basename(path))[0]
-        return synthetic.load_prior(cat, normalise=False)     # fixture copy of config/<cat>_wild6d/<cat>.obj
+        return synthetic.load_prior(cat, normalise=False)     # packaged copy of config/<cat>_wild6d/<cat>.obj
 
     def init_shape(self):
         opts = self.opts

@@ -2,8 +2,9 @@
 
 API of the reference's model/module/network/dino.py (`DINO()`, `forward(img) -> (b, 384, h/8, w/8)`), with
 `self.model` holding the parameters under the reference checkpoint's names so that
-`pretrain_corr_net.net.model.*` keys load unchanged.  No checkpoint is available offline: unless
-`pretrain/dino_deitsmall8_pretrain.pth` exists, seeded synthetic weights are used (vit_weights.py).
+`pretrain_corr_net.net.model.*` keys load unchanged.  Like the reference (network/dino.py:42: torch.load of
+`pretrain/dino_deitsmall8_pretrain.pth`), a missing checkpoint is an error; seeded synthetic weights (vit_weights.py) are
+used only when a state dict is passed or the caller opts in with SCP_SYNTHETIC_WEIGHTS=1 (_flags.py).
 """
 import ctypes
 import math
@@ -13,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .... import _lib
+from .... import _flags, _lib
 from . import vit_weights as VW
 
 
@@ -83,8 +84,13 @@ class DINO(nn.Module):
         if precision not in ('x3', 'bf16'):
             raise ValueError("DINO precision must be 'x3' or 'bf16', got %r" % (precision,))
         self.precision = precision
-        if state_dict is None and os.path.exists(self.pretrain_path):
-            state_dict = torch.load(self.pretrain_path, map_location='cpu')
+        if state_dict is None:
+            if os.path.exists(self.pretrain_path):
+                state_dict = torch.load(self.pretrain_path, map_location='cpu')
+            elif not _flags.synthetic_weights_allowed():
+                raise FileNotFoundError(
+                    'DINO checkpoint %s not found (the pseudo-ground-truth matches are meaningless without it); set '
+                    'SCP_SYNTHETIC_WEIGHTS=1 to run with seeded synthetic weights (tests / benchmarks only)' % self.pretrain_path)
         self.model = ViTSmall8Params(state_dict)
         self._packed = {}
 

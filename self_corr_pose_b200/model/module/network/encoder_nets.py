@@ -7,10 +7,14 @@ Architectures and parameter names follow the reference so its checkpoints load u
   PosePredictor   model/module/network/pose_predictor.py:22-87   (6-D rotation head with fixed offsets, translation head)
   ShapePredictor  model/module/network/shape_predictor.py:12-43  (CondNeRFModel with 2 layers, third-party/nerf/models.py:336-417)
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 import torchvision
+
+from .... import _flags
 
 
 class _CBR(nn.Module):
@@ -24,10 +28,24 @@ class _CBR(nn.Module):
 
 
 class ResNetEncoder(nn.Module):
-    def __init__(self, pretrained=False):
+    """ImageNet-pretrained ResNet-18 trunk (the reference: torchvision resnet18(pretrained=True), image_encoder.py:122).
+    The weights are read from `weights_path` / $SCP_RESNET18_WEIGHTS / the torch hub cache (no download: there is no
+    network); when none exists this raises like a failed download would, unless SCP_SYNTHETIC_WEIGHTS=1 (tests and
+    benchmarks: seeded random initialisation)."""
+    HUB_FILE = 'resnet18-f37072fd.pth'
+
+    def __init__(self, pretrained=True, weights_path=None):
         super().__init__()
-        # no network offline: seeded random initialisation unless a checkpoint is loaded afterwards
         self.resnet = torchvision.models.resnet18(weights=None)
+        if pretrained:
+            cands = [weights_path, os.environ.get('SCP_RESNET18_WEIGHTS'),
+                     os.path.join(torch.hub.get_dir(), 'checkpoints', self.HUB_FILE)]
+            path = next((c for c in cands if c and os.path.exists(c)), None)
+            if path is not None:
+                self.resnet.load_state_dict(torch.load(path, map_location='cpu'))
+            elif not _flags.synthetic_weights_allowed():
+                raise FileNotFoundError('ImageNet ResNet-18 weights not found (looked in %s); pass pretrained=False or set '
+                                        'SCP_SYNTHETIC_WEIGHTS=1 for a seeded random initialisation' % [c for c in cands if c])
         self.resnet.fc = None
 
     def forward(self, x):

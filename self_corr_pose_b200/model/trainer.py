@@ -31,6 +31,11 @@ class Trainer:
             self.model.load_network(opts.model_path)
         self.model.apply(self.set_bn_eval)
         dev = torch.device('cuda', max(getattr(opts, 'local_rank', 0), 0))
+        if getattr(opts, 'allow_tf32', True):
+            # the reference's environment (torch 1.10, README.md:21) multiplies fp32 matrices and convolutions in TF32 by
+            # default; torch >= 1.12 keeps that default only for cuDNN.  Restores it for the encoder's Linear layers.
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(self.model)
         self.model = self.model.to(dev)
@@ -78,7 +83,10 @@ class Trainer:
     def step(self, batch):
         """zero_grad -> forward -> backward -> gradient all-reduce -> clip -> AdamW/OneCycle (trainer.py:118-125)."""
         self.model.iters = self.iters
-        self.optim.zero_grad()
+        if self.reducer.adopted:        # gradients live in one flat buffer (dist.py): one memset
+            self.reducer.zero_()
+        else:
+            self.optim.zero_grad()
         data = self.batch_reshape(batch)
         total_loss, aux_output = self.model(data)
         total_loss.mean().backward()

@@ -1,7 +1,7 @@
 """Synthetic inputs for tests and bench.py (no dataset or checkpoint is available offline).
 
 Meshes: the category priors of the reference (config/<cat>_wild6d/<cat>.obj, shipped as the
-fixture tests/golden/prior_meshes.npz), a UV sphere with exactly 1280 vertices / 2556 faces
+package asset self_corr_pose_b200/data/prior_meshes.npz), a UV sphere with exactly 1280 vertices / 2556 faces
 (the "1280-vertex category mesh" of BASELINE.json) and icospheres.
 Scenes: SURVEY.md section 8(d) configs 0-2.
 """
@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PRIOR_FIXTURE = os.path.join(_ROOT, 'tests', 'golden', 'prior_meshes.npz')
+PRIOR_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'prior_meshes.npz')
 
 
 def uv_sphere(rings=18, segments=71):

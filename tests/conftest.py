@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# no checkpoints offline: the tests run on seeded synthetic weights / the packaged prior meshes (explicit opt-in)
+os.environ.setdefault('SCP_SYNTHETIC_WEIGHTS', '1')
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -110,8 +110,17 @@ def _worker(rank, world, port, out):
     x = torch.full((5, 3), float(rank + 1))
     loss = (w[0] * x).sum() + (w[1] ** 2).sum() * (rank + 1)      # w[2] gets no gradient on any rank
     loss.backward()
-    FlatGradReducer(w).reduce()
-    out[rank] = [p.grad.clone() for p in w]
+    red = FlatGradReducer(w)
+    red.reduce()
+    first = [None if p.grad is None else p.grad.clone() for p in w]
+    # second step: gradients accumulate in place into the views of the flat buffer
+    assert red.adopted and all(p.grad.data_ptr() >= red.flat.data_ptr() for p in w[:2])
+    red.zero_()
+    assert float(w[0].grad.abs().sum()) == 0
+    loss = (w[0] * x).sum() * 3 + (w[1] ** 2).sum() * (rank + 1)
+    loss.backward()
+    red.reduce()
+    out[rank] = first + [p.grad.clone() for p in w[:2]]
     dist.barrier()
     dist.destroy_process_group()
 
@@ -128,7 +137,9 @@ def test_flat_gradient_allreduce_gloo_world2():
     for r in range(world):
         torch.testing.assert_close(out[r][0], exp0)
         torch.testing.assert_close(out[r][1], exp1)
-        torch.testing.assert_close(out[r][2], torch.zeros(2))
+        assert out[r][2] is None                  # never reached by the graph: stays None on every rank (as with 1 GPU)
+        torch.testing.assert_close(out[r][3], 3 * exp0)
+        torch.testing.assert_close(out[r][4], exp1)
 
 
 def test_face_topology_csr():

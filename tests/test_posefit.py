@@ -101,7 +101,6 @@ def test_pose_fitting_matches_reference_tester(gold):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason='added after the round\'s GPU budget was spent: first run on a B200 pending')
 def test_pose_fitting_on_gpu_matches_reference_tester(gold):
     _check_pose(gold, 'cuda', 1e-4)
 

@@ -7,6 +7,7 @@ changed kernel and a timing script, each in its own process with SCP_LIB_VARIANT
 Prints one line per variant: test verdict + the timing script's last output line.  A variant is only worth keeping when
 its tests pass AND it is faster; the product default never changes here (the macro's default has to be flipped in the
 header, rebuilt and re-verified)."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import argparse
 import glob
 import os

@@ -1,4 +1,5 @@
 """One launch of each hot kernel between cudaProfilerStart/Stop, for `ncu --profile-from-start off --set full`."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch.nn.functional as F

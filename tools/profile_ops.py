@@ -1,4 +1,5 @@
 """One eager hot-path step under torch.profiler, grouped by the top-level Python stage (record_function) and by ATen op."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from torch.profiler import profile, ProfilerActivity

@@ -1,4 +1,5 @@
 """One hot-path step under torch.profiler: kernel-time table (names + totals) for finding glue hot spots."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from torch.profiler import profile, ProfilerActivity

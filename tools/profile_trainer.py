@@ -1,5 +1,6 @@
 """Where does Trainer.step go?  (1) wall/device time of the step, (2) torch.profiler kernel table (device time by kernel
 name), (3) device time of the step's sections measured with CUDA events by monkey-patching the model's sub-calls."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import sys, os, json, time, collections, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from self_corr_pose_b200 import synthetic

@@ -1,5 +1,6 @@
 """Per-kernel registers / stack (spill) / static shared memory of libscp_b200.so from `cuobjdump -res-usage`, as a
 markdown table.   python tools/resource_usage.py > profiles/<round>_resource_usage.md   (no GPU needed)"""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import os
 import re
 import subprocess

@@ -3,6 +3,7 @@
     python tools/summarize_launches.py gpurun_out/launches.csv.gz profiles/rN_bench_launch_summary.md "<note>"
 
 The step count is recovered from the attention kernel (nine launches per step)."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import collections
 import csv
 import gzip

@@ -3,6 +3,7 @@
     ncu -i gpurun_out/prof.ncu-rep --page raw --csv > /tmp/raw.csv
     python tools/summarize_ncu.py /tmp/raw.csv profiles/rN_hot_kernels_ncu_full.md profiles/traffic.json "<note>"
 Only kernels of this package are listed (first two instances of each name)."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import csv
 import json
 import re

@@ -4,6 +4,7 @@ SoftRas at 64/128/256/512 px x {642 V / 1280 F icosphere, 1280 V / 2556 F UV sph
 the soft-texture (sigma 1e-3) and depth (sigma 1e-4) renders, forward and backward; fused correspondence at
 P = 256 / 1024 / 4096 patches x 1280 vertices.  Algorithmic bytes per unit are SURVEY.md section 8d's.
 Writes a markdown table (argv[1], default gpurun_out/sweep.md)."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import json
 import os
 import sys

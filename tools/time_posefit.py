@@ -2,6 +2,7 @@
 the reference's one-image / one-round-at-a-time formulation (oracle/posefit.py) on the host cores, and checks the two
 against each other on the same batch.   python tools/time_posefit.py [--batch 32] [--size 256] [--oracle-images 4]
 Wall-clock per batch (the fit contains host synchronisations by construction), after one warm-up call."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import argparse
 import os
 import sys

@@ -1,6 +1,7 @@
 """Legacy reference SoftRas kernel (R-GPU, baseline/_ref) vs this package's operator on a B200: CUDA-event times of the
 model's four renders, forward and backward, at B x size^2 on the 1280-vertex sphere (configs[2] shape by default).
 Prints a JSON object and a markdown table (copied into profiles/)."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import json
 import os
 import sys

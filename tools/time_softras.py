@@ -1,4 +1,5 @@
 """Times the four SoftRas renders of the model (forward + backward) with CUDA events."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,4 +1,5 @@
 """Times Trainer.step (full model: ResNet-18 encoder x2 passes, heads, hot path, AdamW) with CUDA events."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import sys, os, json, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from self_corr_pose_b200 import synthetic

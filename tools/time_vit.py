@@ -1,4 +1,5 @@
 """ViT-S/8 layer-9 key extractor and its attention kernel alone, CUDA events (B = 64, 256x256)."""
+import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
