@@ -1,15 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- images/sec of the self-corr-pose hot path (forward + backward) on N B200s.
+"""bench.py -- images/sec of the self-corr-pose training step (forward + backward) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B_per_gpu] [--impl b200|reference]
+                    [--workload trainer|hotpath|config1]
 
-A "step" = one pass of the hot path (fused correspondence -> texture sampling -> 4 SoftRas renders ->
-silhouette/texture/depth/match/imatch losses -> DINO ViT-S/8 features + pseudo-matches + pre-training cycle
-loss -> backward to the encoder-output gradients) over one synthetic batch of 256x256 images (BASELINE.json
-configs[2]: batch 64 per GPU, 1280-vertex mesh, 64x64 correspondence map, C = 64).  Prints ONE JSON line.
+Default workload: `Trainer(opts).step(batch)` -- the reference's training-loop body (model/trainer.py:118-125 around
+MeshNet.forward, model/model.py:61-152): ResNet-18 encoder (both passes), fused correspondence, texture sampling, 4 SoftRas
+renders, silhouette / texture / depth / match / imatch losses, DINO ViT-S/8 features (fp32-class precision) + pseudo-matches
++ pre-training cycle loss, rotation-cycle loss, symmetry / Laplacian / deformation regularisers, backward, ONE flat-buffer
+gradient all-reduce (N > 1), clipping, AdamW + OneCycle -- over a synthetic batch of 256x256 images, 64 per GPU, the
+1280-vertex / 2556-face category mesh, 64x64 correspondence map, C = 64 (BASELINE.json configs[2]/[3]).
+`--workload hotpath` times the round-1 unit (model.py:73-134 with the encoder outputs as inputs, one CUDA graph); it is
+also reported inside the default line as `hotpath`.  `--workload config1` = BASELINE configs[1] (B = 32: DINO ViT-S/8
+features + P=1024/4096 x N=1280 correspondence + pre-training cycle block).  Prints ONE JSON line.
 
---impl reference: the reference's formulation of the same step on the host cores (oracle/hotpath_cpu.py: the
-reference has no CPU path of its own), on a bounded sample of the workload.
+--impl reference: the same workload in the reference's formulation on the host cores (oracle/trainer_cpu.py /
+oracle/hotpath_cpu.py: the reference has no CPU path of its own), on a bounded sample of the workload.
 """
 import argparse
 import json
@@ -32,6 +38,9 @@ def parse():
     ap.add_argument('--batch', type=int, default=64, help='images per GPU (batch_size x repeat, repeat = 4)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--mesh', default='uv1280')
+    ap.add_argument('--workload', default='trainer', choices=['trainer', 'hotpath', 'config1'])
+    ap.add_argument('--vit-precision', default='x3', choices=['x3', 'bf16'],
+                    help="x3 = fp32-class split-bf16 products (parity mode, default); bf16 = labelled fast mode")
     ap.add_argument('--cpu-batch', type=int, default=2, help='images in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-breakdown', action='store_true')
@@ -81,28 +90,63 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def mesh_prior_path(name):
+    return 'synthetic:uv1280' if name == 'uv1280' else 'config/%s_wild6d/%s.obj' % (name, name)
+
+
+WORKLOAD_TEXT = {
+    'trainer': 'Trainer.step: MeshNet.forward (ResNet-18 encoder x2 passes, fused correspondence P=4096 x N=%d x C=64, texture, '
+               '4 SoftRas renders nf=%d, mask/texture/depth/match/imatch losses, DINO ViT-S/8 layer-9 keys + pseudo-matches + '
+               'pre-train cycle loss, rotation-cycle loss, symmetry/Laplacian/deform regularisers) + backward + flat '
+               'gradient all-reduce + clip + AdamW/OneCycle; laptop_wild6d flag values',
+    'hotpath': 'configs[2] hot path fwd+bwd = fused correspondence (P=4096,N=%d,C=64) -> texture -> 4 SoftRas renders (nf=%d) '
+               '-> mask/texture/depth/match/imatch losses -> DINO ViT-S/8 layer-9 keys + pseudo-matches + pre-train cycle '
+               'loss; encoder outputs are inputs',
+    'config1': 'configs[1]: DINO ViT-S/8 layer-9 keys of the batch + correspondence match fwd+bwd at P=1024 and P=4096 '
+               '(N=%d, C=64) + pre-training cycle block (arg-match, top-k, cycle rows fwd+bwd); nf=%d unused',
+}
+
+
 def cpu_step_rate(args, opts_kw, label):
-    """Reference formulation on the host cores, bounded sample; returns the cpu_baseline object."""
+    """The workload in the reference's formulation on the host cores, bounded sample; returns (cpu_baseline object, seconds)."""
     import torch
     from oracle import hotpath_cpu as H
-    from oracle import softras as osr
     from self_corr_pose_b200.hotpath import default_opts
     from self_corr_pose_b200.model.module.network.vit_weights import synthetic_state_dict
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     Bc = max(2, args.cpu_batch)
-    opts = default_opts(**dict(opts_kw, batch_size=Bc // 2, repeat=2))
+    opts = default_opts(**dict(opts_kw, batch_size=Bc // 2, repeat=2, shape_prior_path=mesh_prior_path(args.mesh)))
     v, f = load_mesh(args.mesh)
-    data, enc = H.make_batch_cpu(opts, v, f, Bc, seed=0)
     sd = synthetic_state_dict(0)
     use_ref = os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'libsoftras_ref_cpu.so'))
-    t0 = time.time()
-    H.step(opts, torch.from_numpy(v), torch.from_numpy(f), data, enc, sd, use_ref=use_ref, all_vit_blocks=False)
-    dt = time.time() - t0
+    if args.workload == 'trainer':
+        from types import SimpleNamespace
+        from oracle import trainer_cpu as TC
+        from self_corr_pose_b200 import synthetic
+        from self_corr_pose_b200.model.module.renderer import Renderer
+        from self_corr_pose_b200.model.trainer import Trainer
+        cpu = TC.CpuTrainer(opts, sd, use_ref=use_ref)
+        mesh = SimpleNamespace(mean_v=torch.from_numpy(v), faces=torch.from_numpy(f), texture_type='vertex')
+        with H.cpu_rasterizer():
+            batch = synthetic.make_trainer_batch(opts, v, f, Bc, device='cpu', seed=0, renderer=Renderer(opts, mesh))
+        shaper = Trainer(opts)
+        shaper.device = torch.device('cpu')
+        data = shaper.batch_reshape(batch)
+        t0 = time.time()
+        cpu.step(data)
+        dt = time.time() - t0
+        what = 'Trainer.step (encoder x2 in torch CPU ops, symmetry / rotation-cycle terms, clip, AdamW)'
+    else:
+        data, enc = H.make_batch_cpu(opts, v, f, Bc, seed=0)
+        t0 = time.time()
+        H.step(opts, torch.from_numpy(v), torch.from_numpy(f), data, enc, sd, use_ref=use_ref, all_vit_blocks=False)
+        dt = time.time() - t0
+        what = 'hot path'
     return {'value': Bc / dt, 'unit': 'images/sec', 'cores': cores, 'kind': 'reference' if use_ref else 'port',
-            'sample': '%s: 1 step of %d images 256x256 (%s mesh), reference formulation on CPU: torch ops + '
+            'sample': '%s: 1 %s step of %d images 256x256 (%s mesh), reference formulation on CPU: torch ops + '
                       '%s SoftRas over all faces per pixel, DINO ViT on the 4x duplicated pair batch up to layer 9; %.1f s'
-                      % (label, Bc, args.mesh, 'the reference kernel source built for the host (oracle/_ref)' if use_ref
+                      % (label, what, Bc, args.mesh, 'the reference kernel source built for the host (oracle/_ref)' if use_ref
                          else 'C restatement (oracle/softras_oracle.c)', dt)}, dt
 
 
@@ -110,6 +154,8 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    if args.workload == 'config1':
+        args.workload = 'hotpath'
     opts_kw = dict(img_size=256, corr_h=64, corr_w=64)
     vals, last = [], None
     for i in range(args.warmup + args.steps):
@@ -122,13 +168,14 @@ def run_reference(args):
             break
     v = sum(vals) / len(vals)
     last['value'] = v
+    vv, ff = load_mesh(args.mesh)
     print(json.dumps({
         'impl': 'reference', 'metric': 'images/sec fwd+bwd (feat+corr+render+loss) 256x256', 'value': v,
         'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': len(vals), 'warmup': args.warmup,
         'ms_per_step': 1e3 * max(2, args.cpu_batch) / v, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'configs[2] hot path fwd+bwd, CPU sample of %d images' % max(2, args.cpu_batch),
-                   'mesh': args.mesh, 'img_size': 256},
+        'config': {'workload': WORKLOAD_TEXT[args.workload] % (vv.shape[0], ff.shape[0]),
+                   'sample': 'CPU sample of %d images' % max(2, args.cpu_batch), 'mesh': args.mesh, 'img_size': 256},
         'cpu_baseline': last,
         'e2e': {'value': v, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
@@ -246,33 +293,55 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
                     unit='GB/s', launches_per_step=1, ncu_name='corr::corr_fwd_kernel #0'))
     out.append(dict(kernel='corr_bwd_rows_kernel<fused cols> (+blocklist)', ms=t_b, bound='hbm', achieved=bytes_b / t_b / 1e6,
                     peak=hbm, unit='GB/s', launches_per_step=1, ncu_name='corr::corr_bwd_rows_kernel<1> #0'))
-    # --- ViT: whole extractor, the attention kernel and the QKV GEMM alone
+    # --- ViT: whole extractor (a chain of 68 launches), its attention kernel and the QKV GEMM alone, in the precision the
+    # step runs (x3: three tensor-core products per logical product -> peak = measured bf16 / 3, labelled derived)
     net = hot.pretrain_corr_net.net
+    x3 = net.precision == 'x3'
+    tf_eff = tf / 3 if x3 else tf
+    tf_note = 'derived: measured bf16 / 3 (x3 split products)' if x3 else which
     t_v = timeit(lambda: net(img), n=5)
-    out.append(dict(kernel='vit_s8_keys (68 launches)', ms=t_v, bound='tensor', achieved=47.62e9 * B / t_v / 1e9,
-                    peak=tf, unit='TFLOP/s', launches_per_step=1))
+    out.append(dict(kernel='vit_s8_keys[%s] (chain of 68 launches)' % net.precision, ms=t_v, bound='tensor',
+                    achieved=47.62e9 * B / t_v / 1e9, peak=tf_eff, unit='TFLOP/s', launches_per_step=1, chain=True,
+                    peak_source=tf_note))
     T = (is_ // 8) ** 2 + 1
-    q = torch.randn(B * 6, T, 64, device=dev).to(torch.bfloat16)
     Tp = (T + 7) // 8 * 8
-    vt = torch.zeros(B * 6, 64, Tp, device=dev, dtype=torch.bfloat16)
-    vt[:, :, :T] = q.transpose(1, 2)
-    o = torch.empty(B, T, 384, device=dev, dtype=torch.bfloat16)
     st = _lib.stream_ptr(dev)
-    t_a = timeit(lambda: L.scp_attention_tc5(_lib.ptr(q), _lib.ptr(q), _lib.ptr(vt), _lib.ptr(o), B, T, st))
-    out.append(dict(kernel='fa2_fwd_kernel (tcgen05 flash attention)', ms=t_a, bound='tensor',
-                    achieved=4.0 * T * T * 64 * 6 * B / t_a / 1e9, peak=tf, unit='TFLOP/s', launches_per_step=9,
-                    ncu_name='fa2::fa2_fwd_kernel #0'))
     M = B * T
-    A = torch.randn(M, 384, device=dev).to(torch.bfloat16)
-    W = torch.randn(1152, 384, device=dev).to(torch.bfloat16)
-    Cc = torch.empty(M, 1152, device=dev)
-    t_g = timeit(lambda: L.scp_gemm_bf16_tn(_lib.ptr(A), _lib.ptr(W), None, _lib.ptr(Cc), M, 1152, 384, st))
-    out.append(dict(kernel='gemm_bf16_tn_kernel (qkv shape, fp32 out)', ms=t_g, bound='tensor',
-                    achieved=2.0 * M * 1152 * 384 / t_g / 1e9, peak=tf, unit='TFLOP/s', launches_per_step=9))
+    if x3:
+        qk = torch.randn(M, 1536, device=dev).to(torch.bfloat16)
+        vt = torch.zeros(2, B * 384, Tp, device=dev, dtype=torch.bfloat16)
+        vt[:, :, :T] = torch.randn(2, B * 384, T, device=dev).to(torch.bfloat16)
+        o = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
+        t_a = timeit(lambda: L.scp_attention_x3(_lib.ptr(qk), _lib.ptr(vt), _lib.ptr(o), B, T, st))
+        out.append(dict(kernel='fa3_fwd_kernel (tcgen05 flash attention, split operands)', ms=t_a, bound='tensor',
+                        achieved=4.0 * T * T * 64 * 6 * B / t_a / 1e9, peak=tf_eff, unit='TFLOP/s', launches_per_step=9,
+                        ncu_name='fa3::fa3_fwd_kernel #0', peak_source=tf_note))
+        A = torch.randn(M, 768, device=dev).to(torch.bfloat16)
+        W = torch.randn(1152, 768, device=dev).to(torch.bfloat16)
+        Cc = torch.empty(M, 1152, device=dev)
+        t_g = timeit(lambda: L.scp_gemm_bf16x3_tn(_lib.ptr(A), _lib.ptr(W), None, _lib.ptr(Cc), M, 1152, 384, st))
+        out.append(dict(kernel='gemm_bf16_tn_kernel<.,3> (qkv shape, fp32 out)', ms=t_g, bound='tensor',
+                        achieved=2.0 * M * 1152 * 384 / t_g / 1e9, peak=tf_eff, unit='TFLOP/s', launches_per_step=9,
+                        peak_source=tf_note))
+    else:
+        q = torch.randn(B * 6, T, 64, device=dev).to(torch.bfloat16)
+        vt = torch.zeros(B * 6, 64, Tp, device=dev, dtype=torch.bfloat16)
+        vt[:, :, :T] = q.transpose(1, 2)
+        o = torch.empty(B, T, 384, device=dev, dtype=torch.bfloat16)
+        t_a = timeit(lambda: L.scp_attention_tc5(_lib.ptr(q), _lib.ptr(q), _lib.ptr(vt), _lib.ptr(o), B, T, st))
+        out.append(dict(kernel='fa2_fwd_kernel (tcgen05 flash attention)', ms=t_a, bound='tensor',
+                        achieved=4.0 * T * T * 64 * 6 * B / t_a / 1e9, peak=tf, unit='TFLOP/s', launches_per_step=9,
+                        ncu_name='fa2::fa2_fwd_kernel #0'))
+        A = torch.randn(M, 384, device=dev).to(torch.bfloat16)
+        W = torch.randn(1152, 384, device=dev).to(torch.bfloat16)
+        Cc = torch.empty(M, 1152, device=dev)
+        t_g = timeit(lambda: L.scp_gemm_bf16_tn(_lib.ptr(A), _lib.ptr(W), None, _lib.ptr(Cc), M, 1152, 384, st))
+        out.append(dict(kernel='gemm_bf16_tn_kernel (qkv shape, fp32 out)', ms=t_g, bound='tensor',
+                        achieved=2.0 * M * 1152 * 384 / t_g / 1e9, peak=tf, unit='TFLOP/s', launches_per_step=9))
     for k in out:
         k['frac'] = k['achieved'] / k['peak']
         k['step_ms'] = k['ms'] * k['launches_per_step']
-    dom = max(out, key=lambda k: k['step_ms'] if 'vit_s8' not in k['kernel'] else 0)
+    dom = max((k for k in out if not k.get('chain')), key=lambda k: k['step_ms'])    # largest single kernel per step
     # DRAM bytes of one launch of that kernel -- and, because these kernels are issue / tensor bound rather than HBM
     # bound, its issue-slot and tensor-pipe utilisation -- from the committed `ncu --set full` capture (profiles/)
     traffic, ncu = None, None
@@ -289,67 +358,21 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
     except Exception:
         pass
     roof = {'kernel': dom['kernel'], 'bound': dom['bound'], 'achieved': dom['achieved'], 'peak': dom['peak'],
-            'unit': dom['unit'], 'frac': dom['frac'], 'traffic': traffic, 'ncu': ncu, 'peak_source': which,
+            'unit': dom['unit'], 'frac': dom['frac'], 'traffic': traffic, 'ncu': ncu, 'peak_source': dom.get('peak_source', which),
             'ms_per_launch': dom['ms'], 'launches_per_step': dom['launches_per_step']}
     return roof, out
 
 
-def main():
-    args = parse()
-    if args.impl == 'reference':
-        return run_reference(args)
-    import torch
-    import torch.distributed as dist
-    from self_corr_pose_b200 import _lib
-    from self_corr_pose_b200.hotpath import HotPath, default_opts
-    from self_corr_pose_b200.model.module.renderer import Renderer
-    from self_corr_pose_b200 import synthetic
-    _lib.lib()   # fail loudly if the native library is missing
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep stdout to the one JSON line (NCCL_DEBUG=VERSION)
-        dist.init_process_group('nccl', init_method='env://', device_id=dev)
-    B = args.batch
-    assert B % 4 == 0
-    opts = default_opts(img_size=256, corr_h=64, corr_w=64, batch_size=B // 4, repeat=4)
-    v, f = load_mesh(args.mesh)
-    mean_v, faces = torch.from_numpy(v), torch.from_numpy(f)
-    hot = HotPath(opts, mean_v, faces, device=dev, overlap_vit=not args.no_overlap)
-    data, enc = synthetic.make_batch(opts, v, f, B, device=dev, seed=rank, renderer=Renderer(opts, hot.mesh))
-    from self_corr_pose_b200.dist import FlatGradReducer
-    # the one parameter shared across the batch on this path: the canonical mesh (pred_v = mean_v + deformation)
-    mean_v_param = torch.nn.Parameter(mean_v.clone().to(dev))
-    reducer = FlatGradReducer([mean_v_param])
+class Timer:
+    """K calls of fn between CUDA events on the current stream, barrier + synchronize on both sides, max over ranks."""
 
-    graphed = None
-    if not args.no_graph:
-        try:   # whole step (forward + backward, ~900 launches) as ONE CUDA graph over static buffers
-            graphed = hot.capture(data, enc)
-        except Exception as e:   # noqa: BLE001 -- report and continue eagerly
-            print('CUDA graph capture failed, running eagerly: %r' % (e,), file=sys.stderr)
-            graphed = None
+    def __init__(self, torch, dist, dev, world):
+        self.torch, self.dist, self.dev, self.world = torch, dist, dev, world
 
-    def step(d):
-        if graphed is not None:
-            if d is not data:
-                graphed.load(data=d)
-            total = graphed.replay()
-            pred_v_grad = graphed.grads[2]
-        else:
-            total, aux = hot.step(d, enc)
-            pred_v_grad = enc[2].grad
-        if world > 1:   # the single flat-buffer gradient all-reduce of the data-parallel step (mean over ranks)
-            mean_v_param.grad = pred_v_grad.sum(0)
-            reducer.reduce()
-        return total
-
-    def timed(fn, k):
-        if world > 1:
-            dist.barrier()
+    def __call__(self, fn, k):
+        torch = self.torch
+        if self.world > 1:
+            self.dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -357,26 +380,45 @@ def main():
             fn()
         e1.record()
         torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t)
+
+
+def hotpath_arm(args, torch, dist, dev, world, rank, timed):
+    """Round-1 unit: HotPath step as ONE CUDA graph.  Returns dict(value, ms, e2e..., objects for the kernel breakdown)."""
+    from self_corr_pose_b200.hotpath import HotPath, default_opts
+    from self_corr_pose_b200.model.module.renderer import Renderer
+    from self_corr_pose_b200 import synthetic
+    B = args.batch
+    opts = default_opts(img_size=256, corr_h=64, corr_w=64, batch_size=B // 4, repeat=4)
+    v, f = load_mesh(args.mesh)
+    mean_v, faces = torch.from_numpy(v), torch.from_numpy(f)
+    hot = HotPath(opts, mean_v, faces, device=dev, overlap_vit=not args.no_overlap)
+    data, enc = synthetic.make_batch(opts, v, f, B, device=dev, seed=rank, renderer=Renderer(opts, hot.mesh))
+    graphed = None
+    if not args.no_graph:
+        try:   # whole step (forward + backward, ~900 launches) as ONE CUDA graph over static buffers
+            graphed = hot.capture(data, enc)
+        except Exception as e:   # noqa: BLE001 -- report and continue eagerly
+            print('CUDA graph capture failed, running eagerly: %r' % (e,), file=sys.stderr)
+
+    def step(d):
+        if graphed is not None:
+            if d is not data:
+                graphed.load(data=d)
+            return graphed.replay()
+        return hot.step(d, enc)[0]
 
     for _ in range(max(3, args.warmup)):
         loss = step(data)
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     ms = timed(lambda: step(data), args.steps)
-    value = B * world * args.steps / (ms / 1e3)
 
     # end to end through the public call with HOST buffers: H2D of the batch + step + D2H of the loss
     host = [t.detach().cpu().pin_memory() for t in data]
     h2d = sum(t.numel() * t.element_size() for t in host)
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-
-    # double-buffered upload: the H2D copy of step i+1's batch (copy stream) overlaps the compute of step i; every
-    # timed step performs one full upload from pinned memory and one loss read-back
     copy_stream = torch.cuda.Stream(dev)
     staging = [tuple(torch.empty_like(t) for t in data) for _ in range(2)]
     uploaded = [torch.cuda.Event() for _ in range(2)]
@@ -414,11 +456,141 @@ def main():
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    return dict(ms=ms / args.steps, ms_e2e=ms_e2e / args.steps, h2d=h2d, d2h=4, loss=float(loss.detach()), hot=hot, data=data,
+                enc=enc, graph=graphed is not None, launches=hot.GPU_LAUNCHES, N=v.shape[0], nf=f.shape[0])
+
+
+def trainer_arm(args, torch, dist, dev, world, rank, local, timed):
+    """Trainer.step on a device-resident batch (value) and on a pinned host batch with the loss read back (e2e)."""
+    from self_corr_pose_b200 import synthetic
+    from self_corr_pose_b200.hotpath import default_opts
+    from self_corr_pose_b200.model.trainer import Trainer
+    from self_corr_pose_b200.model.module.renderer import Renderer
+    B = args.batch
+    torch.backends.cudnn.benchmark = True               # train.py:21 of the reference
+    opts = default_opts(img_size=256, corr_h=64, corr_w=64, batch_size=B // 4, repeat=4, local_rank=local, ngpu=world,
+                        shape_prior_path=mesh_prior_path(args.mesh))
+    torch.manual_seed(0)
+    tr = Trainer(opts)
+    model = tr.define_model()
+    v, f = load_mesh(args.mesh)
+    batch = synthetic.make_trainer_batch(opts, v, f, B, device=dev, seed=rank, renderer=Renderer(opts, model.mesh))
+    for _ in range(max(3, args.warmup)):
+        total, aux, _ = tr.step(batch)
+    ms = timed(lambda: tr.step(batch), args.steps)
+
+    host = {k: (t.detach().cpu().pin_memory() if k not in ('center', 'length') else t) for k, t in batch.items()}
+    h2d = sum(t.numel() * t.element_size() for k, t in host.items() if k not in ('center', 'length'))
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():     # public call with HOST buffers: batch_reshape uploads them, the loss is read back
+        total, _, _ = tr.step(host)
+        loss_host.copy_(total.detach(), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return float(loss_host)
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    comm = None
+    if world > 1:       # the step's one data-path collective, timed alone on the real flat gradient buffer
+        red = tr.reducer
+        nbytes = red.flat.numel() * 4
+        t = timed(lambda: dist.all_reduce(red.flat), 10) / 10
+        n_sync_bn = sum(1 for m in model.modules() if m.__class__.__name__ == 'SyncBatchNorm')
+        comm = {'allreduce_bytes': nbytes, 'allreduce_ms': t, 'bus_gbs': 2 * (world - 1) / world * nbytes / t / 1e6,
+                'bus_gbs_reference_point': 725.0, 'frac_of_step': t / (ms / args.steps),
+                'sync_batchnorm_layers': n_sync_bn,
+                'sync_batchnorm_collectives_per_step': n_sync_bn * 2 * 2,   # (stats gather fwd + reduce bwd) x 2 encoder passes
+                'note': 'one all_reduce(SUM) of the flat fp32 gradient buffer per step (dist.FlatGradReducer), not overlapped '
+                        'with backward; SyncBatchNorm collectives as in the reference (trainer.py:66)'}
+    return dict(ms=ms / args.steps, ms_e2e=ms_e2e / args.steps, h2d=h2d, d2h=4, loss=float(total.detach()), comm=comm,
+                launches=model.GPU_LAUNCHES, N=v.shape[0], nf=f.shape[0],
+                aux={k: float(x) for k, x in aux.items()})
+
+
+def config1_arm(args, torch, dev, timed):
+    """BASELINE configs[1]: B = 32 images -> ViT features; correspondence fwd+bwd at P = 1024 and 4096, N = 1280, C = 64;
+    pre-training cycle block on pointcorr (B, 4096, N)."""
+    import torch.nn.functional as F
+    from self_corr_pose_b200 import synthetic
+    from self_corr_pose_b200.hotpath import default_opts
+    from self_corr_pose_b200.model.module.correspondence import Correspondence
+    from self_corr_pose_b200.model.module.pretrained_corr import PretrainedCorrespondence
+    from types import SimpleNamespace
+    B = args.batch
+    g = torch.Generator().manual_seed(0)
+    v, f = load_mesh(args.mesh)
+    N, C = v.shape[0], 64
+    img = torch.rand(B, 3, 256, 256, generator=g).to(dev)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, 256), torch.linspace(-1, 1, 256), indexing='ij')
+    mask = ((xx ** 2 + yy ** 2) < 0.36).float()[None].repeat(B, 1, 1).to(dev)
+    pred_v = (torch.from_numpy(v)[None] + 0.01 * torch.randn(B, N, 3, generator=g)).to(dev)
+    mesh_feat = F.normalize(torch.relu(torch.randn(B, N, C, generator=g)), 2, -1).to(dev).requires_grad_(True)
+    nets, feats = {}, {}
+    for hf in (32, 64):
+        opts = default_opts(img_size=256, corr_h=hf, corr_w=hf, batch_size=B // 4, repeat=4)
+        nets[hf] = Correspondence(opts, dev)
+        feats[hf] = F.normalize(torch.randn(B, C, hf * hf, generator=g), 2, 1).to(dev).requires_grad_(True)
+    opts = default_opts(img_size=256, corr_h=64, corr_w=64, batch_size=B // 4, repeat=4)
+    pre = PretrainedCorrespondence(opts, SimpleNamespace(), device=dev).to(dev)
+    depth_weight = torch.ones(B, N, device=dev)
+
+    def step():
+        for t in (mesh_feat, feats[32], feats[64]):
+            t.grad = None
+        loss = 0
+        for hf in (32, 64):
+            pointcorr, match, imatch = nets[hf].match_lowres(feats[hf], mesh_feat, mask, pred_v)
+            loss = loss + match.square().mean() + imatch.square().mean()
+        cyc = pre.compute_cycle_loss(img, mask, depth_weight, pointcorr, pooled=True, A=nets[64].pool_A)
+        loss = loss + cyc[0]
+        loss.backward()
+        return loss
+    for _ in range(max(3, args.warmup)):
+        loss = step()
+    ms = timed(step, args.steps)
+    return dict(ms=ms / args.steps, ms_e2e=None, h2d=0, d2h=0, loss=float(loss.detach()), launches=68 + 2 * 8 + 2 + 2,
+                N=N, nf=f.shape[0])
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+    os.environ['SCP_VIT_PRECISION'] = args.vit_precision
+    import torch
+    import torch.distributed as dist
+    from self_corr_pose_b200 import _lib
+    _lib.lib()   # fail loudly if the native library is missing
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep stdout to the one JSON line (NCCL_DEBUG=VERSION)
+        dist.init_process_group('nccl', init_method='env://', device_id=dev)
+    if args.workload == 'config1' and args.batch == 64:
+        args.batch = 32
+    B = args.batch
+    assert B % 4 == 0
+    timed = Timer(torch, dist, dev, world)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    hp = None
+    if args.workload == 'trainer':
+        main_arm = trainer_arm(args, torch, dist, dev, world, rank, local, timed)
+        if world == 1 and not args.no_kernel_breakdown:      # second reported figure + objects for the kernel breakdown
+            hp = hotpath_arm(args, torch, dist, dev, world, rank, timed)
+    elif args.workload == 'hotpath':
+        main_arm = hp = hotpath_arm(args, torch, dist, dev, world, rank, timed)
+    else:
+        main_arm = config1_arm(args, torch, dev, timed)
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
-    e2e_value = B * world * args.steps / (ms_e2e / 1e3)
-
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -430,29 +602,37 @@ def main():
     except Exception:
         pass
     roof, kernels = (None, [])
-    if not args.no_kernel_breakdown:
-        roof, kernels = kernel_breakdown(torch, hot, data, enc, B, peaks)
+    if hp is not None and not args.no_kernel_breakdown:
+        roof, kernels = kernel_breakdown(torch, hp['hot'], hp['data'], hp['enc'], B, peaks)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1 and args.workload != 'config1':
         cpu, _ = cpu_step_rate(args, dict(img_size=256, corr_h=64, corr_w=64), 'cpu_baseline')
+    ms = main_arm['ms']
     line = {
-        'metric': 'images/sec fwd+bwd (feat+corr+render+loss) 256x256', 'value': value, 'unit': 'images/sec',
-        'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (ViT GEMM operands bf16)',
-        'data': 'synthetic',
-        'config': {'workload': 'configs[2]: hot path fwd+bwd = fused correspondence (P=4096,N=%d,C=64) -> texture -> '
-                               '4 SoftRas renders (nf=%d) -> mask/texture/depth/match/imatch losses -> DINO ViT-S/8 '
-                               'layer-9 keys + pseudo-matches + pre-train cycle loss; encoder outputs are inputs'
-                               % (v.shape[0], f.shape[0]),
+        'metric': 'images/sec fwd+bwd (feat+corr+render+loss) 256x256', 'value': B * world / (ms / 1e3), 'unit': 'images/sec',
+        'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 (DINO ViT tensor-core products: %s)' % ('bf16x3 split = fp32-class, the parity mode'
+                                                              if args.vit_precision == 'x3' else 'plain bf16, labelled FAST MODE outside the 1e-3 parity contract'),
+        'data': 'synthetic (seeded synthetic DINO / ResNet weights: no checkpoints offline)',
+        'config': {'workload': WORKLOAD_TEXT[args.workload] % (main_arm['N'], main_arm['nf']),
                    'images_per_gpu': B, 'img_size': 256, 'mesh': args.mesh, 'parallelism': 'dp%d' % world,
-                   'l2': 'working set per step (~1 GB) exceeds the 126 MB L2; no explicit flush',
-                   'cuda_graph': graphed is not None},
-        'e2e': {'value': e2e_value, 'unit': 'images/sec', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                'ms_per_step': ms_e2e / args.steps},
-        'gpu_launches': hot.GPU_LAUNCHES * args.steps,
+                   'vit_precision': args.vit_precision,
+                   'l2': 'working set per step (>1 GB) exceeds the 126 MB L2; no explicit flush',
+                   'cuda_graph': main_arm.get('graph', False)},
+        'e2e': None if main_arm['ms_e2e'] is None else {
+            'value': B * world / (main_arm['ms_e2e'] / 1e3), 'unit': 'images/sec', 'h2d_bytes_per_step': main_arm['h2d'],
+            'd2h_bytes_per_step': main_arm['d2h'], 'ms_per_step': main_arm['ms_e2e']},
+        'gpu_launches': main_arm['launches'] * args.steps,
         'clocks': sampler.summary() if sampler else None,
-        'roofline': roof, 'kernels': kernels, 'cpu_baseline': cpu, 'loss': float(loss.detach()),
+        'roofline': roof, 'kernels': kernels, 'cpu_baseline': cpu, 'loss': main_arm['loss'],
     }
+    if main_arm.get('comm'):
+        line['comm'] = main_arm['comm']
+    if args.workload == 'trainer' and hp is not None:
+        line['hotpath'] = {'value': B / (hp['ms'] / 1e3), 'unit': 'images/sec', 'ms_per_step': hp['ms'],
+                           'e2e_value': B / (hp['ms_e2e'] / 1e3), 'cuda_graph': hp['graph'],
+                           'workload': WORKLOAD_TEXT['hotpath'] % (hp['N'], hp['nf'])}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

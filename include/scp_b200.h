@@ -239,7 +239,8 @@ int scp_symmetry_nn_backward(const float *pred_v, const int *faces, const long l
 /* ---- encoder input: photometric jitter + normalisation ------------------------------------ */
 /*
  * out = Normalize(mean, std)(ColorJitter(img)) of Encoder.encode_img (model/module/encoder.py:30-32), torchvision tensor
- * semantics (one parameter set for the whole batch): img, out [B][3][HW] fp32 planar, values in [0,1] on input.
+ * semantics (one parameter set for the whole batch): img [B][3][HW] fp32 planar, values in [0,1]; out planar like img, or
+ * channels-last [B][HW][3] when nhwc_out != 0 (the layout cuDNN's tensor-core convolutions want).
  * order[4]: torchvision step ids in application order (0 brightness, 1 contrast, 2 saturation, 3 hue; -1 skips a step);
  * ratios[6] = (ratio, 1 - ratio) of brightness, contrast, saturation AS ROUNDED BY THE CALLER (torchvision forms 1 - ratio
  * in double precision); hue in [-0.5, 0.5]; mean/std [3] host arrays.  All of order/ratios/mean/std are HOST pointers
@@ -247,7 +248,8 @@ int scp_symmetry_nn_backward(const float *pred_v, const int *faces, const long l
  */
 size_t scp_color_jitter_workspace_bytes(int B);
 int scp_color_jitter_normalize(const float *img, float *out, int B, int HW, const int *order, const float *ratios, float hue,
-                               const float *mean, const float *std, void *workspace, size_t workspace_bytes, void *stream);
+                               const float *mean, const float *std, int nhwc_out, void *workspace, size_t workspace_bytes,
+                               void *stream);
 
 /* ---- pre-training cycle loss: the k gathered target rows of every image pair ------------------------------ */
 /*

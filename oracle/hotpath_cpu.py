@@ -133,6 +133,7 @@ def forward(opts, mean_v, faces, data, enc, vit_sd, it=0, use_ref=False, nthread
     aux['mask_render'] = mask_render
     aux['match'] = match
     aux['imatch'] = imatch
+    aux['_pointcorr'], aux['_depth_weight'] = pointcorr, depth_weight      # for oracle/trainer_cpu.py
     return total, aux
 
 

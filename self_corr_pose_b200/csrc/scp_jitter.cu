@@ -51,7 +51,7 @@ __device__ __forceinline__ void hue_shift(float &r, float &g, float &b, float hu
     const float hg = ((maxc == g) && (maxc != r)) ? sub(add(2.f, rc), bc) : 0.f;
     const float hb = ((maxc != g) && (maxc != r)) ? sub(add(4.f, gc), rc) : 0.f;
     float h = add(add(hr, hg), hb);
-    h = fmodf(add(h / 6.f, 1.f), 1.f);
+    h = fmodf(add(mul(h, (float)(1.0 / 6.0)), 1.f), 1.f);   // torch divides by a python scalar as a multiply by its reciprocal
     // h = (h + hue_factor) % 1.0  (python-style remainder)
     h = add(h, hue);
     h = sub(h, floorf(h));
@@ -127,7 +127,8 @@ gray_sum_kernel(const float *__restrict__ img, int HW, Params P, int n_before, d
 
 // pass B: all steps + (x - mean) / std
 __global__ void __launch_bounds__(256)
-jitter_norm_kernel(const float *__restrict__ img, float *__restrict__ out, int HW, Params P, const double *__restrict__ gsum)
+jitter_norm_kernel(const float *__restrict__ img, float *__restrict__ out, int HW, Params P, const double *__restrict__ gsum,
+                   int nhwc_out)
 {
     const int b = blockIdx.y;
     const float *base = img + (long)b * 3 * HW;
@@ -145,6 +146,13 @@ jitter_norm_kernel(const float *__restrict__ img, float *__restrict__ out, int H
         g[j] = sub(g[j], P.mean[1]) / P.std[1];
         bl[j] = sub(bl[j], P.mean[2]) / P.std[2];
     }
+    if (nhwc_out) {     // channels-last output [B][HW][3]: 4 pixels = 12 consecutive floats
+        float4 *o4 = reinterpret_cast<float4 *>(ob + 3 * (long)i);
+        o4[0] = make_float4(r[0], g[0], bl[0], r[1]);
+        o4[1] = make_float4(g[1], bl[1], r[2], g[2]);
+        o4[2] = make_float4(bl[2], r[3], g[3], bl[3]);
+        return;
+    }
     *reinterpret_cast<float4 *>(ob + i) = make_float4(r[0], r[1], r[2], r[3]);
     *reinterpret_cast<float4 *>(ob + HW + i) = make_float4(g[0], g[1], g[2], g[3]);
     *reinterpret_cast<float4 *>(ob + 2 * HW + i) = make_float4(bl[0], bl[1], bl[2], bl[3]);
@@ -156,7 +164,7 @@ jitter_norm_kernel(const float *__restrict__ img, float *__restrict__ out, int H
 extern "C" size_t scp_color_jitter_workspace_bytes(int B) { return B > 0 ? (size_t)B * sizeof(double) : 0; }
 
 extern "C" int scp_color_jitter_normalize(const float *img, float *out, int B, int HW, const int *order, const float *ratios,
-                                          float hue, const float *mean, const float *std, void *workspace,
+                                          float hue, const float *mean, const float *std, int nhwc_out, void *workspace,
                                           size_t workspace_bytes, void *stream)
 {
     using namespace scp::jitter;
@@ -190,6 +198,6 @@ extern "C" int scp_color_jitter_normalize(const float *img, float *out, int B, i
         const int bx = (HW / 4 + 255) / 256;
         gray_sum_kernel<<<dim3(bx < 32 ? bx : 32, B), 256, 0, st>>>(img, HW, P, n_before, gsum);
     }
-    jitter_norm_kernel<<<dim3((HW / 4 + 255) / 256, B), 256, 0, st>>>(img, out, HW, P, gsum);
+    jitter_norm_kernel<<<dim3((HW / 4 + 255) / 256, B), 256, 0, st>>>(img, out, HW, P, gsum, nhwc_out);
     return scp::check_launch("scp_color_jitter_normalize");
 }

@@ -102,7 +102,7 @@ class CanonicalMesh(nn.Module):
         v = pred_v[:, None].repeat(1, k, 1, 1).reshape(k * bsz, self.num_verts, 3)
         f = faces[:, None].repeat(1, k, 1, 1).reshape(k * bsz, self.num_faces, 3)
         with torch.no_grad():
-            face_idx, w = sample_faces_and_weights(v, f, npts)
+            face_idx, w = (getattr(self, 'sampler', None) or sample_faces_and_weights)(v, f, npts)
         if getattr(self, '_faces_i32', None) is None or self._faces_i32.device != pred_v.device:
             self._faces_i32 = self.faces.detach().to(pred_v.device, torch.int32).contiguous()
         dist, _ = symmetry_nn(pred_v, self._faces_i32, face_idx, w, self.symm_rots)
@@ -113,7 +113,8 @@ class CanonicalMesh(nn.Module):
         k, bsz = self.symm_rots.shape[0], pred_v.shape[0]
         v = pred_v[:, None].repeat(1, k, 1, 1).reshape(k * bsz, self.num_verts, 3)
         f = faces[:, None].repeat(1, k, 1, 1).reshape(k * bsz, self.num_faces, 3)
-        pts = sample_points_from_meshes(v, f, npts)
+        face_idx, w = (getattr(self, 'sampler', None) or sample_faces_and_weights)(v, f, npts)
+        pts = points_from_samples(v, f, face_idx, w)
         rots = self.symm_rots[None].repeat(bsz, 1, 1, 1).reshape(k * bsz, 3, 3)
         # pts.bmm(rots) of the reference (mesh.py:61), written element-wise: cuBLAS runs a (10000 x 3) x (3 x 3) batch as
         # one gemv launch PER MESH (128 launches, 14 ms per step at B = 64 on a B200)
@@ -121,6 +122,8 @@ class CanonicalMesh(nn.Module):
         return chamfer_single_way(v, rotated)
 
     def _load_prior(self, path):
+        if path == 'synthetic:uv1280':     # the 1280-vertex / 2556-face sphere of BASELINE.json (benchmarks, tests)
+            return synthetic.uv_sphere()
         if os.path.exists(path):
             return read_obj(path)
         if not _flags.synthetic_weights_allowed():

@@ -39,6 +39,10 @@ class Trainer:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(self.model)
         self.model = self.model.to(dev)
+        # NHWC weights for the convolutional encoder / decoder: with the channels-last encoder input (ops/color_jitter.py)
+        # cuDNN runs its tensor-core NHWC kernels end to end without per-call layout conversions (values unchanged)
+        for m in (self.model.encoder.backbone, self.model.encoder.featnet):
+            m.to(memory_format=torch.channels_last)
         self.device = dev
         self.optim = Optimizers(opts, self.model)
         self.reducer = FlatGradReducer([p for n, p in self.model.named_parameters() if 'pretrain_corr_net' not in n])

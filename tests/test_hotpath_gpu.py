@@ -1,8 +1,9 @@
 """GPU step-level parity: HotPath (all native kernels) vs the reference-formulation CPU hot path
 (oracle/hotpath_cpu.py) on the same synthetic batch: every loss term and the gradients w.r.t. the encoder
-outputs.  Tolerance 1e-3 relative (norm-wise for gradients) for everything that does not go through the
-bf16 ViT; the DINO pseudo-matches are arg-max decisions on bf16 features, so the pre-training cycle term is
-compared with its own, stated, looser bound."""
+outputs.  Tolerance 1e-3 relative on every loss term (north star) -- including the pre-training cycle term, whose
+pseudo matches are arg-max / top-k decisions on the DINO features: the ViT runs in its fp32-class (x3) precision by
+default; gradients 1e-3 norm-wise (the SoftRas oracle in its FMA-contracted build = nvcc's rounding model, DESIGN.md
+section 2).  The benchmarked shape (256 px, 1280-vertex sphere, P = 4096, k = 200) is covered at B = 8."""
 import numpy as np
 import pytest
 import torch
@@ -36,29 +37,51 @@ def run_pair(opts, B, mesh):
     return (total, aux, [e.grad for e in enc_d]), (total_o, aux_o, grads_o)
 
 
+GRAD_NAMES = ('img_feat', 'mesh_feat', 'pred_v', 'rotation', 'translation')
+
+
+def check_pair(tag, got, want, loss_rtol=1e-3, grad_rtol=1e-3):
+    (total, aux, grads), (total_o, aux_o, grads_o) = got, want
+    rep = {k: (float(aux[k]), float(aux_o[k])) for k in aux if aux[k].dim() == 0}
+    g = {n: rel(a, b) for n, a, b in zip(GRAD_NAMES, grads, grads_o)}
+    print('PARITY %s losses %s grad rel %s' % (tag, {k: '%.6g/%.6g' % v for k, v in rep.items()},
+                                              {k: '%.2e' % v for k, v in g.items()}))
+    for k, (a, b) in rep.items():
+        assert abs(a - b) <= loss_rtol * abs(b) + 1e-7, (k, a, b)
+    for n in g:
+        assert g[n] < grad_rtol, (n, g[n])
+
+
 def test_step_parity_without_dino_term():
     opts = default_opts(img_size=128, corr_h=32, corr_w=32, batch_size=2, repeat=2, pretrain_k=50,
                         cycle_loss_pretrain_wt=0.0)
-    (total, aux, grads), (total_o, aux_o, grads_o) = run_pair(opts, 4, synthetic.icosphere(3))
-    rep = {k: (float(aux[k]), float(aux_o[k])) for k in aux if aux[k].dim() == 0}
-    g = {n: rel(a, b) for n, a, b in zip(('img_feat', 'mesh_feat', 'pred_v', 'rotation', 'translation'), grads, grads_o)}
-    print('PARITY hotpath(no dino) losses', {k: '%.6g/%.6g' % v for k, v in rep.items()}, 'grad rel', g)
-    for k, (a, b) in rep.items():
-        assert abs(a - b) <= 1e-3 * abs(b) + 1e-7, (k, a, b)
-    # against the FMA build of the SoftRas oracle every gradient is within a few 1e-3 norm-wise (the residual is
-    # the order of the atomic gradient accumulation and single-TF32 correspondence gradient products)
-    for n in g:
-        assert g[n] < 5e-3, (n, g[n])
+    got, want = run_pair(opts, 4, synthetic.icosphere(3))
+    check_pair('hotpath(no dino)', got, want)
 
 
 def test_step_parity_full():
     opts = default_opts(img_size=128, corr_h=32, corr_w=32, batch_size=2, repeat=2, pretrain_k=50)
+    got, want = run_pair(opts, 4, synthetic.icosphere(3))
+    check_pair('hotpath(full)', got, want)
+
+
+def test_step_parity_benchmark_shape():
+    """BASELINE configs[2] shape: 256 px, the 1280-vertex / 2556-face sphere, P = 4096, C = 64, k = 200; B = 8."""
+    opts = default_opts(img_size=256, corr_h=64, corr_w=64, batch_size=2, repeat=4, pretrain_k=200)
+    got, want = run_pair(opts, 8, synthetic.uv_sphere())
+    check_pair('hotpath(configs[2] shape, B=8)', got, want)
+
+
+def test_bf16_fast_mode_is_labelled_and_close(monkeypatch):
+    """The bf16 ViT (SCP_VIT_PRECISION=bf16) is a labelled fast mode: arg-max pseudo matches on bf16 features move the
+    pre-training cycle term by ~1 %, everything else is unaffected."""
+    monkeypatch.setenv('SCP_VIT_PRECISION', 'bf16')
+    opts = default_opts(img_size=128, corr_h=32, corr_w=32, batch_size=2, repeat=2, pretrain_k=50)
     (total, aux, grads), (total_o, aux_o, grads_o) = run_pair(opts, 4, synthetic.icosphere(3))
     a, b = float(aux['cycle_loss_pretrain']), float(aux_o['cycle_loss_pretrain'])
-    print('PARITY hotpath(full) total %.6g/%.6g cycle_pretrain %.6g/%.6g' % (float(total), float(total_o), a, b))
-    assert abs(a - b) <= 0.1 * abs(b) + 1e-6       # arg-max pseudo matches on bf16 ViT features
+    print('PARITY hotpath(bf16 ViT fast mode) total %.6g/%.6g cycle_pretrain %.6g/%.6g' % (float(total), float(total_o), a, b))
+    assert abs(a - b) <= 0.1 * abs(b) + 1e-6
     assert abs(float(total) - float(total_o)) <= 2e-2 * abs(float(total_o))
-    assert all(torch.isfinite(x).all() for x in grads)
 
 
 def test_cuda_graph_replay_matches_eager():

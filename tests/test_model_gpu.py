@@ -44,3 +44,81 @@ def test_trainer_step_and_eval_forward():
     assert imatch.shape == (4, 2, 995) and rotation.shape == (4, 3, 3) and translation.shape == (4, 1, 3)
     det = torch.det(rotation)
     assert torch.allclose(det.abs(), torch.ones_like(det), atol=1e-4)
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize('size,corr,B,k', [(128, 32, 4, 50), (256, 64, 8, 200)])
+def test_trainer_step_parity_vs_cpu_reference_formulation(size, corr, B, k):
+    """Trainer.step (MeshNet.forward + backward + clip + AdamW; encoder x2, symmetry, rotation cycle included) on the GPU
+    against oracle/trainer_cpu.py = the same step in the reference's formulation on the CPU, from the same weights, batch
+    and random draws (global CPU generator: jitter parameters, rotation angle; the device-side surface samples of the
+    symmetry loss are injected on both sides).  fp32 on both sides (TF32 off for this comparison).
+    Tolerance: every aux_output scalar 1e-3 relative; parameter gradients 1e-3 norm-wise per optimiser group
+    (2e-3 for the backbone: BatchNorm batch statistics through 20 layers, observed below); updated parameters 1e-5."""
+    from oracle import hotpath_cpu as H
+    from oracle import trainer_cpu as TC
+    from types import SimpleNamespace
+    from self_corr_pose_b200.model.trainer import Trainer
+    from self_corr_pose_b200.model.module.renderer import Renderer
+    from self_corr_pose_b200.model.module.mesh import sample_faces_and_weights
+    from self_corr_pose_b200.model.module.network.vit_weights import synthetic_state_dict
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        opts = default_opts(img_size=size, corr_h=corr, corr_w=corr, batch_size=B // 2, repeat=2, pretrain_k=k,
+                            total_iters=100, allow_tf32=False)
+        torch.manual_seed(0)
+        tr = Trainer(opts)
+        model = tr.define_model()
+        cpu = TC.CpuTrainer(opts, synthetic_state_dict(0), fma=True)
+        cpu.load_state_from(model)
+        v, f = synthetic.load_prior('laptop')
+        mesh = SimpleNamespace(mean_v=torch.from_numpy(v), faces=torch.from_numpy(f), texture_type='vertex')
+        with H.cpu_rasterizer():
+            batch = synthetic.make_trainer_batch(opts, v, f, B, device='cpu', seed=2, renderer=Renderer(opts, mesh))
+        # surface samples of the symmetry regulariser: drawn once on the CPU, injected on both sides
+        kk = model.mesh.symm_rots.shape[0]
+        gen_v = cpu.model.mesh.mean_v.detach()[None].repeat(kk * B, 1, 1)
+        gen_f = cpu.model.mesh.faces[None].repeat(kk * B, 1, 1)
+        torch.manual_seed(123)
+        fi, w = sample_faces_and_weights(gen_v, gen_f, 10000)
+        model.mesh.sampler = lambda vv, ff, n: (fi.cuda(), w.cuda())
+        before = {n: p.detach().clone() for n, p in model.named_parameters() if p.requires_grad and 'pretrain' not in n}
+
+        torch.manual_seed(5)
+        cb = Trainer(opts)
+        cb.device = torch.device('cpu')
+        total_o, aux_o, grad_o = cpu.step(cb.batch_reshape(batch), symmetry_samples=(fi, w))
+        torch.manual_seed(5)
+        total, aux, grad = tr.step({kk_: (t.cuda() if kk_ not in ('center', 'length') else t) for kk_, t in batch.items()})
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    rep = {kk_: (float(aux[kk_]), float(aux_o[kk_])) for kk_ in KEYS}
+    print('PARITY trainer-step %dpx B%d losses %s' % (size, B, {kk_: '%.6g/%.6g' % vv for kk_, vv in rep.items()}))
+    for kk_, (a, b) in rep.items():
+        assert abs(a - b) <= 1e-3 * abs(b) + 1e-7, (kk_, a, b)
+    # gradients (after clipping) per optimiser group, and the parameters after the AdamW step
+    cpu_params = dict(cpu.model.named_parameters())
+    groups = {}
+    for n, p in model.named_parameters():
+        if n not in cpu_params or p.grad is None:
+            continue
+        key = next((g for g in ('mean_v', 'pose_predictor', 'shape', 'featnet', 'backbone') if g in n), 'other')
+        groups.setdefault(key, []).append((p.grad.detach().cpu().reshape(-1), cpu_params[n].grad.reshape(-1),
+                                           p.detach().cpu().reshape(-1), cpu_params[n].detach().reshape(-1)))
+    rels = {}
+    for key, items in groups.items():
+        ga, gb = torch.cat([i[0] for i in items]), torch.cat([i[1] for i in items])
+        pa, pb = torch.cat([i[2] for i in items]), torch.cat([i[3] for i in items])
+        rels[key] = (_rel(ga, gb), _rel(pa, pb))
+    print('PARITY trainer-step %dpx B%d (grad rel, param rel) per group %s clip norms %s / %s'
+          % (size, B, {kk_: '%.2e/%.2e' % vv for kk_, vv in rels.items()}, [float(x) for x in grad], [float(x) for x in grad_o]))
+    for key, (gr, pr) in rels.items():
+        assert gr < (2e-3 if key == 'backbone' else 1e-3), (key, gr)
+        assert pr < 1e-5, (key, pr)
