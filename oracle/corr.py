@@ -16,6 +16,17 @@ import torch
 import torch.nn.functional as F
 
 
+def select_topk(score, k):
+    """torch.topk(-distance, k) of pretrained_corr.py:97; a hook because the choice among exactly tied distances is
+    implementation-defined (see the product's model/module/pretrained_corr.py::select_topk)."""
+    return torch.topk(score, k=k, dim=1).indices
+
+
+def stable_topk(score, k):
+    """Deterministic variant for CPU <-> GPU parity tests: descending score, lowest index first among equal scores."""
+    return torch.sort(score, dim=1, descending=True, stable=True).indices[:, :k]
+
+
 def meshgrid(hf, wf):
     g = torch.Tensor(np.array(np.meshgrid(range(wf), range(hf)))).reshape(2, -1) + 0.5
     return g / (wf / 2) - 1
@@ -93,7 +104,7 @@ def pretrain_match(src_feat, tgt_feat, src_mask, tgt_mask, grid, feat_size, k):
     cycle = torch.gather(grid, -1, max_cy[:, None].repeat(1, 2, 1))
     distance = (cycle - grid).norm(2, 1)
     distance = distance * (tgt_mask_down > 0) + 1e5 * (tgt_mask_down == 0)
-    _, indices = torch.topk(-distance, k=k, dim=1)
+    indices = select_topk(-distance, k)
     match = torch.gather(match, -1, indices[:, None].repeat(1, 2, 1))
     grid_k = torch.gather(grid, -1, indices[:, None].repeat(1, 2, 1))
     match_mask = torch.gather(tgt_mask_down, -1, indices)

@@ -39,12 +39,15 @@ constexpr int LIST_CAP = 2048;  // tile face list capacity (indices) per phase
 #define SCP_SOFTRAS_FACE_WARPS 2
 #endif
 #ifndef SCP_SOFTRAS_FACE_CTAS
-#define SCP_SOFTRAS_FACE_CTAS 8
+#define SCP_SOFTRAS_FACE_CTAS 10
 #endif
-// Next-round candidate, NOT validated on a GPU yet (default off): the face-centric backward keeps its face record
-// (48 floats) in shared memory instead of registers, so that SCP_SOFTRAS_FACE_CTAS can rise above 8 without spilling.
+// The face-centric backward keeps its face record (48 floats) in shared memory instead of registers, so that
+// SCP_SOFTRAS_FACE_CTAS can rise above 8 without spilling (95 registers, 20 resident warps per SM).  Round-2 A/B on a B200
+// (B = 64, 256 px, 2556 faces; gpurun_out/r2_call1.log): soft-texture backward 3.04 -> 2.87 ms, depth backward 1.26 -> 1.18 ms,
+// parity tests unchanged -> default.  (The other two round-1 candidates lost: 16x2 pixel blocks 3.04 -> 3.13 ms, two pixels
+// per lane in the forward 2.31 -> 2.74 ms.)
 #ifndef SCP_SOFTRAS_FACE_SMEM
-#define SCP_SOFTRAS_FACE_SMEM 0
+#define SCP_SOFTRAS_FACE_SMEM 1
 #endif
 // Pixel block a warp of the face-centric backward covers per iteration: BW x (32 / BW) pixels (default 8 x 4).  16 x 2
 // wastes fewer lanes on the 14-pixel boxes of the sigma = 1e-4 renders and on the 30-pixel boxes of the soft-texture

@@ -24,6 +24,15 @@ from ...ops.cycle_rows import cycle_rows
 from ..util.loss_utils import divide_by_frame, divide_by_instance, divide_by_both
 
 
+def select_topk(score, k):
+    """Indices of the k largest scores per row: `torch.topk(-distance, k)` of pretrained_corr.py:97.  The cycle distances
+    live on a coarse grid, so many are EXACTLY equal (typically more than k pixels close their cycle with distance 0), and
+    which of the tied pixels torch.topk returns is implementation-defined -- it differs between torch's CPU and CUDA
+    kernels; the reference inherits whatever its device gives.  Parity tests replace this function (here and in
+    oracle/corr.py) by a deterministic rule so that both sides select the same pixels."""
+    return torch.topk(score, k=k, dim=1).indices
+
+
 def decode_argmax(best):
     """scp_dino_argmatch packs (order-preserving similarity bits << 32 | 0xffffffff - column) into 64 bits (stored in an
     int64 tensor); 0 = no unmasked column -> index 0 (a constant row of the reference's masked similarity)."""
@@ -106,7 +115,7 @@ class PretrainedCorrespondence(nn.Module):
         cycle = torch.gather(grid, -1, max_cy[:, None].expand(-1, 2, -1))
         distance = (cycle - grid).norm(2, 1)
         distance = distance * (tgt_mask_down > 0) + 1e5 * (tgt_mask_down == 0)
-        _, indices = torch.topk(-distance, k=self.k, dim=1)
+        indices = select_topk(-distance, self.k)
         match = torch.gather(match, -1, indices[:, None].expand(-1, 2, -1))
         grid_k = torch.gather(grid, -1, indices[:, None].expand(-1, 2, -1))
         match_mask = torch.gather(tgt_mask_down, -1, indices)
