@@ -39,12 +39,18 @@ class FlatGradReducer:
         off = 0
         for p in used:
             n = p.numel()
-            view = flat[off:off + n].view(p.shape)
+            view = self._view(flat, p, off)
             view.copy_(p.grad)
             p.grad = view
             off += n
         self.flat, self.used = flat, used
         return self
+
+    @staticmethod
+    def _view(flat, p, off):
+        """Slice [off, off + numel) of the flat buffer with the parameter's own (dense) strides: autograd's layout contract
+        and the fused optimiser kernels want gradient and parameter laid out alike (channels-last convolution weights)."""
+        return torch.as_strided(flat, p.shape, p.stride(), storage_offset=off)
 
     @property
     def adopted(self):
@@ -64,7 +70,7 @@ class FlatGradReducer:
         for p in self.used:
             n = p.numel()
             if p.grad is None:
-                p.grad = self.flat[off:off + n].view(p.shape)
+                p.grad = self._view(self.flat, p, off)
             off += n
 
     def reduce(self, group=None, timed=False):

@@ -107,11 +107,13 @@ def _worker(rank, world, port, out):
     dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
     torch.manual_seed(0)
     w = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7)), torch.nn.Parameter(torch.randn(2))]
+    cl = torch.nn.Parameter(torch.randn(4, 3, 2, 2).to(memory_format=torch.channels_last))   # a channels-last conv weight
     x = torch.full((5, 3), float(rank + 1))
     loss = (w[0] * x).sum() + (w[1] ** 2).sum() * (rank + 1)      # w[2] gets no gradient on any rank
-    loss.backward()
-    red = FlatGradReducer(w)
+    (loss + (cl * (rank + 1)).sum()).backward()
+    red = FlatGradReducer(w + [cl])
     red.reduce()
+    assert cl.grad.stride() == cl.stride() and torch.allclose(cl.grad, torch.full_like(cl, 1.5))
     first = [None if p.grad is None else p.grad.clone() for p in w]
     # second step: gradients accumulate in place into the views of the flat buffer
     assert red.adopted and all(p.grad.data_ptr() >= red.flat.data_ptr() for p in w[:2])
