@@ -475,16 +475,24 @@ def trainer_arm(args, torch, dist, dev, world, rank, local, timed):
     model = tr.define_model()
     v, f = load_mesh(args.mesh)
     batch = synthetic.make_trainer_batch(opts, v, f, B, device=dev, seed=rank, renderer=Renderer(opts, model.mesh))
+    graphed = False
+    if not args.no_graph:
+        try:        # zero-grad + forward + backward of the step as ONE CUDA graph (Trainer.capture)
+            tr.capture(batch, warmup=max(3, args.warmup))
+            graphed = True
+        except Exception as e:   # noqa: BLE001 -- report and continue eagerly
+            print('CUDA graph capture of Trainer.step failed, running eagerly: %r' % (e,), file=sys.stderr)
+    step_fn = tr.step_graphed if graphed else tr.step
     for _ in range(max(3, args.warmup)):
-        total, aux, _ = tr.step(batch)
-    ms = timed(lambda: tr.step(batch), args.steps)
+        total, aux, _ = step_fn(batch)
+    ms = timed(lambda: step_fn(batch), args.steps)
 
     host = {k: (t.detach().cpu().pin_memory() if k not in ('center', 'length') else t) for k, t in batch.items()}
     h2d = sum(t.numel() * t.element_size() for k, t in host.items() if k not in ('center', 'length'))
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def e2e_step():     # public call with HOST buffers: batch_reshape uploads them, the loss is read back
-        total, _, _ = tr.step(host)
+        total, _, _ = step_fn(host)
         loss_host.copy_(total.detach(), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         return float(loss_host)
@@ -505,7 +513,7 @@ def trainer_arm(args, torch, dist, dev, world, rank, local, timed):
                 'note': 'one all_reduce(SUM) of the flat fp32 gradient buffer per step (dist.FlatGradReducer), not overlapped '
                         'with backward; SyncBatchNorm collectives as in the reference (trainer.py:66)'}
     return dict(ms=ms / args.steps, ms_e2e=ms_e2e / args.steps, h2d=h2d, d2h=4, loss=float(total.detach()), comm=comm,
-                launches=model.GPU_LAUNCHES, N=v.shape[0], nf=f.shape[0],
+                launches=model.GPU_LAUNCHES, N=v.shape[0], nf=f.shape[0], graph=graphed,
                 aux={k: float(x) for k, x in aux.items()})
 
 
@@ -558,6 +566,16 @@ def main():
     args = parse()
     if args.impl == 'reference':
         return run_reference(args)
+    # exactly ONE line on stdout: libraries (NCCL's version banner, cuDNN notices) write to fd 1 as well -- park the real
+    # stdout and point fd 1 at stderr until the JSON line is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(line, flush=True)
     os.environ['SCP_VIT_PRECISION'] = args.vit_precision
     import torch
     import torch.distributed as dist
@@ -633,7 +651,7 @@ def main():
         line['hotpath'] = {'value': B / (hp['ms'] / 1e3), 'unit': 'images/sec', 'ms_per_step': hp['ms'],
                            'e2e_value': B / (hp['ms_e2e'] / 1e3), 'cuda_graph': hp['graph'],
                            'workload': WORKLOAD_TEXT['hotpath'] % (hp['N'], hp['nf'])}
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -246,7 +246,16 @@ int scp_symmetry_nn_backward(const float *pred_v, const int *faces, const long l
  * in double precision); hue in [-0.5, 0.5]; mean/std [3] host arrays.  All of order/ratios/mean/std are HOST pointers
  * (read during the call).  workspace: scp_color_jitter_workspace_bytes(B) device bytes (per-image grey sums, fp64).
  */
+typedef struct scp_jitter_params {     /* device-resident parameter block of scp_color_jitter_normalize_dparams */
+    int order[4];                      /* step ids in application order, -1 = skip */
+    float r1[3], r2[3];                /* (ratio, 1 - ratio) of brightness, contrast, saturation */
+    float hue;
+    float mean[3], std[3];
+} scp_jitter_params;
 size_t scp_color_jitter_workspace_bytes(int B);
+/* As scp_color_jitter_normalize, with the parameters read from DEVICE memory at run time (for CUDA-graph replays). */
+int scp_color_jitter_normalize_dparams(const float *img, float *out, int B, int HW, const void *params_dev, int nhwc_out,
+                                       void *workspace, size_t workspace_bytes, void *stream);
 int scp_color_jitter_normalize(const float *img, float *out, int B, int HW, const int *order, const float *ratios, float hue,
                                const float *mean, const float *std, int nhwc_out, void *workspace, size_t workspace_bytes,
                                void *stream);

@@ -85,6 +85,7 @@ _SIGNATURES.update({
 
 _SIGNATURES.update({
     'scp_color_jitter_workspace_bytes': ([_i], _sz),
+    'scp_color_jitter_normalize_dparams': ([_f, _f, _i, _i, _f, _i, _f, _sz, _f], _i),
     'scp_color_jitter_normalize': ([_f, _f, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_fl), _fl, ctypes.POINTER(_fl),
                                     ctypes.POINTER(_fl), _i, _f, _sz, _f], _i),
 })

@@ -98,8 +98,16 @@ __device__ __forceinline__ void apply(const Params &P, int n, float gmean, float
 
 // pass A: per-image sum of the grey value after the steps that precede the contrast step (n_before of them)
 __global__ void __launch_bounds__(256)
-gray_sum_kernel(const float *__restrict__ img, int HW, Params P, int n_before, double *__restrict__ gsum)
+gray_sum_kernel(const float *__restrict__ img, int HW, Params P, const Params *__restrict__ Pdev, int n_before,
+                double *__restrict__ gsum)
 {
+    if (Pdev != nullptr) {      // parameters in device memory (CUDA-graph replays re-read them): find the contrast step here
+        P = *Pdev;
+        n_before = -1;
+        for (int k = 3; k >= 0; k--)
+            if (P.order[k] == 1) n_before = k;
+        if (n_before < 0) return;
+    }
     const int b = blockIdx.y;
     const float *base = img + (long)b * 3 * HW;
     double acc = 0.0;
@@ -127,9 +135,10 @@ gray_sum_kernel(const float *__restrict__ img, int HW, Params P, int n_before, d
 
 // pass B: all steps + (x - mean) / std
 __global__ void __launch_bounds__(256)
-jitter_norm_kernel(const float *__restrict__ img, float *__restrict__ out, int HW, Params P, const double *__restrict__ gsum,
-                   int nhwc_out)
+jitter_norm_kernel(const float *__restrict__ img, float *__restrict__ out, int HW, Params P, const Params *__restrict__ Pdev,
+                   const double *__restrict__ gsum, int nhwc_out)
 {
+    if (Pdev != nullptr) P = *Pdev;
     const int b = blockIdx.y;
     const float *base = img + (long)b * 3 * HW;
     float *ob = out + (long)b * 3 * HW;
@@ -196,8 +205,35 @@ extern "C" int scp_color_jitter_normalize(const float *img, float *out, int B, i
         gsum = (double *)workspace;
         cudaMemsetAsync(gsum, 0, (size_t)B * sizeof(double), st);
         const int bx = (HW / 4 + 255) / 256;
-        gray_sum_kernel<<<dim3(bx < 32 ? bx : 32, B), 256, 0, st>>>(img, HW, P, n_before, gsum);
+        gray_sum_kernel<<<dim3(bx < 32 ? bx : 32, B), 256, 0, st>>>(img, HW, P, nullptr, n_before, gsum);
     }
-    jitter_norm_kernel<<<dim3((HW / 4 + 255) / 256, B), 256, 0, st>>>(img, out, HW, P, gsum, nhwc_out);
+    jitter_norm_kernel<<<dim3((HW / 4 + 255) / 256, B), 256, 0, st>>>(img, out, HW, P, nullptr, gsum, nhwc_out);
     return scp::check_launch("scp_color_jitter_normalize");
+}
+
+// Same operation with the parameter block in DEVICE memory (layout = scp_jitter_params of the header): the launch itself
+// carries no per-step values, so a CUDA graph that contains it can be replayed with new parameters (the caller refreshes
+// the block, e.g. through a captured copy from pinned host memory).
+extern "C" int scp_color_jitter_normalize_dparams(const float *img, float *out, int B, int HW, const void *params_dev,
+                                                  int nhwc_out, void *workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace scp::jitter;
+    static_assert(sizeof(Params) == sizeof(scp_jitter_params), "parameter block layout");
+    if (!img || !out || !params_dev || B <= 0 || HW <= 0 || HW % 4 != 0) {
+        scp::set_last_error("scp_color_jitter_normalize_dparams: bad arguments (B=%d HW=%d)", B, HW);
+        return -1;
+    }
+    if (!workspace || workspace_bytes < scp_color_jitter_workspace_bytes(B)) {
+        scp::set_last_error("scp_color_jitter_normalize_dparams: workspace too small");
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double *gsum = (double *)workspace;
+    const Params *pd = (const Params *)params_dev;
+    Params dummy = {};
+    cudaMemsetAsync(gsum, 0, (size_t)B * sizeof(double), st);
+    const int bx = (HW / 4 + 255) / 256;
+    gray_sum_kernel<<<dim3(bx < 32 ? bx : 32, B), 256, 0, st>>>(img, HW, dummy, pd, -1, gsum);
+    jitter_norm_kernel<<<dim3((HW / 4 + 255) / 256, B), 256, 0, st>>>(img, out, HW, dummy, pd, gsum, nhwc_out);
+    return scp::check_launch("scp_color_jitter_normalize_dparams");
 }

@@ -101,6 +101,28 @@ class MeshNet(nn.Module):
         aux_output.update(aux)
         return total_loss, aux_output
 
+    # ---- CUDA-graph support: per-step host values travel through static device buffers -------------------------------
+    def enable_static_params(self, device):
+        """Switches the three kinds of per-step HOST values of forward() -- the loss-weight schedule, the colour-jitter
+        parameters of the two encoder passes and the angle of the rotation-cycle loss -- to static device buffers fed by
+        (capturable) copies from pinned host memory.  Values and random draws are unchanged; a CUDA graph of
+        forward + backward can then be replayed for new iterations: refresh_static_params(it) before every replay."""
+        from .module.correspondence import RotationSlot
+        self.weights.enable_device_buffer(device)
+        self.encoder.enable_static_params(device)
+        self.corr_net.rotation_slot = RotationSlot(device)
+        self.static_params = True
+
+    def refresh_static_params(self, it):
+        """Host side of one replay: the draws of forward() in forward()'s order (jitter of the first encoder pass, rotation
+        angle, jitter of the second pass: the global CPU generator is consumed exactly as by an eager step) and the
+        weights of iteration `it`, written into the pinned blocks the captured copies read."""
+        enc = self.encoder
+        enc.jitter_slots[0].refresh(enc.random_jitter)
+        self.corr_net.rotation_slot.refresh()
+        enc.jitter_slots[1].refresh(enc.random_jitter)
+        self.weights.fill_host(it)
+
     def load_network(self, model_path, iter=0):
         states = torch.load(model_path, map_location='cpu')
         for name in list(states.keys()):

@@ -10,6 +10,7 @@ import torch.nn.functional as F
 import torchvision
 from torchvision.transforms import InterpolationMode
 
+from ... import _flags
 from ...ops.corr_match import corr_match
 
 
@@ -19,6 +20,35 @@ def make_meshgrid(hf, wf, device):
                             indexing='ij')
     grid = torch.stack([xs.reshape(-1), ys.reshape(-1)], 0) + 0.5
     return (grid / (wf / 2) - 1).to(device)
+
+
+class RotationSlot:
+    """The rotation of the rotation-cycle loss with its affine matrix in device memory: what
+    torchvision.transforms.functional.rotate(img, angle) computes for tensors (functional.py: inverse affine matrix of
+    -angle about the centre; _functional_tensor.rotate: sampling grid from the matrix, grid_sample with zero padding),
+    split into a host part (`refresh`: draws the angle from the global CPU generator like correspondence.py:82 and writes
+    the six matrix entries into pinned memory) and a device part that reads the matrix from a static tensor, so that the
+    call site can be captured into a CUDA graph and replayed with a new angle."""
+
+    def __init__(self, device):
+        self.host = _flags.pinned(torch.zeros(6, dtype=torch.float32))
+        self.theta = torch.zeros(1, 2, 3, dtype=torch.float32, device=device)
+        self.angle = 0.
+
+    def refresh(self):
+        from torchvision.transforms.functional import _get_inverse_affine_matrix
+        self.angle = torch.empty(1).uniform_(0., 360.).item()
+        m = _get_inverse_affine_matrix([0.0, 0.0], -self.angle, [0.0, 0.0], 1.0, [0.0, 0.0])
+        self.host.copy_(torch.tensor(m, dtype=torch.float32))
+
+    def upload(self):
+        self.theta.view(-1).copy_(self.host, non_blocking=True)
+
+    def rotate(self, img, mode):
+        from torchvision.transforms import _functional_tensor as FT
+        w, h = img.shape[-1], img.shape[-2]
+        grid = FT._gen_affine_grid(self.theta, w=w, h=h, ow=w, oh=h)
+        return FT._apply_grid_transform(img, grid, mode, fill=None)
 
 
 class Correspondence:
@@ -90,17 +120,25 @@ class Correspondence:
     def compute_rotation_cycle_loss(self, src_img, src_mask, src_img_feat, encoder):
         bsz = src_img.shape[0]
         hf2, wf2 = self.hf // 2, self.wf // 2
-        angle = torch.empty(1).uniform_(0., 360.).item()
         grid = self.meshgrid.reshape(2, self.hf, self.wf)[None].repeat(bsz, 1, 1, 1)
         grid = F.interpolate(grid, (hf2, wf2), mode='bilinear')
 
         src_mask = src_mask[:, None]
-        rotate = torchvision.transforms.functional.rotate
-        tgt_img = rotate(src_img, angle, interpolation=InterpolationMode.BILINEAR)
-        tgt_mask = rotate(src_mask, angle, interpolation=InterpolationMode.NEAREST)
-        cycle_match_gt = rotate(grid, angle, interpolation=InterpolationMode.NEAREST).reshape(bsz, 2, -1)
+        slot = getattr(self, 'rotation_slot', None)
+        if slot is None:
+            angle = torch.empty(1).uniform_(0., 360.).item()
+            rotate = torchvision.transforms.functional.rotate
+            tgt_img = rotate(src_img, angle, interpolation=InterpolationMode.BILINEAR)
+            tgt_mask = rotate(src_mask, angle, interpolation=InterpolationMode.NEAREST)
+            cycle_match_gt = rotate(grid, angle, interpolation=InterpolationMode.NEAREST).reshape(bsz, 2, -1)
+        else:       # CUDA-graph mode: same draw, the affine matrix travels through device memory
+            slot.refresh()
+            slot.upload()
+            tgt_img = slot.rotate(src_img, 'bilinear')
+            tgt_mask = slot.rotate(src_mask, 'nearest')
+            cycle_match_gt = slot.rotate(grid, 'nearest').reshape(bsz, 2, -1)
 
-        _, tgt_img_feat = encoder.encode_img(tgt_img)
+        _, tgt_img_feat = encoder.encode_img(tgt_img, pass_idx=1)
         C = self.opts.n_corr_feat
         tgt_img_feat = F.normalize(tgt_img_feat.reshape(bsz, C, -1), 2, 1)
 

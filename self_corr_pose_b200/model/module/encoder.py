@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from torchvision import transforms
 
 from .network import encoder_nets as nets
-from ...ops.color_jitter import jitter_normalize
+from ...ops.color_jitter import JitterSlot, jitter_normalize
 
 _IMAGENET_MEAN, _IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 
@@ -35,10 +35,17 @@ class Encoder(nn.Module):
         self.random_jitter = transforms.ColorJitter(0.2, 0.2, 0.2, 0.05)
         self.resnet_transform = transforms.Normalize(mean=list(_IMAGENET_MEAN), std=list(_IMAGENET_STD))
 
-    def encode_img(self, img):
-        """(b,3,H,W) in [0,1] -> (global code (b,512), unit-norm pixel features (b,C,h*w))."""
+    def enable_static_params(self, device):
+        """CUDA-graph mode: the jitter parameters of the two encoder passes of a step travel through device memory."""
+        self.jitter_slots = [JitterSlot(device, _IMAGENET_MEAN, _IMAGENET_STD) for _ in range(2)]
+
+    def encode_img(self, img, pass_idx=0):
+        """(b,3,H,W) in [0,1] -> (global code (b,512), unit-norm pixel features (b,C,h*w)).  pass_idx: 0 = the step's first
+        encoder pass, 1 = the rotated second pass (selects the static parameter slot in CUDA-graph mode)."""
         if img.is_cuda:     # one native pass instead of torchvision's ~70 launches (same random draws, ops/color_jitter.py)
-            x = jitter_normalize(img, self.random_jitter, _IMAGENET_MEAN, _IMAGENET_STD)
+            slots = getattr(self, 'jitter_slots', None)
+            x = jitter_normalize(img, self.random_jitter, _IMAGENET_MEAN, _IMAGENET_STD,
+                                 slot=slots[pass_idx] if slots else None)
         else:
             x = self.resnet_transform(self.random_jitter(img))
         pyramid = self.backbone(x)

@@ -41,12 +41,17 @@ def get_symm_rots(division):
 def sample_faces_and_weights(verts, faces, num_samples):
     """The random part of pytorch3d.ops.sample_points_from_meshes: area-weighted face draws (multinomial with replacement)
     and uniform barycentric weights (w0, w1, w2) = (1 - sqrt(u), sqrt(u) (1 - v), sqrt(u) v).  verts (B,N,3),
-    faces (B,nf,3) -> face_idx (B,S) int64, w (B,S,3).  Consumes the device generator: multinomial, then one rand."""
+    faces (B,nf,3) -> face_idx (B,S) int64, w (B,S,3).  Consumes the device generator: two rand calls."""
     B = verts.shape[0]
     idx = faces.long()
     v0, v1, v2 = (torch.gather(verts, 1, idx[:, :, k:k + 1].expand(-1, -1, 3)) for k in range(3))
     areas = 0.5 * torch.cross(v1 - v0, v2 - v0, dim=-1).norm(dim=-1)
-    face_idx = torch.multinomial(areas.detach().clamp_min(1e-12), num_samples, replacement=True)   # B, S
+    # area-weighted draws with replacement by inverting the cumulative areas: the distribution of
+    # `areas.multinomial(num_samples, replacement=True)` (pytorch3d) without torch.multinomial's host-synchronising input
+    # checks, which cannot be captured into a CUDA graph
+    cdf = areas.detach().clamp_min(1e-12).cumsum(1)
+    r = torch.rand(B, num_samples, device=verts.device) * cdf[:, -1:]
+    face_idx = torch.searchsorted(cdf, r, right=True).clamp_max(areas.shape[1] - 1)                # B, S
     u = torch.rand(B, num_samples, 2, device=verts.device)
     su = u[..., 0].sqrt()
     return face_idx, torch.stack((1 - su, su * (1 - u[..., 1]), su * u[..., 1]), dim=-1)

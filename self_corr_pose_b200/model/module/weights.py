@@ -5,6 +5,8 @@ regularisers and cycle terms decay linearly from their flag value to `decay_rati
 correspondence terms grow the other way round, everything else is constant."""
 import math
 
+from ... import _flags
+
 _CONSTANT = ('mask_wt', 'depth_wt', 'tex_wt', 'pullfar_wt', 'deform_wt', 'camera_wt')
 # attribute -> (flag holding the base value, True = starts at the base value and decays to decay_ratio * base)
 _SCHEDULED = {
@@ -39,9 +41,39 @@ class Weights:
         for name, (flag, _) in _SCHEDULED.items():
             setattr(self, name, getattr(opts, flag))
 
-    def schedule(self, it):
+        self._dev = None
+
+    def values(self, it):
+        """{name: weight at iteration `it`} -- constants and scheduled ones."""
         ratio = self.opts.decay_ratio
+        out = {name: getattr(self.opts, name) for name in _CONSTANT}
         for name, (flag, decays) in _SCHEDULED.items():
             base = getattr(self.opts, flag)
             end_points = (ratio * base, base) if decays else (base, ratio * base)     # (value at the end, value at step 0)
-            setattr(self, name, reg_decay(it, self.total_iters, *end_points))
+            out[name] = reg_decay(it, self.total_iters, *end_points)
+        return out
+
+    def schedule(self, it):
+        vals = self.values(it)
+        if self._dev is None:
+            for name in _SCHEDULED:
+                setattr(self, name, vals[name])
+            return
+        # static mode: the weights are 0-dim views of one device buffer, refreshed through a (capturable) copy from pinned
+        # host memory -- a CUDA graph of the step then follows the schedule: fill_host(it) before every replay
+        self.fill_host(it)
+        self._dev.copy_(self._host, non_blocking=True)
+
+    def enable_device_buffer(self, device):
+        """Switches the weights from python floats to device scalars (same values: a float32 factor either way)."""
+        import torch
+        self._names = list(_CONSTANT) + list(_SCHEDULED)
+        self._host = _flags.pinned(torch.zeros(len(self._names), dtype=torch.float32))
+        self._dev = torch.zeros(len(self._names), dtype=torch.float32, device=device)
+        for i, name in enumerate(self._names):
+            setattr(self, name, self._dev[i])
+
+    def fill_host(self, it):
+        vals = self.values(it)
+        for i, name in enumerate(self._names):
+            self._host[i] = float(vals[name])

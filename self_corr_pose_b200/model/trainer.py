@@ -79,7 +79,11 @@ class Trainer:
         flat = torch.stack([p.grad.isnan().any() for p in self.model.parameters() if p.grad is not None])
         if bool(flat.any()):
             print('bad gradient')
-            self.optim.zero_grad()
+            reducer = getattr(self, 'reducer', None)
+            if reducer is not None and reducer.adopted:
+                reducer.zero_()         # gradients live in the flat buffer: zeroed in place (views stay attached)
+            else:
+                self.optim.zero_grad()
         g_shape = torch.nn.utils.clip_grad_norm_(shapenerf, 1) if shapenerf else 0
         g_pose = torch.nn.utils.clip_grad_norm_(pose, 0.1) if pose else 0
         return grad_meanv_norm, g_shape, g_pose
@@ -94,6 +98,52 @@ class Trainer:
         data = self.batch_reshape(batch)
         total_loss, aux_output = self.model(data)
         total_loss.mean().backward()
+        self.reducer.reduce()
+        grad = self.collect_grad()
+        self.optim.step(self.iters)
+        self.iters += 1
+        return total_loss, aux_output, grad
+
+    # ---- the step as a CUDA graph ----------------------------------------------------------------------------------
+    def capture(self, batch, warmup=3):
+        """Captures zero-grad + batch_reshape + forward + backward of one step into a CUDA graph over a static copy of
+        `batch` (~1500 launches of this package, cuDNN and ATen per step become one graph launch; with SyncBatchNorm the
+        NCCL collectives are captured too).  The gradient all-reduce, clipping (with the reference's NaN check, one host
+        read) and AdamW/OneCycle stay eager after the replay.  Use step_graphed(batch) afterwards.
+        Needs a few eager steps first (cuDNN autotuning, gradient buffer adoption); they are run here and DO advance the
+        optimiser, like any other training step."""
+        dev = self.device
+        self.model.enable_static_params(dev)
+        self._static_batch = {k: (v.to(dev).clone() if torch.is_tensor(v) and k not in ('center', 'length') else v)
+                              for k, v in batch.items()}
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(self._static_batch)
+            if not self.reducer.adopted:
+                self.reducer.adopt()        # .grad of every parameter = a view of one flat buffer: static addresses
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.model.iters = self.iters
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.reducer.zero_()
+            data = self.batch_reshape(self._static_batch)
+            total_loss, aux_output = self.model(data)
+            total_loss.mean().backward()
+        self._graph = (graph, total_loss, aux_output)
+        return self
+
+    def step_graphed(self, batch):
+        """One training step through the captured graph: upload `batch` into the static buffers, refresh the per-step host
+        values, replay, then the eager tail of step()."""
+        graph, total_loss, aux_output = self._graph
+        for k, v in batch.items():
+            if torch.is_tensor(v) and k not in ('center', 'length'):
+                self._static_batch[k].copy_(v, non_blocking=True)
+        self.model.iters = self.iters
+        self.model.refresh_static_params(self.iters)
+        graph.replay()
         self.reducer.reduce()
         grad = self.collect_grad()
         self.optim.step(self.iters)
