@@ -39,6 +39,8 @@ class MeshNet(nn.Module):
         self.renderer = Renderer(opts, self.mesh)
         self.iters = 0
         self.fused_losses = True    # False: the reference's op-by-op loss statements (parity tests)
+        self.overlap_vit = True     # DINO ViT on a side stream, overlapping the encoder
+        self._side = None
         self.triangle_loss_fn = L.LaplacianLoss(self.mesh.mean_v, self.mesh.faces, average=True)
 
     def forward(self, data):
@@ -48,6 +50,21 @@ class MeshNet(nn.Module):
         bsz = img.shape[0]
         mean_v = self.mesh.mean_v[None].repeat(bsz, 1, 1)
         faces = self.mesh.faces[None].repeat(bsz, 1, 1)
+
+        # the frozen DINO features depend on the images only: issued on a side stream (a parallel branch of the step's CUDA
+        # graph), so that the tensor-core GEMMs of the ViT co-run with the memory-bound BatchNorm / activation / pooling
+        # kernels of the encoder; joined before the pre-training cycle loss
+        feat = None
+        if opts.train and self.overlap_vit and img.is_cuda:
+            main = torch.cuda.current_stream(img.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(img.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side), torch.no_grad():
+                want_tokens = (opts.img_size // 8) ** 2 % 256 == 0
+                feat = self.pretrain_corr_net.net(img, tokens=want_tokens)
+            for t in (feat if isinstance(feat, tuple) else (feat,)):
+                t.record_stream(main)
 
         img_feat, mesh_feat, pred_v, rotation, translation, scale = self.encoder(img, mean_v, pp_crop, foc_crop)
         fused = opts.train and self.fused_losses and opts.img_size % 16 == 0 and not opts.use_occ
@@ -87,8 +104,10 @@ class MeshNet(nn.Module):
         aux['pullfar_loss'] = wts.pullfar_wt * F.relu(1 - translation[:, :, -1]).mean()
         aux['symmetry_loss'] = wts.symmetry_wt * self.mesh.compute_symmetry_loss(pred_v, faces)
         aux['imatch_loss'] = wts.imatch_wt * L.compute_imatch_loss(imatch, imatch_gt, depth_weight).mean(0)
+        if feat is not None:
+            torch.cuda.current_stream(img.device).wait_stream(self._side)
         cyc = self.pretrain_corr_net.compute_cycle_loss(img, mask, depth_weight, pointcorr, pooled=True,
-                                                        A=self.corr_net.pool_A)
+                                                        A=self.corr_net.pool_A, feat=feat)
         aux['cycle_loss_pretrain'] = cyc[0] * wts.cycle_loss_pt_wt
         rot_cyc = self.corr_net.compute_rotation_cycle_loss(img, mask, img_feat, self.encoder)
         aux['cycle_loss'] = rot_cyc[0] * wts.cycle_loss_wt

@@ -34,6 +34,7 @@ class RotationSlot:
         self.host = _flags.pinned(torch.zeros(6, dtype=torch.float32))
         self.theta = torch.zeros(1, 2, 3, dtype=torch.float32, device=device)
         self.angle = 0.
+        self._cache = {}
 
     def refresh(self):
         from torchvision.transforms.functional import _get_inverse_affine_matrix
@@ -44,10 +45,24 @@ class RotationSlot:
     def upload(self):
         self.theta.view(-1).copy_(self.host, non_blocking=True)
 
+    def _constants(self, w, h):
+        """Per image size: torchvision's base grid of pixel centres and the (w/2, h/2) divisor (_gen_affine_grid), built
+        once OUTSIDE any graph capture (torchvision creates them with host -> device copies on every call)."""
+        key = (w, h)
+        if key not in self._cache:
+            dev, d = self.theta.device, 0.5
+            base = torch.empty(1, h, w, 3, dtype=torch.float32, device=dev)
+            base[..., 0].copy_(torch.linspace(-w * 0.5 + d, w * 0.5 + d - 1, steps=w, device=dev))
+            base[..., 1].copy_(torch.linspace(-h * 0.5 + d, h * 0.5 + d - 1, steps=h, device=dev).unsqueeze_(-1))
+            base[..., 2].fill_(1)
+            self._cache[key] = (base.view(1, h * w, 3), torch.tensor([0.5 * w, 0.5 * h], dtype=torch.float32, device=dev))
+        return self._cache[key]
+
     def rotate(self, img, mode):
         from torchvision.transforms import _functional_tensor as FT
         w, h = img.shape[-1], img.shape[-2]
-        grid = FT._gen_affine_grid(self.theta, w=w, h=h, ow=w, oh=h)
+        base, half = self._constants(w, h)
+        grid = base.bmm(self.theta.transpose(1, 2) / half).view(1, h, w, 2)       # _gen_affine_grid's statements
         return FT._apply_grid_transform(img, grid, mode, fill=None)
 
 
