@@ -56,6 +56,11 @@ class FlatGradReducer:
     def adopted(self):
         return self.flat is not None
 
+    def covers(self, model):
+        """True when every gradient of `model` lives in the flat buffer (so a scan of the buffer is a scan of all of them)."""
+        mine = {id(p) for p in self.used}
+        return all(id(p) in mine for p in model.parameters() if p.grad is not None)
+
     def zero_(self):
         """Replacement of optimizer.zero_grad() once adopted: one memset, the views stay attached."""
         if self.flat is not None:

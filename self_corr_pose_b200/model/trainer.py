@@ -75,11 +75,15 @@ class Trainer:
                 shapenerf.append(p)
             elif 'pose_predictor' in name:
                 pose.append(p)
-        # one fused NaN check instead of a host sync per parameter (trainer.py:144-147)
-        flat = torch.stack([p.grad.isnan().any() for p in self.model.parameters() if p.grad is not None])
+        # one fused NaN check instead of a host sync per parameter (trainer.py:144-147); two launches over the flat
+        # gradient buffer once the reducer has adopted the gradients, else one pair of launches per parameter
+        reducer = getattr(self, 'reducer', None)
+        if reducer is not None and reducer.adopted and reducer.covers(self.model):
+            flat = reducer.flat.isnan().any()
+        else:
+            flat = torch.stack([p.grad.isnan().any() for p in self.model.parameters() if p.grad is not None])
         if bool(flat.any()):
             print('bad gradient')
-            reducer = getattr(self, 'reducer', None)
             if reducer is not None and reducer.adopted:
                 reducer.zero_()         # gradients live in the flat buffer: zeroed in place (views stay attached)
             else:
