@@ -485,7 +485,13 @@ def trainer_arm(args, torch, dist, dev, world, rank, local, timed):
     step_fn = tr.step_graphed if graphed else tr.step
     for _ in range(max(3, args.warmup)):
         total, aux, _ = step_fn(batch)
+    prof = os.environ.get('SCP_BENCH_CUDA_PROFILER') == '1'     # ncu --profile-from-start off: launch list of the timed steps only
+    if prof:
+        torch.cuda.profiler.start()
     ms = timed(lambda: step_fn(batch), args.steps)
+    if prof:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 
     host = {k: (t.detach().cpu().pin_memory() if k not in ('center', 'length') else t) for k, t in batch.items()}
     h2d = sum(t.numel() * t.element_size() for k, t in host.items() if k not in ('center', 'length'))

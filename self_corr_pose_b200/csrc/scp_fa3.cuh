@@ -41,6 +41,12 @@ constexpr int TMEM_COLS = 256;
 constexpr uint32_t COL_S = 0, COL_PH = 128, COL_PL = 160, COL_O = 192;
 constexpr float LAZY = 8.f;                           // log2 units: P stays below 2^8
 
+// Issue S(j+2) = Q K(j+2)^T as soon as the softmax warps have READ S(j) (a separate "S consumed" barrier) instead of after
+// P(j) has been written: the tensor pipe then works on the next-but-one score tile during the softmax of tile j.
+#ifndef SCP_FA3_EARLY_QK
+#define SCP_FA3_EARLY_QK 1
+#endif
+
 __device__ __forceinline__ float ex2(float x)
 {
     float y;
@@ -58,8 +64,8 @@ fa3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constan
     uint8_t *sQ = smem, *sK = sQ + Q_BYTES, *sV = sK + NK * KT_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sV + NV * VT_BYTES);
     uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = k_full + NK, *v_full = k_empty + NK, *v_empty = v_full + NV,
-             *s_full = v_empty + NV, *p_full = s_full + 2, *pv_done = p_full + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pv_done + 1);
+             *s_full = v_empty + NV, *p_full = s_full + 2, *pv_done = p_full + 1, *s_free = pv_done + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(s_free + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.y, q0 = blockIdx.x * BQ;
@@ -77,7 +83,7 @@ fa3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constan
         tc5::mbar_init(q_full, 1);
         for (int i = 0; i < NK; i++) { tc5::mbar_init(k_full + i, 1); tc5::mbar_init(k_empty + i, 1); }
         for (int i = 0; i < NV; i++) { tc5::mbar_init(v_full + i, 1); tc5::mbar_init(v_empty + i, 1); }
-        for (int i = 0; i < 2; i++) tc5::mbar_init(s_full + i, 1);
+        for (int i = 0; i < 2; i++) { tc5::mbar_init(s_full + i, 1); tc5::mbar_init(s_free + i, n_active); }
         tc5::mbar_init(p_full, n_active);
         tc5::mbar_init(pv_done, 1);
         tc5::mbar_fence_init();
@@ -133,7 +139,14 @@ fa3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constan
             if (nt > 1) issue_qk(1);
             for (int j = 0; j < nt; j++) {
                 const int vs = j % NV;
-                tc5::mbar_wait(p_full, j & 1);                    // P(j) is in TMEM, S buffer j & 1 is free again
+#if SCP_FA3_EARLY_QK
+                if (j + 2 < nt) {          // S(j) is in the softmax warps' registers: its buffer can take S(j+2) NOW, a whole
+                    tc5::mbar_wait(s_free + (j & 1), (j >> 1) & 1);   // softmax tile earlier than after P(j) -- ncu: the
+                    tc5::tc_fence_after();                            // softmax warps spent 38 % of their time waiting for S
+                    issue_qk(j + 2);
+                }
+#endif
+                tc5::mbar_wait(p_full, j & 1);                    // P(j) is in TMEM
                 tc5::mbar_wait(v_full + vs, (j / NV) & 1);
                 tc5::tc_fence_after();
                 const int ncols = min(BKV, (T - j * BKV + 15) & ~15);
@@ -146,7 +159,9 @@ fa3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constan
                 }
                 tc5::umma_commit(v_empty + vs);
                 tc5::umma_commit(pv_done);
+#if !SCP_FA3_EARLY_QK
                 if (j + 2 < nt) issue_qk(j + 2);
+#endif
             }
         }
     } else if ((warp & 3) < n_active) {
@@ -161,6 +176,11 @@ fa3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constan
             tc5::tc_fence_after();
             float v[BKV];
             tc5::tmem_ld64(tmem_base + t_lane + COL_S + buf * BKV, v);
+#if SCP_FA3_EARLY_QK
+            tc5::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc5::mbar_arrive(s_free + buf);        // S(j) consumed: the buffer may be overwritten
+#endif
             const int nvalid = T - j * BKV;
             if (nvalid < BKV) {                                  // last tile: keys past the sequence
 #pragma unroll

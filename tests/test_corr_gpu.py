@@ -131,7 +131,7 @@ def test_rotation_cycle_vs_oracle():
         def __init__(self, t):
             self.t = t
 
-        def encode_img(self, img):
+        def encode_img(self, img, pass_idx=0):
             return None, self.t
 
     # oracle (CPU)

@@ -22,9 +22,9 @@ for r in rows[1:]:
     name = re.sub(r'\(.*', '', r[ki])[:110]
     agg[name][0] += 1
     agg[name][1] += float(r[vi].replace(',', '')) * scale[r[ui]]
-steps = max(v[0] for k, v in agg.items() if 'fa2::fa2_fwd_kernel' in k or 'fa::fa_fwd_kernel' in k) // 9
+steps = max(v[0] for k, v in agg.items() if re.search(r'fa[23]?::fa[23]?_fwd_kernel', k)) // 9
 total = sum(v[1] for v in agg.values()) / steps
-mine = sum(v[1] for k, v in agg.items() if re.search(r'softras::|corr::|gemm::|vit::|fa2?::|loss::|geom::|cycle::', k)) / steps
+mine = sum(v[1] for k, v in agg.items() if re.search(r'softras::|corr::|gemm::|vit::|fa[23]?::|loss::|geom::|cycle::|sym::|jitter::', k)) / steps
 with open(dst, 'w') as f:
     f.write('# ncu launch list of `bench.py`, aggregated per step\n\n%s\n\n' % note)
     f.write('%d launches over %d steps (warm-up, timed and end-to-end steps all run under the profiler); times are '
