@@ -41,10 +41,13 @@ constexpr int TMEM_COLS = 256;
 constexpr uint32_t COL_S = 0, COL_PH = 128, COL_PL = 160, COL_O = 192;
 constexpr float LAZY = 8.f;                           // log2 units: P stays below 2^8
 
-// Issue S(j+2) = Q K(j+2)^T as soon as the softmax warps have READ S(j) (a separate "S consumed" barrier) instead of after
-// P(j) has been written: the tensor pipe then works on the next-but-one score tile during the softmax of tile j.
+// Measured and rejected (round 2, B = 64, per layer; gpurun_out/r2_call11.log): issuing S(j+2) = Q K(j+2)^T as soon as the
+// softmax warps have READ S(j) (a separate "S consumed" barrier) instead of after P(j) has been written.  The ncu source
+// page (profiles/r2_fa3_source_page.csv.gz) shows the softmax warps waiting for the next S tile during 38 % of their time,
+// but the early issue puts the 12 score MMAs of tile j+2 AHEAD of the 12 P V MMAs of tile j in the in-order tensor queue:
+// O(j) and with it the P buffer are released later, 0.364 -> 0.459 ms.  Kept behind the macro; parity-tested in both forms.
 #ifndef SCP_FA3_EARLY_QK
-#define SCP_FA3_EARLY_QK 1
+#define SCP_FA3_EARLY_QK 0
 #endif
 
 __device__ __forceinline__ float ex2(float x)
