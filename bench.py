@@ -473,6 +473,8 @@ def trainer_arm(args, torch, dist, dev, world, rank, local, timed):
     torch.manual_seed(0)
     tr = Trainer(opts)
     model = tr.define_model()
+    model.overlap_rotation = os.environ.get('SCP_OVERLAP_ROTATION', '1') != '0'     # A/B switch of the second side stream
+    model.overlap_vit = not args.no_overlap
     v, f = load_mesh(args.mesh)
     batch = synthetic.make_trainer_batch(opts, v, f, B, device=dev, seed=rank, renderer=Renderer(opts, model.mesh))
     graphed = False

@@ -40,7 +40,9 @@ class MeshNet(nn.Module):
         self.iters = 0
         self.fused_losses = True    # False: the reference's op-by-op loss statements (parity tests)
         self.overlap_vit = True     # DINO ViT on a side stream, overlapping the encoder
+        self.overlap_rotation = True    # rotation-cycle loss (second encoder pass) on a second side stream
         self._side = None
+        self._side2 = None
         self.triangle_loss_fn = L.LaplacianLoss(self.mesh.mean_v, self.mesh.faces, average=True)
 
     def forward(self, data):
@@ -67,6 +69,19 @@ class MeshNet(nn.Module):
                 t.record_stream(main)
 
         img_feat, mesh_feat, pred_v, rotation, translation, scale = self.encoder(img, mean_v, pp_crop, foc_crop)
+        # the rotation-cycle loss (second encoder pass on the rotated images) depends on the first pass only: issued on a
+        # second side stream so that its convolutions co-run with the issue-bound SoftRas / correspondence kernels of the
+        # main stream, forward and -- autograd replays every node on its forward stream -- backward.  Same position in
+        # the global CPU generator's sequence as in the reference (jitter, angle, jitter).
+        rot_cyc = None
+        if opts.train and self.overlap_rotation and img.is_cuda:
+            main = torch.cuda.current_stream(img.device)
+            if self._side2 is None:
+                self._side2 = torch.cuda.Stream(img.device)
+            self._side2.wait_stream(main)
+            with torch.cuda.stream(self._side2):
+                rot_cyc = self.corr_net.compute_rotation_cycle_loss(img, mask, img_feat, self.encoder)
+            rot_cyc[0].record_stream(main)
         fused = opts.train and self.fused_losses and opts.img_size % 16 == 0 and not opts.use_occ
         if fused:
             pointcorr, match_lr, imatch = self.corr_net.match_lowres(img_feat, mesh_feat, mask, pred_v)
@@ -109,7 +124,10 @@ class MeshNet(nn.Module):
         cyc = self.pretrain_corr_net.compute_cycle_loss(img, mask, depth_weight, pointcorr, pooled=True,
                                                         A=self.corr_net.pool_A, feat=feat)
         aux['cycle_loss_pretrain'] = cyc[0] * wts.cycle_loss_pt_wt
-        rot_cyc = self.corr_net.compute_rotation_cycle_loss(img, mask, img_feat, self.encoder)
+        if rot_cyc is None:
+            rot_cyc = self.corr_net.compute_rotation_cycle_loss(img, mask, img_feat, self.encoder)
+        else:
+            torch.cuda.current_stream(img.device).wait_stream(self._side2)
         aux['cycle_loss'] = rot_cyc[0] * wts.cycle_loss_wt
         if getattr(opts, 'camera_loss', False):     # model.py:124-127: rotation against the next frame's of the same video
             nxt = rotation.detach().clone().reshape(-1, opts.repeat, 3, 3)

@@ -170,3 +170,39 @@ def test_graphed_step_equals_eager_step():
             assert abs(aux_g[k] - aux_e[k]) <= tol * abs(aux_e[k]) + 1e-8, (k, aux_g[k], aux_e[k])
         worst = max(_rel(params_g[n], p.detach()) for n, p in model.named_parameters() if p.requires_grad)
         assert worst < 1e-4, worst
+
+
+def test_side_streams_do_not_change_the_step():
+    """MeshNet.forward issues the frozen ViT and the rotation-cycle loss (second encoder pass) on side streams; with both
+    switched off the same step (same state, same generator states) gives the same losses and gradients."""
+    import copy
+    from self_corr_pose_b200.model.trainer import Trainer
+    from self_corr_pose_b200.model.module.renderer import Renderer
+    torch.manual_seed(0)
+    opts = default_opts(batch_size=2, repeat=2, total_iters=50)
+    tr = Trainer(opts)
+    model = tr.define_model()
+    v, f = synthetic.load_prior('laptop')
+    batch = synthetic.make_trainer_batch(opts, v, f, 4, device=tr.device, seed=3, renderer=Renderer(opts, model.mesh))
+    tr.step(batch)                                       # cuDNN autotuning settles
+    snap = (copy.deepcopy(model.state_dict()), copy.deepcopy(tr.optim.optimizer.state_dict()),
+            copy.deepcopy(tr.optim.scheduler.state_dict()), tr.iters)
+    out = {}
+    for flag in (True, False):
+        model.load_state_dict(snap[0])
+        tr.optim.optimizer.load_state_dict(snap[1])
+        tr.optim.scheduler.load_state_dict(snap[2])
+        tr.iters = snap[3]
+        model.overlap_vit = model.overlap_rotation = flag
+        torch.manual_seed(21)
+        torch.cuda.manual_seed(21)
+        total, aux, _ = tr.step(batch)
+        torch.cuda.synchronize()
+        out[flag] = ({k: float(x) for k, x in aux.items()},
+                     {n: p.detach().clone() for n, p in model.named_parameters() if p.requires_grad})
+    for k in out[True][0]:
+        a, b = out[True][0][k], out[False][0][k]
+        assert abs(a - b) <= 1e-5 * abs(b) + 1e-8, (k, a, b)
+    worst = max(_rel(out[True][1][n], out[False][1][n]) for n in out[True][1])
+    print('PARITY side-streams on/off: total %.6g/%.6g, params rel %.2e' % (out[True][0]['total_loss'], out[False][0]['total_loss'], worst))
+    assert worst < 1e-4

@@ -13,7 +13,7 @@ torch.backends.cudnn.benchmark = True
 opts = default_opts(batch_size=B // 4, repeat=4, shape_prior_path='synthetic:uv1280')
 tr = Trainer(opts)
 model = tr.define_model()
-model.overlap_vit = False            # serialised kernels: one stream
+model.overlap_vit = model.overlap_rotation = False            # serialised kernels: one stream
 v, f = synthetic.uv_sphere()
 batch = synthetic.make_trainer_batch(opts, v, f, B, device=tr.device, seed=0, renderer=Renderer(opts, model.mesh))
 for _ in range(3):
