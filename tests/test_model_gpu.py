@@ -203,6 +203,9 @@ def test_side_streams_do_not_change_the_step():
     for k in out[True][0]:
         a, b = out[True][0][k], out[False][0][k]
         assert abs(a - b) <= 1e-5 * abs(b) + 1e-8, (k, a, b)
-    worst = max(_rel(out[True][1][n], out[False][1][n]) for n in out[True][1])
+    # all parameters as one vector: a zero-initialised bias whose gradient is summation noise moves by +-lr under AdamW
+    # whichever way the noise points, so a per-parameter relative difference says nothing
+    cat = lambda d: torch.cat([d[n].reshape(-1) for n in sorted(d)])
+    worst = _rel(cat(out[True][1]), cat(out[False][1]))
     print('PARITY side-streams on/off: total %.6g/%.6g, params rel %.2e' % (out[True][0]['total_loss'], out[False][0]['total_loss'], worst))
-    assert worst < 1e-4
+    assert worst < 1e-5
