@@ -499,8 +499,15 @@ def trainer_arm(args, torch, dist, dev, world, rank, local, timed):
     h2d = sum(t.numel() * t.element_size() for k, t in host.items() if k not in ('center', 'length'))
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def e2e_step():     # public call with HOST buffers: batch_reshape uploads them, the loss is read back
-        total, _, _ = step_fn(host)
+    state = {'slot': tr.stage(host) if graphed else None}
+
+    def e2e_step():     # public call with HOST buffers: every step uploads one full batch from pinned memory and reads the
+        if graphed:     # loss back; the upload of the NEXT step's batch (copy stream) overlaps this step's compute
+            slot = state['slot']
+            state['slot'] = tr.stage(host)
+            total, _, _ = tr.step_graphed(slot)
+        else:
+            total, _, _ = tr.step(host)         # batch_reshape uploads the batch
         loss_host.copy_(total.detach(), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         return float(loss_host)

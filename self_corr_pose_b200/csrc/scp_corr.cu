@@ -815,6 +815,13 @@ extern "C" int scp_corr_match_forward(const float *img_feat, const float *mesh_f
                             "wf in {8,16,32,64}, hf*wf %% 128 == 0)", B, hf, wf, N, Cc);
         return -1;
     }
+    if (!(tau > 0.f) || tau > 40.f) {
+        // both soft-maxes use the fixed reference point exp(tau * (S - 1)) (valid for L2-normalised features, |S| <= 1):
+        // for tau * 2 * log2(e) > 126 an entry with S = -1 underflows ex2.approx.ftz to 0
+        scp::set_last_error("scp_corr_match_forward: tau = %g outside (0, 40] (fixed-reference-point soft-max; the shipped "
+                            "configs use 10)", (double)tau);
+        return -1;
+    }
     if (!workspace || workspace_bytes < scp_corr_workspace_bytes(B, hf, wf, N)) {
         scp::set_last_error("scp_corr_match_forward: workspace too small");
         return -1;

@@ -46,6 +46,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
+// wait by ONE lane of a converged warp, then reconverge: the other lanes do not spin, and the warp's control flow stays
+// uniform for the compiler (values computed around the wait keep living in uniform registers)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity)
+{
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
+
 // ---- TMA --------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m)
 {
@@ -98,6 +106,34 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- warp-convergent issue (round 2) -------------------------------------------------------------------------------
+// The *_e variants are executed by ALL 32 lanes of the issuing warp in uniform control flow and elect the issuing thread
+// inside the instruction sequence (elect.sync is deterministic for a given member mask, so MMAs and their commits come from
+// the same thread).  Why: with the issue loop inside `if (lane == 0)` ptxas cannot prove the operands warp-uniform and
+// wraps EVERY tcgen05.mma in a uniformisation loop (ELECT / R2UR.BROADCAST / BRA.U.ANY) behind a serial descriptor chain
+// (UIADD3 -> USHF -> ULOP3): ~11 dependent instructions, 60-85 cycles per MMA -- slower than the tensor core executes a
+// 128 x 64 x 16 product (32 cycles) and about the duration of a 128 x 128 x 16 one (64 cycles): the round-1 kernels were
+// bound by the issuing thread (ncu: tensor pipe 47 % in the attention kernel, 69 % of peak in the GEMMs).  In uniform
+// control flow the descriptors live in uniform registers and the UTCHMMA instructions are emitted back to back.
+__device__ __forceinline__ void umma_bf16_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint64_t *bar)
+{
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {

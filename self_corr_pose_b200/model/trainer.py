@@ -81,7 +81,8 @@ class Trainer:
         if reducer is not None and reducer.adopted and reducer.covers(self.model):
             flat = reducer.flat.isnan().any()
         else:
-            flat = torch.stack([p.grad.isnan().any() for p in self.model.parameters() if p.grad is not None])
+            flags = [p.grad.isnan().any() for p in self.model.parameters() if p.grad is not None]
+            flat = torch.stack(flags) if flags else torch.zeros(1, dtype=torch.bool)
         if bool(flat.any()):
             print('bad gradient')
             if reducer is not None and reducer.adopted:
@@ -138,13 +139,43 @@ class Trainer:
         self._graph = (graph, total_loss, aux_output)
         return self
 
+    def stage(self, batch):
+        """Starts the upload of a (pinned host) batch into one of two device staging slots on a copy stream and returns
+        the slot: `step_graphed(slot)` then only copies device-to-device into the graph's static buffers, so the H2D
+        transfer of step i+1 overlaps the compute of step i (a data loader would call this one batch ahead)."""
+        dev = self.device
+        if getattr(self, '_staging', None) is None:
+            keys = [k for k, v in self._static_batch.items() if torch.is_tensor(v) and k not in ('center', 'length')]
+            self._staging = [{k: torch.empty_like(self._static_batch[k]) for k in keys} for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._uploaded = [torch.cuda.Event() for _ in range(2)]
+            self._consumed = [torch.cuda.Event() for _ in range(2)]
+            for ev in self._consumed:
+                ev.record(torch.cuda.current_stream(dev))
+            self._stage_i = 0
+        slot = self._stage_i & 1
+        self._stage_i += 1
+        self._copy_stream.wait_event(self._consumed[slot])      # the step that read this slot has copied it out
+        with torch.cuda.stream(self._copy_stream):
+            for k, dst in self._staging[slot].items():
+                dst.copy_(batch[k], non_blocking=True)
+            self._uploaded[slot].record(self._copy_stream)
+        return slot
+
     def step_graphed(self, batch):
-        """One training step through the captured graph: upload `batch` into the static buffers, refresh the per-step host
-        values, replay, then the eager tail of step()."""
+        """One training step through the captured graph: upload `batch` (a batch dict, or a slot returned by `stage`) into
+        the static buffers, refresh the per-step host values, replay, then the eager tail of step()."""
         graph, total_loss, aux_output = self._graph
-        for k, v in batch.items():
-            if torch.is_tensor(v) and k not in ('center', 'length'):
+        if isinstance(batch, int):
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(self._uploaded[batch])
+            for k, v in self._staging[batch].items():
                 self._static_batch[k].copy_(v, non_blocking=True)
+            self._consumed[batch].record(main)
+        else:
+            for k, v in batch.items():
+                if torch.is_tensor(v) and k not in ('center', 'length'):
+                    self._static_batch[k].copy_(v, non_blocking=True)
         self.model.iters = self.iters
         self.model.refresh_static_params(self.iters)
         graph.replay()

@@ -3,6 +3,8 @@
 Replaces the torch op chain of model/module/correspondence.py:42-53 of the reference
 (bmm, mask, softmax(dim=1), softmax(dim=2), meshgrid.bmm, broadcast-multiply-sum).
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -54,15 +56,14 @@ class CorrMatchFunction(Function):
                 _lib.ptr(imatch), _lib.ptr(rsum), _lib.ptr(csum), _lib.ptr(A_pool), _lib.ptr(csum_pool), _lib.ptr(ws),
                 ws_bytes, _lib.stream_ptr(dev))
         _lib.check(rc, 'scp_corr_match_forward')
-        ctx.save_for_backward(img_feat, mesh_feat, mask_down, pred_v, meshgrid, match, imatch, rsum, csum)
-        ctx.pool_saved = (A_pool, csum_pool)
+        ctx.save_for_backward(img_feat, mesh_feat, mask_down, pred_v, meshgrid, match, imatch, rsum, csum, A_pool, csum_pool)
         ctx.geom = (float(tau), B, hf, wf, N, C)
         ctx.set_materialize_grads(False)
         return pc_full, pc_pool, match, imatch, A_pool
 
     @staticmethod
     def backward(ctx, g_full, g_pool, g_match, g_imatch, g_A):
-        img_feat, mesh_feat, mask_down, pred_v, meshgrid, match, imatch, rsum, csum = ctx.saved_tensors
+        img_feat, mesh_feat, mask_down, pred_v, meshgrid, match, imatch, rsum, csum, A_pool, csum_pool = ctx.saved_tensors
         tau, B, hf, wf, N, C = ctx.geom
         dev = img_feat.device
 
@@ -71,7 +72,6 @@ class CorrMatchFunction(Function):
                 return None
             return g.float().contiguous()
         g_full, g_pool, g_A = prep(g_full, None), prep(g_pool, None), prep(g_A, None)
-        A_pool, csum_pool = ctx.pool_saved
         g_match = prep(g_match, None) if g_match is not None else torch.zeros_like(match)
         g_imatch = prep(g_imatch, None) if g_imatch is not None else torch.zeros_like(imatch)
         g_img = torch.empty_like(img_feat)
@@ -90,7 +90,17 @@ class CorrMatchFunction(Function):
 
 
 def corr_match(img_feat, mesh_feat, mask_down, pred_v, meshgrid, tau, hf, wf, want_full=False, want_pool=True):
+    """The kernels' soft-maxes use the fixed reference point tau * 1: `img_feat` (over C) and `mesh_feat` (over C) must be
+    L2-normalised, as the reference's encoder produces them (encoder.py:36,45), and 0 < tau <= 40.  SCP_DEBUG_CHECKS=1
+    verifies the norms on every call (one host synchronisation)."""
     if not img_feat.is_cuda:
         raise TypeError('corr_match supports only CUDA tensors (no CPU path)')
+    if not 0. < float(tau) <= 40.:
+        raise ValueError('corr_match: tau = %g outside (0, 40]' % float(tau))
+    if os.environ.get('SCP_DEBUG_CHECKS') == '1':
+        worst = max(float(img_feat.detach().norm(dim=1).max()), float(mesh_feat.detach().norm(dim=2).max()))
+        if worst > 1. + 1e-3:
+            raise ValueError('corr_match: features are not L2-normalised (largest norm %.4f): the fixed-reference-point '
+                             'soft-max would overflow / lose accuracy' % worst)
     return CorrMatchFunction.apply(img_feat, mesh_feat, mask_down, pred_v, meshgrid, tau, hf, wf, want_full,
                                    want_pool)
