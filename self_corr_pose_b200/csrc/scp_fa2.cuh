@@ -139,46 +139,46 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        {   // ===== MMA issuer: whole warp in uniform control flow, one elected thread issues (scp_tc5.cuh) =====
+        if (lane == 0) {   // ===== MMA issuer =====
             constexpr uint32_t idesc_pv = tc5::umma_idesc_bf16(BQ, HD);
             const uint32_t aQ = tc5::smem_u32(sQ);
             // S(jj) = Q K(jj)^T into S buffer jj & 1 (4 x K = 16); frees the K stage and publishes S when done
             auto issue_qk = [&](int jj) {
                 const int ks = jj % NK;
-                tc5::mbar_wait_warp(k_full + ks, (jj / NK) & 1);
+                tc5::mbar_wait(k_full + ks, (jj / NK) & 1);
                 tc5::tc_fence_after();
                 const int ncols = min(BKV, (T - jj * BKV + 15) & ~15);   // keys that exist, MMA N granularity 16
                 const uint32_t idesc = tc5::umma_idesc_bf16(BQ, ncols);
                 const uint32_t aK = tc5::smem_u32(sK + ks * KT_BYTES);
 #pragma unroll
                 for (int k = 0; k < HD / 16; k++)
-                    tc5::umma_bf16_e(tmem_base + COL_S + (jj & 1) * BKV, tc5::umma_desc_sw128(aQ + k * 32),
+                    tc5::umma_bf16(tmem_base + COL_S + (jj & 1) * BKV, tc5::umma_desc_sw128(aQ + k * 32),
                                    tc5::umma_desc_sw128(aK + k * 32), idesc, k != 0);
-                tc5::umma_commit_e(k_empty + ks);
-                tc5::umma_commit_e(s_full + (jj & 1));
+                tc5::umma_commit(k_empty + ks);
+                tc5::umma_commit(s_full + (jj & 1));
             };
-            tc5::mbar_wait_warp(q_full, 0);
+            tc5::mbar_wait(q_full, 0);
             issue_qk(0);
             if (nt > 1) issue_qk(1);
             for (int j = 0; j < nt; j++) {
                 const int buf = j & 1, vs = j % NV;
 #if SCP_FA2_EARLY_QK
                 if (j + 2 < nt) {                                // S(j) has been read: its buffer can take S(j+2) now
-                    tc5::mbar_wait_warp(s_free + buf, (j >> 1) & 1);
+                    tc5::mbar_wait(s_free + buf, (j >> 1) & 1);
                     tc5::tc_fence_after();
                     issue_qk(j + 2);
                 }
 #endif
-                tc5::mbar_wait_warp(p_full + buf, (j >> 1) & 1);      // P(j) is in TMEM, S buffer `buf` is free again
-                tc5::mbar_wait_warp(v_full + vs, (j / NV) & 1);
+                tc5::mbar_wait(p_full + buf, (j >> 1) & 1);      // P(j) is in TMEM, S buffer `buf` is free again
+                tc5::mbar_wait(v_full + vs, (j / NV) & 1);
                 tc5::tc_fence_after();
                 const int ncols = min(BKV, (T - j * BKV + 15) & ~15);
                 const uint32_t aV = tc5::smem_u32(sV + vs * VT_BYTES);
                 for (int k = 0; k < ncols / 16; k++)             // O += P(:, 16k..16k+15) V(16k..16k+15, :)
-                    tc5::umma_bf16_ts_e(tmem_base + COL_O, tmem_base + COL_P + buf * (BKV / 2) + k * 8,
+                    tc5::umma_bf16_ts(tmem_base + COL_O, tmem_base + COL_P + buf * (BKV / 2) + k * 8,
                                       tc5::umma_desc_sw128(aV + k * 32), idesc_pv, (j | k) != 0);
-                tc5::umma_commit_e(v_empty + vs);
-                tc5::umma_commit_e(pv_done);
+                tc5::umma_commit(v_empty + vs);
+                tc5::umma_commit(pv_done);
 #if !SCP_FA2_EARLY_QK
                 if (j + 2 < nt) issue_qk(j + 2);
 #endif

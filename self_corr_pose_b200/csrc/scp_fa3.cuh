@@ -115,13 +115,13 @@ fa3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        {   // ===== MMA issuer: whole warp in uniform control flow, one elected thread issues (scp_tc5.cuh) =====
+        if (lane == 0) {   // ===== MMA issuer =====
             constexpr uint32_t idesc_pv = tc5::umma_idesc_bf16(BQ, HD);
             const uint32_t aQ = tc5::smem_u32(sQ);
             // S(jj) = Q K(jj)^T into S buffer jj & 1: four K=16 steps over d, three split products each
             auto issue_qk = [&](int jj) {
                 const int ks = jj % NK;
-                tc5::mbar_wait_warp(k_full + ks, (jj / NK) & 1);
+                tc5::mbar_wait(k_full + ks, (jj / NK) & 1);
                 tc5::tc_fence_after();
                 const int ncols = min(BKV, (T - jj * BKV + 15) & ~15);   // keys that exist, MMA N granularity 16
                 const uint32_t idesc = tc5::umma_idesc_bf16(BQ, ncols);
@@ -130,38 +130,38 @@ fa3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constan
 #pragma unroll
                 for (int s = 0; s < HD / 16; s++) {
                     const uint32_t qh = aQ + (s >> 1) * Q_TILE + (s & 1) * 32, kh = aK + (s >> 1) * K_TILE + (s & 1) * 32;
-                    tc5::umma_bf16_e(dS, tc5::umma_desc_sw128(qh), tc5::umma_desc_sw128(kh), idesc, s != 0);
-                    tc5::umma_bf16_e(dS, tc5::umma_desc_sw128(qh), tc5::umma_desc_sw128(kh + 64), idesc, 1);
-                    tc5::umma_bf16_e(dS, tc5::umma_desc_sw128(qh + 64), tc5::umma_desc_sw128(kh), idesc, 1);
+                    tc5::umma_bf16(dS, tc5::umma_desc_sw128(qh), tc5::umma_desc_sw128(kh), idesc, s != 0);
+                    tc5::umma_bf16(dS, tc5::umma_desc_sw128(qh), tc5::umma_desc_sw128(kh + 64), idesc, 1);
+                    tc5::umma_bf16(dS, tc5::umma_desc_sw128(qh + 64), tc5::umma_desc_sw128(kh), idesc, 1);
                 }
-                tc5::umma_commit_e(k_empty + ks);
-                tc5::umma_commit_e(s_full + (jj & 1));
+                tc5::umma_commit(k_empty + ks);
+                tc5::umma_commit(s_full + (jj & 1));
             };
-            tc5::mbar_wait_warp(q_full, 0);
+            tc5::mbar_wait(q_full, 0);
             issue_qk(0);
             if (nt > 1) issue_qk(1);
             for (int j = 0; j < nt; j++) {
                 const int vs = j % NV;
 #if SCP_FA3_EARLY_QK
                 if (j + 2 < nt) {          // S(j) is in the softmax warps' registers: its buffer can take S(j+2) NOW, a whole
-                    tc5::mbar_wait_warp(s_free + (j & 1), (j >> 1) & 1);   // softmax tile earlier than after P(j) -- ncu: the
+                    tc5::mbar_wait(s_free + (j & 1), (j >> 1) & 1);   // softmax tile earlier than after P(j) -- ncu: the
                     tc5::tc_fence_after();                            // softmax warps spent 38 % of their time waiting for S
                     issue_qk(j + 2);
                 }
 #endif
-                tc5::mbar_wait_warp(p_full, j & 1);                    // P(j) is in TMEM
-                tc5::mbar_wait_warp(v_full + vs, (j / NV) & 1);
+                tc5::mbar_wait(p_full, j & 1);                    // P(j) is in TMEM
+                tc5::mbar_wait(v_full + vs, (j / NV) & 1);
                 tc5::tc_fence_after();
                 const int ncols = min(BKV, (T - j * BKV + 15) & ~15);
                 const uint32_t aV = tc5::smem_u32(sV + vs * VT_BYTES);
                 for (int k = 0; k < ncols / 16; k++) {            // O += P(:, 16k..16k+15) V(16k..16k+15, :)
                     const uint32_t ph = tmem_base + COL_PH + k * 8, pl = tmem_base + COL_PL + k * 8;
-                    tc5::umma_bf16_ts_e(tmem_base + COL_O, ph, tc5::umma_desc_sw128(aV + k * 32), idesc_pv, (j | k) != 0);
-                    tc5::umma_bf16_ts_e(tmem_base + COL_O, ph, tc5::umma_desc_sw128(aV + V_TILE + k * 32), idesc_pv, 1);
-                    tc5::umma_bf16_ts_e(tmem_base + COL_O, pl, tc5::umma_desc_sw128(aV + k * 32), idesc_pv, 1);
+                    tc5::umma_bf16_ts(tmem_base + COL_O, ph, tc5::umma_desc_sw128(aV + k * 32), idesc_pv, (j | k) != 0);
+                    tc5::umma_bf16_ts(tmem_base + COL_O, ph, tc5::umma_desc_sw128(aV + V_TILE + k * 32), idesc_pv, 1);
+                    tc5::umma_bf16_ts(tmem_base + COL_O, pl, tc5::umma_desc_sw128(aV + k * 32), idesc_pv, 1);
                 }
-                tc5::umma_commit_e(v_empty + vs);
-                tc5::umma_commit_e(pv_done);
+                tc5::umma_commit(v_empty + vs);
+                tc5::umma_commit(pv_done);
 #if !SCP_FA3_EARLY_QK
                 if (j + 2 < nt) issue_qk(j + 2);
 #endif

@@ -139,16 +139,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp runs the loop in uniform control flow, one elected thread issues (scp_tc5.cuh) =====
-        {
+        // ===== MMA issuer =====
+        if (lane == 0) {
             constexpr uint32_t idesc = tc5::umma_idesc_bf16(128, BN);
             int stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                tc5::mbar_wait_warp(tempty + acc, acc_phase ^ 1);       // epilogue has drained this accumulator
+                tc5::mbar_wait(tempty + acc, acc_phase ^ 1);       // epilogue has drained this accumulator
                 tc5::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 for (int kb = 0; kb < nkb; kb++) {
-                    tc5::mbar_wait_warp(full + stage, phase);           // TMA bytes have landed
+                    tc5::mbar_wait(full + stage, phase);           // TMA bytes have landed
                     tc5::tc_fence_after();
                     const uint32_t sa = tc5::smem_u32(smem + stage * STAGE_BYTES), sb = sa + BM * BK * 2;
 #pragma unroll
@@ -159,24 +159,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                             for (int c = 0; c < 2; c++) {
                                 const uint32_t ah = sa + mh * (128 * BK * 2) + c * 32, bh = sb + c * 32;
-                                tc5::umma_bf16_e(d_tmem + mh * BN, tc5::umma_desc_sw128(ah), tc5::umma_desc_sw128(bh), idesc,
+                                tc5::umma_bf16(d_tmem + mh * BN, tc5::umma_desc_sw128(ah), tc5::umma_desc_sw128(bh), idesc,
                                                (kb | c) != 0);
-                                tc5::umma_bf16_e(d_tmem + mh * BN, tc5::umma_desc_sw128(ah), tc5::umma_desc_sw128(bh + 64), idesc, 1);
-                                tc5::umma_bf16_e(d_tmem + mh * BN, tc5::umma_desc_sw128(ah + 64), tc5::umma_desc_sw128(bh), idesc, 1);
+                                tc5::umma_bf16(d_tmem + mh * BN, tc5::umma_desc_sw128(ah), tc5::umma_desc_sw128(bh + 64), idesc, 1);
+                                tc5::umma_bf16(d_tmem + mh * BN, tc5::umma_desc_sw128(ah + 64), tc5::umma_desc_sw128(bh), idesc, 1);
                             }
                         } else {
 #pragma unroll
                             for (int k = 0; k < BK / 16; k++) {
                                 // advance 16 elements (32 B) along K inside the 128-byte swizzle atom
-                                tc5::umma_bf16_e(d_tmem + mh * BN, tc5::umma_desc_sw128(sa + mh * (128 * BK * 2) + k * 32),
+                                tc5::umma_bf16(d_tmem + mh * BN, tc5::umma_desc_sw128(sa + mh * (128 * BK * 2) + k * 32),
                                                tc5::umma_desc_sw128(sb + k * 32), idesc, (kb | k) != 0);
                             }
                         }
                     }
-                    tc5::umma_commit_e(empty + stage);               // frees the smem slot when the MMAs retire
+                    tc5::umma_commit(empty + stage);               // frees the smem slot when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc5::umma_commit_e(tfull + acc);                     // accumulator complete -> epilogue
+                tc5::umma_commit(tfull + acc);                     // accumulator complete -> epilogue
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }

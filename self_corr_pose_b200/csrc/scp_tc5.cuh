@@ -106,15 +106,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// ---- warp-convergent issue (round 2) -------------------------------------------------------------------------------
+// ---- warp-convergent issue: measured and rejected (round 2) --------------------------------------------------------------
 // The *_e variants are executed by ALL 32 lanes of the issuing warp in uniform control flow and elect the issuing thread
-// inside the instruction sequence (elect.sync is deterministic for a given member mask, so MMAs and their commits come from
-// the same thread).  Why: with the issue loop inside `if (lane == 0)` ptxas cannot prove the operands warp-uniform and
-// wraps EVERY tcgen05.mma in a uniformisation loop (ELECT / R2UR.BROADCAST / BRA.U.ANY) behind a serial descriptor chain
-// (UIADD3 -> USHF -> ULOP3): ~11 dependent instructions, 60-85 cycles per MMA -- slower than the tensor core executes a
-// 128 x 64 x 16 product (32 cycles) and about the duration of a 128 x 128 x 16 one (64 cycles): the round-1 kernels were
-// bound by the issuing thread (ncu: tensor pipe 47 % in the attention kernel, 69 % of peak in the GEMMs).  In uniform
-// control flow the descriptors live in uniform registers and the UTCHMMA instructions are emitted back to back.
+// inside the instruction sequence.  Motivation: with the issue loop inside `if (lane == 0)` ptxas wraps every tcgen05.mma in
+// a uniformisation loop (ELECT / R2UR.BROADCAST / BRA.U.ANY) behind a serial descriptor chain (UIADD3 -> USHF -> ULOP3),
+// ~11 dependent instructions per MMA, and the attention kernel's tensor pipe is only 47 % busy.  In uniform control flow
+// the loop disappears from the SASS -- but on the B200 the kernels got SLOWER (gpurun_out/r2_call15.log: fa3 0.364 -> 0.488
+// ms, QKV GEMM 0.152 -> 0.181 ms, bf16 ViT 5.35 -> 5.71 ms) and one fa2 case lost parity, so the issuing thread is not what
+// bounds them.  Kept for reference; nothing uses them.
 __device__ __forceinline__ void umma_bf16_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile("{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
