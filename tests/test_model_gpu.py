@@ -199,13 +199,13 @@ def test_side_streams_do_not_change_the_step():
         total, aux, _ = tr.step(batch)
         torch.cuda.synchronize()
         out[flag] = ({k: float(x) for k, x in aux.items()},
-                     {n: p.detach().clone() for n, p in model.named_parameters() if p.requires_grad})
+                     {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
     for k in out[True][0]:
         a, b = out[True][0][k], out[False][0][k]
         assert abs(a - b) <= 1e-5 * abs(b) + 1e-8, (k, a, b)
-    # all parameters as one vector: a zero-initialised bias whose gradient is summation noise moves by +-lr under AdamW
-    # whichever way the noise points, so a per-parameter relative difference says nothing
+    # the (clipped) gradients as one vector -- not the updated parameters: AdamW moves an element whose gradient is summation
+    # noise by +-lr whichever way the noise points
     cat = lambda d: torch.cat([d[n].reshape(-1) for n in sorted(d)])
     worst = _rel(cat(out[True][1]), cat(out[False][1]))
-    print('PARITY side-streams on/off: total %.6g/%.6g, params rel %.2e' % (out[True][0]['total_loss'], out[False][0]['total_loss'], worst))
-    assert worst < 1e-5
+    print('PARITY side-streams on/off: total %.6g/%.6g, gradient rel %.2e' % (out[True][0]['total_loss'], out[False][0]['total_loss'], worst))
+    assert worst < 1e-4
