@@ -260,6 +260,28 @@ int scp_color_jitter_normalize(const float *img, float *out, int B, int HW, cons
                                const float *mean, const float *std, int nhwc_out, void *workspace, size_t workspace_bytes,
                                void *stream);
 
+/* ---- multi-GPU: small-vector exchange over NVLink peer memory (SyncBatchNorm statistics) ------------------------ */
+/*
+ * The reference converts every BatchNorm of the encoder to SyncBatchNorm (model/trainer.py:66): per training step 80
+ * collectives of at most 2*512+1 floats.  These entry points replace NCCL for them by ONE kernel per collective that stores
+ * the rank's vector into every peer's buffer over NVLink, raises a flag and waits for the peers' flags (csrc/scp_peer.cu).
+ * Set-up (once per channel, host side): every rank creates a buffer and publishes its 64-byte IPC handle; every rank opens
+ * the other ranks' handles; `peers[q]` = address of rank q's buffer in THIS process (own buffer for q == rank).
+ * scp_peer_exchange: dst[world][n] = the ranks' vectors in rank order (reduce == 0) or dst[n] = their sum in rank order
+ * (reduce != 0).  `counter` is one zero-initialised device word per channel (advanced by the kernel: CUDA-graph replays keep
+ * counting).  All ranks must issue the same sequence of exchanges on a channel, in stream order.  A peer that never arrives
+ * traps the kernel after a bounded spin instead of hanging the GPU.
+ */
+#define SCP_PEER_SLOTS 4
+#define SCP_PEER_MAX_WORLD 16
+#define SCP_PEER_MAX_FLOATS 1088
+size_t scp_peer_buffer_bytes(void);
+int scp_peer_buffer_create(void **ptr, unsigned char *handle64);
+int scp_peer_buffer_open(const unsigned char *handle64, void **ptr);
+int scp_peer_buffer_close(void *ptr, int own);
+int scp_peer_exchange(void *const *peers, const float *src, int n, int rank, int world, unsigned *counter, float *dst,
+                      int reduce, void *stream);
+
 /* ---- pre-training cycle loss: the k gathered target rows of every image pair ------------------------------ */
 /*
  * pointcorr_pool[B,P4,N] (2x2-pooled similarity), A_pool[B,2,N] (= pooled grid . softmax over pixels, from

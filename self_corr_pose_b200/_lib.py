@@ -90,6 +90,14 @@ _SIGNATURES.update({
                                     ctypes.POINTER(_fl), _i, _f, _sz, _f], _i),
 })
 
+_SIGNATURES.update({
+    'scp_peer_buffer_bytes': ([], _sz),
+    'scp_peer_buffer_create': ([_pp, ctypes.c_char_p], _i),
+    'scp_peer_buffer_open': ([ctypes.c_char_p, _pp], _i),
+    'scp_peer_buffer_close': ([_f, _i], _i),
+    'scp_peer_exchange': ([_pp, _f, _i, _i, _i, _f, _f, _i, _f], _i),
+})
+
 _lib = None
 
 

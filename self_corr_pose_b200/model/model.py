@@ -15,6 +15,7 @@ from .module.pretrained_corr import PretrainedCorrespondence
 from .module.renderer import Renderer
 from .util import loss_utils as L
 from ..ops.image_losses import image_losses
+from ..ops import peer_sync_bn
 
 
 class MeshNet(nn.Module):
@@ -79,7 +80,7 @@ class MeshNet(nn.Module):
             if self._side2 is None:
                 self._side2 = torch.cuda.Stream(img.device)
             self._side2.wait_stream(main)
-            with torch.cuda.stream(self._side2):
+            with torch.cuda.stream(self._side2), peer_sync_bn.channel(1):
                 rot_cyc = self.corr_net.compute_rotation_cycle_loss(img, mask, img_feat, self.encoder)
             rot_cyc[0].record_stream(main)
         fused = opts.train and self.fused_losses and opts.img_size % 16 == 0 and not opts.use_occ
@@ -125,7 +126,8 @@ class MeshNet(nn.Module):
                                                         A=self.corr_net.pool_A, feat=feat)
         aux['cycle_loss_pretrain'] = cyc[0] * wts.cycle_loss_pt_wt
         if rot_cyc is None:
-            rot_cyc = self.corr_net.compute_rotation_cycle_loss(img, mask, img_feat, self.encoder)
+            with peer_sync_bn.channel(1):
+                rot_cyc = self.corr_net.compute_rotation_cycle_loss(img, mask, img_feat, self.encoder)
         else:
             torch.cuda.current_stream(img.device).wait_stream(self._side2)
         aux['cycle_loss'] = rot_cyc[0] * wts.cycle_loss_wt
