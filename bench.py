@@ -520,10 +520,11 @@ def trainer_arm(args, torch, dist, dev, world, rank, local, timed):
         red = tr.reducer
         nbytes = red.flat.numel() * 4
         t = timed(lambda: dist.all_reduce(red.flat), 10) / 10
-        n_sync_bn = sum(1 for m in model.modules() if m.__class__.__name__ == 'SyncBatchNorm')
+        n_sync_bn = sum(1 for m in model.modules() if isinstance(m, torch.nn.SyncBatchNorm))
         comm = {'allreduce_bytes': nbytes, 'allreduce_ms': t, 'bus_gbs': 2 * (world - 1) / world * nbytes / t / 1e6,
                 'bus_gbs_reference_point': 725.0, 'frac_of_step': t / (ms / args.steps),
                 'sync_batchnorm_layers': n_sync_bn,
+                'sync_batchnorm_transport': 'NVLink peer-memory exchange kernel (csrc/scp_peer.cu)' if tr.peer_bn else 'NCCL',
                 'sync_batchnorm_collectives_per_step': n_sync_bn * 2 * 2,   # (stats gather fwd + reduce bwd) x 2 encoder passes
                 'note': 'one all_reduce(SUM) of the flat fp32 gradient buffer per step (dist.FlatGradReducer), not overlapped '
                         'with backward; SyncBatchNorm collectives as in the reference (trainer.py:66)'}

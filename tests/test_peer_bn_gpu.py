@@ -47,33 +47,36 @@ def _worker(rank, world, port, out):
             res.append((y.detach(), xi.grad, net[1].weight.grad, net[4].running_mean.clone(), net[4].running_var.clone()))
         for a, b in zip(*res):
             worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-12)))
-    # CUDA graph: capture one forward + backward, replay three times with new inputs
-    x_static = torch.randn(4, 3, 16, 16, device=dev).requires_grad_(True)
+    # CUDA graph (as Trainer.capture does it: gradients pre-allocated and zeroed inside the graph, warm-up on a side stream):
+    # capture one forward + backward, replay three times with new inputs
+    x_static = torch.randn(4, 3, 16, 16, device=dev)
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
         for _ in range(2):
-            mine.zero_grad()
+            mine.zero_grad(set_to_none=False)
             (mine(x_static) ** 2).mean().backward()
     torch.cuda.current_stream(dev).wait_stream(side)
-    x_static.grad = None
+    torch.cuda.synchronize()
+    dist.barrier()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
+        for p in mine.parameters():
+            p.grad.zero_()
         y_static = mine(x_static)
         (y_static ** 2).mean().backward()
     for it in range(3):
         g = torch.Generator().manual_seed(900 + 10 * it + rank)
         xn = torch.randn(4, 3, 16, 16, generator=g).to(dev)
         ref.load_state_dict(mine.state_dict())          # same running statistics going in
-        with torch.no_grad():
-            x_static.copy_(xn)
-        x_static.grad.zero_()
+        x_static.copy_(xn)
         graph.replay()
-        xr = xn.clone().requires_grad_(True)
-        yr = ref(xr)
+        ref.zero_grad()
+        yr = ref(xn)
         (yr ** 2).mean().backward()
+        torch.cuda.synchronize()
         worst = max(worst, float((y_static - yr).abs().max() / yr.abs().max()),
-                    float((x_static.grad - xr.grad).abs().max() / xr.grad.abs().max()))
+                    float((mine[0].weight.grad - ref[0].weight.grad).abs().max() / ref[0].weight.grad.abs().max()))
     out[rank] = worst
     dist.barrier()
     dist.destroy_process_group()
