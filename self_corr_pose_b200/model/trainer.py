@@ -137,7 +137,8 @@ class Trainer:
         torch.cuda.current_stream(dev).wait_stream(side)
         self.model.iters = self.iters
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # thread_local: with a process group alive, NCCL's watchdog thread polls its events while we capture
+        with torch.cuda.graph(graph, capture_error_mode='thread_local'):
             self.reducer.zero_()
             data = self.batch_reshape(self._static_batch)
             total_loss, aux_output = self.model(data)

@@ -60,7 +60,7 @@ def _worker(rank, world, port, out):
     torch.cuda.synchronize()
     dist.barrier()
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, capture_error_mode='thread_local'):      # NCCL's watchdog thread polls events meanwhile
         for p in mine.parameters():
             p.grad.zero_()
         y_static = mine(x_static)
