@@ -188,7 +188,7 @@ def test_side_streams_do_not_change_the_step():
     snap = (copy.deepcopy(model.state_dict()), copy.deepcopy(tr.optim.optimizer.state_dict()),
             copy.deepcopy(tr.optim.scheduler.state_dict()), tr.iters)
     out = {}
-    for flag in (True, False):
+    for run, flag in enumerate((True, True, False)):      # two runs with side streams (run-to-run noise), one without
         model.load_state_dict(snap[0])
         tr.optim.optimizer.load_state_dict(snap[1])
         tr.optim.scheduler.load_state_dict(snap[2])
@@ -198,14 +198,17 @@ def test_side_streams_do_not_change_the_step():
         torch.cuda.manual_seed(21)
         total, aux, _ = tr.step(batch)
         torch.cuda.synchronize()
-        out[flag] = ({k: float(x) for k, x in aux.items()},
-                     {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
-    for k in out[True][0]:
-        a, b = out[True][0][k], out[False][0][k]
+        out[run] = ({k: float(x) for k, x in aux.items()},
+                    {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
+    for k in out[0][0]:
+        a, b = out[0][0][k], out[2][0][k]
         assert abs(a - b) <= 1e-5 * abs(b) + 1e-8, (k, a, b)
-    # the (clipped) gradients as one vector -- not the updated parameters: AdamW moves an element whose gradient is summation
-    # noise by +-lr whichever way the noise points
+    # the (clipped) gradients as one vector.  The SoftRas / correspondence backward kernels accumulate with float reductions
+    # whose order changes from run to run, and the reference's BatchNorm-on-batch-statistics encoder amplifies that noise
+    # (section 2 of DESIGN.md): the yardstick is the difference between two IDENTICAL runs
     cat = lambda d: torch.cat([d[n].reshape(-1) for n in sorted(d)])
-    worst = _rel(cat(out[True][1]), cat(out[False][1]))
-    print('PARITY side-streams on/off: total %.6g/%.6g, gradient rel %.2e' % (out[True][0]['total_loss'], out[False][0]['total_loss'], worst))
-    assert worst < 1e-4
+    noise = _rel(cat(out[0][1]), cat(out[1][1]))
+    diff = _rel(cat(out[0][1]), cat(out[2][1]))
+    print('PARITY side-streams on/off: total %.6g/%.6g, gradient rel %.2e (two identical runs: %.2e)'
+          % (out[0][0]['total_loss'], out[2][0]['total_loss'], diff, noise))
+    assert diff < max(5 * noise, 1e-5)

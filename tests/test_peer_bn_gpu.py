@@ -63,8 +63,18 @@ def _worker(rank, world, port, out):
     with torch.cuda.graph(graph, capture_error_mode='thread_local'):      # NCCL's watchdog thread polls events meanwhile
         for p in mine.parameters():
             p.grad.zero_()
-        y_static = mine(x_static)
-        (y_static ** 2).mean().backward()
+        dbg = [('zero', torch.cuda.is_current_stream_capturing())]
+        h = x_static
+        for i, layer in enumerate(mine):
+            h = layer(h)
+            dbg.append(('fwd%d' % i, torch.cuda.is_current_stream_capturing()))
+        y_static = h
+        loss = (y_static ** 2).mean()
+        dbg.append(('loss', torch.cuda.is_current_stream_capturing()))
+        loss.backward()
+        dbg.append(('bwd', torch.cuda.is_current_stream_capturing()))
+        if rank == 0:
+            print('CAPTURE-STATUS', dbg, flush=True)
     for it in range(3):
         g = torch.Generator().manual_seed(900 + 10 * it + rank)
         xn = torch.randn(4, 3, 16, 16, generator=g).to(dev)
