@@ -122,7 +122,9 @@ class Trainer:
         NCCL collectives are captured too).  The gradient all-reduce, clipping (with the reference's NaN check, one host
         read) and AdamW/OneCycle stay eager after the replay.  Use step_graphed(batch) afterwards.
         Needs a few eager steps first (cuDNN autotuning, gradient buffer adoption); they are run here and DO advance the
-        optimiser, like any other training step."""
+        optimiser, like any other training step.  Call it before holding on to the loss of an eager step run on the default
+        stream: a live autograd graph keeps its gradient-accumulation nodes tied to that stream, which cannot be joined to
+        a capturing stream (torch raises `cudaErrorStreamCaptureImplicit`)."""
         dev = self.device
         self.model.enable_static_params(dev)
         self._static_batch = {k: (v.to(dev).clone() if torch.is_tensor(v) and k not in ('center', 'length') else v)

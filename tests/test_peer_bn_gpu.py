@@ -47,6 +47,7 @@ def _worker(rank, world, port, out):
             res.append((y.detach(), xi.grad, net[1].weight.grad, net[4].running_mean.clone(), net[4].running_var.clone()))
         for a, b in zip(*res):
             worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-12)))
+        del y, xi, res      # no live autograd graph (its AccumulateGrad nodes are tied to the default stream) into the capture
     # CUDA graph (as Trainer.capture does it: gradients pre-allocated and zeroed inside the graph, warm-up on a side stream):
     # capture one forward + backward, replay three times with new inputs
     x_static = torch.randn(4, 3, 16, 16, device=dev)
@@ -63,18 +64,8 @@ def _worker(rank, world, port, out):
     with torch.cuda.graph(graph, capture_error_mode='thread_local'):      # NCCL's watchdog thread polls events meanwhile
         for p in mine.parameters():
             p.grad.zero_()
-        dbg = [('zero', torch.cuda.is_current_stream_capturing())]
-        h = x_static
-        for i, layer in enumerate(mine):
-            h = layer(h)
-            dbg.append(('fwd%d' % i, torch.cuda.is_current_stream_capturing()))
-        y_static = h
-        loss = (y_static ** 2).mean()
-        dbg.append(('loss', torch.cuda.is_current_stream_capturing()))
-        loss.backward()
-        dbg.append(('bwd', torch.cuda.is_current_stream_capturing()))
-        if rank == 0:
-            print('CAPTURE-STATUS', dbg, flush=True)
+        y_static = mine(x_static)
+        (y_static ** 2).mean().backward()
     for it in range(3):
         g = torch.Generator().manual_seed(900 + 10 * it + rank)
         xn = torch.randn(4, 3, 16, 16, generator=g).to(dev)
