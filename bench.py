@@ -308,16 +308,19 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
     st = _lib.stream_ptr(dev)
     M = B * T
     if x3:
-        qk = torch.randn(M, 1536, device=dev).to(torch.bfloat16)
+        from self_corr_pose_b200.model.module.network.dino import split_bf16_i32
+        qk = split_bf16_i32(torch.randn(M, 768, device=dev))            # proper (hi, lo) pairs of N(0,1) queries / keys
         vt = torch.zeros(2, B * 384, Tp, device=dev, dtype=torch.bfloat16)
-        vt[:, :, :T] = torch.randn(2, B * 384, T, device=dev).to(torch.bfloat16)
+        vv = torch.randn(B * 384, T, device=dev)
+        vt[0, :, :T] = vv.to(torch.bfloat16)
+        vt[1, :, :T] = (vv - vt[0, :, :T].float()).to(torch.bfloat16)
         o = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
         t_a = timeit(lambda: L.scp_attention_x3(_lib.ptr(qk), _lib.ptr(vt), _lib.ptr(o), B, T, st))
         out.append(dict(kernel='fa3_fwd_kernel (tcgen05 flash attention, split operands)', ms=t_a, bound='tensor',
                         achieved=4.0 * T * T * 64 * 6 * B / t_a / 1e9, peak=tf_eff, unit='TFLOP/s', launches_per_step=9,
                         ncu_name='fa3::fa3_fwd_kernel #0', peak_source=tf_note))
-        A = torch.randn(M, 768, device=dev).to(torch.bfloat16)
-        W = torch.randn(1152, 768, device=dev).to(torch.bfloat16)
+        A = split_bf16_i32(torch.randn(M, 384, device=dev))
+        W = split_bf16_i32(torch.randn(1152, 384, device=dev))
         Cc = torch.empty(M, 1152, device=dev)
         t_g = timeit(lambda: L.scp_gemm_bf16x3_tn(_lib.ptr(A), _lib.ptr(W), None, _lib.ptr(Cc), M, 1152, 384, st))
         out.append(dict(kernel='gemm_bf16_tn_kernel<.,3> (qkv shape, fp32 out)', ms=t_g, bound='tensor',
