@@ -302,3 +302,91 @@ def test_unimplemented_reference_options_fail_loudly():
         setattr(opts, flag, True)
         with pytest.raises(NotImplementedError, match=flag):
             MeshNet(opts)
+
+
+# ---- round 2: host pieces of the graphed training step ------------------------------------------------------------------
+def test_rotation_slot_equals_torchvision_rotate():
+    """RotationSlot (affine matrix through a static tensor, sampling grid from cached constants) reproduces
+    torchvision.transforms.functional.rotate bit for bit and draws the angle like correspondence.py:82."""
+    import torchvision
+    from torchvision.transforms import InterpolationMode
+    from self_corr_pose_b200.model.module.correspondence import RotationSlot
+    slot = RotationSlot('cpu')
+    for shape in ((2, 3, 32, 32), (2, 1, 48, 32), (1, 2, 16, 16)):
+        img = torch.rand(*shape)
+        torch.manual_seed(3)
+        slot.refresh()
+        slot.upload()
+        after = torch.rand(1)
+        torch.manual_seed(3)
+        angle = torch.empty(1).uniform_(0., 360.).item()
+        assert torch.equal(after, torch.rand(1)) and angle == slot.angle
+        for mode, im in (('bilinear', InterpolationMode.BILINEAR), ('nearest', InterpolationMode.NEAREST)):
+            want = torchvision.transforms.functional.rotate(img, angle, interpolation=im)
+            assert torch.equal(slot.rotate(img, mode), want)
+
+
+def test_weights_device_buffer_follows_the_schedule():
+    from self_corr_pose_b200.hotpath import default_opts
+    from self_corr_pose_b200.model.module.weights import Weights
+    a, b = Weights(default_opts()), Weights(default_opts())
+    b.enable_device_buffer('cpu')
+    for it in (0, 1, 777, 19999, 30000):
+        a.schedule(it)
+        b.schedule(it)
+        for name in ('mask_wt', 'tex_wt', 'depth_wt', 'triangle_wt', 'symmetry_wt', 'cycle_loss_wt', 'cycle_loss_pt_wt',
+                     'match_wt', 'imatch_wt', 'pullfar_wt', 'deform_wt'):
+            assert float(getattr(b, name)) == pytest.approx(float(getattr(a, name)), rel=1e-7), (it, name)
+        assert getattr(b, 'match_wt').dim() == 0 and getattr(b, 'match_wt').data_ptr() != 0     # a view of the static buffer
+
+
+def test_jitter_slot_packs_what_get_params_draws():
+    import struct
+    from torchvision import transforms
+    from self_corr_pose_b200.ops.color_jitter import JitterSlot, _pack
+    jit = transforms.ColorJitter(0.2, 0.2, 0.2, 0.05)
+    slot = JitterSlot('cpu', (0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+    torch.manual_seed(9)
+    slot.refresh(jit)
+    after = torch.rand(1)
+    torch.manual_seed(9)
+    params = transforms.ColorJitter.get_params(jit.brightness, jit.contrast, jit.saturation, jit.hue)
+    assert torch.equal(after, torch.rand(1))                       # same consumption of the global CPU generator
+    order, ratios, hue = _pack(params, None, None)
+    got = struct.unpack(JitterSlot.FMT, bytes(slot.host.tolist()))
+    assert list(got[:4]) == order
+    assert got[4:7] == pytest.approx(ratios[0::2]) and got[7:10] == pytest.approx(ratios[1::2]) and got[10] == pytest.approx(hue)
+    assert got[11:14] == pytest.approx((0.485, 0.456, 0.406)) and got[14:17] == pytest.approx((0.229, 0.224, 0.225))
+
+
+def test_surface_sampling_is_area_weighted_and_capturable_ops_only():
+    """Inverse-CDF face draws (no torch.multinomial): indices in range, frequencies follow the face areas, barycentric
+    weights are a partition of unity."""
+    from self_corr_pose_b200 import synthetic
+    from self_corr_pose_b200.model.module.mesh import sample_faces_and_weights, points_from_samples
+    v, f = synthetic.icosphere(1)
+    verts = torch.from_numpy(v)[None].clone()
+    verts[0, :, 0] *= 3.0                                            # unequal face areas
+    faces = torch.from_numpy(f)[None]
+    torch.manual_seed(0)
+    idx, w = sample_faces_and_weights(verts, faces, 200000)
+    assert idx.min() >= 0 and idx.max() < faces.shape[1] and torch.allclose(w.sum(-1), torch.ones(1, 200000), atol=1e-6)
+    assert (w >= 0).all()
+    tri = verts[0][faces[0]]
+    area = 0.5 * torch.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0], dim=-1).norm(dim=-1)
+    freq = torch.bincount(idx[0], minlength=faces.shape[1]).float() / idx.shape[1]
+    assert torch.allclose(freq, area / area.sum(), atol=3e-3)
+    pts = points_from_samples(verts, faces, idx[:, :1000], w[:, :1000])
+    assert pts.shape == (1, 1000, 3) and torch.isfinite(pts).all()
+
+
+def test_split_bf16_pairs_carry_sixteen_mantissa_bits():
+    from self_corr_pose_b200.model.module.network.dino import split_bf16_i32, merge_bf16_i32
+    x = torch.randn(5, 96, generator=torch.Generator().manual_seed(1)) * torch.logspace(-3, 3, 96)
+    s = split_bf16_i32(x)
+    assert s.shape == (5, 192) and s.dtype == torch.bfloat16
+    # i32 layout: groups of 32 columns stored [32 hi | 32 lo]
+    assert torch.equal(s[:, :32].float(), x[:, :32].to(torch.bfloat16).float())
+    assert torch.equal(s[:, 64:96].float(), x[:, 32:64].to(torch.bfloat16).float())
+    rel = ((merge_bf16_i32(s) - x).abs() / x.abs()).max()
+    assert float(rel) < 2.0 ** -16
