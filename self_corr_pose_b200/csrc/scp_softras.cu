@@ -1027,12 +1027,28 @@ __global__ void __launch_bounds__(FACE_WARPS * 32, SCP_SOFTRAS_FACE_CTAS) backwa
     bool any = false;
     constexpr int BW = SCP_SOFTRAS_FACE_BW, BH = 32 / BW;
     static_assert(BW == 8 || BW == 16 || BW == 32, "block width");
+#if SCP_SOFTRAS_FACE_LINEAR
+    // the bounding box's pixels in row-major order, 32 consecutive ones per round: every lane holds a pixel of the box
+    // except in the last round (8x4 blocks leave 19-25 % of the lanes outside a 35x37 / 18x20 pixel box)
+    const int bw = ix1 - ix0 + 1, npx = bw * (iy1 - iy0 + 1);
+    const float inv_bw = 1.f / (float)bw;
+    (void)BH;
+    for (int i0 = 0; i0 < npx; i0 += 32) {
+        {
+            Pixel px;
+            const int i = i0 + lane;
+            const int row = (int)(((float)i + 0.5f) * inv_bw);   // exact: the quotient is >= 0.5 / 256 away from an integer
+            px.px = ix0 + (i - row * bw);
+            px.py = iy0 + row;
+            px.valid = i < npx;
+#else
     for (int y0 = iy0; y0 <= iy1; y0 += BH) {
         for (int x0 = ix0; x0 <= ix1; x0 += BW) {
             Pixel px;
             px.px = x0 + (lane % BW);
             px.py = y0 + (lane / BW);
             px.valid = px.px <= ix1 && px.py <= iy1;
+#endif
             px.pn = px.py * p.is + px.px;
             px.xp = centre_x(px.px, p.is);
             px.yp = centre_y(px.py, p.is);

@@ -18,10 +18,16 @@ class Optimizers:
                     groups[gi].append(p)
                     break
         lr = opts.learning_rate
-        # one multi-tensor kernel per group on the GPU (same update rule; the CPU path is pinned to the reference's optimiser)
+        # one multi-tensor kernel per group on the GPU (same update rule; the CPU path is pinned to the reference's optimiser).
+        # capturable + one learning-rate TENSOR per group: the step can be recorded into a CUDA graph (Trainer.capture) and
+        # OneCycleLR keeps writing the schedule into those tensors in place
         fused = all(p.is_cuda for g in groups for p in g) and any(len(g) for g in groups)
-        self.optimizer = torch.optim.AdamW([{'params': g} for g in groups], lr=lr, betas=(0.9, 0.999), weight_decay=1e-4,
-                                           fused=fused)
+        if fused:
+            dev = next(p.device for g in groups for p in g)
+            specs = [{'params': g, 'lr': torch.tensor(lr, dtype=torch.float32, device=dev)} for g in groups]
+            self.optimizer = torch.optim.AdamW(specs, lr=lr, betas=(0.9, 0.999), weight_decay=1e-4, fused=True, capturable=True)
+        else:
+            self.optimizer = torch.optim.AdamW([{'params': g} for g in groups], lr=lr, betas=(0.9, 0.999), weight_decay=1e-4)
         max_lrs = [opts.vert_lr_ratio * lr, opts.cam_lr_ratio * lr, lr, lr, lr]
         self.scheduler = torch.optim.lr_scheduler.OneCycleLR(self.optimizer, max_lrs, total_steps=self.total_steps,
                                                              pct_start=0.05, cycle_momentum=False, anneal_strategy='cos',

@@ -68,7 +68,9 @@ class Trainer:
         return (img, mask, depth, occ, batch['center'], batch['length'], foc, foc_crop, pp, pp_crop,
                 batch['idx'].to(dev), None)
 
-    def collect_grad(self):
+    def _clip_groups(self):
+        """mean_v clipped to norm 1 (its norm AFTER clipping is what the reference logs), the shape MLP to 1, the pose head
+        to 0.1 (trainer.py:132-150); device ops only."""
         shapenerf, pose = [], []
         grad_meanv_norm = 0
         for name, p in self.model.named_parameters():
@@ -81,6 +83,10 @@ class Trainer:
                 shapenerf.append(p)
             elif 'pose_predictor' in name:
                 pose.append(p)
+        return grad_meanv_norm, shapenerf, pose
+
+    def collect_grad(self):
+        grad_meanv_norm, shapenerf, pose = self._clip_groups()
         # one fused NaN check instead of a host sync per parameter (trainer.py:144-147); two launches over the flat
         # gradient buffer once the reducer has adopted the gradients, else one pair of launches per parameter
         reducer = getattr(self, 'reducer', None)
@@ -146,7 +152,36 @@ class Trainer:
             total_loss, aux_output = self.model(data)
             total_loss.mean().backward()
         self._graph = (graph, total_loss, aux_output)
+        self._tail = None
+        if getattr(self.opts, 'graph_optimizer', True):
+            try:
+                self._capture_tail()
+            except Exception as e:   # noqa: BLE001 -- the eager tail of step() is always available
+                print('CUDA graph capture of the clip + AdamW tail failed, keeping it eager: %r' % (e,))
+                self._tail = None
         return self
+
+    def _capture_tail(self):
+        """Second graph, replayed after the gradient all-reduce: the reference's NaN rule + clipping + the fused AdamW step,
+        without the host read of collect_grad.  A non-finite gradient zero-fills ALL gradients before clipping and the
+        optimiser still steps -- what `self.optim.zero_grad()` of trainer.py:146 does in the reference's torch 1.10 (it
+        zeroes, it does not set to None); the flag is copied to pinned memory and reported one step later.
+        The graph holds the optimiser's state tensors: after `optimizer.load_state_dict` (which replaces them) capture again."""
+        dev = self.device
+        flat = self.reducer.flat
+        self._bad_host = torch.zeros(1, dtype=torch.bool).pin_memory()
+        self._bad_event = None
+        for p in self.reducer.used:        # AdamW state must exist before capture (created by the warm-up steps)
+            assert p in self.optim.optimizer.state, 'optimizer state missing: run eager steps before capture'
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+            bad = flat.isnan().any()
+            flat.masked_fill_(bad, 0.0)
+            grad_meanv_norm, shapenerf, pose = self._clip_groups()
+            g_shape = torch.nn.utils.clip_grad_norm_(shapenerf, 1) if shapenerf else torch.zeros((), device=dev)
+            g_pose = torch.nn.utils.clip_grad_norm_(pose, 0.1) if pose else torch.zeros((), device=dev)
+            self.optim.optimizer.step()
+        self._tail = (graph, bad, (grad_meanv_norm, g_shape, g_pose))
 
     def stage(self, batch):
         """Starts the upload of a (pinned host) batch into one of two device staging slots on a copy stream and returns
@@ -189,8 +224,18 @@ class Trainer:
         self.model.refresh_static_params(self.iters)
         graph.replay()
         self.reducer.reduce()
-        grad = self.collect_grad()
-        self.optim.step(self.iters)
+        if self._tail is None:
+            grad = self.collect_grad()
+            self.optim.step(self.iters)
+        else:                                   # no host synchronisation: the CPU runs ahead of the GPU
+            if self._bad_event is not None and self._bad_event.query() and bool(self._bad_host):
+                print('bad gradient')           # of an earlier step (its gradients were zero-filled on the device)
+            tail, bad, grad = self._tail
+            tail.replay()
+            self._bad_host.copy_(bad.reshape(1), non_blocking=True)
+            self._bad_event = torch.cuda.Event()
+            self._bad_event.record(torch.cuda.current_stream(self.device))
+            self.optim.scheduler.step()         # writes the next learning rates into the groups' lr tensors
         self.iters += 1
         return total_loss, aux_output, grad
 

@@ -132,6 +132,35 @@ def test_trainer_step_parity_vs_cpu_reference_formulation(size, corr, B, k, dete
         assert pr < 1e-4, (key, pr)
 
 
+def _snapshot(tr):
+    """Values of everything a step changes, for an IN-PLACE restore (the captured graphs hold the tensors themselves)."""
+    opt = tr.optim.optimizer
+    return dict(model={k: v.detach().clone() for k, v in tr.model.state_dict().items()},
+                state={p: {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()} for p, st in opt.state.items()},
+                lrs=[g['lr'].detach().clone() if torch.is_tensor(g['lr']) else g['lr'] for g in opt.param_groups],
+                sched=tr.optim.scheduler.state_dict().copy(), iters=tr.iters)
+
+
+def _restore(tr, snap):
+    opt = tr.optim.optimizer
+    with torch.no_grad():
+        for k, v in tr.model.state_dict().items():
+            v.copy_(snap['model'][k])
+        for p, st in snap['state'].items():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    opt.state[p][k].copy_(v)
+                else:
+                    opt.state[p][k] = v
+        for g, lr in zip(opt.param_groups, snap['lrs']):
+            if torch.is_tensor(g['lr']):
+                g['lr'].copy_(lr)
+            else:
+                g['lr'] = lr
+    tr.optim.scheduler.load_state_dict(dict(snap['sched']))
+    tr.iters = snap['iters']
+
+
 def test_graphed_step_equals_eager_step():
     """Trainer.capture / step_graphed (zero-grad + forward + backward as ONE CUDA graph, per-step host values through
     static device buffers) against the eager step from the same model / optimiser state and the same generator states:
@@ -149,17 +178,13 @@ def test_graphed_step_equals_eager_step():
     batch2 = synthetic.make_trainer_batch(opts, v, f, 4, device=tr.device, seed=1, renderer=Renderer(opts, model.mesh))
     tr.capture(batch, warmup=3)
     for trial, b in enumerate((batch, batch2)):          # second trial: new inputs through the static buffers, later iteration
-        snap = (copy.deepcopy(model.state_dict()), copy.deepcopy(tr.optim.optimizer.state_dict()),
-                copy.deepcopy(tr.optim.scheduler.state_dict()), tr.iters)
+        snap = _snapshot(tr)
         torch.manual_seed(11 + trial)
         torch.cuda.manual_seed(11 + trial)
         total_g, aux_g, _ = tr.step_graphed(b)
         aux_g = {k: float(x) for k, x in aux_g.items()}
         params_g = {n: p.detach().clone() for n, p in model.named_parameters() if p.requires_grad}
-        model.load_state_dict(snap[0])
-        tr.optim.optimizer.load_state_dict(snap[1])
-        tr.optim.scheduler.load_state_dict(snap[2])
-        tr.iters = snap[3]
+        _restore(tr, snap)
         torch.manual_seed(11 + trial)
         torch.cuda.manual_seed(11 + trial)
         total_e, aux_e, _ = tr.step(b)
@@ -185,14 +210,10 @@ def test_side_streams_do_not_change_the_step():
     v, f = synthetic.load_prior('laptop')
     batch = synthetic.make_trainer_batch(opts, v, f, 4, device=tr.device, seed=3, renderer=Renderer(opts, model.mesh))
     tr.step(batch)                                       # cuDNN autotuning settles
-    snap = (copy.deepcopy(model.state_dict()), copy.deepcopy(tr.optim.optimizer.state_dict()),
-            copy.deepcopy(tr.optim.scheduler.state_dict()), tr.iters)
+    snap = _snapshot(tr)
     out = {}
     for run, flag in enumerate((True, True, False)):      # two runs with side streams (run-to-run noise), one without
-        model.load_state_dict(snap[0])
-        tr.optim.optimizer.load_state_dict(snap[1])
-        tr.optim.scheduler.load_state_dict(snap[2])
-        tr.iters = snap[3]
+        _restore(tr, snap)
         model.overlap_vit = model.overlap_rotation = flag
         torch.manual_seed(21)
         torch.cuda.manual_seed(21)
