@@ -33,6 +33,39 @@ __device__ __forceinline__ float ex2_approx(float x)
 #endif
 }
 
+#ifndef SCP_HOST_EMU
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2: two independent fp32 operations per issue slot, each rounded like the scalar
+// instruction) for issue-bound per-element loops.  A pair lives in a 64-bit register: {lo = first, hi = second}.
+__device__ __forceinline__ uint64_t f2_pack(float a, float b)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+#endif
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll

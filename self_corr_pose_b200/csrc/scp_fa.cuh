@@ -67,7 +67,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {   // ===== TMA producer =====
+        if (tc5::elect_one()) {   // ===== TMA producer =====
             tc5::mbar_expect_tx(q_full, Q_BYTES);
             tc5::tma_load_2d(sQ, &tmap_q, q_full, 0, bh * T + q0);
             for (int j = 0; j < ntiles; j++) {
@@ -80,7 +80,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {   // ===== MMA issuer =====
+        if (tc5::elect_one()) {   // ===== MMA issuer =====
             constexpr uint32_t idesc_qk = tc5::umma_idesc_bf16(BQ, BKV), idesc_pv = tc5::umma_idesc_bf16(BQ, HD);
             const uint32_t aQ = tc5::smem_u32(sQ), aP = tc5::smem_u32(sP);
             tc5::mbar_wait(q_full, 0);

@@ -125,7 +125,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {   // ===== TMA producer =====
+        if (tc5::elect_one()) {   // ===== TMA producer =====
             tc5::mbar_expect_tx(q_full, Q_BYTES);
             tc5::tma_load_2d(sQ, &tmap_q, q_full, q_col, qk_row0 + q0);
             for (int j = 0; j < nt; j++) {
@@ -139,7 +139,7 @@ fa2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {   // ===== MMA issuer =====
+        if (tc5::elect_one()) {   // ===== MMA issuer =====
             constexpr uint32_t idesc_pv = tc5::umma_idesc_bf16(BQ, HD);
             const uint32_t aQ = tc5::smem_u32(sQ);
             // S(jj) = Q K(jj)^T into S buffer jj & 1 (4 x K = 16); frees the K stage and publishes S when done

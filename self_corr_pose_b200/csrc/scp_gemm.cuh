@@ -52,10 +52,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 // the plain one over 2K physical columns with six K=16 instructions per stage and accumulator instead of four, and an
 // epilogue's 32-column accumulator chunk maps to exactly one 128-byte box row of the split output.
 // Split a pair of fp32 values: returns the packed hi pair, writes the packed lo pair.
+// The residual x - float(hi) is ONE mixed-precision instruction per element (fma.rn.f32.bf16: hi * (-1) + x, the bf16 half
+// selected inside the instruction, FHFMA.BF16 in SASS) instead of unpack + subtract: 4 instructions per pair, was 6; the
+// difference is exact in fp32 either way, so the result is bit-identical to the unpack form.
+#ifndef SCP_SPLIT_MIXED
+#define SCP_SPLIT_MIXED 1
+#endif
 __device__ __forceinline__ uint32_t split_bf16x2(float a, float b, uint32_t &lo_pair)
 {
     const uint32_t h = pack_bf16x2(a, b);
+#if SCP_SPLIT_MIXED
+    uint16_t h0, h1;
+    asm("mov.b32 {%0, %1}, %2;" : "=h"(h0), "=h"(h1) : "r"(h));
+    const uint16_t m1 = 0xBF80;   // bf16 -1.0
+    float la, lb;
+    asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(la) : "h"(h0), "h"(m1), "f"(a));
+    asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(lb) : "h"(h1), "h"(m1), "f"(b));
+    lo_pair = pack_bf16x2(la, lb);
+#else
     lo_pair = pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xffff0000u));
+#endif
     return h;
 }
 
@@ -118,7 +134,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (tc5::elect_one()) {
             int stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;   // n fastest: A tile reused from L2
@@ -139,8 +155,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer =====   (elect.sync, not lane == 0: ptxas then knows a single thread runs the loop and
+        // emits the tcgen05.mma sequence without a per-instruction uniformisation loop -- see scp_tc5.cuh)
+        if (tc5::elect_one()) {
             constexpr uint32_t idesc = tc5::umma_idesc_bf16(128, BN);
             int stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {

@@ -637,10 +637,9 @@ extern "C" int scp_attention_tc5(const void *q, const void *k, const void *vt, v
 // q | k split token-major [B*T][1536] (i32 layout), vt planes [2][B*6*64][Tp], o split [B*T][768]
 static int launch_fa3(const bf16 *qk, const bf16 *vt, bf16 *o, int B, int T, int Tp, cudaStream_t st)
 {
-    CUtensorMap tq, tk, tv;
+    CUtensorMap tk, tv;
     const uint64_t rows = (uint64_t)B * T, inner = 4 * D;
-    if (!scp::gemm::make_tmap_bf16(&tq, qk, inner, rows, inner, scp::fa3::BQ) ||
-        !scp::gemm::make_tmap_bf16(&tk, qk, inner, rows, inner, scp::fa3::BKV) ||
+    if (!scp::gemm::make_tmap_bf16(&tk, qk, inner, rows, inner, scp::fa3::BKV) ||
         !scp::gemm::make_tmap_bf16(&tv, vt, Tp, (uint64_t)2 * B * HEADS * HD, Tp, 64)) {
         scp::set_last_error("tcgen05 attention (x3): cuTensorMapEncodeTiled failed");
         return -1;
@@ -652,7 +651,7 @@ static int launch_fa3(const bf16 *qk, const bf16 *vt, bf16 *o, int B, int T, int
     }
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     scp::fa3::fa3_fwd_kernel<<<dim3((T + scp::fa3::BQ - 1) / scp::fa3::BQ, B * HEADS), scp::fa3::NTHREADS,
-                               scp::fa3::SMEM_BYTES, st>>>(tq, tk, tv, o, T, scale_log2e, B * HEADS * HD);
+                               scp::fa3::SMEM_BYTES, st>>>(qk, tk, tv, o, T, scale_log2e, B * HEADS * HD);
     return 0;
 }
 

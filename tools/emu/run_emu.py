@@ -26,7 +26,8 @@ from tests import _scenes  # noqa: E402
 
 VARIANTS = [('', []), ('fwd2px', ['-DSCP_SOFTRAS_FWD_2PX=1']),
             ('facesmem', ['-DSCP_SOFTRAS_FACE_SMEM=1', '-DSCP_SOFTRAS_FACE_CTAS=10']),
-            ('face16x2', ['-DSCP_SOFTRAS_FACE_BW=16', '-DSCP_SOFTRAS_FACE_SMEM=1', '-DSCP_SOFTRAS_FACE_CTAS=10'])]
+            ('face16x2', ['-DSCP_SOFTRAS_FACE_BW=16', '-DSCP_SOFTRAS_FACE_SMEM=1', '-DSCP_SOFTRAS_FACE_CTAS=10']),
+            ('facelinear', ['-DSCP_SOFTRAS_FACE_LINEAR=1'])]
 _fp = ctypes.c_void_p
 
 
