@@ -646,12 +646,28 @@ static int launch_fa3(const bf16 *qk, const bf16 *vt, bf16 *o, int B, int T, int
     }
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(scp::fa3::fa3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scp::fa3::SMEM_BYTES);
+        cudaFuncSetAttribute(scp::fa3::fa3_fwd_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, scp::fa3::SMEM_BYTES);
+        cudaFuncSetAttribute(scp::fa3::fa3_fwd_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, scp::fa3::SMEM_BYTES);
+        cudaFuncSetAttribute(scp::fa3::fa3_fwd_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, scp::fa3::SMEM_BYTES);
         attr_done = true;
     }
+    const char *e = getenv("SCP_FA3_WARPS");
+    const int fa3_warps = (e && atoi(e) == 8) ? 8 : 4;
     const float scale_log2e = 0.125f * 1.4426950408889634f;
-    scp::fa3::fa3_fwd_kernel<<<dim3((T + scp::fa3::BQ - 1) / scp::fa3::BQ, B * HEADS), scp::fa3::NTHREADS,
-                               scp::fa3::SMEM_BYTES, st>>>(qk, tk, tv, o, T, scale_log2e, B * HEADS * HD);
+    const dim3 grid((T + scp::fa3::BQ - 1) / scp::fa3::BQ, B * HEADS);
+    if (fa3_warps == 8) {
+        void *flags = nullptr;
+        if (cudaGetSymbolAddress(&flags, scp::fa3::g_retry) != cudaSuccess ||
+            cudaMemsetAsync(flags, 0, sizeof(int) * scp::fa3::NFLAGS, st) != cudaSuccess) {
+            scp::set_last_error("tcgen05 attention (x3): retry flags");
+            return -1;
+        }
+        // two threads per query row with a fixed reference point, then the robust form on the query tiles it flagged
+        scp::fa3::fa3_fwd_kernel<8, false><<<grid, 64 + 32 * 8, scp::fa3::SMEM_BYTES, st>>>(qk, tk, tv, o, T, scale_log2e, B * HEADS * HD);
+        scp::fa3::fa3_fwd_kernel<4, true><<<grid, 64 + 32 * 4, scp::fa3::SMEM_BYTES, st>>>(qk, tk, tv, o, T, scale_log2e, B * HEADS * HD);
+    } else {
+        scp::fa3::fa3_fwd_kernel<4, false><<<grid, 64 + 32 * 4, scp::fa3::SMEM_BYTES, st>>>(qk, tk, tv, o, T, scale_log2e, B * HEADS * HD);
+    }
     return 0;
 }
 

@@ -120,12 +120,17 @@ def _split_heads_tokens(q, k, v, B, T):
 
 
 @pytest.mark.parametrize('B,T,ramp', [(1, 128, 0.), (2, 65, 0.), (1, 1025, 0.), (3, 300, 0.), (1, 64, 0.), (2, 1025, 7.),
-                                      (1, 449, -7.), (1, 1025, 3.)])
-def test_attention_x3(B, T, ramp):
-    """scp_fa3.cuh: fp32-class flash attention (split q, k, v; P split by the softmax warps).  ramp as above; the peaked
-    cases (ramp != 0) are where bf16 P loses 2^-9 and the split keeps ~1e-5."""
+                                      (1, 449, -7.), (1, 1025, 3.), (1, 1025, 30.), (2, 300, 40.), (1, 97, 30.)])
+@pytest.mark.parametrize('warps', [4, 8])
+def test_attention_x3(B, T, ramp, warps, monkeypatch):
+    """warps: softmax warps of the kernel form (4 = thread per query row, the default; 8 = two threads per row + retry).
+    scp_fa3.cuh: fp32-class flash attention (split q, k, v; P split by the softmax warps).  ramp as above; the peaked
+    cases (ramp != 0) are where bf16 P loses 2^-9 and the split keeps ~1e-5.  ramp >= 30 drives later logits more than
+    2^100 above the first key tile's maximum (past the fp32 range of the fast form's fixed reference point): those query
+    tiles are flagged and recomputed by the robust form."""
     from self_corr_pose_b200 import _lib
     from self_corr_pose_b200.model.module.network.dino import merge_bf16_i32
+    monkeypatch.setenv('SCP_FA3_WARPS', str(warps))
     g = torch.Generator().manual_seed(1)
     q, k, v = (torch.randn(B * 6, T, 64, generator=g) for _ in range(3))
     if ramp:

@@ -2,7 +2,7 @@
 set -u
 mkdir -p gpurun_out
 {
-  echo "== ViT tests (mixed-precision split, packed fp32 softmax in fa3)"
+  echo "== ViT tests"
   timeout 900 python -m pytest tests/test_vit_gpu.py -m gpu -q -x 2>&1 | tail -5
   echo "== ViT timing B=64"
   timeout 600 python tools/time_vit.py 64 2>&1 | tail -12
