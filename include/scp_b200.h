@@ -28,6 +28,9 @@
  *       model/util/loss_utils.py:236-244 (compute_mask_loss), :246-252 (compute_texture_loss), :273-284
  *       (compute_depth_loss), :317-320 (compute_match_loss) with the nearest upsampling of `match`
  *       (model/module/correspondence.py:71), reached through torch ops in the reference.
+ *   scp_data_bbox_crop / scp_data_resized_crop
+ *       data/dataset_wild6d.py:131-163 (Wild6DDataset.__getitem__ after the file decode: numpy bounding box, crop
+ *       intrinsics, three torchvision resized_crop calls on CPU workers in the reference).
  *   scp_vit_*  — see the ViT section below
  *       third-party/zsp/zsp/method/vision_transformer_flexible.py:85-101,116-132,214-262 and
  *       model/module/network/dino.py:102-109.
@@ -353,6 +356,31 @@ int scp_image_losses_forward(const void *const *maps, const long long *bstrides,
 int scp_image_losses_backward(const void *const *maps, const long long *bstrides, const float *match_lr, int B, int H,
                               int W, int hf, int wf, int use_depth, const float *g_losses, const void *workspace,
                               void *const *g_maps, const long long *g_bstrides, float *g_match_lr, void *stream);
+
+/* ---- data path: crop box + resized crop of decoded frames ------------------------------------------ */
+/*
+ * Wild6DDataset.__getitem__ after the file decode (data/dataset_wild6d.py:131-163): per frame the foreground bounding box of
+ * the mask, center / length as the reference computes them (integer `//`, python int() of the float64 products with
+ * rand_scale[b] = the two np.random.uniform(1.2, 1.5) draws), the crop box, and the crop intrinsics in float64.
+ * mask[B][H][W] uint8 (non-zero = foreground), rand_scale[B][2], intr[B][4] = (fx, fy, cx, cy) float64.
+ * Outputs (device): crop[B][4] = (top, left, height, width) int32; center[B][2], length[B][2] int64 (x, y);
+ * foc_crop[B][2], pp_crop[B][2] float64 (pixels of the crop, before Trainer.batch_reshape's NDC scaling);
+ * status[B] = 1 where the mask has no foreground pixel (the reference raises there; such a frame's crop is empty).
+ */
+int scp_data_bbox_crop(const unsigned char *mask, const double *rand_scale, const double *intr, int B, int H, int W,
+                       int img_size, int no_stretch, int *crop, long long *center, long long *length, double *foc_crop,
+                       double *pp_crop, int *status, void *stream);
+/*
+ * The three torchvision.transforms.functional.resized_crop calls of data/dataset_wild6d.py:152-160 on a batch:
+ * img[B][H][W][3] uint8 (RGB, or BGR as cv2 decodes when bgr != 0) -> img_out[B][3][S][S] fp32 in [0,1]: bilinear resize of
+ * the zero-padded crop, evaluated in float64 on u8 / 255.0 like the reference's float64 tensor (antialias = 0: torchvision
+ * 0.11, the reference's pinned environment; antialias = 1: the triangle filter current torchvision applies by default);
+ * mask[B][H][W] uint8 -> mask_out[B][S][S] fp32 {0,1} and depth[B][H][W] uint16 -> depth_out[B][S][S] fp32: nearest resize
+ * with torch's float32 source-index rule.  Any of the three output pointers may be NULL (that map is skipped).
+ */
+int scp_data_resized_crop(const unsigned char *img, const unsigned char *mask, const unsigned short *depth, const int *crop,
+                          int B, int H, int W, int img_size, int bgr, int antialias, float *img_out, float *mask_out,
+                          float *depth_out, void *stream);
 
 #ifdef __cplusplus
 }

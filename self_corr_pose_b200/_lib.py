@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libscp_b200.so')
 _VARIANT = os.environ.get('SCP_LIB_VARIANT', '')
 if _VARIANT:
     LIB_PATH = os.path.join(_HERE, 'libscp_b200.%s.so' % _VARIANT)
-ABI_VERSION = 5
+ABI_VERSION = 6
 VIT_BF16, VIT_X3 = 0, 1      # `precision` of the ViT entry points (include/scp_b200.h)
 
 _f = ctypes.c_void_p   # device pointers travel as integers
@@ -96,6 +96,11 @@ _SIGNATURES.update({
     'scp_peer_buffer_open': ([ctypes.c_char_p, _pp], _i),
     'scp_peer_buffer_close': ([_f, _i], _i),
     'scp_peer_exchange': ([_pp, _f, _i, _i, _i, _f, _f, _i, _f], _i),
+})
+
+_SIGNATURES.update({
+    'scp_data_bbox_crop': ([_f, _f, _f, _i, _i, _i, _i, _i] + [_f] * 6 + [_f], _i),
+    'scp_data_resized_crop': ([_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f], _i),
 })
 
 _lib = None
