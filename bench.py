@@ -581,6 +581,63 @@ def config1_arm(args, torch, dev, timed):
                 N=N, nf=f.shape[0])
 
 
+def data_path_figure(torch, B, peaks, with_cpu):
+    """the loader's per-frame work after the file decode (mask bounding box, crop box + intrinsics, three
+    resized crops) for one batch of decoded 640 x 480 frames resident in HBM -> the 256 x 256 training batch, on the GPU, and
+    the same statements (oracle/data_cpu.py = the reference's __getitem__ body) on ONE host core for a few frames."""
+    import numpy as np
+    from oracle import data_cpu
+    from self_corr_pose_b200.ops import crop_resize
+    H, W, S = 480, 640, 256
+    frames, Ks = data_cpu.synthetic_frames(8, H, W, seed=0)
+    rep = (B + 7) // 8
+    img = torch.from_numpy(np.stack([f[0] for f in frames])).cuda().repeat(rep, 1, 1, 1)[:B].contiguous()
+    mask = torch.from_numpy(np.stack([f[1] for f in frames])).cuda().repeat(rep, 1, 1)[:B].contiguous()
+    depth = torch.from_numpy(np.stack([f[2] for f in frames]).view(np.int16)).cuda().repeat(rep, 1, 1)[:B].contiguous()
+    K = np.stack(Ks)
+    intr = torch.from_numpy(np.stack([K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2]], 1)).cuda().repeat(rep, 1)[:B].contiguous()
+    rs = torch.from_numpy(np.random.RandomState(1).uniform(1.2, 1.5, size=(B, 2))).cuda()
+    out = (torch.empty(B, 3, S, S, device='cuda'), torch.empty(B, 1, S, S, device='cuda'), torch.empty(B, 1, S, S, device='cuda'))
+    res = {}
+    for aa in (False, True):
+        def run():
+            box = crop_resize.bbox_crop(mask, rs, intr, S)
+            crop_resize.resized_crop(img, mask, depth, box['crop'], S, bgr=True, antialias=aa, out=out)
+            return box
+        for _ in range(3):
+            box = run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 20
+        e0.record()
+        for _ in range(n):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        res[aa] = e0.elapsed_time(e1) / n
+    crop = box['crop'].cpu().numpy().astype(np.int64)
+    # algorithmic bytes: the mask once (bounding box) + the crop's share of the three frames + the five fp32 output planes
+    inside = (np.clip(crop[:, 2], 0, H) * np.clip(crop[:, 3], 0, W)).sum()
+    alg = B * H * W + inside * (3 + 1 + 2) + B * 5 * S * S * 4
+    peak = float(peaks.get('hbm_gbs', 6551.0))
+    fig = {'workload': 'loader after decode: %d frames %dx%d (u8 BGR + u8 mask + u16 depth) -> bbox, crop box, intrinsics, 3 resized '
+                       'crops -> (img, mask, depth) %dx%d fp32' % (B, W, H, S, S),
+           'ms_per_batch': res[False], 'images_per_sec': B / (res[False] / 1e3), 'ms_per_batch_antialias': res[True],
+           'launches_per_batch': 2, 'bound': 'hbm', 'algorithmic_bytes': int(alg), 'achieved': alg / (res[False] / 1e3) / 1e9,
+           'peak': peak, 'unit': 'GB/s', 'frac': alg / (res[False] / 1e3) / 1e9 / peak}
+    if with_cpu:
+        torch.set_num_threads(1)
+        t0 = time.time()
+        ncpu = 4
+        data_cpu.make_batch(frames[:ncpu], Ks[:ncpu], rs[:ncpu].cpu().numpy(), S)
+        dt = (time.time() - t0) / ncpu
+        torch.set_num_threads(os.cpu_count() or 1)
+        fig['cpu_baseline'] = {'value': 1.0 / dt, 'unit': 'images/sec', 'cores': 1, 'kind': 'port',
+                               'sample': '%d frames through oracle/data_cpu.py (the statements of Wild6DDataset.__getitem__ after the '
+                                         'file reads: numpy bounding box + 3 torchvision resized_crop), one DataLoader worker' % ncpu}
+    return fig
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -670,6 +727,8 @@ def main():
         line['hotpath'] = {'value': B / (hp['ms'] / 1e3), 'unit': 'images/sec', 'ms_per_step': hp['ms'],
                            'e2e_value': B / (hp['ms_e2e'] / 1e3), 'cuda_graph': hp['graph'],
                            'workload': WORKLOAD_TEXT['hotpath'] % (hp['N'], hp['nf'])}
+    if world == 1 and args.workload == 'trainer' and not args.no_kernel_breakdown:
+        line['data_path'] = data_path_figure(torch, B, peaks, not args.no_cpu_baseline)
     emit(json.dumps(line))
     if world > 1:
         dist.barrier()

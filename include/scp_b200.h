@@ -243,7 +243,9 @@ int scp_symmetry_nn_backward(const float *pred_v, const int *faces, const long l
 /*
  * out = Normalize(mean, std)(ColorJitter(img)) of Encoder.encode_img (model/module/encoder.py:30-32), torchvision tensor
  * semantics (one parameter set for the whole batch): img [B][3][HW] fp32 planar, values in [0,1]; out planar like img, or
- * channels-last [B][HW][3] when nhwc_out != 0 (the layout cuDNN's tensor-core convolutions want).
+ * channels-last [B][HW][3] when nhwc_out == 1 (the layout cuDNN's tensor-core convolutions want), or channels-last with a
+ * zero fourth channel [B][HW][4] when nhwc_out == 2 (the stem convolution with a zero-padded weight then runs cuDNN's
+ * vectorised NHWC kernels instead of the 3-channel fallback; same result).
  * order[4]: torchvision step ids in application order (0 brightness, 1 contrast, 2 saturation, 3 hue; -1 skips a step);
  * ratios[6] = (ratio, 1 - ratio) of brightness, contrast, saturation AS ROUNDED BY THE CALLER (torchvision forms 1 - ratio
  * in double precision); hue in [-0.5, 0.5]; mean/std [3] host arrays.  All of order/ratios/mean/std are HOST pointers
@@ -381,6 +383,27 @@ int scp_data_bbox_crop(const unsigned char *mask, const double *rand_scale, cons
 int scp_data_resized_crop(const unsigned char *img, const unsigned char *mask, const unsigned short *depth, const int *crop,
                           int B, int H, int W, int img_size, int bgr, int antialias, float *img_out, float *mask_out,
                           float *depth_out, void *stream);
+
+/* ---- channels-last glue of the convolutional encoder ------------------------------------------------ */
+/*
+ * NHWC fp32 tensors, C % 4 == 0.  Replaces at::native's NHWC kernels reached from the reference through
+ * torchvision resnet18's `maxpool` (model/module/network/image_encoder.py:122,127-130), F.interpolate(mode='bilinear') of the
+ * feature decoder (image_encoder.py:170-178) and F.normalize(img_feat, 2, 1) (model/module/encoder.py:36).
+ * max-pool: kernel 3, stride 2, padding 1; idx[B][OH][OW][C] = winning window position kh*3+kw (first maximum in scan
+ * order, NaN propagates -- at::native's rule); OH = (H - 1) / 2 + 1.
+ */
+int scp_nhwc_maxpool3x3s2_forward(const float *x, float *y, unsigned char *idx, int B, int H, int W, int C, void *stream);
+int scp_nhwc_maxpool3x3s2_backward(const float *gy, const unsigned char *idx, float *gx, int B, int H, int W, int C,
+                                   void *stream);
+/* bilinear resize, align_corners = False (at::native::upsample_bilinear2d formulas); the backward is the exact 2x case
+ * (gy[B][2H][2W][C] -> gx[B][H][W][C], gather form: no atomics) */
+int scp_nhwc_upsample_bilinear_forward(const float *x, float *y, int B, int H, int W, int C, int OH, int OW, void *stream);
+int scp_nhwc_upsample2x_bilinear_backward(const float *gy, float *gx, int B, int H, int W, int C, void *stream);
+/* y[B][C][P] = x[B][P][C] / max(||x[b][p][:]||_2, eps) (NHWC in, channel-major out: the correspondence kernel's operand),
+ * inv_norm[B][P] = 1 / max(norm, eps), negated where the clamp was active; backward: gx[B][P][C] from gy[B][C][P].  C <= 128. */
+int scp_nhwc_l2norm_forward(const float *x, float *y, float *inv_norm, int B, int P, int C, float eps, void *stream);
+int scp_nhwc_l2norm_backward(const float *gy, const float *y, const float *inv_norm, float *gx, int B, int P, int C,
+                             void *stream);
 
 #ifdef __cplusplus
 }

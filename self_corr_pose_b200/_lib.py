@@ -103,6 +103,15 @@ _SIGNATURES.update({
     'scp_data_resized_crop': ([_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f], _i),
 })
 
+_SIGNATURES.update({
+    'scp_nhwc_maxpool3x3s2_forward': ([_f, _f, _f, _i, _i, _i, _i, _f], _i),
+    'scp_nhwc_maxpool3x3s2_backward': ([_f, _f, _f, _i, _i, _i, _i, _f], _i),
+    'scp_nhwc_upsample_bilinear_forward': ([_f, _f, _i, _i, _i, _i, _i, _i, _f], _i),
+    'scp_nhwc_upsample2x_bilinear_backward': ([_f, _f, _i, _i, _i, _i, _f], _i),
+    'scp_nhwc_l2norm_forward': ([_f, _f, _f, _i, _i, _i, _fl, _f], _i),
+    'scp_nhwc_l2norm_backward': ([_f, _f, _f, _f, _i, _i, _i, _f], _i),
+})
+
 _lib = None
 
 

@@ -12,6 +12,7 @@ import torch.nn.functional as F
 from torchvision import transforms
 
 from .network import encoder_nets as nets
+from ...ops import nhwc
 from ...ops.color_jitter import JitterSlot, jitter_normalize
 
 _IMAGENET_MEAN, _IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
@@ -45,13 +46,15 @@ class Encoder(nn.Module):
         if img.is_cuda:     # one native pass instead of torchvision's ~70 launches (same random draws, ops/color_jitter.py)
             slots = getattr(self, 'jitter_slots', None)
             x = jitter_normalize(img, self.random_jitter, _IMAGENET_MEAN, _IMAGENET_STD,
-                                 slot=slots[pass_idx] if slots else None)
+                                 slot=slots[pass_idx] if slots else None, pad_c4=True)
         else:
             x = self.resnet_transform(self.random_jitter(img))
         pyramid = self.backbone(x)
         code = pyramid[-1].mean(dim=(2, 3))
-        feat = self.featnet(*pyramid).flatten(2)
-        return code, F.normalize(feat, p=2, dim=1)
+        feat = self.featnet(*pyramid)
+        if nhwc.usable(feat) and feat.shape[1] <= 128:       # NHWC in, contiguous (b, C, h*w) unit vectors out (csrc/scp_nhwc.cu)
+            return code, nhwc.l2norm_cp(feat)
+        return code, F.normalize(feat.flatten(2), p=2, dim=1)
 
     def _shape(self, code, mean_v):
         return self.shape_predictor(mean_v, self.shape_code_predictor(code))

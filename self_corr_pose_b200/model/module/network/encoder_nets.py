@@ -15,6 +15,7 @@ import torch.nn.functional as F
 import torchvision
 
 from .... import _flags
+from ....ops import nhwc
 
 
 class _CBR(nn.Module):
@@ -50,7 +51,13 @@ class ResNetEncoder(nn.Module):
 
     def forward(self, x):
         r = self.resnet
-        c1 = r.maxpool(r.relu(r.bn1(r.conv1(x))))
+        if x.shape[1] == 4:     # zero fourth input channel (ops/color_jitter.py pad_c4): same values, cuDNN's vectorised NHWC kernels
+            w = F.pad(r.conv1.weight, (0, 0, 0, 0, 0, 1)).contiguous(memory_format=torch.channels_last)
+            h = F.conv2d(x, w, None, r.conv1.stride, r.conv1.padding)
+        else:
+            h = r.conv1(x)
+        h = r.relu(r.bn1(h))
+        c1 = nhwc.maxpool3x3s2(h) if nhwc.usable(h) else r.maxpool(h)     # csrc/scp_nhwc.cu on the GPU
         c2 = r.layer1(c1)
         c3 = r.layer2(c2)
         c4 = r.layer3(c3)
@@ -69,7 +76,10 @@ class ResNetDecoder(nn.Module):
             self.proj = nn.Conv2d(64 if downsample == 4 else 128, out_channel, 1)
 
     def forward(self, c2, c3, c4, c5):
-        up = lambda x, ref: F.interpolate(x, ref.shape[2:], mode='bilinear', align_corners=False)
+        def up(x, ref):
+            if nhwc.usable(x) and ref.shape[2] == 2 * x.shape[2] and ref.shape[3] == 2 * x.shape[3]:
+                return nhwc.upsample2x(x)                                  # csrc/scp_nhwc.cu on the GPU
+            return F.interpolate(x, ref.shape[2:], mode='bilinear', align_corners=False)
         c4 = self.iconv4(torch.cat((c4, self.upconv5(up(c5, c4))), dim=1))
         c3 = self.iconv3(torch.cat((c3, self.upconv4(up(c4, c3))), dim=1))
         c2 = self.iconv2(torch.cat((c2, self.upconv3(up(c3, c2))), dim=1))

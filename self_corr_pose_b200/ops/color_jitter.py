@@ -47,17 +47,24 @@ class JitterSlot:
         self.dev.copy_(self.host, non_blocking=True)
 
 
-def jitter_normalize(img, jitter, mean, std, params=None, channels_last=True, slot=None):
+def jitter_normalize(img, jitter, mean, std, params=None, channels_last=True, slot=None, pad_c4=False):
     """img (B,3,H,W) fp32 CUDA in [0,1]; jitter: a torchvision ColorJitter; returns Normalize(mean,std)(jitter(img)).
     params = (fn_idx, b, c, s, h) as returned by ColorJitter.get_params, drawn here when None.
     channels_last: the result is laid out NHWC in memory (torch.channels_last strides, same logical (B,3,H,W) tensor), so
     that the ResNet that consumes it runs cuDNN's NHWC kernels end to end without layout conversions.
-    slot: a JitterSlot -> the parameters travel through device memory (CUDA-graph capturable call site)."""
+    slot: a JitterSlot -> the parameters travel through device memory (CUDA-graph capturable call site).
+    pad_c4: channels-last result with a zero FOURTH channel, (B,4,H,W) -- feed it to the stem convolution with the weight
+    zero-padded to 4 input channels (same values; cuDNN's 3-channel NHWC path is a slow legacy kernel)."""
     if not img.is_cuda:
         raise TypeError('jitter_normalize supports only CUDA tensors (no CPU path)')
     img = img.detach().float().contiguous()
     B, _, H, W = img.shape
-    out = torch.empty_like(img, memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    if pad_c4:
+        assert channels_last
+        out = torch.empty(B, 4, H, W, device=img.device, dtype=img.dtype).contiguous(memory_format=torch.channels_last)
+    else:
+        out = torch.empty_like(img, memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    layout = 2 if pad_c4 else (1 if channels_last else 0)
     L = _lib.lib()
     dev = img.device
     ws_bytes = L.scp_color_jitter_workspace_bytes(B)
@@ -69,7 +76,7 @@ def jitter_normalize(img, jitter, mean, std, params=None, channels_last=True, sl
         slot.upload()
         with torch.cuda.device(dev):
             rc = L.scp_color_jitter_normalize_dparams(_lib.ptr(img), out.data_ptr(), B, H * W, _lib.ptr(slot.dev),
-                                                      1 if channels_last else 0, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+                                                      layout, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
         _lib.check(rc, 'scp_color_jitter_normalize_dparams')
         return out
     if params is None:
@@ -81,6 +88,6 @@ def jitter_normalize(img, jitter, mean, std, params=None, channels_last=True, sl
     c_std = (ctypes.c_float * 3)(*[float(np.float32(m)) for m in std])
     with torch.cuda.device(dev):
         rc = L.scp_color_jitter_normalize(_lib.ptr(img), out.data_ptr(), B, H * W, c_order, c_rat, hue, c_mean, c_std,
-                                          1 if channels_last else 0, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+                                          layout, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
     _lib.check(rc, 'scp_color_jitter_normalize')
     return out
