@@ -6,6 +6,8 @@ model/module/encoder.py:13-52 -- pinned to it by tests/test_reference_encoder_cp
 consumption, same outputs).  Submodule names are part of the contract: checkpoints and the optimiser's name-keyed
 parameter groups (model/module/optimizers.py) depend on them.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -43,10 +45,12 @@ class Encoder(nn.Module):
     def encode_img(self, img, pass_idx=0):
         """(b,3,H,W) in [0,1] -> (global code (b,512), unit-norm pixel features (b,C,h*w)).  pass_idx: 0 = the step's first
         encoder pass, 1 = the rotated second pass (selects the static parameter slot in CUDA-graph mode)."""
-        if img.is_cuda:     # one native pass instead of torchvision's ~70 launches (same random draws, ops/color_jitter.py)
+        if img.is_cuda:     # one native pass instead of torchvision's ~70 launches (same random draws, ops/color_jitter.py).
+            # SCP_STEM_C4=1: zero fourth input channel for the stem convolution -- measured, no gain (39.73 vs 39.65 ms per step)
             slots = getattr(self, 'jitter_slots', None)
             x = jitter_normalize(img, self.random_jitter, _IMAGENET_MEAN, _IMAGENET_STD,
-                                 slot=slots[pass_idx] if slots else None, pad_c4=True)
+                                 slot=slots[pass_idx] if slots else None,
+                                 pad_c4=os.environ.get('SCP_STEM_C4', '0') == '1')
         else:
             x = self.resnet_transform(self.random_jitter(img))
         pyramid = self.backbone(x)

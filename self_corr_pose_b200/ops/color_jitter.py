@@ -61,7 +61,7 @@ def jitter_normalize(img, jitter, mean, std, params=None, channels_last=True, sl
     B, _, H, W = img.shape
     if pad_c4:
         assert channels_last
-        out = torch.empty(B, 4, H, W, device=img.device, dtype=img.dtype).contiguous(memory_format=torch.channels_last)
+        out = torch.empty(B, 4, H, W, device=img.device, dtype=img.dtype, memory_format=torch.channels_last)
     else:
         out = torch.empty_like(img, memory_format=torch.channels_last if channels_last else torch.contiguous_format)
     layout = 2 if pad_c4 else (1 if channels_last else 0)

@@ -22,7 +22,7 @@ class _MaxPool3x3s2(torch.autograd.Function):
         x = _nhwc(x)
         B, C, H, W = x.shape
         OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-        y = torch.empty(B, C, OH, OW, device=x.device, dtype=x.dtype).contiguous(memory_format=torch.channels_last)
+        y = torch.empty(B, C, OH, OW, device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
         idx = torch.empty(B, OH, OW, C, device=x.device, dtype=torch.uint8)
         with torch.cuda.device(x.device):
             rc = _lib.lib().scp_nhwc_maxpool3x3s2_forward(x.data_ptr(), y.data_ptr(), idx.data_ptr(), B, H, W, C,
@@ -37,7 +37,7 @@ class _MaxPool3x3s2(torch.autograd.Function):
         idx, = ctx.saved_tensors
         B, C, H, W = ctx.shape
         gy = _nhwc(gy)
-        gx = torch.empty(B, C, H, W, device=gy.device, dtype=gy.dtype).contiguous(memory_format=torch.channels_last)
+        gx = torch.empty(B, C, H, W, device=gy.device, dtype=gy.dtype, memory_format=torch.channels_last)
         with torch.cuda.device(gy.device):
             rc = _lib.lib().scp_nhwc_maxpool3x3s2_backward(gy.data_ptr(), idx.data_ptr(), gx.data_ptr(), B, H, W, C,
                                                            _lib.stream_ptr(gy.device))
@@ -50,7 +50,7 @@ class _Upsample2x(torch.autograd.Function):
     def forward(ctx, x):
         x = _nhwc(x)
         B, C, H, W = x.shape
-        y = torch.empty(B, C, 2 * H, 2 * W, device=x.device, dtype=x.dtype).contiguous(memory_format=torch.channels_last)
+        y = torch.empty(B, C, 2 * H, 2 * W, device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
         with torch.cuda.device(x.device):
             rc = _lib.lib().scp_nhwc_upsample_bilinear_forward(x.data_ptr(), y.data_ptr(), B, H, W, C, 2 * H, 2 * W,
                                                                _lib.stream_ptr(x.device))
@@ -62,7 +62,7 @@ class _Upsample2x(torch.autograd.Function):
     def backward(ctx, gy):
         B, C, H, W = ctx.shape
         gy = _nhwc(gy)
-        gx = torch.empty(B, C, H, W, device=gy.device, dtype=gy.dtype).contiguous(memory_format=torch.channels_last)
+        gx = torch.empty(B, C, H, W, device=gy.device, dtype=gy.dtype, memory_format=torch.channels_last)
         with torch.cuda.device(gy.device):
             rc = _lib.lib().scp_nhwc_upsample2x_bilinear_backward(gy.data_ptr(), gx.data_ptr(), B, H, W, C,
                                                                   _lib.stream_ptr(gy.device))
@@ -91,7 +91,7 @@ class _L2NormCP(torch.autograd.Function):
         y, inv = ctx.saved_tensors
         B, C, H, W = ctx.shape
         gy = gy.contiguous()
-        gx = torch.empty(B, C, H, W, device=gy.device, dtype=gy.dtype).contiguous(memory_format=torch.channels_last)
+        gx = torch.empty(B, C, H, W, device=gy.device, dtype=gy.dtype, memory_format=torch.channels_last)
         with torch.cuda.device(gy.device):
             rc = _lib.lib().scp_nhwc_l2norm_backward(gy.data_ptr(), y.data_ptr(), inv.data_ptr(), gx.data_ptr(), B, H * W, C,
                                                      _lib.stream_ptr(gy.device))

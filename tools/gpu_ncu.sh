@@ -9,6 +9,7 @@ echo "launch list rc=$?"
 gzip -f gpurun_out/launches.csv
 KERNELS="forward_kernel|backward_kernel|backward_face_kernel|pack_kernel|corr_|gemm_bf16_tn_kernel|fa3_fwd_kernel|layernorm"
 KERNELS="$KERNELS|image_loss_kernel|depth_sums|project_faces|spmm3|cycle_rows|im2col|nn_fwd_kernel|nn_bwd_kernel|jitter_norm_kernel|gray_sum_kernel"
+KERNELS="$KERNELS|maxpool_fwd_kernel|maxpool_bwd_kernel|upsample_fwd_kernel|upsample2x_bwd_kernel|l2norm_fwd_kernel|l2norm_bwd_kernel"
 timeout 2400 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"$KERNELS" \
     -o /tmp/step python tools/ncu_targets.py > gpurun_out/ncu_step.log 2>&1
 echo "full rc=$?"
