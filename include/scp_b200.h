@@ -245,7 +245,7 @@ int scp_symmetry_nn_backward(const float *pred_v, const int *faces, const long l
  * semantics (one parameter set for the whole batch): img [B][3][HW] fp32 planar, values in [0,1]; out planar like img, or
  * channels-last [B][HW][3] when nhwc_out == 1 (the layout cuDNN's tensor-core convolutions want), or channels-last with a
  * zero fourth channel [B][HW][4] when nhwc_out == 2 (the stem convolution with a zero-padded weight then runs cuDNN's
- * vectorised NHWC kernels instead of the 3-channel fallback; same result).
+ * vectorised NHWC kernels instead of the 3-channel fallback; same result; nhwc_out == 3: padded to eight channels).
  * order[4]: torchvision step ids in application order (0 brightness, 1 contrast, 2 saturation, 3 hue; -1 skips a step);
  * ratios[6] = (ratio, 1 - ratio) of brightness, contrast, saturation AS ROUNDED BY THE CALLER (torchvision forms 1 - ratio
  * in double precision); hue in [-0.5, 0.5]; mean/std [3] host arrays.  All of order/ratios/mean/std are HOST pointers

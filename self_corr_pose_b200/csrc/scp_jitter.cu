@@ -141,7 +141,7 @@ jitter_norm_kernel(const float *__restrict__ img, float *__restrict__ out, int H
     if (Pdev != nullptr) P = *Pdev;
     const int b = blockIdx.y;
     const float *base = img + (long)b * 3 * HW;
-    float *ob = out + (long)b * (nhwc_out == 2 ? 4 : 3) * HW;
+    float *ob = out + (long)b * (nhwc_out == 3 ? 8 : nhwc_out == 2 ? 4 : 3) * HW;
     const float gmean = gsum ? (float)(gsum[b] / (double)HW) : 0.f;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= HW) return;
@@ -154,6 +154,12 @@ jitter_norm_kernel(const float *__restrict__ img, float *__restrict__ out, int H
         r[j] = sub(r[j], P.mean[0]) / P.std[0];
         g[j] = sub(g[j], P.mean[1]) / P.std[1];
         bl[j] = sub(bl[j], P.mean[2]) / P.std[2];
+    }
+    if (nhwc_out == 3) {   // channels-last padded to EIGHT channels [B][HW][8]
+        float4 *o4 = reinterpret_cast<float4 *>(ob + 8 * (long)i);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { o4[2 * j] = make_float4(r[j], g[j], bl[j], 0.f); o4[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        return;
     }
     if (nhwc_out == 2) {   // channels-last with a zero fourth channel [B][HW][4]: one 16-byte store per pixel; the stem
         float4 *o4 = reinterpret_cast<float4 *>(ob + 4 * (long)i);   // convolution then runs cuDNN's vectorised NHWC kernels

@@ -50,7 +50,7 @@ class Encoder(nn.Module):
             slots = getattr(self, 'jitter_slots', None)
             x = jitter_normalize(img, self.random_jitter, _IMAGENET_MEAN, _IMAGENET_STD,
                                  slot=slots[pass_idx] if slots else None,
-                                 pad_c4=os.environ.get('SCP_STEM_C4', '0') == '1')
+                                 pad_c4={'1': True, '8': 8}.get(os.environ.get('SCP_STEM_C4', '0'), False))
         else:
             x = self.resnet_transform(self.random_jitter(img))
         pyramid = self.backbone(x)

@@ -51,8 +51,8 @@ class ResNetEncoder(nn.Module):
 
     def forward(self, x):
         r = self.resnet
-        if x.shape[1] == 4:     # zero fourth input channel (ops/color_jitter.py pad_c4): same values, cuDNN's vectorised NHWC kernels
-            w = F.pad(r.conv1.weight, (0, 0, 0, 0, 0, 1)).contiguous(memory_format=torch.channels_last)
+        if x.shape[1] in (4, 8):     # zero-padded input channels (ops/color_jitter.py pad_c4): same values, cuDNN's vectorised NHWC kernels
+            w = F.pad(r.conv1.weight, (0, 0, 0, 0, 0, x.shape[1] - 3)).contiguous(memory_format=torch.channels_last)
             h = F.conv2d(x, w, None, r.conv1.stride, r.conv1.padding)
         else:
             h = r.conv1(x)

@@ -53,7 +53,7 @@ def jitter_normalize(img, jitter, mean, std, params=None, channels_last=True, sl
     channels_last: the result is laid out NHWC in memory (torch.channels_last strides, same logical (B,3,H,W) tensor), so
     that the ResNet that consumes it runs cuDNN's NHWC kernels end to end without layout conversions.
     slot: a JitterSlot -> the parameters travel through device memory (CUDA-graph capturable call site).
-    pad_c4: channels-last result with a zero FOURTH channel, (B,4,H,W) -- feed it to the stem convolution with the weight
+    pad_c4: channels-last result with a zero FOURTH channel, (B,4,H,W) (pad_c4 = 8: padded to eight channels) -- feed it to the stem convolution with the weight
     zero-padded to 4 input channels (same values; cuDNN's 3-channel NHWC path is a slow legacy kernel)."""
     if not img.is_cuda:
         raise TypeError('jitter_normalize supports only CUDA tensors (no CPU path)')
@@ -61,10 +61,10 @@ def jitter_normalize(img, jitter, mean, std, params=None, channels_last=True, sl
     B, _, H, W = img.shape
     if pad_c4:
         assert channels_last
-        out = torch.empty(B, 4, H, W, device=img.device, dtype=img.dtype, memory_format=torch.channels_last)
+        out = torch.empty(B, 8 if pad_c4 == 8 else 4, H, W, device=img.device, dtype=img.dtype, memory_format=torch.channels_last)
     else:
         out = torch.empty_like(img, memory_format=torch.channels_last if channels_last else torch.contiguous_format)
-    layout = 2 if pad_c4 else (1 if channels_last else 0)
+    layout = (3 if pad_c4 == 8 else 2) if pad_c4 else (1 if channels_last else 0)
     L = _lib.lib()
     dev = img.device
     ws_bytes = L.scp_color_jitter_workspace_bytes(B)
