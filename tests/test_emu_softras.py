@@ -23,11 +23,13 @@ def test_emulated_softras_kernels_and_candidates_match_the_oracle(capsys):
 
 @pytest.mark.skipif(shutil.which('g++') is None, reason='no host C++ compiler')
 def test_emulated_loss_geometry_cycle_and_correspondence_kernels_match_reference_statements(capsys):
-    """csrc/scp_loss.cu, scp_geom.cu, scp_cycle.cu and scp_corr.cu (its mma.sync / cp.async helpers in their host
-    statement) compiled for the host and called through the C ABI with host pointers: values and gradients against the
-    reference's op-by-op statements in fp64 (the references of the -m gpu tests)."""
+    """csrc/scp_loss.cu, scp_geom.cu, scp_cycle.cu, scp_corr.cu (its mma.sync / cp.async helpers in their host statement),
+    scp_nhwc.cu and scp_data.cu compiled for the host and called through the C ABI with host pointers: values and gradients
+    against the reference's op-by-op statements in fp64 (the references of the -m gpu tests), the torch operators the
+    encoder-glue kernels replace, and -- for the data path -- the reference dataset class's golden batch (bit-identical)."""
     sys.path.insert(0, os.path.join(ROOT, 'tools', 'emu'))
     import run_emu_ops
     rc = run_emu_ops.main()
     out = capsys.readouterr().out
     assert rc == 0 and 'EMU OPS CHECK PASSED' in out, out
+    assert 'nhwc glue' in out and 'data path' in out

@@ -39,6 +39,8 @@ struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
+struct uchar4 { unsigned char x, y, z, w; };
+static inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char z, unsigned char w) { return uchar4{ x, y, z, w }; }
 static inline float2 make_float2(float x, float y) { return float2{ x, y }; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{ x, y, z, w }; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{ x, y, z, w }; }
@@ -161,6 +163,13 @@ static inline int atomicMin(int *p, int v)
     std::lock_guard<std::mutex> g(scp_emu::atomic_mutex);
     const int old = *p;
     if (v < old) *p = v;
+    return old;
+}
+static inline int atomicMax(int *p, int v)
+{
+    std::lock_guard<std::mutex> g(scp_emu::atomic_mutex);
+    const int old = *p;
+    if (v > old) *p = v;
     return old;
 }
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };

@@ -1,5 +1,5 @@
-"""Functional check WITHOUT a GPU of the fused loss / geometry / cycle / correspondence kernels: the shipped
-csrc/scp_loss.cu, scp_geom.cu, scp_cycle.cu and scp_corr.cu compiled for the host (tools/emu/build_emu.py) and called through their C ABI with host
+"""Functional check WITHOUT a GPU of the fused loss / geometry / cycle / correspondence / encoder-glue / data-path kernels: the
+shipped csrc/scp_loss.cu, scp_geom.cu, scp_cycle.cu, scp_corr.cu, scp_nhwc.cu and scp_data.cu compiled for the host (tools/emu/build_emu.py) and called through their C ABI with host
 pointers, against the reference's op-by-op statements evaluated in fp64 with torch autograd (the same references the
 -m gpu tests use).  Values and gradients.      python tools/emu/run_emu_ops.py"""
 import ctypes
@@ -193,10 +193,90 @@ def check_correspondence(B=2, hf=16, wf=16, N=70, C=64, seed=0):
     return out
 
 
+def check_nhwc(seed=3):
+    """scp_nhwc.cu: max-pool, bilinear 2x, channel L2 norm (forward + backward) against the torch operators on CPU."""
+    names = ('scp_nhwc_maxpool3x3s2_forward', 'scp_nhwc_maxpool3x3s2_backward', 'scp_nhwc_upsample_bilinear_forward',
+             'scp_nhwc_upsample2x_bilinear_backward', 'scp_nhwc_l2norm_forward', 'scp_nhwc_l2norm_backward')
+    lib = load('scp_nhwc', names)
+    g = torch.Generator().manual_seed(seed)
+    cl = lambda t: t.contiguous(memory_format=torch.channels_last)
+    out = {}
+    # max-pool (exact ties at 0 as after a ReLU; odd sizes)
+    B, C, H, W = 2, 8, 9, 7
+    x = cl(torch.relu(torch.randn(B, C, H, W, generator=g)))
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y, idx = cl(torch.empty(B, C, OH, OW)), torch.empty(B, OH, OW, C, dtype=torch.uint8)
+    assert lib.scp_nhwc_maxpool3x3s2_forward(ptr(x), ptr(y), ptr(idx), B, H, W, C, None) == 0
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    gy = cl(torch.randn(B, C, OH, OW, generator=g))
+    yr.backward(gy)
+    gx = cl(torch.empty(B, C, H, W))
+    assert lib.scp_nhwc_maxpool3x3s2_backward(ptr(gy), ptr(idx), ptr(gx), B, H, W, C, None) == 0
+    out['pool'], out['pool_g'] = float((y - yr).abs().max()), rel(gx, xr.grad)
+    # bilinear 2x
+    B, C, H, W = 2, 12, 5, 6
+    x = cl(torch.randn(B, C, H, W, generator=g))
+    y = cl(torch.empty(B, C, 2 * H, 2 * W))
+    assert lib.scp_nhwc_upsample_bilinear_forward(ptr(x), ptr(y), B, H, W, C, 2 * H, 2 * W, None) == 0
+    xr = x.clone().requires_grad_(True)
+    yr = F.interpolate(xr, (2 * H, 2 * W), mode='bilinear', align_corners=False)
+    gy = cl(torch.randn(B, C, 2 * H, 2 * W, generator=g))
+    yr.backward(gy)
+    gx = cl(torch.empty(B, C, H, W))
+    assert lib.scp_nhwc_upsample2x_bilinear_backward(ptr(gy), ptr(gx), B, H, W, C, None) == 0
+    out['up'], out['up_g'] = rel(y, yr), rel(gx, xr.grad)
+    # L2 norm over channels: NHWC in -> (B, C, P) out
+    B, C, H, W = 2, 64, 5, 9
+    x = cl(torch.randn(B, C, H, W, generator=g) * 3)
+    P = H * W
+    y, inv = torch.empty(B, C, P), torch.empty(B, P)
+    assert lib.scp_nhwc_l2norm_forward(ptr(x), ptr(y), ptr(inv), B, P, C, 1e-12, None) == 0
+    xr = x.clone().requires_grad_(True)
+    yr = F.normalize(xr.flatten(2), p=2, dim=1)
+    gy = torch.randn(B, C, P, generator=g)
+    yr.backward(gy)
+    gx = cl(torch.empty(B, C, H, W))
+    assert lib.scp_nhwc_l2norm_backward(ptr(gy), ptr(y), ptr(inv), ptr(gx), B, P, C, None) == 0
+    out['l2'], out['l2_g'] = rel(y, yr), rel(gx, xr.grad)
+    return out
+
+
+def check_data(seed=4):
+    """scp_data.cu: crop box + resized crops against the reference's dataset class (golden) -- mismatching elements."""
+    import numpy as np
+    lib = load('scp_data', ('scp_data_bbox_crop', 'scp_data_resized_crop'))
+    G = np.load(os.path.join(ROOT, 'tests', 'golden', 'data_golden.npz'))
+    n, S = G['raw_img'].shape[0], 64
+    img, mask = torch.from_numpy(G['raw_img']).contiguous(), torch.from_numpy(G['raw_mask']).contiguous()
+    depth = torch.from_numpy(G['raw_depth'].astype(np.uint16).view(np.int16)).contiguous()
+    H, W = mask.shape[1:]
+    K = G['K']
+    intr = torch.from_numpy(np.stack([K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2]], 1)).contiguous()
+    out = {}
+    for tag, no_stretch, aa in (('stretch_noaa', 0, 0), ('nostretch_aa', 1, 1)):
+        rs = torch.from_numpy(G[tag + '_rand_scale']).contiguous()
+        crop, status = torch.empty(n, 4, dtype=torch.int32), torch.empty(n, dtype=torch.int32)
+        center, length = torch.empty(n, 2, dtype=torch.int64), torch.empty(n, 2, dtype=torch.int64)
+        fc, pc = torch.empty(n, 2, dtype=torch.float64), torch.empty(n, 2, dtype=torch.float64)
+        assert lib.scp_data_bbox_crop(ptr(mask), ptr(rs), ptr(intr), n, H, W, S, no_stretch, ptr(crop), ptr(center), ptr(length),
+                                      ptr(fc), ptr(pc), ptr(status), None) == 0
+        o_img, o_mask, o_depth = torch.empty(n, 3, S, S), torch.empty(n, 1, S, S), torch.empty(n, 1, S, S)
+        assert lib.scp_data_resized_crop(ptr(img), ptr(mask), ptr(depth), ptr(crop), n, H, W, S, 1, aa, ptr(o_img), ptr(o_mask),
+                                         ptr(o_depth), None) == 0
+        bad = int((center.numpy() != G[tag + '_center']).sum() + (length.numpy() != G[tag + '_length']).sum() +
+                  (o_mask.numpy() != G[tag + '_mask']).sum() + (o_depth.numpy() != G[tag + '_depth']).sum() +
+                  (o_img.numpy() != G[tag + '_img']).sum() + int(status.sum()))
+        out[tag + '_mismatches'] = float(bad)
+        out[tag + '_intr'] = max(float(np.abs(fc.numpy() - G[tag + '_foc_crop']).max()), float(np.abs(pc.numpy() - G[tag + '_pp_crop']).max()))
+    return out
+
+
 def main():
     ok = True
     for name, fn, tol in (('image losses', check_image_losses, 1e-5), ('geometry', check_geometry, 1e-5),
-                          ('cycle rows', check_cycle_rows, 1e-4), ('correspondence', check_correspondence, 1e-3)):
+                          ('cycle rows', check_cycle_rows, 1e-4), ('correspondence', check_correspondence, 1e-3),
+                          ('nhwc glue', check_nhwc, 2e-6), ('data path', check_data, 1e-12)):
         res = fn()
         ok &= all(v <= tol for v in res.values())
         print('%-13s %s' % (name, '  '.join('%s %.1e' % kv for kv in res.items())), flush=True)
