@@ -107,8 +107,11 @@ int scp_softras_forward_dual(const float *faces, const float *textures_soft, con
 
 /* ---- dense 2D<->3D correspondence (Correspondence.match) --------------------------------- */
 
-/* Scratch bytes of scp_corr_match_forward / _backward (foreground block lists, per-row-block column partials). */
+/* Scratch bytes of scp_corr_match_forward (foreground block lists, per-row-block column partials; for the shapes the
+ * tensor-core forward covers also its split operands and per-tile partials). */
 size_t scp_corr_workspace_bytes(int B, int hf, int wf, int N);
+/* Scratch bytes of scp_corr_match_backward (foreground block lists only; scp_corr_workspace_bytes is always enough). */
+size_t scp_corr_backward_workspace_bytes(int B, int hf, int wf, int N);
 
 /*
  * Correspondence.match (model/module/correspondence.py:36-73), training path.
@@ -125,6 +128,10 @@ size_t scp_corr_workspace_bytes(int B, int hf, int wf, int N);
  *                                        POOLED similarity times the pooled meshgrid = "grid.bmm(softmax(tau*
  *                                        pointcorr_src, dim=1))" of pretrained_corr.py:125,131-136, per image
  * Supported shapes: C == 64, wf in {8,16,32,64}, hf*wf a multiple of 128 with 128/wf even.
+ * Two machine mappings, same results: with pointcorr_full == NULL and hf*wf a multiple of 256 (every training call of the
+ * reference's configs) the similarity is formed on the tcgen05 tensor cores with the accumulator in tensor memory and both
+ * soft-maxes in the GEMM epilogue (csrc/scp_corr_tc.cu); otherwise, or with SCP_CORR_FWD=legacy in the environment, by the
+ * mma.sync kernel of csrc/scp_corr.cu.
  * Background pixels (mask_down == 0) are not traversed: the kernels walk a per-image list of the 2x2 pixel blocks that
  * contain foreground; the constant outputs of the other blocks (uniform row softmax, -1e5 rows) are filled directly.
  */

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libscp_b200.so')
 _VARIANT = os.environ.get('SCP_LIB_VARIANT', '')
 if _VARIANT:
     LIB_PATH = os.path.join(_HERE, 'libscp_b200.%s.so' % _VARIANT)
-ABI_VERSION = 6
+ABI_VERSION = 7
 VIT_BF16, VIT_X3 = 0, 1      # `precision` of the ViT entry points (include/scp_b200.h)
 
 _f = ctypes.c_void_p   # device pointers travel as integers
@@ -32,6 +32,7 @@ _SIGNATURES = {
     'scp_softras_backward': ([_f] * 8 + _SOFTRAS_SCALARS + [_f, _sz, _f], _i),
     'scp_softras_forward_dual': ([_f] * 8 + [_i, _i, _i, _fl, _fl, _fl, _fl, _fl, _fl, _i, _f, _sz, _f], _i),
     'scp_corr_workspace_bytes': ([_i, _i, _i, _i], _sz),
+    'scp_corr_backward_workspace_bytes': ([_i, _i, _i, _i], _sz),
     'scp_corr_match_forward': ([_f] * 5 + [_fl, _i, _i, _i, _i, _i] + [_f] * 8 + [_f, _sz, _f], _i),
     'scp_corr_match_backward': ([_f] * 5 + [_fl, _i, _i, _i, _i, _i] + [_f] * 13 + [_f, _sz, _f], _i),
 }

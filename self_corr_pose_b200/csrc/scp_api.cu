@@ -17,5 +17,5 @@ void set_last_error(const char *fmt, ...)
 }
 }  // namespace scp
 
-extern "C" int scp_abi_version(void) { return 6; }
+extern "C" int scp_abi_version(void) { return 7; }
 extern "C" const char *scp_last_error(void) { return scp::g_err; }

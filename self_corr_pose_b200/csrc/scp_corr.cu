@@ -792,15 +792,47 @@ static bool make_geo(Geo &g, int B, int hf, int wf, int N, int Cc, float tau)
 }
 
 }  // namespace corr
+
+// scp_corr_tc.cu: the training-mode forward on tcgen05 (S in tensor memory, soft-max statistics in the GEMM epilogue)
+namespace corr_tc {
+bool eligible(int B, int hf, int wf, int N, int Cc);
+size_t workspace_bytes(int B, int hf, int wf, int N);
+int forward(const float *img_feat, const float *mesh_feat, const float *mask_down, const float *pred_v,
+            const float *meshgrid, float tau, int B, int hf, int wf, int N, float *pc_pool, float *match,
+            float *imatch, float *rsum, float *csum, float *A_pool, float *csum_pool, const float *vmean, void *ws,
+            cudaStream_t st);
+}  // namespace corr_tc
 }  // namespace scp
 
 using namespace scp::corr;
 
+// SCP_CORR_FWD=legacy keeps the mma.sync forward for every call (A/B runs, parity tests of both paths)
+static bool tc_forward_enabled()
+{
+    const char *m = getenv("SCP_CORR_FWD");
+    return !(m && m[0] == 'l');
+}
+static size_t legacy_ws_bytes(int B, int hf, int wf, int N)
+{
+    // foreground block lists, mean vertices, full-res + pooled column partials
+    return blocks_bytes(B, hf * wf) + vmean_bytes(B) + 2 * (size_t)B * ((size_t)hf * wf / BM) * N * 4 * sizeof(float);
+}
+
 extern "C" size_t scp_corr_workspace_bytes(int B, int hf, int wf, int N)
 {
     if (B <= 0 || hf <= 0 || wf <= 0 || N <= 0) return 0;
-    // foreground block lists, mean vertices, full-res + pooled column partials
-    return blocks_bytes(B, hf * wf) + vmean_bytes(B) + 2 * (size_t)B * ((size_t)hf * wf / BM) * N * 4 * sizeof(float);
+    size_t n = legacy_ws_bytes(B, hf, wf, N);
+    if (scp::corr_tc::eligible(B, hf, wf, N, C)) {   // the tensor-core forward keeps the block lists / mean vertices in front
+        const size_t t = blocks_bytes(B, hf * wf) + vmean_bytes(B) + scp::corr_tc::workspace_bytes(B, hf, wf, N);
+        if (t > n) n = t;
+    }
+    return n;
+}
+
+extern "C" size_t scp_corr_backward_workspace_bytes(int B, int hf, int wf, int N)
+{
+    if (B <= 0 || hf <= 0 || wf <= 0 || N <= 0) return 0;
+    return blocks_bytes(B, hf * wf) + vmean_bytes(B);
 }
 
 extern "C" int scp_corr_match_forward(const float *img_feat, const float *mesh_feat, const float *mask_down,
@@ -840,6 +872,13 @@ extern "C" int scp_corr_match_forward(const float *img_feat, const float *mesh_f
     corr_blocklist_kernel<<<B, NT, 0, st>>>(geo, mask_down, pred_v, blocks, vmean);
     corr_fill_kernel<<<dim3(((geo.P >> 2) + NT / 32 - 1) / (NT / 32), B), NT, 0, st>>>(geo, mask_down, vmean, pointcorr_full,
                                                                                  pointcorr_pool, match, rsum);
+    if (pointcorr_full == nullptr && tc_forward_enabled() && scp::corr_tc::eligible(B, hf, wf, N, Cc)) {
+        // training path: similarity on tcgen05, accumulator in tensor memory, both soft-maxes in the GEMM epilogue
+        const int rc = scp::corr_tc::forward(img_feat, mesh_feat, mask_down, pred_v, meshgrid, tau, B, hf, wf, N, pointcorr_pool,
+                                             match, imatch, rsum, csum, A_pool, csum_pool, vmean, (char *)part, st);
+        if (rc != 0) return rc;
+        return scp::check_launch("scp_corr_match_forward (tcgen05)");
+    }
     corr_fwd_kernel<<<dim3(geo.npblk, B), NT, smem, st>>>(geo, img_feat, mesh_feat, mask_down, pred_v, meshgrid,
                                                          pointcorr_full, pointcorr_pool, match, rsum, part, part_pool,
                                                          blocks);

@@ -106,6 +106,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem], fp32 bit patterns read as TF32 (the low 13 mantissa bits are ignored), fp32
+// accumulate; K = 8 (32 bytes) per instruction; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // ---- warp-convergent issue: measured and rejected (round 2) --------------------------------------------------------------
 // The *_e variants are executed by ALL 32 lanes of the issuing warp in uniform control flow and elect the issuing thread
 // inside the instruction sequence.  Motivation: with the issue loop inside `if (lane == 0)` ptxas wraps every tcgen05.mma in
@@ -224,6 +232,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N)
     return (1u << 4)             // c_format  = F32
            | (1u << 7)           // a_format  = BF16
            | (1u << 10)          // b_format  = BF16
+           | (0u << 15) | (0u << 16)   // a_major, b_major = K
+           | ((N >> 3) << 17)    // n_dim
+           | ((M >> 4) << 24);   // m_dim
+}
+
+// Instruction descriptor, kind::tf32: D fp32, A/B TF32 (format code 2), both K-major, shape M x N (K = 8 per instruction)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N)
+{
+    return (1u << 4)             // c_format  = F32
+           | (2u << 7)           // a_format  = TF32
+           | (2u << 10)          // b_format  = TF32
            | (0u << 15) | (0u << 16)   // a_major, b_major = K
            | ((N >> 3) << 17)    // n_dim
            | ((M >> 4) << 24);   // m_dim

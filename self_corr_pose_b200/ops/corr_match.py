@@ -76,7 +76,7 @@ class CorrMatchFunction(Function):
         g_imatch = prep(g_imatch, None) if g_imatch is not None else torch.zeros_like(imatch)
         g_img = torch.empty_like(img_feat)
         g_mesh = torch.empty_like(mesh_feat)
-        ws_bytes = _lib.lib().scp_corr_workspace_bytes(B, hf, wf, N)
+        ws_bytes = _lib.lib().scp_corr_backward_workspace_bytes(B, hf, wf, N)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = _lib.lib().scp_corr_match_backward(

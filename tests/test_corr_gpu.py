@@ -100,6 +100,67 @@ def test_corr_match_forward_backward(B, hf, wf, N, bwd, monkeypatch):
     assert torch.equal(pc_full.cpu()[o[0] == -1e5], o[0][o[0] == -1e5])
 
 
+@pytest.mark.parametrize('B,hf,wf,N,want_pool,masks', [
+    (2, 16, 16, 70, True, 'disc'), (2, 32, 32, 1280, True, 'disc'), (2, 64, 64, 995, True, 'disc'),
+    (1, 64, 64, 64, False, 'disc'), (3, 32, 32, 1024, False, 'empty1'), (3, 64, 64, 1280, True, 'empty1'),
+    (2, 64, 64, 1280, True, 'full')])
+def test_corr_tc_forward(B, hf, wf, N, want_pool, masks, monkeypatch):
+    """Training-mode forward (no full-resolution output) = the tcgen05 path of csrc/scp_corr_tc.cu (similarity on
+    kind::tf32 split products with the accumulator in tensor memory, soft-max statistics in the GEMM epilogue): against the
+    fp64 oracle, against the mma.sync kernel (SCP_CORR_FWD=legacy) on the same call, and the gradients of the (shared)
+    backward from its saved denominators.  'empty1': image 1 has no foreground at all (uniform soft-max fallbacks);
+    'full': no background."""
+    from self_corr_pose_b200.ops.corr_match import corr_match
+    from self_corr_pose_b200.model.module.correspondence import make_meshgrid
+    monkeypatch.delenv('SCP_CORR_FWD', raising=False)
+    img_feat, mesh_feat, mask, pred_v = make_inputs(B, hf, wf, N, seed=7)
+    if masks == 'empty1':
+        mask[1] = 0.
+    elif masks == 'full':
+        mask[:] = 1.
+    g = torch.Generator().manual_seed(2)
+    w_match = torch.randn(B, hf * wf, 3, generator=g)
+    w_imatch = torch.randn(B, 2, N, generator=g)
+    w_pool = torch.randn(B, hf * wf // 4, N, generator=g) * 0.01
+    w_A = torch.randn(B, 2, N, generator=g)
+    if not want_pool:
+        w_pool, w_A = w_pool * 0, w_A * 0
+    o64 = oracle_fwd_bwd(img_feat, mesh_feat, mask, pred_v, hf, wf, w_match, w_imatch, w_pool, w_A, torch.float64)
+    mask_down = F.interpolate(mask[:, None], (hf, wf), mode='nearest').reshape(B, -1).cuda()
+    grid = make_meshgrid(hf, wf, 'cuda')
+
+    def run():
+        a = img_feat.cuda().requires_grad_(True)
+        m = mesh_feat.cuda().requires_grad_(True)
+        pc_full, pc_pool, match, imatch, A_pool = corr_match(a, m, mask_down, pred_v.cuda(), grid, 10.0, hf, wf,
+                                                             want_full=False, want_pool=want_pool)
+        assert pc_full is None and (pc_pool is not None) == want_pool
+        loss = (match * w_match.cuda()).sum() + (imatch * w_imatch.cuda()).sum()
+        if want_pool:
+            loss = loss + (pc_pool * w_pool.cuda()).sum() + (A_pool * w_A.cuda()).sum()
+        loss.backward()
+        torch.cuda.synchronize()
+        return dict(pointcorr_pool=pc_pool, match=match, imatch=imatch, A_pool=A_pool, g_img_feat=a.grad, g_mesh_feat=m.grad)
+
+    got = run()
+    monkeypatch.setenv('SCP_CORR_FWD', 'legacy')
+    old = run()
+    ref = dict(pointcorr_pool=o64[1], match=o64[2], imatch=o64[3], A_pool=o64[4], g_img_feat=o64[5], g_mesh_feat=o64[6])
+    line = []
+    for k, x in got.items():
+        if x is None:
+            continue
+        r, r_old, r_pair = rel(x, ref[k]), rel(old[k], ref[k]), rel(x, old[k])
+        line.append('%s=%.2e(mma.sync %.1e, pair %.1e)' % (k, r, r_old, r_pair))
+        if k.startswith('g_'):
+            assert r < 1e-3, (k, r)
+        else:
+            assert r < 1e-5 and frac(x, ref[k].float()) >= 0.999, (k, r)
+    print('PARITY corr tcgen05 B%d P%d N%d %s ' % (B, hf * wf, N, masks) + ' '.join(line))
+    if want_pool:   # rows of all-background 2x2 blocks are exactly -1e5, like the reference
+        assert torch.equal(got['pointcorr_pool'].cpu()[o64[1] == -1e5], o64[1][o64[1] == -1e5].float())
+
+
 def test_module_match_golden():
     """Correspondence.match module on the golden inputs of the reference run."""
     from self_corr_pose_b200.model.module.correspondence import Correspondence

@@ -24,7 +24,7 @@ def test_c_abi_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), 'libscp_b200.so does not export %s' % n
     lib.scp_abi_version.restype = ctypes.c_int
-    assert lib.scp_abi_version() == 6
+    assert lib.scp_abi_version() == 7
     # size queries are pure host code
     lib.scp_softras_workspace_bytes.restype = ctypes.c_size_t
     assert lib.scp_softras_workspace_bytes(2, 100) >= 2 * 100 * (16 + 192)

@@ -182,6 +182,24 @@ def check_correspondence(B=2, hf=16, wf=16, N=70, C=64, seed=0):
                                       ptr(A_pool), ptr(csum_pool), ptr(ws), ws_n, None) == 0
     out = dict(pointcorr=rel(pc_full, pc), pool=rel(pc_pool, pool_r), match=rel(match, match_r), imatch=rel(imatch, imatch_r),
                A_pool=rel(A_pool, A_r))
+    # training path (no full-resolution output): scp_corr_tc.cu -- operand preparation, epilogue functors and combining
+    # kernels as shipped, the tcgen05 GEMM replaced by its host statement; with and without the pooled outputs
+    t_pool, t_match, t_imatch = torch.full((B, P // 4, N), 7.0), f32(B, P, 3), f32(B, 2, N)
+    t_rsum, t_csum, t_A, t_cp = f32(B, P), f32(B, N), f32(B, 2, N), f32(B, N)
+    assert lib.scp_corr_match_forward(*common, None, ptr(t_pool), ptr(t_match), ptr(t_imatch), ptr(t_rsum), ptr(t_csum),
+                                      ptr(t_A), ptr(t_cp), ptr(ws), ws_n, None) == 0
+    out.update(tc_pool=rel(t_pool, pool_r), tc_match=rel(t_match, match_r), tc_imatch=rel(t_imatch, imatch_r),
+               tc_A_pool=rel(t_A, A_r), tc_rsum=rel(t_rsum, rsum), tc_csum=rel(t_csum, csum), tc_csum_pool=rel(t_cp, csum_pool))
+    n_match, n_imatch, n_rsum, n_csum = f32(B, P, 3), f32(B, 2, N), f32(B, P), f32(B, N)
+    assert lib.scp_corr_match_forward(*common, None, None, ptr(n_match), ptr(n_imatch), ptr(n_rsum), ptr(n_csum),
+                                      None, None, ptr(ws), ws_n, None) == 0
+    out.update(tc_nopool_match=rel(n_match, match_r), tc_nopool_imatch=rel(n_imatch, imatch_r))
+    os.environ['SCP_CORR_FWD'] = 'legacy'        # the mma.sync kernel on the same call
+    l_pool, l_match = f32(B, P // 4, N), f32(B, P, 3)
+    assert lib.scp_corr_match_forward(*common, None, ptr(l_pool), ptr(l_match), ptr(imatch), ptr(rsum), ptr(csum),
+                                      ptr(A_pool), ptr(csum_pool), ptr(ws), ws_n, None) == 0
+    os.environ.pop('SCP_CORR_FWD')
+    out.update(tc_vs_legacy_pool=rel(t_pool, l_pool), tc_vs_legacy_match=rel(t_match, l_match))
     for mode in ('fused', 'split'):
         os.environ['SCP_CORR_BWD'] = mode
         g_img, g_mesh = f32(B, C, P), f32(B, N, C)

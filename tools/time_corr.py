@@ -1,37 +1,47 @@
-"""Times the fused correspondence kernels (forward, backward) with CUDA events."""
-import os as _os; _os.environ.setdefault("SCP_SYNTHETIC_WEIGHTS", "1")
-import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+"""Correspondence forward on a B200: the tcgen05 path (csrc/scp_corr_tc.cu) against the mma.sync kernel (SCP_CORR_FWD=legacy)
+at the training shapes (B = 64: P = 4096 x N = 1280 with the pooled outputs; the rotation cycle's 1024 x 1024), CUDA events."""
+import os
+import sys
+
 import torch
 import torch.nn.functional as F
-from self_corr_pose_b200.ops.corr_match import corr_match
-from self_corr_pose_b200.model.module.correspondence import make_meshgrid
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-hf = wf = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-N = int(sys.argv[3]) if len(sys.argv) > 3 else 1280
-C = 64
-img_feat = F.normalize(torch.randn(B, C, hf * wf, device='cuda'), 2, 1).requires_grad_(True)
-mesh_feat = F.normalize(torch.relu(torch.randn(B, N, C, device='cuda')), 2, -1).requires_grad_(True)
-mask_down = (torch.rand(B, hf * wf, device='cuda') > 0.4).float()
-pred_v = torch.randn(B, N, 3, device='cuda')
-grid = make_meshgrid(hf, wf, 'cuda')
-res = {}
-for full in (False, True):
-    def fwd():
-        return corr_match(img_feat, mesh_feat, mask_down, pred_v, grid, 10.0, hf, wf, want_full=full, want_pool=not full)
-    pf, pp, m, im, _A = fwd()
-    gpc = torch.randn_like(pf if full else pp); gm = torch.randn_like(m); gi = torch.randn_like(im)
-    for _ in range(3):
-        pf, pp, m, im, _A = fwd(); torch.autograd.backward([pf if full else pp, m, im], [gpc, gm, gi])
-    torch.cuda.synchronize()
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    tf = tb = 0.0
-    n = 10
-    for _ in range(n):
-        e[0].record(); pf, pp, m, im, _A = fwd(); e[1].record()
-        torch.autograd.backward([pf if full else pp, m, im], [gpc, gm, gi]); e[2].record()
-        torch.cuda.synchronize()
-        tf += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
-    res['full' if full else 'pooled'] = dict(fwd_ms=tf / n, bwd_ms=tb / n, fwd_us_img=1e3 * tf / n / B, bwd_us_img=1e3 * tb / n / B)
-print(json.dumps(dict(B=B, P=hf * wf, N=N, **res)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from self_corr_pose_b200.ops.corr_match import corr_match                      # noqa: E402
+from self_corr_pose_b200.model.module.correspondence import make_meshgrid     # noqa: E402
+
+
+def case(B, hf, wf, N, want_pool, iters=30):
+    g = torch.Generator().manual_seed(0)
+    img = F.normalize(torch.randn(B, 64, hf * wf, generator=g), 2, 1).cuda()
+    mesh = F.normalize(torch.relu(torch.randn(B, N, 64, generator=g)), 2, -1).cuda()
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, hf), torch.linspace(-1, 1, wf), indexing='ij')
+    mask = torch.stack([(((xx - 0.002 * b) ** 2 + yy ** 2) < 0.72 ** 2).float() for b in range(B)]).reshape(B, -1).cuda()
+    v = torch.randn(B, N, 3, generator=g).cuda()
+    grid = make_meshgrid(hf, wf, 'cuda')
+    out = {}
+    for mode in ('legacy', 'tcgen05'):
+        if mode == 'legacy':
+            os.environ['SCP_CORR_FWD'] = 'legacy'
+        else:
+            os.environ.pop('SCP_CORR_FWD', None)
+        with torch.no_grad():
+            for _ in range(5):
+                r = corr_match(img, mesh, mask, v, grid, 10.0, hf, wf, want_full=False, want_pool=want_pool)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                r = corr_match(img, mesh, mask, v, grid, 10.0, hf, wf, want_full=False, want_pool=want_pool)
+            e1.record()
+            torch.cuda.synchronize()
+        out[mode] = (e0.elapsed_time(e1) / iters, r)
+    d = max(float((a - b).abs().max()) for a, b in zip(out['legacy'][1], out['tcgen05'][1]) if a is not None)
+    print('corr fwd B=%d P=%d N=%d pool=%d fg=%.2f: mma.sync %.3f ms, tcgen05 %.3f ms (max abs diff %.2e)' %
+          (B, hf * wf, N, want_pool, float(mask.mean()), out['legacy'][0], out['tcgen05'][0], d), flush=True)
+
+
+if __name__ == '__main__':
+    case(64, 64, 64, 1280, True)
+    case(64, 32, 32, 1024, False)
+    case(32, 64, 64, 1280, True)
