@@ -799,8 +799,8 @@ bool eligible(int B, int hf, int wf, int N, int Cc);
 size_t workspace_bytes(int B, int hf, int wf, int N);
 int forward(const float *img_feat, const float *mesh_feat, const float *mask_down, const float *pred_v,
             const float *meshgrid, float tau, int B, int hf, int wf, int N, float *pc_pool, float *match,
-            float *imatch, float *rsum, float *csum, float *A_pool, float *csum_pool, const float *vmean, void *ws,
-            cudaStream_t st);
+            float *imatch, float *rsum, float *csum, float *A_pool, float *csum_pool, const int *blocks,
+            const float *vmean, void *ws, cudaStream_t st);
 }  // namespace corr_tc
 }  // namespace scp
 
@@ -875,7 +875,7 @@ extern "C" int scp_corr_match_forward(const float *img_feat, const float *mesh_f
     if (pointcorr_full == nullptr && tc_forward_enabled() && scp::corr_tc::eligible(B, hf, wf, N, Cc)) {
         // training path: similarity on tcgen05, accumulator in tensor memory, both soft-maxes in the GEMM epilogue
         const int rc = scp::corr_tc::forward(img_feat, mesh_feat, mask_down, pred_v, meshgrid, tau, B, hf, wf, N, pointcorr_pool,
-                                             match, imatch, rsum, csum, A_pool, csum_pool, vmean, (char *)part, st);
+                                             match, imatch, rsum, csum, A_pool, csum_pool, blocks, vmean, (char *)part, st);
         if (rc != 0) return rc;
         return scp::check_launch("scp_corr_match_forward (tcgen05)");
     }

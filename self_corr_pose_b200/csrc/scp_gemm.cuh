@@ -92,17 +92,6 @@ struct tma_store_mode { static constexpr bool value = false; };
 template <class E>
 struct tma_store_mode<E, decltype((void)E::kTmaStoreBf16)> { static constexpr bool value = E::kTmaStoreBf16; };
 
-// optional fifth epilogue mode (Epi::kRowStats == true): the tile's accumulator is consumed in registers and folded into
-// eight per-row accumulators that live across the tile's four 32-column chunks (soft-max statistics of the
-// correspondence kernels, scp_corr_tc.cu); nothing of the tile itself is stored by the kernel:
-//   __device__ bool chunk_live(int row0, int col0) const;   warp-uniform: false skips the chunk (no TMEM load)
-//   __device__ void accum(int row, int col0, const float (&acc)[32], float (&a)[8]) const;     lane = row
-//   __device__ void finish(int row, int n_blk, const float (&a)[8]) const;                     once per row and tile
-template <class E, class = void>
-struct rowstats_mode { static constexpr bool value = false; };
-template <class E>
-struct rowstats_mode<E, decltype((void)E::kRowStats)> { static constexpr bool value = E::kRowStats; };
-
 // Epi: struct with
 //   static constexpr bool kStaged;
 //   kStaged == true : __device__ void chunk(int row0, int nrows, int col, const float *stg, int lane) const;
@@ -169,7 +158,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===== MMA issuer =====   (elect.sync, not lane == 0: ptxas then knows a single thread runs the loop and
         // emits the tcgen05.mma sequence without a per-instruction uniformisation loop -- see scp_tc5.cuh)
         if (tc5::elect_one()) {
-            constexpr uint32_t idesc = NT == 4 ? tc5::umma_idesc_tf32(128, BN) : tc5::umma_idesc_bf16(128, BN);
+            constexpr uint32_t idesc = tc5::umma_idesc_bf16(128, BN);
             int stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 tc5::mbar_wait(tempty + acc, acc_phase ^ 1);       // epilogue has drained this accumulator
@@ -181,18 +170,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t sa = tc5::smem_u32(smem + stage * STAGE_BYTES), sb = sa + BM * BK * 2;
 #pragma unroll
                     for (int mh = 0; mh < MH; mh++) {
-                        if constexpr (NT == 4) {
-                            // fp32 operands split into two TF32 numbers: a 128-byte tile row = [16 hi | 16 lo] of 16
-                            // logical k values; per K=8 chunk c (32 bytes): hi*hi, hi*lo, lo*hi on kind::tf32
-#pragma unroll
-                            for (int c = 0; c < 2; c++) {
-                                const uint32_t ah = sa + mh * (128 * BK * 2) + c * 32, bh = sb + c * 32;
-                                tc5::umma_tf32(d_tmem + mh * BN, tc5::umma_desc_sw128(ah), tc5::umma_desc_sw128(bh), idesc,
-                                               (kb | c) != 0);
-                                tc5::umma_tf32(d_tmem + mh * BN, tc5::umma_desc_sw128(ah), tc5::umma_desc_sw128(bh + 64), idesc, 1);
-                                tc5::umma_tf32(d_tmem + mh * BN, tc5::umma_desc_sw128(ah + 64), tc5::umma_desc_sw128(bh), idesc, 1);
-                            }
-                        } else if constexpr (NT == 3) {
+                        if constexpr (NT == 3) {
                             // split operands: a 128-byte tile row = [32 hi | 32 lo] of 32 logical k values; per K=16
                             // chunk c: hi*hi, hi*lo, lo*hi (byte offsets c*32 for hi, 64 + c*32 for lo)
 #pragma unroll
@@ -230,19 +208,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tc5::mbar_wait(tfull + acc, acc_phase);
             tc5::tc_fence_after();
             const int row0 = m_blk * BM + half * 128 + quarter * 32;
-            if constexpr (rowstats_mode<Epi>::value) {
-              float a8[8];
-#pragma unroll
-              for (int k = 0; k < 8; k++) a8[k] = 0.f;
-#pragma unroll 1
-              for (int c0 = 0; c0 < BN; c0 += 32) {
-                if (!epi.chunk_live(row0, n_blk * BN + c0)) continue;          // warp-uniform (same address in every lane)
-                float v[32];
-                tc5::tmem_ld32(tmem_base + t_acc + acc * ACC_COLS + c0, v);
-                epi.accum(row0 + lane, n_blk * BN + c0, v, a8);
-              }
-              epi.finish(row0 + lane, n_blk, a8);
-            } else if constexpr (tma_store_mode<Epi>::value && NT == 3) {
+            if constexpr (tma_store_mode<Epi>::value && NT == 3) {
               // split output: one 32-column accumulator chunk -> one box row [32 hi | 32 lo] (128 B); physical column 2c
               uint8_t *box = epi_buf + (warp - 2) * TMA_TILE_BYTES;
 #pragma unroll 1
@@ -432,9 +398,6 @@ inline int num_sms()
 // c_out / ldc: fp32 output matrix of the kTmaReduceAdd epilogue / bf16 output of the kTmaStoreBf16 epilogue (ignored otherwise)
 // NT = 3: A and W are split operands in the i32 layout (see above): K is the LOGICAL depth (K % 32 == 0), lda / ldw /
 // ldc are PHYSICAL pitches in bf16 elements (>= 2K); a bf16 output (kTmaStoreBf16) is written split as well.
-// NT = 4: A and W are fp32 matrices split into TF32 (hi, lo) pairs, groups of 16 logical columns stored as
-// [16 hi | 16 lo] fp32 (128 bytes); products on kind::tf32 (hi*hi + hi*lo + lo*hi, ~fp32 accuracy); K is the LOGICAL
-// depth (K % 16 == 0), lda / ldw are physical pitches in 2-BYTE units (>= 4K): the tensor maps only move bytes.
 template <class Epi, int NT = 1>
 int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, const Epi &epi, cudaStream_t st,
            void *c_out = nullptr, int ldc = 0, const long long *a_idx = nullptr, const long long *w_idx = nullptr,
@@ -446,12 +409,11 @@ int launch(const void *A, int lda, const void *W, int ldw, int M, int N, int K, 
         set_last_error("tcgen05 gemm: batched mode needs rows_per_batch %% %d == 0", BM);
         return -1;
     }
-    if (M <= 0 || N % BN != 0 || (NT == 4 ? K % 16 : NT == 3 ? K % 32 : K % BK) != 0) {
+    if (M <= 0 || N % BN != 0 || (NT == 3 ? K % 32 : K % BK) != 0) {
         set_last_error("tcgen05 gemm: unsupported shape M=%d N=%d K=%d", M, N, K);
         return -1;
     }
     if (NT == 3) K *= 2;   // physical columns of the split operands
-    if (NT == 4) K *= 4;   // fp32 operands split into (hi, lo) TF32 pairs, counted in 2-byte units like the tensor maps
     CUtensorMap ta, tw;
     int a_box = BM;
     if (!make_tmap_bf16(&ta, A, K, batched ? a_rows_total : M, lda, BM)) {

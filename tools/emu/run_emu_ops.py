@@ -184,6 +184,7 @@ def check_correspondence(B=2, hf=16, wf=16, N=70, C=64, seed=0):
                A_pool=rel(A_pool, A_r))
     # training path (no full-resolution output): scp_corr_tc.cu -- operand preparation, epilogue functors and combining
     # kernels as shipped, the tcgen05 GEMM replaced by its host statement; with and without the pooled outputs
+    ws.fill_(255)       # scratch the kernels do not write must not be read: NaN patterns instead of zeros
     t_pool, t_match, t_imatch = torch.full((B, P // 4, N), 7.0), f32(B, P, 3), f32(B, 2, N)
     t_rsum, t_csum, t_A, t_cp = f32(B, P), f32(B, N), f32(B, 2, N), f32(B, N)
     assert lib.scp_corr_match_forward(*common, None, ptr(t_pool), ptr(t_match), ptr(t_imatch), ptr(t_rsum), ptr(t_csum),
