@@ -289,8 +289,8 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
     t_b = timeit(lambda: torch.autograd.grad([pool, mt, im], [a, m], gs, retain_graph=True))
     bytes_f = B * (4 * (C * P + N * C + P + 3 * N) + 4 * (P * N // 4 + 2 * N + 3 * P))
     bytes_b = B * 4 * (2 * C * P + 2 * N * C + P * N // 4 + 6 * P + 7 * N)
-    out.append(dict(kernel='corr_fwd_kernel(+colreduce)', ms=t_f, bound='hbm', achieved=bytes_f / t_f / 1e6, peak=hbm,
-                    unit='GB/s', launches_per_step=1, ncu_name='corr::corr_fwd_kernel #0'))
+    out.append(dict(kernel='correspondence forward: gemm_rowstats_kernel x2 (tcgen05 kind::tf32, S and S^T) + prep / fill / combine', ms=t_f, bound='hbm', achieved=bytes_f / t_f / 1e6, peak=hbm,
+                    unit='GB/s', launches_per_step=1, ncu_name='gemm_rs::gemm_rowstats_kernel<corr_tc::EpiCols<1>> #0'))
     out.append(dict(kernel='corr_bwd_rows_kernel<fused cols> (+blocklist)', ms=t_b, bound='hbm', achieved=bytes_b / t_b / 1e6,
                     peak=hbm, unit='GB/s', launches_per_step=1, ncu_name='corr::corr_bwd_rows_kernel<1> #0'))
     # --- ViT: whole extractor (a chain of 68 launches), its attention kernel and the QKV GEMM alone, in the precision the

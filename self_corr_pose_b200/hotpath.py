@@ -43,10 +43,10 @@ class HotPath:
     rotation[B,3,3], translation[B,1,3]).  forward() -> (total_loss, aux dict with the reference's keys)."""
 
     # kernels of this package launched by one forward+backward (see DESIGN.md): SoftRas 2x(pack+fwd) + 2x(pack+bwd)
-    # (mask, depth and NOCS share one traversal), correspondence 5 fwd + 3 bwd (block list, fill, main, 2 column
-    # reductions / block list, rows, columns), ViT 3 + 9*7 + 2, image losses 2 fwd + 1 bwd, geometry 2 fwd + 2 bwd,
+    # (mask, depth and NOCS share one traversal), correspondence 9 fwd + 3 bwd (block list, fill, 2 operand
+    # preparations, 2 tcgen05 row-statistics GEMMs, 3 combining kernels / block list, rows, columns), ViT 3 + 9*7 + 2, image losses 2 fwd + 1 bwd, geometry 2 fwd + 2 bwd,
     # pre-training cycle rows 1 fwd + 1 bwd, DINO arg-match 2, sparse Laplacian 1 fwd + 1 bwd
-    GPU_LAUNCHES = 4 + 4 + 8 + 68 + 3 + 4 + 2 + 2 + 2
+    GPU_LAUNCHES = 4 + 4 + 12 + 68 + 3 + 4 + 2 + 2 + 2
 
     def __init__(self, opts, mean_v, faces, device='cuda', fused_losses=True, overlap_vit=True):
         self.opts = opts

@@ -21,9 +21,9 @@ from ..ops import peer_sync_bn
 class MeshNet(nn.Module):
 
     # kernels of this package launched by one forward + backward of the training graph: the hot path (hotpath.HotPath:
-    # SoftRas 8, correspondence 8, ViT 68, image losses 3, geometry 4, pre-training cycle rows 2, DINO arg-match 2,
-    # sparse Laplacian 2) + colour jitter 2 x 2 passes + symmetry NN fwd/bwd 2 + rotation-cycle correspondence 5 + 3
-    GPU_LAUNCHES = 97 + 4 + 2 + 8
+    # SoftRas 8, correspondence 12 (tcgen05 forward: 9), ViT 68, image losses 3, geometry 4, pre-training cycle rows 2, DINO arg-match 2,
+    # sparse Laplacian 2) + colour jitter 2 x 2 passes + symmetry NN fwd/bwd 2 + rotation-cycle correspondence 8 + 3
+    GPU_LAUNCHES = 101 + 4 + 2 + 11
 
     def __init__(self, opts):
         super().__init__()
