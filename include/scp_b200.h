@@ -412,6 +412,29 @@ int scp_nhwc_l2norm_forward(const float *x, float *y, float *inv_norm, int B, in
 int scp_nhwc_l2norm_backward(const float *gy, const float *y, const float *inv_norm, float *gx, int B, int P, int C,
                              void *stream);
 
+/* ---- inference pose fit: the point-cloud passes of RANSAC + Umeyama -------------------------------- */
+/*
+ * Replaces, inside Tester.pose_fitting -> estimateSimilarityTransform (model/tester.py:324-427, model/util/umeyama.py:95-159),
+ * the per-round evaluateModel calls (residual norm of a candidate transform over all correspondences, :143-159) and the
+ * inlier selection + means / covariance of the final closed-form fit (:28-41, :165-201), for a batch of L images at once.
+ *   src, tgt [L][n_max][3]     model-space / camera-space correspondences, image l's counts[l] real ones first
+ *   hyp_A [L][H][9], hyp_t [L][H][3]   candidate transforms x -> A x + t (A = scale * rotation, row-major), H <= 128
+ *   partial [L][scp_posefit_chunks(n_max)][H]   sums of squared point residuals per 512-point chunk; the residual norm of
+ *                                      candidate h of image l is sqrt(sum over the chunks)
+ */
+size_t scp_posefit_chunks(int n_max);
+int scp_posefit_residual_table(const float *src, const float *tgt, const int *counts, const float *hyp_A,
+                               const float *hyp_t, int L, int n_max, int H, float *partial, void *stream);
+/*
+ * Winning transform best_A [L][9], best_t [L][3], pass threshold pass_t [L], found [L] (1 = a RANSAC round was accepted).
+ * out [L][18] = points used, inlier count, mean of src (3), mean of tgt (3), sum of (tgt - mean)(src - mean)^T (9, target
+ * rows), sum of |src - mean|^2 -- over the inliers (point residual < pass_t) when the image is accepted (found and at least
+ * 10 % inliers, umeyama.py:29-31), over all real points otherwise.  Fixed-order reductions: bit-reproducible.
+ */
+int scp_posefit_inlier_moments(const float *src, const float *tgt, const int *counts, const float *best_A,
+                               const float *best_t, const float *pass_t, const unsigned char *found, int L, int n_max,
+                               float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,6 +113,12 @@ _SIGNATURES.update({
     'scp_nhwc_l2norm_backward': ([_f, _f, _f, _f, _i, _i, _i, _f], _i),
 })
 
+_SIGNATURES.update({
+    'scp_posefit_chunks': ([_i], _sz),
+    'scp_posefit_residual_table': ([_f] * 5 + [_i, _i, _i, _f, _f], _i),
+    'scp_posefit_inlier_moments': ([_f] * 7 + [_i, _i, _f, _f], _i),
+})
+
 _lib = None
 
 

@@ -52,14 +52,20 @@ def _closed_form(src, tgt, weight=None, strict=True):
         xs, xt = torch.where(w, src - cs[..., None, :], zero), torch.where(w, tgt - ct[..., None, :], zero)
         cov = xt.transpose(-1, -2) @ xs / n[..., None, None]
         var = xs.pow(2).sum((-1, -2)) / (n - 1)
+    return _from_moments(cs, ct, cov, var, strict)
+
+
+def _from_moments(cs, ct, cov, var, strict=True):
+    """Closed form from the means cs / ct (..., 3), the covariance cov (..., 3, 3) of the centred points (target rows x source
+    columns, divided by n) and the unbiased source variance var (...)."""
     bad = torch.isnan(cov).any(-1).any(-1)
     if strict:
         if bad.any():
             raise RuntimeError('There are NANs in the input.')
     else:       # LAPACK / cuSOLVER refuse non-finite input: decompose a stand-in and blank the result below
-        cov = torch.where(bad[..., None, None], torch.eye(3, device=src.device, dtype=src.dtype), cov)
+        cov = torch.where(bad[..., None, None], torch.eye(3, device=cov.device, dtype=cov.dtype), cov)
     U, D, Vh = torch.linalg.svd(cov, full_matrices=True)
-    sign = torch.where(_det3(U) * _det3(Vh) < 0.0, -1.0, 1.0).to(src.dtype)
+    sign = torch.where(_det3(U) * _det3(Vh) < 0.0, -1.0, 1.0).to(cov.dtype)
     D = torch.cat((D[..., :2], D[..., 2:] * sign[..., None]), -1)
     U = torch.cat((U[..., :, :2], U[..., :, 2:] * sign[..., None, None]), -1)
     R = (U @ Vh).transpose(-1, -2)
@@ -139,19 +145,31 @@ def fit_similarity_batch(src, tgt, counts, max_table_bytes=1 << 30):
         pass_t, stop_t = _thresholds(s_l, t_l, valid)
         rows = torch.arange(len(live), device=dev)[:, None, None]
         hs, hR, ht, hbad = _closed_form(s_l[rows, idx], t_l[rows, idx], strict=False)  # (L,H), (L,H,3,3), (L,H,3), (L,H)
-        # residual table, a slab of rounds at a time
-        slab = max(1, min(N_ROUNDS, max_table_bytes // max(1, len(live) * n_max * 3 * src.element_size() * 2)))
-        residual = torch.empty(len(live), N_ROUNDS, device=dev, dtype=dt)
-        for h0 in range(0, N_ROUNDS, slab):
-            pr = _point_residuals(hs[:, h0:h0 + slab], hR[:, h0:h0 + slab], ht[:, h0:h0 + slab], s_l, t_l)
-            residual[:, h0:h0 + slab] = torch.linalg.norm(torch.where(valid[:, None], pr, 0 * pr), dim=-1)
+        native = src.is_cuda and dt == torch.float32        # the two point-cloud passes as kernels (csrc/scp_posefit.cu)
+        if native:
+            from ...ops import posefit as K
+            cnt32 = cnt.to(torch.int32)
+            residual = K.residual_table(s_l, t_l, cnt32, hs, hR, ht)
+        else:
+            # residual table, a slab of rounds at a time
+            slab = max(1, min(N_ROUNDS, max_table_bytes // max(1, len(live) * n_max * 3 * src.element_size() * 2)))
+            residual = torch.empty(len(live), N_ROUNDS, device=dev, dtype=dt)
+            for h0 in range(0, N_ROUNDS, slab):
+                pr = _point_residuals(hs[:, h0:h0 + slab], hR[:, h0:h0 + slab], ht[:, h0:h0 + slab], s_l, t_l)
+                residual[:, h0:h0 + slab] = torch.linalg.norm(torch.where(valid[:, None], pr, 0 * pr), dim=-1)
         best, last, found = _sequential_choice(residual, stop_t, hbad)
         pick = lambda x: x[torch.arange(len(live), device=dev), best]
-        pr = _point_residuals(pick(hs)[:, None], pick(hR)[:, None], pick(ht)[:, None], s_l, t_l)[:, 0]
-        inlier = (pr < pass_t[:, None]) & valid
-        ratio_ok = inlier.sum(-1).to(dt) / cnt.to(dt) >= 0.1
-        safe = inlier | ~(found & ratio_ok)[:, None] & valid        # keep the closed form finite for rejected images
-        fs, fR, ft, _ = _closed_form(s_l, t_l, safe, strict=False)
+        if native:
+            m = K.inlier_moments(s_l, t_l, cnt32, pick(hs), pick(hR), pick(ht), pass_t, found)
+            ratio_ok = m['n_inliers'] / cnt.to(dt) >= 0.1
+            fs, fR, ft, _ = _from_moments(m['mean_src'], m['mean_tgt'], m['cov'] / m['n_used'][:, None, None],
+                                          m['sq'] / (m['n_used'] - 1), strict=False)
+        else:
+            pr = _point_residuals(pick(hs)[:, None], pick(hR)[:, None], pick(ht)[:, None], s_l, t_l)[:, 0]
+            inlier = (pr < pass_t[:, None]) & valid
+            ratio_ok = inlier.sum(-1).to(dt) / cnt.to(dt) >= 0.1
+            safe = inlier | ~(found & ratio_ok)[:, None] & valid        # keep the closed form finite for rejected images
+            fs, fR, ft, _ = _closed_form(s_l, t_l, safe, strict=False)
         last_h, ok_h = last.tolist(), (found & ratio_ok).tolist()                     # the one host synchronisation
         early = next((i for i, l in enumerate(last_h) if l < N_ROUNDS - 1), None)
         done = len(live) if early is None else early + 1

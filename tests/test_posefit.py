@@ -203,3 +203,69 @@ def test_sequential_choice_equals_a_literal_loop_on_random_tables():
         assert bool(found[t]) == (inc_i is not None and not raised), t
         if inc_i is not None and not raised:
             assert int(best[t]) == inc_i, t
+
+
+@pytest.mark.gpu
+def test_posefit_kernels_match_host_formulation():
+    """csrc/scp_posefit.cu through the C ABI (ops/posefit.py): the residual table of 100 candidates x 3 images and the inlier
+    moments of the winning rounds against the torch statements of model/util/umeyama.py evaluated in fp64 -- including a
+    short image (37 points), padding rows, outliers and an image whose fit is rejected (all real points are used)."""
+    from self_corr_pose_b200.model.util import umeyama as U
+    from self_corr_pose_b200.ops import posefit as K
+    L, n, H = 3, 9000, 100
+    g = torch.Generator().manual_seed(5)
+    src = torch.rand(L, n, 3, generator=g) - 0.5
+    R0 = torch.linalg.qr(torch.randn(L, 3, 3, generator=g))[0]
+    tgt = 300 * src @ R0 + torch.tensor([0., 0., 900.]) + 3 * torch.randn(L, n, 3, generator=g)
+    tgt[:, ::7] += 80 * torch.randn(L, (n + 6) // 7, 3, generator=g)
+    counts = torch.tensor([n, n - 4001, 37], dtype=torch.int32)
+    valid = torch.arange(n)[None] < counts[:, None]
+    idx = torch.stack([torch.randint(0, int(c), (H, 5), generator=g) for c in counts])
+    rows = torch.arange(L)[:, None, None]
+    hs, hR, ht, _ = U._closed_form(src[rows, idx], tgt[rows, idx], strict=False)
+    pr = U._point_residuals(hs.double(), hR.double(), ht.double(), src.double(), tgt.double())
+    want = torch.linalg.norm(torch.where(valid[:, None], pr, 0 * pr), dim=-1)
+    c = lambda t: t.cuda()
+    got = K.residual_table(c(src), c(tgt), c(counts), c(hs), c(hR), c(ht))
+    assert _rel(got.cpu(), want) < 1e-5
+    best = want.argmin(-1)
+    pick = lambda x: x[torch.arange(L), best]
+    pass_t, _ = U._thresholds(src, tgt, valid)
+    found = torch.tensor([True, False, True])
+    prb = U._point_residuals(pick(hs)[:, None], pick(hR)[:, None], pick(ht)[:, None], src, tgt)[:, 0]
+    inl = (prb < pass_t[:, None]) & valid
+    ok = found & (inl.sum(-1).float() / counts.float() >= 0.1)
+    safe = torch.where(ok[:, None], inl, valid)
+    fs, fR, ft, _ = U._closed_form(src.double(), tgt.double(), safe, strict=False)
+    m = K.inlier_moments(c(src), c(tgt), c(counts), c(pick(hs)), c(pick(hR)), c(pick(ht)), c(pass_t), c(found))
+    assert torch.equal(m['n_used'].cpu().long(), safe.sum(-1)) and torch.equal(m['n_inliers'].cpu().long(), inl.sum(-1))
+    gs, gR, gt, _ = U._from_moments(m['mean_src'], m['mean_tgt'], m['cov'] / m['n_used'][:, None, None],
+                                    m['sq'] / (m['n_used'] - 1), strict=False)
+    print('PARITY posefit table %.2e scale %.2e rotation %.2e translation %.2e' %
+          (_rel(got.cpu(), want), _rel(gs.cpu(), fs), _rel(gR.cpu(), fR), _rel(gt.cpu(), ft)))
+    assert _rel(gs.cpu(), fs) < 1e-5 and _rel(gR.cpu(), fR) < 1e-5 and _rel(gt.cpu(), ft) < 1e-5
+    m2 = K.inlier_moments(c(src), c(tgt), c(counts), c(pick(hs)), c(pick(hR)), c(pick(ht)), c(pass_t), c(found))
+    assert all(torch.equal(m[k], m2[k]) for k in m)          # fixed-order reductions
+
+
+@pytest.mark.gpu
+def test_batched_fit_on_gpu_equals_host_fit_with_the_same_draws():
+    """fit_similarity_batch on CUDA tensors (kernels) against the same call on the CPU (torch statements pinned to the
+    reference above): same generator consumption, same verdicts, transforms within fp32 rounding."""
+    from self_corr_pose_b200.model.util import umeyama as U
+    B, n = 5, 6000
+    g = torch.Generator().manual_seed(8)
+    src = torch.rand(B, n, 3, generator=g) - 0.5
+    R0 = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))[0]
+    tgt = 250 * src @ R0 + torch.tensor([10., -20., 800.]) + 2 * torch.randn(B, n, 3, generator=g)
+    tgt[:, ::5] += 60 * torch.randn(B, (n + 4) // 5, 3, generator=g)
+    counts = [n, 4500, 0, 800, 5]
+    torch.manual_seed(3)
+    s0, R0_, t0, ok0 = U.fit_similarity_batch(src, tgt, counts)
+    state = torch.get_rng_state()
+    torch.manual_seed(3)
+    s1, R1, t1, ok1 = U.fit_similarity_batch(src.cuda(), tgt.cuda(), counts)
+    assert torch.equal(torch.get_rng_state(), state) and ok0 == ok1
+    keep = torch.tensor(ok0)
+    assert keep.any()
+    assert _rel(s1.cpu()[keep], s0[keep]) < 1e-4 and _rel(R1.cpu()[keep], R0_[keep]) < 1e-4 and _rel(t1.cpu()[keep], t0[keep]) < 1e-4

@@ -291,11 +291,54 @@ def check_data(seed=4):
     return out
 
 
+def check_posefit(L=3, n=1300, H=100, seed=5):
+    """scp_posefit.cu: residual table and inlier moments against the host formulation (model/util/umeyama.py) on CPU."""
+    from self_corr_pose_b200.model.util import umeyama as U
+    lib = load('scp_posefit', ('scp_posefit_chunks', 'scp_posefit_residual_table', 'scp_posefit_inlier_moments'))
+    g = torch.Generator().manual_seed(seed)
+    src = torch.rand(L, n, 3, generator=g) - 0.5
+    R0 = torch.linalg.qr(torch.randn(L, 3, 3, generator=g))[0]
+    tgt = 300 * src @ R0 + torch.tensor([0., 0., 900.]) + 3 * torch.randn(L, n, 3, generator=g)
+    tgt[:, ::7] += 80 * torch.randn(L, (n + 6) // 7, 3, generator=g)          # outliers
+    counts = torch.tensor([n, n - 401, 37][:L], dtype=torch.int32)
+    valid = torch.arange(n)[None] < counts[:, None]
+    idx = torch.stack([torch.randint(0, int(c), (H, 5), generator=g) for c in counts])
+    rows = torch.arange(L)[:, None, None]
+    hs, hR, ht, _ = U._closed_form(src[rows, idx], tgt[rows, idx], strict=False)
+    pr = U._point_residuals(hs, hR, ht, src, tgt)
+    want = torch.linalg.norm(torch.where(valid[:, None], pr, 0 * pr), dim=-1)
+    A = (hs[..., None, None] * hR).contiguous()
+    nchunk = lib.scp_posefit_chunks(n)
+    partial = torch.full((L, nchunk, H), float('nan'))
+    ht = ht.contiguous()
+    assert lib.scp_posefit_residual_table(ptr(src), ptr(tgt), ptr(counts), ptr(A), ptr(ht), L, n, H, ptr(partial), None) == 0
+    out = dict(table=rel(partial.sum(1).sqrt(), want))
+    best = want.argmin(-1)
+    pick = lambda x: x[torch.arange(L), best]
+    pass_t, _ = U._thresholds(src, tgt, valid)
+    found = torch.tensor([1, 0, 1][:L], dtype=torch.uint8)                      # image 1: rejected -> all real points
+    prb = U._point_residuals(pick(hs)[:, None], pick(hR)[:, None], pick(ht)[:, None], src, tgt)[:, 0]
+    inl = (prb < pass_t[:, None]) & valid
+    okk = found.bool() & (inl.sum(-1).float() / counts.float() >= 0.1)
+    safe = torch.where(okk[:, None], inl, valid)
+    fs, fR, ft, _ = U._closed_form(src.double(), tgt.double(), safe, strict=False)
+    mom = torch.full((L, 18), float('nan'))
+    bA, bt, pt = pick(A).contiguous(), pick(ht).contiguous(), pass_t.contiguous()      # keep the buffers alive over the call
+    assert lib.scp_posefit_inlier_moments(ptr(src), ptr(tgt), ptr(counts), ptr(bA), ptr(bt), ptr(pt), ptr(found), L, n, ptr(mom),
+                                          None) == 0
+    gs, gR, gt, _ = U._from_moments(mom[:, 2:5], mom[:, 5:8], mom[:, 8:17].reshape(L, 3, 3) / mom[:, 0, None, None],
+                                    mom[:, 17] / (mom[:, 0] - 1), strict=False)
+    out.update(n_used=float((mom[:, 0] - safe.sum(-1)).abs().max()), n_inl=float((mom[:, 1] - inl.sum(-1)).abs().max()),
+               scale=rel(gs, fs), rotation=rel(gR, fR), translation=rel(gt, ft))
+    return out
+
+
 def main():
     ok = True
     for name, fn, tol in (('image losses', check_image_losses, 1e-5), ('geometry', check_geometry, 1e-5),
                           ('cycle rows', check_cycle_rows, 1e-4), ('correspondence', check_correspondence, 1e-3),
-                          ('nhwc glue', check_nhwc, 2e-6), ('data path', check_data, 1e-12)):
+                          ('nhwc glue', check_nhwc, 2e-6), ('data path', check_data, 1e-12),
+                          ('pose fit', check_posefit, 2e-5)):
         res = fn()
         ok &= all(v <= tol for v in res.values())
         print('%-13s %s' % (name, '  '.join('%s %.1e' % kv for kv in res.items())), flush=True)
