@@ -32,6 +32,10 @@
 namespace scp {
 namespace gemm_rs {
 constexpr int BM = 256, BN = 128;
+#ifndef SCP_RS_EPI_WARPS
+#define SCP_RS_EPI_WARPS 8
+#endif
+constexpr int CSPLIT = SCP_RS_EPI_WARPS / 4;
 template <class Epi>
 int launch(const void *A, const void *W, int nb, int rows_a, int rows_w, int nu, const Epi &epi, cudaStream_t)
 {
@@ -45,12 +49,12 @@ int launch(const void *A, const void *W, int nb, int rows_a, int rows_w, int nu,
         const int lim = epi.live_n_tiles(m_blk), n_end = n_beg + nu < lim ? n_beg + nu : lim;
         const int w_base = (m_blk / tpb) * rows_w;
         for (int n_blk = n_beg; n_blk < n_end; n_blk++)
-            for (int sub = 0; sub < 8; sub++) {           // epilogue warp: column half sub / 4, TMEM lane quarter sub % 4
+            for (int sub = 0; sub < 4 * CSPLIT; sub++) {  // epilogue warp: column range sub / 4, TMEM lane quarter sub % 4
                 const int row0 = m_blk * BM + (sub & 3) * 32, chalf = sub >> 2;
                 for (int lane = 0; lane < 32; lane++) {
                     float a0[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f }, a1[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
-                    for (int cc = 0; cc < 2; cc++) {
-                        const int c0 = chalf * 64 + cc * 32;
+                    for (int cc = 0; cc < BN / 32 / CSPLIT; cc++) {
+                        const int c0 = chalf * (BN / CSPLIT) + cc * 32;
                         if (!epi.chunk_live(row0, n_blk * BN + c0)) continue;
                         float v[2][32];
                         for (int h = 0; h < 2; h++) {
@@ -87,7 +91,11 @@ constexpr int C = 64;            // feature channels
 constexpr int ROWF = 2 * C;      // floats per split operand row: 4 groups of [16 hi | 16 lo]
 constexpr int NT = 256;
 constexpr int TM = gemm_rs::BM, TN = gemm_rs::BN;   // GEMM tile: 256 rows x 128 columns
+constexpr int CS = gemm_rs::CSPLIT;                  // partial slots per row and tile (column ranges of the epilogue warps)
 constexpr float LOG2E = 1.4426950408889634f;
+#ifndef SCP_CORR_SLIM
+#define SCP_CORR_SLIM 1       // partial loads of the per-column weight records (0.466 -> 0.454 ms at B = 64, profiles/r2_corr_tcgen05.md)
+#endif
 
 __device__ __forceinline__ float tf32_rna(float x)
 {
@@ -112,7 +120,7 @@ __device__ __forceinline__ int row_pixel(const int *__restrict__ blk, int i, int
 }
 
 // ---- operand preparation ----------------------------------------------------------------------------------------
-// img_feat[b][c][p] -> a_img[b][i][128] (compacted block-major rows, split), wc[b][i] = mask * (1, gx, gy, 0),
+// img_feat[b][c][p] -> a_img[b][i][128] (compacted block-major rows, split), wc[b][i] = mask * (gx, gy, 1, 0),
 // wp[b][i / 4] = (pooled gx, pooled gy, pooled-pixel id as int bits, 1), live[b][i / 32] = bit mask of the foreground
 // rows.  CTA = 64 rows; CTAs past the image's last (256-row) tile exit.
 __global__ void __launch_bounds__(NT) prep_img_kernel(int P, int wf, const float *__restrict__ img_feat,
@@ -136,7 +144,7 @@ __global__ void __launch_bounds__(NT) prep_img_kernel(int P, int wf, const float
         s_pix[tid] = p;
         s_g[0][tid] = gx;
         s_g[1][tid] = gy;
-        wc[(size_t)b * P + i0 + tid] = fg ? make_float4(1.f, gx, gy, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wc[(size_t)b * P + i0 + tid] = fg ? make_float4(gx, gy, 1.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t bal = __ballot_sync(0xffffffffu, fg);
         if ((tid & 31) == 0) live[((size_t)b * P + i0 + tid) >> 5] = bal;
     }
@@ -171,7 +179,7 @@ __global__ void __launch_bounds__(NT) prep_img_kernel(int P, int wf, const float
     }
 }
 
-// mesh_feat[b][n][c] -> a_mesh[b][n][128] (split; rows N..Npad-1 zero), wr[b][n] = (1, v) (zero past N)
+// mesh_feat[b][n][c] -> a_mesh[b][n][128] (split; rows N..Npad-1 zero), wr[b][n] = (v, 1) (zero past N)
 __global__ void __launch_bounds__(NT) prep_mesh_kernel(int N, int Npad, const float *__restrict__ mesh_feat,
                                                        const float *__restrict__ pred_v, float *__restrict__ a_mesh,
                                                        float4 *__restrict__ wr)
@@ -192,20 +200,20 @@ __global__ void __launch_bounds__(NT) prep_mesh_kernel(int N, int Npad, const fl
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
         if (n < N) {
             const float *v = pred_v + ((size_t)b * N + n) * 3;
-            w = make_float4(1.f, v[0], v[1], v[2]);
+            w = make_float4(v[0], v[1], v[2], 1.f);
         }
         wr[(size_t)b * Npad + n] = w;
     }
 }
 
 // ---- epilogues ---------------------------------------------------------------------------------------------------
-// pass S (rows = compacted pixels, columns = vertices): a[0..3] += e * (1, v.x, v.y, v.z)
+// pass S (rows = compacted pixels, columns = vertices): a[0..3] += e * (1, v.x, v.y, v.z); wr holds (v, valid)
 struct EpiRows {
     const float4 *wr;        // [B][Npad]
     const uint32_t *live;    // [B * P / 32]
     const int *blocks;       // [B][P / 4 + 1]
-    float4 *part;            // [2 * Npad / 128][B * P]: per n tile and 64-column half
-    int P, Npad, M;
+    float4 *part;            // [CS * Npad / 128][B * P]: per n tile and column range
+    int P, Npad, M, nreal;   // nreal = N: columns past it are padding
     float kexp;
     // an m tile is visited when its first row lies inside the image's compacted list
     __device__ int live_n_tiles(int m_blk) const
@@ -218,23 +226,44 @@ struct EpiRows {
                            float (&a1)[8]) const
     {
         const float4 *w = wr + (size_t)(row / P) * Npad + col0;
+#if SCP_CORR_SLIM
+        // chunks that hold only real vertices (all but the image's last): 12 of the record's 16 bytes are loaded (three
+        // L1 write-back cycles per warp instead of four; the loads share the data port with the tensor core's operand reads)
+        if (col0 + 32 <= nreal) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const float2 q = __ldg(reinterpret_cast<const float2 *>(w + j) + 0);
+                const float qz = __ldg(reinterpret_cast<const float *>(w + j) + 2);
+                const float e0 = ex2_approx(fmaf(v0[j], kexp, -kexp)), e1 = ex2_approx(fmaf(v1[j], kexp, -kexp));
+                a0[0] += e0;
+                a0[1] = fmaf(e0, q.x, a0[1]);
+                a0[2] = fmaf(e0, q.y, a0[2]);
+                a0[3] = fmaf(e0, qz, a0[3]);
+                a1[0] += e1;
+                a1[1] = fmaf(e1, q.x, a1[1]);
+                a1[2] = fmaf(e1, q.y, a1[2]);
+                a1[3] = fmaf(e1, qz, a1[3]);
+            }
+            return;
+        }
+#endif
 #pragma unroll
         for (int j = 0; j < 32; j++) {
             const float4 q = __ldg(w + j);
             const float e0 = ex2_approx(fmaf(v0[j], kexp, -kexp)), e1 = ex2_approx(fmaf(v1[j], kexp, -kexp));
-            a0[0] = fmaf(e0, q.x, a0[0]);
-            a0[1] = fmaf(e0, q.y, a0[1]);
-            a0[2] = fmaf(e0, q.z, a0[2]);
-            a0[3] = fmaf(e0, q.w, a0[3]);
-            a1[0] = fmaf(e1, q.x, a1[0]);
-            a1[1] = fmaf(e1, q.y, a1[1]);
-            a1[2] = fmaf(e1, q.z, a1[2]);
-            a1[3] = fmaf(e1, q.w, a1[3]);
+            a0[0] = fmaf(e0, q.w, a0[0]);
+            a0[1] = fmaf(e0, q.x, a0[1]);
+            a0[2] = fmaf(e0, q.y, a0[2]);
+            a0[3] = fmaf(e0, q.z, a0[3]);
+            a1[0] = fmaf(e1, q.w, a1[0]);
+            a1[1] = fmaf(e1, q.x, a1[1]);
+            a1[2] = fmaf(e1, q.y, a1[2]);
+            a1[3] = fmaf(e1, q.z, a1[3]);
         }
     }
     __device__ void finish(int row, int n_blk, int chalf, const float (&a)[8]) const
     {
-        part[(size_t)(2 * n_blk + chalf) * M + row] = make_float4(a[0], a[1], a[2], a[3]);
+        part[(size_t)(CS * n_blk + chalf) * M + row] = make_float4(a[0], a[1], a[2], a[3]);
     }
 };
 
@@ -246,7 +275,7 @@ struct EpiCols {
     const float4 *wp;        // [B][P / 4]
     const uint32_t *live;    // [B][P / 32]
     const int *blocks;       // [B][P / 4 + 1]
-    float4 *part, *part_pool;   // [2 * P / 128][B * Npad]: per n tile and 64-column half
+    float4 *part, *part_pool;   // [CS * P / 128][B * Npad]: per n tile and column range
     float *pc_pool;          // [B][P / 4][N]
     int P, N, Npad, M;
     float kexp;
@@ -262,22 +291,39 @@ struct EpiCols {
     {
         const int b = row / Npad, n = row - b * Npad;     // rows n and n + 128 of the same image (Npad % 256 == 0)
         const float4 *w = wc + (size_t)b * P + col0;
+#if SCP_CORR_SLIM
+        const uint32_t bits = live[(size_t)b * (P >> 5) + (col0 >> 5)];   // foreground flags of the chunk's 32 pixels
+#endif
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             float s0[4], s1[4];
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-                const float4 q = __ldg(w + 4 * k + t);
                 const float x0 = v0[4 * k + t], x1 = v1[4 * k + t];
+#if SCP_CORR_SLIM
+                // 8 of the record's 16 bytes (grid x, y); the mask comes from the warp-uniform liveness word
+                const float2 q = __ldg(reinterpret_cast<const float2 *>(w + 4 * k + t) + 0);
+                const bool on = (bits >> (4 * k + t)) & 1u;
+                const float e0 = on ? ex2_approx(fmaf(x0, kexp, -kexp)) : 0.f, e1 = on ? ex2_approx(fmaf(x1, kexp, -kexp)) : 0.f;
+                a0[0] += e0;
+                a0[1] = fmaf(e0, q.x, a0[1]);
+                a0[2] = fmaf(e0, q.y, a0[2]);
+                a1[0] += e1;
+                a1[1] = fmaf(e1, q.x, a1[1]);
+                a1[2] = fmaf(e1, q.y, a1[2]);
+#else
+                const float4 q = __ldg(w + 4 * k + t);
+                const bool on = q.z != 0.f;
                 const float e0 = ex2_approx(fmaf(x0, kexp, -kexp)), e1 = ex2_approx(fmaf(x1, kexp, -kexp));
-                a0[0] = fmaf(e0, q.x, a0[0]);
-                a0[1] = fmaf(e0, q.y, a0[1]);
-                a0[2] = fmaf(e0, q.z, a0[2]);
-                a1[0] = fmaf(e1, q.x, a1[0]);
-                a1[1] = fmaf(e1, q.y, a1[1]);
-                a1[2] = fmaf(e1, q.z, a1[2]);
-                s0[t] = q.x != 0.f ? x0 : -1e5f;
-                s1[t] = q.x != 0.f ? x1 : -1e5f;
+                a0[0] = fmaf(e0, q.z, a0[0]);
+                a0[1] = fmaf(e0, q.x, a0[1]);
+                a0[2] = fmaf(e0, q.y, a0[2]);
+                a1[0] = fmaf(e1, q.z, a1[0]);
+                a1[1] = fmaf(e1, q.x, a1[1]);
+                a1[2] = fmaf(e1, q.y, a1[2]);
+#endif
+                s0[t] = on ? x0 : -1e5f;
+                s1[t] = on ? x1 : -1e5f;
             }
             if constexpr (POOL) {
                 const float4 g = __ldg(wp + (size_t)b * (P >> 2) + (col0 >> 2) + k);
@@ -300,8 +346,8 @@ struct EpiCols {
     }
     __device__ void finish(int row, int n_blk, int chalf, const float (&a)[8]) const
     {
-        part[(size_t)(2 * n_blk + chalf) * M + row] = make_float4(a[0], a[1], a[2], 0.f);
-        if constexpr (POOL) part_pool[(size_t)(2 * n_blk + chalf) * M + row] = make_float4(a[4], a[5], a[6], 0.f);
+        part[(size_t)(CS * n_blk + chalf) * M + row] = make_float4(a[0], a[1], a[2], 0.f);
+        if constexpr (POOL) part_pool[(size_t)(CS * n_blk + chalf) * M + row] = make_float4(a[4], a[5], a[6], 0.f);
     }
 };
 
@@ -324,7 +370,7 @@ __global__ void finish_rows_kernel(int P, int N, int wf, int tiles, size_t M, co
         return;
     }
     float l = 0.f, x = 0.f, y = 0.f, z = 0.f;
-    for (int t = 0; t < 2 * tiles; t++) {
+    for (int t = 0; t < CS * tiles; t++) {
         const float4 q = part[(size_t)t * M + (size_t)b * P + i];
         l += q.x; x += q.y; y += q.z; z += q.w;
     }
@@ -345,7 +391,7 @@ __global__ void finish_cols_kernel(int P, int N, int Npad, size_t M, const float
     if (n >= N) return;
     const int tiles = (4 * blocks[(size_t)b * ((P >> 2) + 1)] + TN - 1) / TN;
     float s = 0.f, gx = 0.f, gy = 0.f;
-    for (int t = 0; t < 2 * tiles; t++) {
+    for (int t = 0; t < CS * tiles; t++) {
         const float4 q = part[(size_t)t * M + (size_t)b * Npad + n];
         s += q.x; gx += q.y; gy += q.z;
     }
@@ -380,9 +426,9 @@ static Layout make_layout(int B, int P, int N)
     L.wp = o;      o += al((size_t)B * (P / 4) * 16);
     L.wr = o;      o += al((size_t)B * L.Npad * 16);
     L.live = o;    o += al((size_t)B * (P / 32) * 4);
-    L.part_r = o;  o += al((size_t)(2 * L.Npad / TN) * B * P * 16);
-    L.part_c = o;  o += al((size_t)(2 * P / TN) * B * L.Npad * 16);
-    L.part_cp = o; o += al((size_t)(2 * P / TN) * B * L.Npad * 16);
+    L.part_r = o;  o += al((size_t)(CS * L.Npad / TN) * B * P * 16);
+    L.part_c = o;  o += al((size_t)(CS * P / TN) * B * L.Npad * 16);
+    L.part_cp = o; o += al((size_t)(CS * P / TN) * B * L.Npad * 16);
     L.total = o;
     return L;
 }
@@ -421,7 +467,7 @@ int forward(const float *img_feat, const float *mesh_feat, const float *mask_dow
     prep_mesh_kernel<<<dim3((Npad * 32 + NT - 1) / NT, B), NT, 0, st>>>(N, Npad, mesh_feat, pred_v, a_mesh, wr);
 
     // pass S: rows = pixels (B problems of P rows), columns = vertices; one unit = all n tiles of an m tile
-    EpiRows er{ wr, live, blocks, part_r, P, Npad, B * P, kexp };
+    EpiRows er{ wr, live, blocks, part_r, P, Npad, B * P, N, kexp };
     int rc = gemm_rs::launch(a_img, a_mesh, B, P, Npad, 16, er, st);
     if (rc != 0) return rc;
     // pass S^T: rows = vertices (B problems of Npad rows), columns = pixels; units of 4 n tiles

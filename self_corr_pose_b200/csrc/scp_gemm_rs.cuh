@@ -38,7 +38,11 @@ using gemm::BK;
 constexpr int KB = 4;                                 // k-blocks of 128 bytes = ring stages (K = 64 logical columns)
 constexpr int STAGES = KB;
 constexpr int ACC_STAGES = 2;
-constexpr int EPI_WARPS = 8;
+#ifndef SCP_RS_EPI_WARPS
+#define SCP_RS_EPI_WARPS 8          // 8: a warp owns 64 columns (two chunks) of a lane quarter; 16: 32 columns (one chunk)
+#endif
+constexpr int EPI_WARPS = SCP_RS_EPI_WARPS;
+constexpr int CSPLIT = EPI_WARPS / 4;                 // column ranges per tile = partial slots per row and tile
 constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 constexpr int STAGE_BYTES = (BM + BN) * BK * 2;     // 48 KiB: [A 256 rows | W 128 rows] x 128 B
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
@@ -151,7 +155,7 @@ gemm_rowstats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
     } else {
         // ===== epilogue warps: TMEM lane quarter = warp % 4, column half of the tile = (warp - 2) / 4, both M halves =====
-        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
+        const int quarter = warp & 3, chalf = (warp - 2) >> 2;     // chalf: column range 0 .. CSPLIT-1 of BN / CSPLIT columns
         const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
         int acc = 0, acc_phase = 0;
         for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -166,8 +170,8 @@ gemm_rowstats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
                 for (int k = 0; k < 8; k++) a0[k] = a1[k] = 0.f;
 #pragma unroll 1
-                for (int cc = 0; cc < 2; cc++) {
-                    const int c0 = chalf * 64 + cc * 32;
+                for (int cc = 0; cc < BN / 32 / CSPLIT; cc++) {
+                    const int c0 = chalf * (BN / CSPLIT) + cc * 32;
                     if (!epi.chunk_live(row0, n_blk * BN + c0)) continue;      // warp-uniform (same address in every lane)
                     uint32_t r0[32], r1[32];
                     tc5::tmem_ld32_nowait(tmem_base + t_lane + acc * ACC_COLS + c0, r0);

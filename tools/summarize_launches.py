@@ -24,7 +24,7 @@ for r in rows[1:]:
     agg[name][1] += float(r[vi].replace(',', '')) * scale[r[ui]]
 steps = max(v[0] for k, v in agg.items() if re.search(r'fa[23]?::fa[23]?_fwd_kernel', k)) // 9
 total = sum(v[1] for v in agg.values()) / steps
-mine = sum(v[1] for k, v in agg.items() if re.search(r'softras::|corr::|gemm::|vit::|fa[23]?::|loss::|geom::|cycle::|sym::|jitter::|nhwc::|data::', k)) / steps
+mine = sum(v[1] for k, v in agg.items() if re.search(r'softras::|corr::|corr_tc::|gemm_rs::|gemm::|vit::|fa[23]?::|loss::|geom::|cycle::|sym::|jitter::|nhwc::|data::|posefit::', k)) / steps
 with open(dst, 'w') as f:
     f.write('# ncu launch list of `bench.py`, aggregated per step\n\n%s\n\n' % note)
     f.write('%d launches over %d steps (warm-up, timed and end-to-end steps all run under the profiler); times are '
