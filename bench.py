@@ -318,7 +318,7 @@ def kernel_breakdown(torch, hot, data, enc, B, peaks):
         t_a = timeit(lambda: L.scp_attention_x3(_lib.ptr(qk), _lib.ptr(vt), _lib.ptr(o), B, T, st))
         out.append(dict(kernel='fa3_fwd_kernel (tcgen05 flash attention, split operands)', ms=t_a, bound='tensor',
                         achieved=4.0 * T * T * 64 * 6 * B / t_a / 1e9, peak=tf_eff, unit='TFLOP/s', launches_per_step=9,
-                        ncu_name='fa3::fa3_fwd_kernel #0', peak_source=tf_note))
+                        ncu_name='fa3::fa3_fwd_kernel<4, 0> #0', peak_source=tf_note))
         A = split_bf16_i32(torch.randn(M, 384, device=dev))
         W = split_bf16_i32(torch.randn(1152, 384, device=dev))
         Cc = torch.empty(M, 1152, device=dev)

@@ -34,7 +34,7 @@ for part in src.split(','):            # several captures of the same step (diff
     for r in rows[2:]:
         name = re.sub(r'\(.*', '', r[col['Kernel Name']])
         name = name.replace('void ', '').replace('scp::', '')
-        if not re.search(r'softras::|corr::|gemm::|vit::|fa[23]?::|loss::|geom::|cycle::|sym::|jitter::|nhwc::|data::', name):
+        if not re.search(r'softras::|corr::|corr_tc::|gemm_rs::|gemm::|vit::|fa[23]?::|loss::|geom::|cycle::|sym::|jitter::|nhwc::|data::|posefit::', name):
             continue
         k = seen.get(name, 0)
         seen[name] = k + 1
