@@ -146,7 +146,7 @@ def check_cycle_rows(B=4, P4=64, N=90, k=12, seed=2):
                 g_A=rel(g_A, A_r.grad))
 
 
-def check_correspondence(B=2, hf=16, wf=16, N=70, C=64, seed=0):
+def check_correspondence(B=2, hf=16, wf=16, N=70, C=64, seed=0, masks='disc'):
     """scp_corr.cu (mma.sync replaced by its host statement in scp_mma.cuh): forward outputs and both feature gradients,
     fused (row kernel reduces g_mesh_feat too) and split backward, against the reference formulation in fp64."""
     from oracle import corr as ocorr
@@ -158,6 +158,9 @@ def check_correspondence(B=2, hf=16, wf=16, N=70, C=64, seed=0):
     H = 4 * hf
     yy, xx = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, H), indexing='ij')
     mask = torch.stack([(((xx - 0.1 * b) ** 2 + yy ** 2) < 0.6 ** 2).float() for b in range(B)])
+    if masks == 'mixed':        # image 1 without any foreground (uniform soft-max fallbacks), image 2 without background
+        mask[1] = 0.
+        mask[2] = 1.
     pred_v = torch.randn(B, N, 3, generator=g)
     w_match, w_imatch = torch.randn(B, P, 3, generator=g), torch.randn(B, 2, N, generator=g)
     w_pool, w_A = torch.randn(B, P // 4, N, generator=g) * 0.01, torch.randn(B, 2, N, generator=g)
@@ -337,6 +340,7 @@ def main():
     ok = True
     for name, fn, tol in (('image losses', check_image_losses, 1e-5), ('geometry', check_geometry, 1e-5),
                           ('cycle rows', check_cycle_rows, 1e-4), ('correspondence', check_correspondence, 1e-3),
+                          ('corr. masks', lambda: check_correspondence(B=3, hf=16, wf=32, N=200, seed=2, masks='mixed'), 1e-3),
                           ('nhwc glue', check_nhwc, 2e-6), ('data path', check_data, 1e-12),
                           ('pose fit', check_posefit, 2e-5)):
         res = fn()
